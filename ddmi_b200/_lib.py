@@ -1,0 +1,109 @@
+"""ctypes binding of libddmi_b200.so (the C ABI declared in include/ddmi_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or a call
+returns a non-zero status, a RuntimeError is raised (the reference's native ops
+behave the same way: TORCH_CHECK -> RuntimeError, op/fused_bias_act.cpp:7-13).
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libddmi_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+PREC_FP32 = 0
+PREC_BF16X3 = 1
+
+EXPORTS = (
+    "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
+    "ddmi_decode_image", "ddmi_decode_occupancy", "ddmi_decode_video",
+    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma",
+)
+
+
+class Plane(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("height", ctypes.c_int32), ("width", ctypes.c_int32)]
+
+
+class Weights(ctypes.Structure):
+    _fields_ = [("precision", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("gemm", ctypes.c_void_p), ("gemm_bytes", ctypes.c_uint64),
+                ("vec", ctypes.c_void_p), ("vec_floats", ctypes.c_uint64)]
+
+
+def build_library(verbose=False):
+    """Compile the CUDA sources for sm_100a into LIB_PATH (nvcc cross-compiles
+    without a GPU).  Used by __graft_entry__.build()."""
+    cmd = ["make", "-C", CSRC_DIR, "-j", str(min(8, os.cpu_count() or 1))]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libddmi_b200.so failed (see output above)")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C {CSRC_DIR}` "
+                "(or __graft_entry__.build()). ddmi_b200 has no CPU / eager fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i32, i64, f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
+        L.ddmi_abi_version.restype = ctypes.c_int
+        L.ddmi_last_error.restype = ctypes.c_char_p
+        L.ddmi_status_string.restype = ctypes.c_char_p
+        L.ddmi_status_string.argtypes = [ctypes.c_int]
+        L.ddmi_device_info.argtypes = [ctypes.POINTER(i32)] * 3
+        L.ddmi_decode_image.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, i64,
+                                        ctypes.POINTER(Weights), vp, vp]
+        L.ddmi_decode_occupancy.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, i64, i64, f32,
+                                            ctypes.POINTER(Weights), vp, vp]
+        L.ddmi_decode_video.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
+                                        ctypes.POINTER(Weights), vp, vp]
+        L.ddmi_nerf_mlp.argtypes = [vp, i64, i32, i32, f32, ctypes.POINTER(Weights), vp, vp]
+        L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, i64, i32, vp, i32, f32, f32,
+                                       i32, ctypes.POINTER(Weights), vp, vp, vp]
+        L.ddmi_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
+        for name in EXPORTS:
+            getattr(L, name)  # AttributeError here = header / library out of sync
+        if L.ddmi_abi_version() != 1:
+            raise RuntimeError("libddmi_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        L = lib()
+        kind = L.ddmi_status_string(status).decode()
+        msg = L.ddmi_last_error().decode()
+        raise RuntimeError(f"ddmi_b200: {kind}: {msg}")
+
+
+def planes_array(tensors):
+    """ctypes array of ddmi_plane_t from contiguous fp32 CUDA tensors (B,C,H,W)."""
+    arr = (Plane * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i].data = t.data_ptr()
+        arr[i].height = t.shape[-2]
+        arr[i].width = t.shape[-1]
+    return arr
+
+
+def weights_struct(packed):
+    """packed: packing.Packed (precision, gemm tensor, vec tensor)."""
+    w = Weights()
+    w.precision = packed.precision
+    w.gemm = packed.gemm.data_ptr()
+    w.gemm_bytes = packed.gemm.numel() * packed.gemm.element_size()
+    w.vec = packed.vec.data_ptr()
+    w.vec_floats = packed.vec.numel()
+    return w

@@ -1,0 +1,234 @@
+// extern "C" boundary of libddmi_b200.so: argument validation + dispatch.
+// Declarations and the reference interfaces they replace: include/ddmi_b200.h.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace ddmi {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return DDMI_ERR_CUDA;
+}
+
+// fp32 CUDA-core path (decode_fp32.cu)
+int launch_image_fp32(const PlaneSet&, int, int, const float*, const float*, long long, const float*, const float*, float*, cudaStream_t);
+int launch_occupancy_fp32(const PlaneSet&, int, int, const float*, long long, long long, float, float, const float*, const float*, float*, cudaStream_t);
+int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const float*, const float*, float*, cudaStream_t);
+int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
+int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
+// tcgen05 path (decode_umma.cu)
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const float*, size_t, float*, cudaStream_t);
+int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
+
+static int check_planes(const ddmi_plane_t* planes, int count, PlaneSet* ps) {
+  DDMI_REQUIRE(planes != nullptr, "planes is NULL");
+  for (int i = 0; i < count; ++i) {
+    DDMI_REQUIRE(planes[i].data != nullptr, "planes[%d].data is NULL", i);
+    DDMI_REQUIRE(planes[i].height >= 1 && planes[i].width >= 1, "planes[%d] has empty extent %dx%d", i,
+                 planes[i].height, planes[i].width);
+    ps->data[i] = planes[i].data;
+    ps->h[i] = planes[i].height;
+    ps->w[i] = planes[i].width;
+  }
+  return DDMI_OK;
+}
+
+static int check_weights(const ddmi_weights_t* w, uint64_t need_gemm_bytes, uint64_t need_vec) {
+  DDMI_REQUIRE(w != nullptr, "weights is NULL");
+  DDMI_REQUIRE(w->gemm != nullptr && w->vec != nullptr, "weights->gemm / weights->vec is NULL");
+  DDMI_REQUIRE(((uintptr_t)w->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
+  DDMI_REQUIRE(((uintptr_t)w->vec & 15) == 0, "weights->vec must be 16-byte aligned");
+  DDMI_REQUIRE(w->gemm_bytes == need_gemm_bytes, "packed gemm blob is %llu bytes, this decoder expects %llu",
+               (unsigned long long)w->gemm_bytes, (unsigned long long)need_gemm_bytes);
+  DDMI_REQUIRE(w->vec_floats == need_vec, "packed vec blob is %llu floats, this decoder expects %llu",
+               (unsigned long long)w->vec_floats, (unsigned long long)need_vec);
+  return DDMI_OK;
+}
+
+}  // namespace ddmi
+
+using namespace ddmi;
+
+extern "C" {
+
+DDMI_API int ddmi_abi_version(void) { return DDMI_ABI_VERSION; }
+
+DDMI_API const char* ddmi_last_error(void) { return g_err; }
+
+DDMI_API const char* ddmi_status_string(int status) {
+  switch (status) {
+    case DDMI_OK: return "ok";
+    case DDMI_ERR_BAD_ARG: return "bad argument";
+    case DDMI_ERR_UNSUPPORTED: return "unsupported configuration";
+    case DDMI_ERR_CUDA: return "CUDA error";
+    default: return "unknown status";
+  }
+}
+
+DDMI_API int ddmi_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  int dev = 0;
+  DDMI_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  DDMI_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return DDMI_OK;
+}
+
+DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                      const float* coord_x, const float* coord_y, int64_t n_coords,
+                      const ddmi_weights_t* weights, float* out, void* stream) {
+  PlaneSet ps = {};
+  int rc = check_planes(planes, 3, &ps);
+  if (rc) return rc;
+  DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
+  DDMI_REQUIRE(n_coords >= 1, "n_coords must be >= 1 (got %lld)", (long long)n_coords);
+  DDMI_REQUIRE(coord_x && coord_y && out, "coord_x / coord_y / out is NULL");
+  if (channels != 64) {
+    set_error("image decode is built for latent_dim = 64 planes (got %d channels)", channels);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (weights->precision == DDMI_PREC_FP32) {
+    // res1: c1[64] c2 c3 skip[64]; res2/3: c1[320] c2 c3 skip[320]; res4: c1 c2 c3
+    const uint64_t kfl = (64 + 256 + 256 + 64) + 2 * (320 + 256 + 256 + 320) + 3 * 256;
+    rc = check_weights(weights, kfl * 256 * sizeof(float), 4096 + 768 + 3);
+    if (rc) return rc;
+    return launch_image_fp32(ps, batch, channels, coord_x, coord_y, n_coords, (const float*)weights->gemm,
+                             weights->vec, out, st);
+  } else if (weights->precision == DDMI_PREC_BF16X3) {
+    DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
+    DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
+    return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm,
+                             weights->gemm_bytes, weights->vec, weights->vec_floats, out, st);
+  }
+  set_error("unknown precision %d", weights->precision);
+  return DDMI_ERR_UNSUPPORTED;
+}
+
+DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                          const float* points, int64_t n_points, int64_t point_batch_stride,
+                          float padding, const ddmi_weights_t* weights, float* logits, void* stream) {
+  PlaneSet ps = {};
+  int rc = check_planes(planes, 9, &ps);
+  if (rc) return rc;
+  DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
+  DDMI_REQUIRE(n_points >= 1, "n_points must be >= 1 (got %lld)", (long long)n_points);
+  DDMI_REQUIRE(points && logits, "points / logits is NULL");
+  DDMI_REQUIRE(point_batch_stride == 0 || point_batch_stride >= 3 * n_points,
+               "point_batch_stride %lld overlaps items", (long long)point_batch_stride);
+  if (channels != 64) {
+    set_error("occupancy decode is built for latent_dim = 64 planes (got %d channels)", channels);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  if (weights->precision != DDMI_PREC_FP32) {
+    set_error("occupancy decode: precision %d has no kernel in this build (fp32 only)", weights->precision);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  const uint64_t gfl = (64 * 64 + 64 * 256 + 64 * 256) + 2 * ((320 + 320 + 256) * 256) + 2 * 256 * 256;
+  rc = check_weights(weights, gfl * sizeof(float), 1856 + 768 + 256 + 1);
+  if (rc) return rc;
+  // the Python scalars of normalize_coordinate: double arithmetic, then fp32
+  const float divisor = (float)(1.0 + (double)padding + 10e-6);
+  const float upper = (float)(1.0 - 10e-6);
+  return launch_occupancy_fp32(ps, batch, channels, points, n_points, point_batch_stride, divisor, upper,
+                               (const float*)weights->gemm, weights->vec, logits, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                      const float* coords_xy, const float* coords_yt, const float* coords_xt,
+                      int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, float* out,
+                      void* stream) {
+  PlaneSet ps = {};
+  int rc = check_planes(planes, 9, &ps);
+  if (rc) return rc;
+  DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
+  DDMI_REQUIRE(T >= 1 && H >= 1 && W >= 1, "empty query volume %dx%dx%d", T, H, W);
+  DDMI_REQUIRE(coords_xy && coords_yt && coords_xt && out, "coords / out is NULL");
+  if (channels != 64) {
+    set_error("video decode is built for latent_dim = 64 planes (got %d channels)", channels);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  if (weights->precision != DDMI_PREC_FP32) {
+    set_error("video decode: precision %d has no kernel in this build (fp32 only)", weights->precision);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  const uint64_t gfl = (192 * 192 + 192 * 256 + 192 * 256) + 2 * ((448 + 448 + 256) * 256) + 2 * 256 * 256;
+  rc = check_weights(weights, gfl * sizeof(float), 448 + 3 * 512 + 768 + 3);
+  if (rc) return rc;
+  return launch_video_fp32(ps, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W,
+                           (const float*)weights->gemm, weights->vec, out, (cudaStream_t)stream);
+}
+
+static const uint64_t kNerfGemmFloats =
+    (uint64_t)(160 + 256 + (160 + 256) + 256 + (160 + 256) + 256 + 256) * 256 + (256 + 32) * 128;
+static const uint64_t kNerfVecFloats = 7 * 256 + 128 + 256 + 1 + 384 + 3;
+
+DDMI_API int ddmi_nerf_mlp(const float* x, int64_t n, int32_t x_stride, int32_t sigma_only, float negative_slope,
+                  const ddmi_weights_t* weights, float* out, void* stream) {
+  DDMI_REQUIRE(x && out, "x / out is NULL");
+  DDMI_REQUIRE(n >= 1, "n must be >= 1 (got %lld)", (long long)n);
+  DDMI_REQUIRE(x_stride >= (sigma_only ? 159 : 186), "x_stride %d too small", x_stride);
+  DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  if (weights->precision != DDMI_PREC_FP32) {
+    set_error("nerf mlp: precision %d has no kernel in this build (fp32 only)", weights->precision);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  int rc = check_weights(weights, kNerfGemmFloats * sizeof(float), kNerfVecFloats);
+  if (rc) return rc;
+  return launch_nerf_mlp_fp32(x, n, x_stride, sigma_only ? 1 : 0, negative_slope, (const float*)weights->gemm,
+                              weights->vec, out, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, const float* rays,
+                     int64_t n_rays, int32_t ray_stride, const float* t_vals, int32_t n_samples,
+                     float plane_extent, float negative_slope, int32_t white_bkgd,
+                     const ddmi_weights_t* weights, float* rgb_map, float* raw, void* stream) {
+  PlaneSet ps = {};
+  int rc = check_planes(planes, 3, &ps);
+  if (rc) return rc;
+  DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
+  DDMI_REQUIRE(n_rays >= 1 && n_samples >= 1, "empty ray set (%lld rays x %d samples)", (long long)n_rays, n_samples);
+  DDMI_REQUIRE(rays && t_vals && rgb_map, "rays / t_vals / rgb_map is NULL");
+  DDMI_REQUIRE(ray_stride >= 11, "ray rows need [o d near far viewdir] = 11 floats (stride %d)", ray_stride);
+  DDMI_REQUIRE(plane_extent > 0.f, "plane_extent must be positive");
+  if (channels != 32) {
+    set_error("nerf render is built for 32-channel triplanes (got %d)", channels);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  if (weights->precision != DDMI_PREC_FP32) {
+    set_error("nerf render: precision %d has no kernel in this build (fp32 only)", weights->precision);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  rc = check_weights(weights, kNerfGemmFloats * sizeof(float), kNerfVecFloats);
+  if (rc) return rc;
+  DDMI_REQUIRE(raw != nullptr, "the fp32 render kernel composites from `raw`; pass a (batch,n_rays,n_samples,4) buffer");
+  DDMI_REQUIRE(((uintptr_t)raw & 15) == 0, "raw must be 16-byte aligned");
+  return launch_nerf_render_fp32(ps, batch, channels, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent,
+                                 negative_slope, white_bkgd, (const float*)weights->gemm, weights->vec, rgb_map,
+                                 raw, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_t N, int32_t K, void* stream) {
+  DDMI_REQUIRE(a && b && d, "a / b / d is NULL");
+  DDMI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "N must be a multiple of 16 in [16,256] (got %d)", N);
+  DDMI_REQUIRE(K >= 16 && K <= 256 && K % 16 == 0, "K must be a multiple of 16 in [16,256] (got %d)", K);
+  return launch_selftest_umma(a, b, d, N, K, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Shared device/host helpers for the ddmi_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ddmi_b200.h"
+
+namespace ddmi {
+
+// ---------------------------------------------------------------------------
+// error plumbing (no exceptions cross the C ABI)
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define DDMI_REQUIRE(cond, ...)                      \
+  do {                                               \
+    if (!(cond)) {                                   \
+      ::ddmi::set_error(__VA_ARGS__);                \
+      return DDMI_ERR_BAD_ARG;                       \
+    }                                                \
+  } while (0)
+
+#define DDMI_CUDA(call)                                              \
+  do {                                                               \
+    cudaError_t e__ = (call);                                        \
+    if (e__ != cudaSuccess) return ::ddmi::cuda_fail(e__, #call);    \
+  } while (0)
+
+// Nine planes at most (3 axes x 3 scales); passed to kernels by value.
+struct PlaneSet {
+  const float* data[9];
+  int h[9];
+  int w[9];
+};
+
+// ---------------------------------------------------------------------------
+// Bilinear tap of F.grid_sample(mode='bilinear', padding_mode='border').
+// Index maps as in ATen's grid_sampler (the arithmetic behind
+// utils/general_utils.py:122-137 and utils/nerf_helpers.py:391-393):
+//   align_corners = true : ix = ((g + 1) / 2) * (W - 1)
+//   align_corners = false: ix = ((g + 1) * W - 1) / 2
+//   border: ix = min(W - 1, max(ix, 0)); 4 taps around floor(ix).
+// The +1 neighbour is clamped into range; its weight is exactly 0 whenever the
+// clamp is active, so the result equals ATen's "skip out-of-bounds tap".
+// ---------------------------------------------------------------------------
+struct Tap {
+  int o00, o01, o10, o11;      // element offsets inside one channel image
+  float w00, w01, w10, w11;    // nw, ne, sw, se
+};
+
+template <bool kAlignCorners>
+__device__ __forceinline__ float unnormalize(float g, int size) {
+  if (kAlignCorners) {
+    return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+  } else {
+    return __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), 1.f), 2.f);
+  }
+}
+
+template <bool kAlignCorners>
+__device__ __forceinline__ Tap make_tap(float gx, float gy, int H, int W) {
+  float ix = unnormalize<kAlignCorners>(gx, W);
+  float iy = unnormalize<kAlignCorners>(gy, H);
+  ix = fminf((float)(W - 1), fmaxf(ix, 0.f));
+  iy = fminf((float)(H - 1), fmaxf(iy, 0.f));
+  float fx = floorf(ix), fy = floorf(iy);
+  int x0 = (int)fx, y0 = (int)fy;
+  float tx1 = __fsub_rn(__fadd_rn(fx, 1.f), ix);  // ix_se - ix
+  float tx0 = __fsub_rn(ix, fx);                  // ix - ix_nw
+  float ty1 = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+  float ty0 = __fsub_rn(iy, fy);
+  int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  Tap t;
+  t.o00 = y0 * W + x0; t.o01 = y0 * W + x1;
+  t.o10 = y1 * W + x0; t.o11 = y1 * W + x1;
+  t.w00 = __fmul_rn(tx1, ty1); t.w01 = __fmul_rn(tx0, ty1);
+  t.w10 = __fmul_rn(tx1, ty0); t.w11 = __fmul_rn(tx0, ty0);
+  return t;
+}
+
+__device__ __forceinline__ float tap_sample(const float* __restrict__ ch, const Tap& t) {
+  float v00 = __ldg(ch + t.o00), v01 = __ldg(ch + t.o01);
+  float v10 = __ldg(ch + t.o10), v11 = __ldg(ch + t.o11);
+  float acc = v00 * t.w00;
+  acc = fmaf(v01, t.w01, acc);
+  acc = fmaf(v10, t.w10, acc);
+  acc = fmaf(v11, t.w11, acc);
+  return acc;
+}
+
+// normalize_coordinate + sample_plane_feature (utils/general_utils.py:71-94,
+// 115-119): u = p / (1 + padding + 10e-6) + 0.5, clamped to [0, 1 - 10e-6],
+// g = 2u - 1.  `divisor` and `upper` are computed on the host exactly the way
+// the Python scalars are (double arithmetic, then cast to fp32).
+__device__ __forceinline__ float occ_normalize(float p, float divisor, float upper) {
+  float u = __fadd_rn(__fdiv_rn(p, divisor), 0.5f);
+  if (u >= 1.f) u = upper;
+  if (u < 0.f) u = 0.f;
+  return __fsub_rn(__fmul_rn(2.f, u), 1.f);
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// torch.nn.functional.softplus (beta = 1, threshold = 20)
+__device__ __forceinline__ float softplus20(float v) { return v > 20.f ? v : log1pf(expf(v)); }
+
+}  // namespace ddmi

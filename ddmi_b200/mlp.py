@@ -1,0 +1,276 @@
+"""Drop-in INR decoders of the D2C-VAE (reference: models/d2c_vae/mlp.py).
+
+Same constructors, parameter names / shapes (state-dict compatible) and
+``forward`` signatures as the reference classes; ``forward`` is host-side weight
+folding + ONE fused CUDA launch through the C ABI (include/ddmi_b200.h).
+Inference only: if autograd would need a gradient through the decode, we raise
+instead of silently detaching (the reference back-props through this path during
+training; that is out of scope).
+"""
+import os
+
+import torch
+from torch import distributions as dist
+from torch import nn
+
+from . import _lib, packing
+from .blocks import ResnetBlockFC, SinusoidalPosEmb, StyledResBlock, ToRGB
+
+_PREC = {'fp32': _lib.PREC_FP32, 'bf16x3': _lib.PREC_BF16X3}
+
+
+def _resolve_precision(name, supported, default):
+    name = name or os.environ.get('DDMI_B200_PRECISION') or default
+    if name not in _PREC:
+        raise ValueError(f"precision must be one of {sorted(_PREC)} (got {name!r})")
+    if name not in supported:
+        raise NotImplementedError(f"precision {name!r} has no kernel for this decoder (supported: {supported})")
+    return _PREC[name]
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_plane(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (ddmi_b200 has no CPU path)")
+    if t.dim() != 4:
+        raise RuntimeError(f"{name} must be (B,C,H,W), got {tuple(t.shape)}")
+    return t.detach().to(torch.float32).contiguous()
+
+
+class _FusedDecoder(nn.Module):
+    """Common plumbing: grad guard + packed-weight cache."""
+
+    _supported = ('fp32',)
+    _default_precision = 'fp32'
+
+    def _init_fused(self, precision=None):
+        self.precision = precision
+        self._pack_cache = {}
+
+    def _guard_grad(self, *tensors):
+        if torch.is_grad_enabled() and (
+                any(p.requires_grad for p in self.parameters())
+                or any(torch.is_tensor(t) and t.requires_grad for t in tensors)):
+            raise RuntimeError(
+                "ddmi_b200 decoders are forward/inference only; call them under "
+                "torch.no_grad() / torch.inference_mode() (no autograd graph is built)")
+
+    def _packed(self, key, builder):
+        fp = (key, packing.param_fingerprint(self))
+        hit = self._pack_cache.get('entry')
+        if hit is None or hit[0] != fp:
+            hit = (fp, builder())
+            self._pack_cache['entry'] = hit
+        return hit[1]
+
+    def _check_device(self, t):
+        dev = next(self.parameters()).device
+        if not t.is_cuda or dev != t.device:
+            raise RuntimeError(
+                f"decoder parameters are on {dev} but inputs on {t.device}; both must be the same CUDA device")
+
+
+class MLP(_FusedDecoder):
+    """Image decoder.  Reference: models/d2c_vae/mlp.py:12-66."""
+
+    _supported = ('fp32', 'bf16x3')
+    _default_precision = 'bf16x3'
+
+    def __init__(self, *, in_ch=2, latent_dim=64, out_ch=3, ch=256, precision=None):
+        super().__init__()
+        if (in_ch, latent_dim, out_ch, ch) != (2, 64, 3, 256):
+            raise NotImplementedError(
+                "the fused image kernel is specialised for in_ch=2, latent_dim=64, out_ch=3, ch=256 "
+                "(configs/d2c-vae/afhq.yaml:44-48)")
+        self.latent_dim = latent_dim
+        dim = ch // 4
+        self.time_mlp = nn.Sequential(SinusoidalPosEmb(dim), nn.Linear(dim, ch), nn.GELU(), nn.Linear(ch, ch))
+        self.net_res1 = StyledResBlock(in_ch + latent_dim, ch, 1, ch, demodulate=True)
+        self.net_res2 = StyledResBlock(ch + in_ch + latent_dim, ch, 1, ch, demodulate=True)
+        self.net_res3 = StyledResBlock(ch + in_ch + latent_dim, ch, 1, ch, demodulate=True)
+        self.net_res4 = StyledResBlock(ch, ch, 1, ch, demodulate=True)
+        self.torgb = ToRGB(ch, out_ch, ch)
+        self._init_fused(precision)
+
+    def forward(self, coords, hdbf, si=1):
+        """coords (1,2,h,w) in [-1,1]; hdbf = 3 planes (b,64,S,S) coarse->fine;
+        returns (b,3,h,w).  mlp.py:34-66."""
+        assert hdbf is not None and len(hdbf) == 3
+        self._guard_grad(*hdbf)
+        planes = [_as_plane(t, f'hdbf[{i}]') for i, t in enumerate(hdbf)]
+        self._check_device(planes[0])
+        if coords.dim() != 4 or coords.shape[0] != 1 or coords.shape[1] != 2:
+            raise RuntimeError(f"coords must be (1,2,h,w), got {tuple(coords.shape)}")
+        _, _, h, w = coords.shape
+        b = planes[0].shape[0]
+        c = coords.detach().to(device=planes[0].device, dtype=torch.float32).contiguous()
+        prec = _resolve_precision(self.precision, self._supported, self._default_precision)
+        si = float(si)
+        packed = self._packed(('image', prec, si), lambda: packing.pack_image(self, si, prec))
+        out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
+        n = h * w
+        cx, cy = c[0, 0], c[0, 1]
+        with torch.cuda.device(c.device):
+            wst = _lib.weights_struct(packed)
+            _lib.check(_lib.lib().ddmi_decode_image(
+                _lib.planes_array(planes), b, planes[0].shape[1], cx.data_ptr(), cy.data_ptr(), n,
+                wst, out.data_ptr(), _stream_ptr(c.device)))
+        return out
+
+
+class MLP3D(_FusedDecoder):
+    """Occupancy decoder.  Reference: models/d2c_vae/mlp.py:69-111."""
+
+    def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None):
+        super().__init__()
+        if (in_ch, latent_dim, out_ch, ch) != (3, 64, 1, 256):
+            raise NotImplementedError(
+                "the fused occupancy kernel is specialised for in_ch=3, latent_dim=64, out_ch=1, ch=256 "
+                "(configs/d2c-vae/shapenet.yaml:44-48)")
+        self.latent_dim = latent_dim
+        self.net_p = nn.Linear(in_ch, ch)
+        self.net_res1 = ResnetBlockFC(latent_dim, ch)
+        self.net_res2 = ResnetBlockFC(ch + latent_dim, ch)
+        self.net_res3 = ResnetBlockFC(ch + latent_dim, ch)
+        self.net_res4 = ResnetBlockFC(ch, ch)
+        self.net_out = nn.Linear(ch, out_ch)
+        self._init_fused(precision)
+
+    def decode_logits(self, coords, hdbf):
+        assert len(hdbf) == 3
+        for axis in hdbf:
+            assert len(axis) == 3
+        self._guard_grad(coords, *[t for axis in hdbf for t in axis])
+        planes = [_as_plane(hdbf[a][s], f'hdbf[{a}][{s}]') for a in range(3) for s in range(3)]
+        self._check_device(planes[0])
+        b = planes[0].shape[0]
+        if coords.dim() != 3 or coords.shape[-1] != 3 or coords.shape[0] not in (1, b):
+            raise RuntimeError(f"coords must be ({b},N,3), got {tuple(coords.shape)}")
+        pts = coords.detach().to(device=planes[0].device, dtype=torch.float32)
+        if pts.shape[0] == 1 and b > 1:
+            pts = pts.expand(b, -1, -1)
+        n = pts.shape[1]
+        if pts.stride(0) == 0 or b == 1:
+            base, bstride = pts[0].contiguous(), 0
+        else:
+            base = pts.contiguous()
+            bstride = n * 3
+        prec = _resolve_precision(self.precision, self._supported, self._default_precision)
+        packed = self._packed(('occ', prec), lambda: packing.pack_occupancy(self, prec))
+        logits = torch.empty((b, n), device=base.device, dtype=torch.float32)
+        with torch.cuda.device(base.device):
+            _lib.check(_lib.lib().ddmi_decode_occupancy(
+                _lib.planes_array(planes), b, planes[0].shape[1], base.data_ptr(), n, bstride, 0.1,
+                _lib.weights_struct(packed), logits.data_ptr(), _stream_ptr(base.device)))
+        return logits
+
+    def forward(self, coords, hdbf):
+        """coords (B,N,3); hdbf = (xy, yz, xz), each a 3-list of (B,64,R,R);
+        returns Bernoulli(logits (B,N)).  mlp.py:82-111."""
+        return dist.Bernoulli(logits=self.decode_logits(coords, hdbf))
+
+
+class MLPVideo(_FusedDecoder):
+    """Video decoder.  Reference: models/d2c_vae/mlp.py:114-157."""
+
+    def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None, **ignore_kwargs):
+        super().__init__()
+        if (latent_dim, out_ch, ch) != (64, 3, 256):
+            raise NotImplementedError(
+                "the fused video kernel is specialised for latent_dim=64, out_ch=3, ch=256 "
+                "(configs/d2c-vae/skytimelapse.yaml:49-53)")
+        self.latent_dim = latent_dim
+        self.out_ch = out_ch
+        self.net_res1 = ResnetBlockFC(latent_dim * 3, ch)
+        self.net_res2 = ResnetBlockFC(ch + latent_dim * 3, ch)
+        self.net_res3 = ResnetBlockFC(ch + latent_dim * 3, ch)
+        self.net_res4 = ResnetBlockFC(ch)
+        self.net_out = nn.Linear(ch, out_ch)
+        self._init_fused(precision)
+
+    def forward(self, coords, hdbf):
+        """coords = {'xy':(1,2,H,W),'xt':(1,2,T,W),'yt':(1,2,T,H)}; hdbf =
+        (xy, yt, xt) 3-lists; returns (b,3,t,h,w) with t,h,w taken from the
+        finest planes exactly as the reference does (mlp.py:135-136,155-156)."""
+        assert len(hdbf) == 3
+        xy_hdbf, yt_hdbf, xt_hdbf = hdbf
+        assert len(xy_hdbf) == 3 and len(yt_hdbf) == 3 and len(xt_hdbf) == 3
+        self._guard_grad(*xy_hdbf, *yt_hdbf, *xt_hdbf)
+        planes = [_as_plane(hdbf[a][s], f'hdbf[{a}][{s}]') for a in range(3) for s in range(3)]
+        self._check_device(planes[0])
+        dev = planes[0].device
+        b, _, h, w = xy_hdbf[-1].shape
+        t = yt_hdbf[-1].shape[2]
+        cxy = coords['xy'].detach().to(device=dev, dtype=torch.float32).contiguous()
+        cyt = coords['yt'].detach().to(device=dev, dtype=torch.float32).contiguous()
+        cxt = coords['xt'].detach().to(device=dev, dtype=torch.float32).contiguous()
+        if cxy.shape[0] != 1 or cyt.shape[0] != 1 or cxt.shape[0] != 1:
+            raise RuntimeError("coords grids must have batch 1 (they are shared by all items)")
+        _, _, H, W = cxy.shape
+        T = cyt.shape[2]
+        if tuple(cyt.shape[1:]) != (2, T, H) or tuple(cxt.shape[1:]) != (2, T, W):
+            raise RuntimeError("inconsistent coords grids: expected xy (1,2,H,W), yt (1,2,T,H), xt (1,2,T,W)")
+        prec = _resolve_precision(self.precision, self._supported, self._default_precision)
+        packed = self._packed(('video', prec), lambda: packing.pack_video(self, prec))
+        out = torch.empty((b, self.out_ch, T * H * W), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddmi_decode_video(
+                _lib.planes_array(planes), b, planes[0].shape[1], cxy.data_ptr(), cyt.data_ptr(),
+                cxt.data_ptr(), T, H, W, _lib.weights_struct(packed), out.data_ptr(), _stream_ptr(dev)))
+        return out.reshape(b, self.out_ch, t, h, w)
+
+
+class MLPNeRF(_FusedDecoder):
+    """NeRF density/colour MLP.  Reference: models/d2c_vae/mlp.py:199-281."""
+
+    def __init__(self, D=8, W=256, in_channels_xyz=96, in_channels_dir=27, skips=[2, 4, 6], precision=None):
+        super().__init__()
+        self.D, self.W = D, W
+        self.in_channels_xyz, self.in_channels_dir = in_channels_xyz, in_channels_dir
+        self.skips = skips
+        # nn.LeakyReLU(True): the positional argument is negative_slope, so the
+        # slope is 1.0 and the activation is the identity.  Kept
+        # as a module so state dicts / repr line up; the kernel takes the slope.
+        for i in range(D):
+            if i == 0:
+                layer = nn.Linear(in_channels_xyz, W)
+            elif i in skips:
+                layer = nn.Linear(W + in_channels_xyz, W)
+            else:
+                layer = nn.Linear(W, W)
+            setattr(self, f"xyz_encoding_{i + 1}", nn.Sequential(layer, nn.LeakyReLU(True)))
+        self.xyz_encoding_final = nn.Linear(W, W)
+        self.dir_encoding = nn.Sequential(nn.Linear(W + in_channels_dir, W // 2), nn.LeakyReLU(True))
+        self.sigma = nn.Linear(W, 1)
+        self.rgb = nn.Sequential(nn.Linear(W // 2, 3), nn.Sigmoid())
+        self._init_fused(precision)
+
+    @property
+    def negative_slope(self):
+        return float(self.dir_encoding[1].negative_slope)
+
+    def packed_weights(self):
+        prec = _resolve_precision(self.precision, self._supported, self._default_precision)
+        return self._packed(('nerf', prec), lambda: packing.pack_nerf(self, prec))
+
+    def forward(self, x, sigma_only=False):
+        """x (B,186) [or (B,159) if sigma_only] -> (B,4) [rgb, sigma] or (B,1).  mlp.py:241-281."""
+        self._guard_grad(x)
+        self._check_device(x)
+        need = self.in_channels_xyz if sigma_only else self.in_channels_xyz + self.in_channels_dir
+        if x.dim() != 2 or x.shape[1] != need:
+            raise RuntimeError(f"x must be (B,{need}), got {tuple(x.shape)}")
+        xx = x.detach().to(torch.float32).contiguous()
+        n = xx.shape[0]
+        out = torch.empty((n, 1 if sigma_only else 4), device=xx.device, dtype=torch.float32)
+        if n == 0:
+            return out
+        packed = self.packed_weights()
+        with torch.cuda.device(xx.device):
+            _lib.check(_lib.lib().ddmi_nerf_mlp(
+                xx.data_ptr(), n, xx.shape[1], 1 if sigma_only else 0, self.negative_slope,
+                _lib.weights_struct(packed), out.data_ptr(), _stream_ptr(xx.device)))
+        return out

@@ -1,0 +1,186 @@
+"""NeRF query + volume renderer of the D2C-VAE decode path.
+
+Mirrors the call surface of the reference's ``utils/nerf_helpers.py`` that the
+trainers use (``get_embedder``, ``get_render_kwargs``, ``pose_spherical``,
+``get_rays``, ``render``); everything between "rays" and "rgb_map" --
+sample generation, triplane gather, positional embedding, MLPNeRF and
+``raw2outputs`` compositing (nerf_helpers.py:296-530) -- is one call into the
+C ABI (``ddmi_nerf_render``).  Ray generation stays host-side tensor plumbing.
+
+Out of scope here and rejected loudly (SURVEY.md §8f "next" row 4): stratified
+``perturb``, hierarchical ``N_importance`` / ``sample_pdf``, ``raw_noise_std``,
+``ndc`` rays, ``lindisp``, ``c2w_staticcam``.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .mlp import MLPNeRF, _stream_ptr
+
+PLANE_EXTENT = 3.5   # pts / 3.5 before the triplane lookup (nerf_helpers.py:384)
+
+
+class _Embedder:
+    """gamma(x) = [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)]
+    (nerf_helpers.py:82-112).  The fused kernel evaluates this in-kernel; the
+    callable exists for API parity and for feeding MLPNeRF.forward directly."""
+
+    def __init__(self, multires, input_dims=3):
+        self.multires = multires
+        self.input_dims = input_dims
+        self.out_dim = input_dims * (1 + 2 * multires)
+        self.freq_bands = 2. ** torch.linspace(0., multires - 1, steps=multires)
+
+    def __call__(self, x):
+        parts = [x]
+        for f in self.freq_bands:
+            parts.append(torch.sin(x * f))
+            parts.append(torch.cos(x * f))
+        return torch.cat(parts, -1)
+
+
+def get_embedder(multires, i=0):
+    """(embed_fn, out_dim); ``i == -1`` -> identity (nerf_helpers.py:115-130)."""
+    if i == -1:
+        return torch.nn.Identity(), 3
+    e = _Embedder(multires)
+    return e, e.out_dim
+
+
+class NetworkFn:
+    """``network_fn`` of the render kwargs: callable like the reference's
+    ``lambda x: nerf(x)`` (nerf_helpers.py:55) but keeps the module reachable so
+    ``render`` can hand its packed weights to the fused kernel."""
+
+    def __init__(self, module):
+        self.module = module
+
+    def __call__(self, x):
+        return self.module(x)
+
+
+def get_render_kwargs(config, nerf, embed_fn, embeddirs_fn):
+    """Same keys as the reference's dict (nerf_helpers.py:40-64)."""
+    tn = config['model']['TN']
+    return {
+        'embed_fn': embed_fn,
+        'embeddirs_fn': embeddirs_fn,
+        'netchunk': tn['netchunk'],
+        'perturb': tn['peturb'],
+        'N_importance': tn['N_importance'],
+        'network_fine': None,
+        'N_samples': tn['N_samples'],
+        'network_fn': NetworkFn(nerf),
+        'use_viewdirs': tn['use_viewdirs'],
+        'white_bkgd': tn['white_bkgd'],
+        'raw_noise_std': tn['raw_noise_std'],
+        'near': 2.,
+        'far': 6.,
+        'ndc': False,
+    }
+
+
+def pose_spherical(theta, phi, radius):
+    """Camera-to-world of a camera on a sphere (nerf_helpers.py:22-38,66-71)."""
+    ph, th = phi / 180. * np.pi, theta / 180. * np.pi
+    trans = torch.Tensor([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, radius], [0, 0, 0, 1]]).float()
+    rphi = torch.Tensor([[1, 0, 0, 0], [0, np.cos(ph), -np.sin(ph), 0],
+                         [0, np.sin(ph), np.cos(ph), 0], [0, 0, 0, 1]]).float()
+    rth = torch.Tensor([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0],
+                        [np.sin(th), 0, np.cos(th), 0], [0, 0, 0, 1]]).float()
+    flip = torch.Tensor(np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]]))
+    return flip @ (rth @ (rphi @ trans))
+
+
+def get_rays(H, W, K, c2w, device):
+    """Pinhole rays, row j / column i, d = dirs . R^T (nerf_helpers.py:134-143)."""
+    cols = torch.linspace(0, W - 1, W)
+    rows = torch.linspace(0, H - 1, H)
+    i = cols.view(1, W).expand(H, W).to(device)
+    j = rows.view(H, 1).expand(H, W).to(device)
+    dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)
+    c2w = c2w.to(device)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def _find_module(network_fn):
+    if isinstance(network_fn, MLPNeRF):
+        return network_fn
+    mod = getattr(network_fn, 'module', None)
+    if isinstance(mod, MLPNeRF):
+        return mod
+    for cell in getattr(network_fn, '__closure__', None) or ():
+        try:
+            if isinstance(cell.cell_contents, MLPNeRF):
+                return cell.cell_contents
+        except ValueError:
+            pass
+    raise RuntimeError(
+        "render(): network_fn must wrap a ddmi_b200.MLPNeRF (use ddmi_b200.nerf_helpers.get_render_kwargs, "
+        "or pass the module itself); an opaque callable cannot be fused")
+
+
+def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False):
+    """rays (N,11) [o d near far viewdir]; fea = dict of (B,32,R,R) planes.
+    Returns rgb_map (B,N,3) (and raw (B,N,S,4))."""
+    planes = []
+    for k in ('xy', 'yz', 'xz'):
+        t = fea[k]
+        if not t.is_cuda:
+            raise RuntimeError("fea planes must be CUDA tensors (ddmi_b200 has no CPU path)")
+        planes.append(t.detach().to(torch.float32).contiguous())
+    dev = planes[0].device
+    b = planes[0].shape[0]
+    rays = rays.detach().to(device=dev, dtype=torch.float32).contiguous()
+    n = rays.shape[0]
+    t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)
+    rgb = torch.empty((b, n, 3), device=dev, dtype=torch.float32)
+    raw = torch.empty((b, n, N_samples, 4), device=dev, dtype=torch.float32)
+    packed = module.packed_weights()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().ddmi_nerf_render(
+            _lib.planes_array(planes), b, planes[0].shape[1], rays.data_ptr(), n, rays.shape[1],
+            t_vals.data_ptr(), N_samples, PLANE_EXTENT, module.negative_slope, 1 if white_bkgd else 0,
+            _lib.weights_struct(packed), rgb.data_ptr(), raw.data_ptr(), _stream_ptr(dev)))
+    return (rgb, raw) if return_raw else rgb
+
+
+def render(H, W, K, fea, pose, idx, device, chunk=1024 * 32, rays=None, c2w=None, ndc=False,
+           near=0., far=1., use_viewdirs=False, c2w_staticcam=None, **kwargs):
+    """Render rays -> rgb_map (N_rays, 3).  Signature of nerf_helpers.py:211-279.
+
+    ``chunk`` / ``netchunk`` only bound the reference's memory use and do not
+    change results; the fused kernel streams 128-row tiles, so they are accepted
+    and ignored.  With planes of batch B > 1 (an extension: B objects seen from
+    the same camera) the result is (B, N_rays, 3).
+    """
+    if ndc or c2w_staticcam is not None:
+        raise NotImplementedError("ndc rays / c2w_staticcam are outside the fused decode path")
+    if not use_viewdirs:
+        raise NotImplementedError("the fused NeRF kernel is built for use_viewdirs=True (in_channels_dir=27)")
+    for key, bad in (('perturb', lambda v: v and v > 0), ('N_importance', lambda v: v and v > 0),
+                     ('raw_noise_std', lambda v: v and v > 0), ('lindisp', bool)):
+        if bad(kwargs.get(key, 0)):
+            raise NotImplementedError(f"render(): {key}={kwargs[key]!r} is outside the fused decode path "
+                                      "(SURVEY.md §8f row 4)")
+    module = _find_module(kwargs['network_fn'])
+    N_samples = int(kwargs['N_samples'])
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w, device)
+    else:
+        rays_o, rays_d = rays
+    viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near_t, far_t = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    ray_batch = torch.cat([rays_o, rays_d, near_t, far_t, viewdirs], -1)
+    hw_idx = kwargs.get('hw_idx')
+    if hw_idx is not None:
+        ray_batch = ray_batch[hw_idx]
+    rgb = render_rays_fused(ray_batch, fea, module, N_samples, bool(kwargs.get('white_bkgd', False)))
+    return rgb[0] if rgb.shape[0] == 1 else rgb

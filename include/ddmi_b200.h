@@ -1,0 +1,166 @@
+/*
+ * ddmi_b200.h -- C ABI of the B200-native D2C-VAE continuous-decoding path.
+ *
+ * One entry point per decoder family of the reference (mlvlab/DDMI).  Only PODs
+ * cross this boundary: device pointers, sizes, scalars and a CUDA stream handle.
+ * No torch / C++ types, no exceptions: every function returns an int status
+ * (DDMI_OK == 0) and ddmi_last_error() gives the message for the calling thread.
+ *
+ * Ownership: the caller owns every buffer (planes, coordinates, packed weights,
+ * outputs); the library keeps no state between calls besides per-device kernel
+ * attributes.  All work is enqueued on `stream` of the CURRENT device and is
+ * stream-ordered; calls are re-entrant.  There is no CPU path: a machine without
+ * an sm_100 device gets DDMI_ERR_CUDA / DDMI_ERR_UNSUPPORTED, never a fallback.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   ddmi_decode_image      models/d2c_vae/mlp.py:34-66   MLP.forward
+ *                          (+ utils/general_utils.py:122-123, blocks.py:187-356,
+ *                             604-638, op/fused_bias_act_kernel.cu:18-49)
+ *   ddmi_decode_occupancy  models/d2c_vae/mlp.py:82-111  MLP3D.forward
+ *                          (+ general_utils.py:71-94,115-119,126-131, blocks.py:673-716)
+ *   ddmi_decode_video      models/d2c_vae/mlp.py:128-157 MLPVideo.forward
+ *                          (+ general_utils.py:134-145)
+ *   ddmi_nerf_mlp          models/d2c_vae/mlp.py:241-281 MLPNeRF.forward
+ *   ddmi_nerf_render       utils/nerf_helpers.py:296-452 render_rays
+ *                          (+ :455-475 run_network, :82-112 Embedder.embed,
+ *                             :487-530 raw2outputs)
+ * The reference binds its native ops with pybind11 inside a JIT torch extension
+ * (models/d2c_vae/op/fused_bias_act.cpp:18-20); INTEGRATION.md shows the ctypes
+ * stub a maintainer adds instead.
+ *
+ * Packed weights: produced by ddmi_b200/packing.py (layouts in DESIGN.md §4);
+ * `precision` selects both the layout and the kernel family:
+ *   DDMI_PREC_FP32    fp32 CUDA-core kernels (exact-arithmetic path)
+ *   DDMI_PREC_BF16X3  tcgen05 tensor-core kernels, bf16 hi/lo split operands,
+ *                     3 MMAs per product, fp32 accumulation in TMEM
+ */
+#ifndef DDMI_B200_H
+#define DDMI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DDMI_API __attribute__((visibility("default")))
+#else
+#define DDMI_API
+#endif
+
+#define DDMI_ABI_VERSION 1
+
+enum {
+  DDMI_OK = 0,
+  DDMI_ERR_BAD_ARG = 1,      /* null pointer, non-positive size, misaligned buffer */
+  DDMI_ERR_UNSUPPORTED = 2,  /* shape / width / precision this build has no kernel for */
+  DDMI_ERR_CUDA = 3          /* CUDA runtime error (launch, attribute, no device)    */
+};
+
+enum { DDMI_PREC_FP32 = 0, DDMI_PREC_BF16X3 = 1 };
+
+/* One positional-embedding plane batch: fp32, contiguous (batch, channels, height, width). */
+typedef struct {
+  const float* data;
+  int32_t height;
+  int32_t width;
+} ddmi_plane_t;
+
+/* Host-folded, packed MLP weights (device memory). */
+typedef struct {
+  int32_t precision;   /* DDMI_PREC_* */
+  int32_t reserved;
+  const void* gemm;    /* GEMM operands, layout per precision                     */
+  uint64_t gemm_bytes;
+  const float* vec;    /* fp32 vectors: biases, folded constants, small heads     */
+  uint64_t vec_floats;
+} ddmi_weights_t;
+
+DDMI_API int ddmi_abi_version(void);
+DDMI_API const char* ddmi_last_error(void);
+DDMI_API const char* ddmi_status_string(int status);
+
+/* Device properties the host side shards / sizes by.  Returns status. */
+DDMI_API int ddmi_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/*
+ * Image decode.  planes[s] = hdbf[s], s = 0 (coarse) .. 2 (fine), each
+ * (batch, channels=64, S_s, S_s).  coord_x / coord_y: n_coords query positions in
+ * [-1,1] (channel 0 / 1 of the reference's (1,2,h,w) coords tensor, flattened);
+ * shared by all batch items.  Sampling: bilinear, border padding,
+ * align_corners = false.  out: (batch, 3, n_coords) fp32.
+ */
+DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                      const float* coord_x, const float* coord_y, int64_t n_coords,
+                      const ddmi_weights_t* weights, float* out, void* stream);
+
+/*
+ * Occupancy decode.  planes[a*3+s]: axis a = 0 'xy', 1 'yz', 2 'xz'; scale s =
+ * 0..2; each (batch, 64, R_s, R_s).  points: (batch, n_points, 3) fp32 with
+ * batch stride `point_batch_stride` floats (0 = the same points for every item).
+ * Coordinates are normalised as normalize_coordinate(padding) does, then sampled
+ * bilinear / border / align_corners = true and summed over the three axes.
+ * logits: (batch, n_points) fp32.
+ */
+DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                          const float* points, int64_t n_points, int64_t point_batch_stride,
+                          float padding, const ddmi_weights_t* weights, float* logits,
+                          void* stream);
+
+/*
+ * Video decode.  planes[a*3+s]: a = 0 'xy' (batch,64,Hs,Ws), 1 'yt' (batch,64,Ts,Hs),
+ * 2 'xt' (batch,64,Ts,Ws).  coords_xy (2,H,W), coords_yt (2,T,H), coords_xt (2,T,W):
+ * the reference's grids taken literally -- channel 0 indexes the plane's LAST
+ * axis, channel 1 its second-to-last (so yt/xt are read with transposed axes,
+ * SURVEY.md F6).  Features are concatenated [xy,yt,xt] per scale.
+ * out: (batch, 3, T, H, W) fp32.
+ */
+DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                      const float* coords_xy, const float* coords_yt, const float* coords_xt,
+                      int32_t T, int32_t H, int32_t W,
+                      const ddmi_weights_t* weights, float* out, void* stream);
+
+/*
+ * NeRF MLP on pre-embedded rows.  x: (n, 186) = [latent 96 | embed(pts) 63 |
+ * embed(dir) 27] (or (n,159) when sigma_only).  out: (n,4) = [rgb, sigma]
+ * (or (n,1)).  `negative_slope` is the LeakyReLU slope (the reference's
+ * nn.LeakyReLU(True) => 1.0).
+ */
+DDMI_API int ddmi_nerf_mlp(const float* x, int64_t n, int32_t x_stride, int32_t sigma_only,
+                  float negative_slope, const ddmi_weights_t* weights, float* out,
+                  void* stream);
+
+/*
+ * NeRF ray render: sample generation, triplane gather, positional embedding,
+ * MLP and volume compositing for `batch` objects that share one ray set.
+ * planes[a] = 'xy','yz','xz', each (batch, 32, R, R).  rays: (n_rays, ray_stride)
+ * rows [o(3) d(3) near far viewdir(3)].  t_vals: (n_samples) the caller's
+ * linspace(0,1,n_samples).  pts are divided by `plane_extent` (3.5) before
+ * sampling (bilinear / border / align_corners = true).
+ * rgb_map: (batch, n_rays, 3).  raw: optional (batch, n_rays, n_samples, 4)
+ * model outputs [rgb, sigma] (pass NULL to skip the store when the kernel
+ * composites in place; some kernels need it as workspace and then it is required
+ * -- the function says so with DDMI_ERR_BAD_ARG).
+ */
+DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                     const float* rays, int64_t n_rays, int32_t ray_stride,
+                     const float* t_vals, int32_t n_samples, float plane_extent,
+                     float negative_slope, int32_t white_bkgd,
+                     const ddmi_weights_t* weights, float* rgb_map, float* raw,
+                     void* stream);
+
+/*
+ * Bring-up self test of the tcgen05 path: one 128 x N x K bf16 GEMM through the
+ * same descriptors / TMEM epilogue the decode kernels use.  a: (128,K) fp32,
+ * b: (N,K) fp32 (device); d: (128,N) fp32 = a * b^T computed with the bf16x3
+ * split.  N in {16..256, multiple of 16}, K multiple of 16, K <= 256.
+ */
+DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_t N, int32_t K,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDMI_B200_H */

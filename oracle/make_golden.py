@@ -1,0 +1,112 @@
+"""Generate tests/golden/*.pt by running the REFERENCE itself (build container only).
+
+Run:  python oracle/make_golden.py          (needs /root/reference, nvcc + ninja for the
+                                             reference's JIT ops; ~2 min the first time)
+Imports models/d2c_vae/mlp.py and utils/nerf_helpers.py from /root/reference with the
+two CPU shims of SURVEY.md Appendix A (imageio stub; CPU restatement of
+fused_leaky_relu, semantics from op/fused_bias_act_kernel.cu:28-47), loads the
+package's seeded weights into the reference modules (which also proves state-dict
+compatibility), runs them on the seeded inputs of oracle/cases.py and stores the
+outputs.  It also prints oracle-vs-reference differences.
+"""
+import os
+import sys
+import types
+
+os.environ.setdefault('TORCH_CUDA_ARCH_LIST', '10.0')
+os.environ.setdefault('TORCH_EXTENSIONS_DIR', '/tmp/refext')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+sys.modules['imageio'] = types.ModuleType('imageio')
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import models.d2c_vae.blocks as rblocks  # noqa: E402  (triggers the reference's JIT build)
+
+_cpu_flr = lambda x, b, ns=0.2, sc=2 ** 0.5: F.leaky_relu(x + b.view(1, -1, *[1] * (x.ndim - 2)), ns) * sc
+rblocks.fused_leaky_relu = _cpu_flr
+rblocks.FusedLeakyReLU.forward = lambda self, x: _cpu_flr(x, self.bias, self.negative_slope, self.scale)
+
+from models.d2c_vae import mlp as rmlp  # noqa: E402
+from utils import nerf_helpers as rnh  # noqa: E402
+
+from oracle import cases, ddmi_oracle as orc  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+os.makedirs(OUT, exist_ok=True)
+torch.set_grad_enabled(False)
+
+
+def save(name, out, inputs, extra=None):
+    d = {'out': out.float().contiguous(), 'input_checksum': cases.checksum(inputs)}
+    d.update(extra or {})
+    torch.save(d, os.path.join(OUT, name + '.pt'))
+    print(f'{name}: out {tuple(out.shape)} |out|max {float(out.abs().max()):.4f}')
+
+
+def flat(x):
+    return [t for a in x for t in (a if isinstance(a, (list, tuple)) else [a])]
+
+
+# ---- image ---------------------------------------------------------------
+m = cases.build_module('image')
+sd = cases.state_dict32(m)
+ref = rmlp.MLP(in_ch=2, latent_dim=64, out_ch=3, ch=256)
+ref.load_state_dict(sd, strict=True)
+for tag, kw in (('image_96', dict(batch=2, sizes=(16, 32, 64), res=96)),
+                ('image_native', dict(batch=1, sizes=(8, 16, 32), res=32))):
+    coords, planes, si = cases.image_inputs(**kw)
+    out = ref(coords, hdbf=planes, si=si)
+    o2 = orc.image_decode(sd, coords, planes, si)
+    print(f'  oracle-vs-reference {tag}: {float((out - o2).abs().max()):.3e}')
+    save(tag, out, planes + list(sd.values()), {'si': si})
+
+# ---- occupancy -------------------------------------------------------------
+m = cases.build_module('occupancy')
+sd = cases.state_dict32(m)
+ref = rmlp.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256)
+ref.load_state_dict(sd, strict=True)
+pts, hdbf = cases.occupancy_inputs()
+out = ref(pts, hdbf).logits
+o2 = orc.occupancy_logits(sd, pts, hdbf)
+print(f'  oracle-vs-reference occupancy: {float((out - o2).abs().max()):.3e}')
+save('occupancy', out, flat(hdbf) + [pts] + list(sd.values()))
+
+# ---- video -----------------------------------------------------------------
+m = cases.build_module('video')
+sd = cases.state_dict32(m)
+ref = rmlp.MLPVideo(in_ch=2, latent_dim=64, out_ch=3, ch=256)
+ref.load_state_dict(sd, strict=True)
+coords, hdbf = cases.video_inputs()
+out = ref(coords, hdbf)
+o2 = orc.video_decode(sd, coords, hdbf)
+print(f'  oracle-vs-reference video: {float((out - o2).abs().max()):.3e}')
+save('video', out, flat(hdbf) + list(sd.values()))
+
+# ---- nerf --------------------------------------------------------------------
+m = cases.build_module('nerf')
+sd = cases.state_dict32(m)
+ref = rmlp.MLPNeRF(D=6, W=256, in_channels_xyz=159, skips=[2, 4], in_channels_dir=27)
+ref.load_state_dict(sd, strict=True)
+x = cases.nerf_mlp_inputs()
+out = ref(x)
+o2 = orc.nerf_mlp(sd, x)
+print(f'  oracle-vs-reference nerf_mlp: {float((out - o2).abs().max()):.3e}')
+save('nerf_mlp', out, [x] + list(sd.values()))
+
+res, K, fea, c2w = cases.nerf_inputs()
+embed_fn, _ = rnh.get_embedder(10, 0)
+embeddirs_fn, _ = rnh.get_embedder(4, 0)
+kw = rnh.get_render_kwargs(cases.NERF_CFG, ref, embed_fn, embeddirs_fn)
+rgb = rnh.render(res, res, K, fea, None, 0, 'cpu', chunk=4096, c2w=c2w, verbose=True, retraw=True,
+                 hw_idx=None, **kw)
+# oracle on the same rays
+ro, rd = rnh.get_rays(res, res, K, c2w, 'cpu')
+vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
+rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(res * res, 1), 6. * torch.ones(res * res, 1), vd], -1)
+o2 = orc.nerf_render_rays(sd, rays, fea, 64, True)
+print(f'  oracle-vs-reference nerf_render: {float((rgb - o2).abs().max()):.3e}; rgb range {float(rgb.min()):.3f}..{float(rgb.max()):.3f}')
+save('nerf_render', rgb, list(fea.values()) + list(sd.values()), {'rays': rays})
+print('done')
