@@ -1,0 +1,91 @@
+"""CPU: the oracle restatement vs the outputs of the REFERENCE itself
+(tests/golden/*.pt, produced by oracle/make_golden.py in the build container).
+This is the pin of SURVEY.md §8c: the reference has no tests of its own."""
+import os
+
+import pytest
+import torch
+
+from oracle import cases, ddmi_oracle as orc
+
+torch.set_grad_enabled(False)
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + '.pt'))
+
+
+def _flat(x):
+    return [t for a in x for t in (a if isinstance(a, (list, tuple)) else [a])]
+
+
+def _check_inputs(g, inputs):
+    cs = cases.checksum(inputs)
+    assert abs(cs - g['input_checksum']) <= 1e-9 * abs(cs), (
+        "seeded inputs differ from the ones the golden outputs were generated from "
+        "(torch RNG drift?) -- regenerate with oracle/make_golden.py")
+
+
+@pytest.mark.parametrize("tag,kw", [("image_96", dict(batch=2, sizes=(16, 32, 64), res=96)),
+                                    ("image_native", dict(batch=1, sizes=(8, 16, 32), res=32))])
+def test_image(golden_dir, tag, kw):
+    g = _load(golden_dir, tag)
+    sd = cases.state_dict32(cases.build_module('image'))
+    coords, planes, si = cases.image_inputs(**kw)
+    _check_inputs(g, planes + list(sd.values()))
+    out = orc.image_decode(sd, coords, planes, si)
+    assert out.shape == g['out'].shape
+    assert float((out - g['out']).abs().max()) < 2e-5
+
+
+def test_occupancy(golden_dir):
+    g = _load(golden_dir, 'occupancy')
+    sd = cases.state_dict32(cases.build_module('occupancy'))
+    pts, hdbf = cases.occupancy_inputs()
+    _check_inputs(g, _flat(hdbf) + [pts] + list(sd.values()))
+    out = orc.occupancy_logits(sd, pts, hdbf)
+    assert float((out - g['out']).abs().max()) < 1e-5
+    assert bool(((out > 0) == (g['out'] > 0)).all())
+
+
+def test_video(golden_dir):
+    g = _load(golden_dir, 'video')
+    sd = cases.state_dict32(cases.build_module('video'))
+    coords, hdbf = cases.video_inputs()
+    _check_inputs(g, _flat(hdbf) + list(sd.values()))
+    out = orc.video_decode(sd, coords, hdbf)
+    assert out.shape == g['out'].shape == (1, 3, 4, 32, 32)
+    assert float((out - g['out']).abs().max()) < 1e-5
+
+
+def test_nerf_mlp(golden_dir):
+    g = _load(golden_dir, 'nerf_mlp')
+    sd = cases.state_dict32(cases.build_module('nerf'))
+    x = cases.nerf_mlp_inputs()
+    _check_inputs(g, [x] + list(sd.values()))
+    assert float((orc.nerf_mlp(sd, x) - g['out']).abs().max()) < 1e-5
+    # LeakyReLU(True) is the identity: the xyz trunk is affine
+    s1 = orc.nerf_mlp(sd, x[:, :159], sigma_only=True)
+    s2 = orc.nerf_mlp(sd, 2 * x[:, :159], sigma_only=True)
+    s0 = orc.nerf_mlp(sd, 0 * x[:, :159], sigma_only=True)
+    assert float(((s2 - s0) - 2 * (s1 - s0)).abs().max()) < 1e-3
+
+
+def test_nerf_render(golden_dir):
+    g = _load(golden_dir, 'nerf_render')
+    sd = cases.state_dict32(cases.build_module('nerf'))
+    res, K, fea, c2w = cases.nerf_inputs()
+    _check_inputs(g, list(fea.values()) + list(sd.values()))
+    out = orc.nerf_render_rays(sd, g['rays'], fea, 64, True)
+    assert float((out - g['out']).abs().max()) < 1e-5
+    assert float(g['out'].max() - g['out'].min()) > 0.3   # the fixture is not degenerate
+
+
+def test_oracle_fp64_agrees():
+    """fp64 evaluation of the oracle bounds the fp32 reference's own rounding noise."""
+    sd = cases.state_dict32(cases.build_module('occupancy'))
+    pts, hdbf = cases.occupancy_inputs(n=2000)
+    o32 = orc.occupancy_logits(sd, pts, hdbf)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    o64 = orc.occupancy_logits(sd64, pts.double(), tuple([t.double() for t in a] for a in hdbf))
+    assert float((o32.double() - o64).abs().max()) < 5e-5

@@ -1,0 +1,210 @@
+"""GPU parity: the CUDA path (through the drop-in modules -> C ABI) against
+(a) the reference's own outputs committed under tests/golden/ and (b) the CPU
+oracle on further seeded shapes / edge cases.  Tolerances are the north star's:
+max-abs 1e-3 on RGB / density / logits, same occupancy sign on >= 99.99 %."""
+import os
+
+import pytest
+import torch
+
+import ddmi_b200
+from ddmi_b200 import nerf_helpers as nh
+from oracle import cases, ddmi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = 'cuda:0'
+TOL = 1e-3
+
+
+def _golden(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + '.pt'))
+
+
+def _cuda(x):
+    if isinstance(x, (list, tuple)):
+        return type(x)(_cuda(t) for t in x)
+    if isinstance(x, dict):
+        return {k: _cuda(v) for k, v in x.items()}
+    return x.to(DEV)
+
+
+def _sign_agreement(a, b):
+    return float(((a > 0) == (b > 0)).float().mean())
+
+
+def test_device_is_blackwell():
+    from ddmi_b200 import _lib
+    import ctypes
+    sm, maj, mnr = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.lib().ddmi_device_info(ctypes.byref(sm), ctypes.byref(maj), ctypes.byref(mnr)))
+    assert maj.value == 10 and sm.value >= 100
+
+
+# ---------------------------------------------------------------- image
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("tag,kw", [("image_96", dict(batch=2, sizes=(16, 32, 64), res=96)),
+                                    ("image_native", dict(batch=1, sizes=(8, 16, 32), res=32))])
+def test_image_golden(golden_dir, tag, kw, precision):
+    g = _golden(golden_dir, tag)
+    m = cases.build_module('image').to(DEV)
+    m.precision = precision
+    coords, planes, si = cases.image_inputs(**kw)
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=si).cpu()
+    assert out.shape == g['out'].shape
+    err = float((out - g['out']).abs().max())
+    assert err < (2e-5 if precision == 'fp32' else TOL), err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_image_ragged_and_scattered_coords(precision):
+    """n_coords not a multiple of the tile; out-of-range coords hit the border clamp."""
+    m = cases.build_module('image').to(DEV)
+    m.precision = precision
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(5)
+    planes = [torch.randn(3, 64, s, s, generator=g) for s in (8, 16, 24)]
+    coords = (torch.rand(1, 2, 7, 19, generator=g) * 2.4 - 1.2)
+    ref = orc.image_decode(sd, coords, planes, 0.7)
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=0.7).cpu()
+    assert float((out - ref).abs().max()) < (2e-5 if precision == 'fp32' else TOL)
+
+
+def test_image_style_cache_tracks_si_and_weights():
+    m = cases.build_module('image').to(DEV)
+    m.precision = 'fp32'
+    sd = cases.state_dict32(m)
+    coords, planes, _ = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=16)
+    a = m(coords.to(DEV), hdbf=_cuda(planes), si=1.0).cpu()
+    b = m(coords.to(DEV), hdbf=_cuda(planes), si=0.5).cpu()
+    assert float((b - orc.image_decode(sd, coords, planes, 0.5)).abs().max()) < 2e-5
+    assert float((a - b).abs().max()) > 1e-3
+    m.torgb.bias.data += 1.0
+    c = m(coords.to(DEV), hdbf=_cuda(planes), si=0.5).cpu()
+    assert float((c - b - 1.0).abs().max()) < 1e-5
+
+
+# ---------------------------------------------------------------- occupancy
+def test_occupancy_golden(golden_dir):
+    g = _golden(golden_dir, 'occupancy')
+    m = cases.build_module('occupancy').to(DEV)
+    pts, hdbf = cases.occupancy_inputs()
+    d = m(pts.to(DEV), _cuda(hdbf))
+    assert isinstance(d, torch.distributions.Bernoulli)
+    out = d.logits.cpu()
+    assert float((out - g['out']).abs().max()) < 2e-5
+    assert _sign_agreement(out, g['out']) >= 0.9999
+
+
+def test_occupancy_shared_points_and_single_point():
+    m = cases.build_module('occupancy').to(DEV)
+    sd = cases.state_dict32(m)
+    pts, hdbf = cases.occupancy_inputs(batch=3, n=1)
+    out = m(pts.to(DEV), _cuda(hdbf)).logits.cpu()
+    assert float((out - orc.occupancy_logits(sd, pts, hdbf)).abs().max()) < 2e-5
+    pts, hdbf = cases.occupancy_inputs(batch=2, n=777)
+    shared = pts[:1]
+    out = m(shared.to(DEV).expand(2, -1, -1), _cuda(hdbf)).logits.cpu()
+    ref = orc.occupancy_logits(sd, shared.expand(2, -1, -1).contiguous(), hdbf)
+    assert float((out - ref).abs().max()) < 2e-5
+
+
+def test_occupancy_dense_grid_chunks_like_eval_points():
+    """Generator3D.eval_points call shape: 1.1*make_3d_grid, split into chunks, mlp(pi[None], c).logits."""
+    m = cases.build_module('occupancy').to(DEV)
+    sd = cases.state_dict32(m)
+    _, hdbf = cases.occupancy_inputs(batch=1, n=1)
+    p = 1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (20,) * 3)
+    c = _cuda(hdbf)
+    got = torch.cat([m(pi[None].to(DEV), c).logits.squeeze(0).cpu() for pi in torch.split(p, 3000)])
+    ref = orc.occupancy_logits(sd, p[None], hdbf)[0]
+    assert float((got - ref).abs().max()) < 2e-5
+
+
+# ---------------------------------------------------------------- video
+def test_video_golden(golden_dir):
+    g = _golden(golden_dir, 'video')
+    m = cases.build_module('video').to(DEV)
+    coords, hdbf = cases.video_inputs()
+    out = m(_cuda(coords), _cuda(hdbf)).cpu()
+    assert out.shape == g['out'].shape
+    assert float((out - g['out']).abs().max()) < 2e-5
+
+
+def test_video_batch_and_anisotropic():
+    m = cases.build_module('video').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(9)
+    T, H, W = 3, 10, 14
+    xy = [torch.randn(2, 64, H // s, W // s, generator=g) for s in (2, 1, 1)]
+    yt = [torch.randn(2, 64, T, H // s, generator=g) for s in (2, 1, 1)]
+    xt = [torch.randn(2, 64, T, W // s, generator=g) for s in (2, 1, 1)]
+    coords = ddmi_b200.convert_to_coord_format_3d(1, H, W, T, hstart=-.9, hend=.9, wstart=-.8, wend=.8, tstart=-.5, tend=.5)
+    ref = orc.video_decode(sd, coords, (xy, yt, xt))
+    out = m(_cuda(coords), _cuda((xy, yt, xt))).cpu()
+    assert float((out - ref).abs().max()) < 2e-5
+
+
+# ---------------------------------------------------------------- nerf
+def test_nerf_mlp_golden(golden_dir):
+    g = _golden(golden_dir, 'nerf_mlp')
+    m = cases.build_module('nerf').to(DEV)
+    x = cases.nerf_mlp_inputs()
+    out = m(x.to(DEV)).cpu()
+    assert float((out - g['out']).abs().max()) < 2e-5
+    sig = m(x[:, :159].to(DEV), sigma_only=True).cpu()
+    assert float((sig[:, 0] - g['out'][:, 3]).abs().max()) < 2e-5
+
+
+def test_nerf_render_golden(golden_dir):
+    g = _golden(golden_dir, 'nerf_render')
+    m = cases.build_module('nerf').to(DEV)
+    res, K, fea, c2w = cases.nerf_inputs()
+    e1, _ = nh.get_embedder(10, 0)
+    e2, _ = nh.get_embedder(4, 0)
+    kw = nh.get_render_kwargs(cases.NERF_CFG, m, e1, e2)
+    rgb = nh.render(res, res, K, _cuda(fea), None, 0, DEV, chunk=4096, c2w=c2w, verbose=True, retraw=True,
+                    hw_idx=None, **kw).cpu()
+    assert rgb.shape == g['out'].shape == (res * res, 3)
+    assert float((rgb - g['out']).abs().max()) < 1e-4
+
+
+def test_nerf_render_batch_and_ray_subset():
+    m = cases.build_module('nerf').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(11)
+    fea = {k: torch.randn(2, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
+    gold_rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][100:165]
+    rgb, raw = nh.render_rays_fused(gold_rays.to(DEV), _cuda(fea), m, 48, True, return_raw=True)
+    for b in range(2):
+        fb = {k: v[b:b + 1] for k, v in fea.items()}
+        ref, ref_raw = orc.nerf_render_rays(sd, gold_rays, fb, 48, True, return_raw=True)
+        assert float((raw[b].cpu() - ref_raw).abs().max()) < 1e-4
+        assert float((rgb[b].cpu() - ref).abs().max()) < 1e-4
+
+
+def test_unsupported_render_options_raise():
+    m = cases.build_module('nerf').to(DEV)
+    res, K, fea, c2w = cases.nerf_inputs()
+    e1, _ = nh.get_embedder(10, 0)
+    e2, _ = nh.get_embedder(4, 0)
+    kw = nh.get_render_kwargs(cases.NERF_CFG, m, e1, e2)
+    kw['perturb'] = 1.0
+    with pytest.raises(NotImplementedError):
+        nh.render(res, res, K, _cuda(fea), None, 0, DEV, c2w=c2w, **kw)
+
+
+# ---------------------------------------------------------------- tcgen05 bring-up
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 64), (16, 256), (128, 32)])
+def test_umma_selftest(N, K):
+    from ddmi_b200 import _lib
+    g = torch.Generator().manual_seed(N * 1000 + K)
+    a = torch.randn(128, K, generator=g).to(DEV)
+    b = torch.randn(N, K, generator=g).to(DEV)
+    d = torch.full((128, N), float('nan'), device=DEV)
+    _lib.check(_lib.lib().ddmi_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K,
+                                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    assert float((d.double() - ref).abs().max()) < 2e-3 * float(ref.abs().max())
+    assert float((d.double() - ref).abs().max()) < 1e-3
