@@ -75,8 +75,9 @@ def occupancy_inputs(batch=2, sizes=(16, 32, 64), n=20000, spread=0.65, seed=SEE
     g = _gen(seed + 20)
     hdbf = tuple([_randn(g, batch, 64, s, s) for s in sizes] for _ in range(3))
     pts = (torch.rand(batch, n, 3, generator=g) * 2 - 1) * spread   # beyond +-0.55: exercises the clamp
-    pts[0, 0] = torch.tensor([0.55, -0.55, 0.0])
-    pts[0, 1] = torch.tensor([0.7, -0.7, 0.56])
+    if n >= 2:
+        pts[0, 0] = torch.tensor([0.55, -0.55, 0.0])
+        pts[0, 1] = torch.tensor([0.7, -0.7, 0.56])
     return pts, hdbf
 
 

@@ -79,7 +79,7 @@ def test_image_style_cache_tracks_si_and_weights():
     b = m(coords.to(DEV), hdbf=_cuda(planes), si=0.5).cpu()
     assert float((b - orc.image_decode(sd, coords, planes, 0.5)).abs().max()) < 2e-5
     assert float((a - b).abs().max()) > 1e-3
-    m.torgb.bias.data += 1.0
+    m.torgb.bias += 1.0   # in-place on the parameter bumps its version (as optimizers / load_state_dict do)
     c = m(coords.to(DEV), hdbf=_cuda(planes), si=0.5).cpu()
     assert float((c - b - 1.0).abs().max()) < 1e-5
 
