@@ -59,12 +59,15 @@ class _FusedDecoder(nn.Module):
                 "torch.no_grad() / torch.inference_mode() (no autograd graph is built)")
 
     def _packed(self, key, builder):
-        fp = (key, packing.param_fingerprint(self))
-        hit = self._pack_cache.get('entry')
-        if hit is None or hit[0] != fp:
-            hit = (fp, builder())
-            self._pack_cache['entry'] = hit
-        return hit[1]
+        fp = packing.param_fingerprint(self)
+        if self._pack_cache.get('fingerprint') != fp:      # parameters changed: drop every packed blob
+            self._pack_cache = {'fingerprint': fp, 'entries': {}}
+        entries = self._pack_cache['entries']
+        if key not in entries:
+            if len(entries) >= 16:                         # bounded (one entry per (precision, si))
+                entries.pop(next(iter(entries)))
+            entries[key] = builder()
+        return entries[key]
 
     def _check_device(self, t):
         dev = next(self.parameters()).device
