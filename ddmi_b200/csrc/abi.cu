@@ -29,6 +29,7 @@ int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, 
 // tcgen05 path (decode_umma.cu)
 int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const float*, size_t, float*, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
+int debug_profile(unsigned long long*, int);
 
 static int check_planes(const ddmi_plane_t* planes, int count, PlaneSet* ps) {
   DDMI_REQUIRE(planes != nullptr, "planes is NULL");
@@ -229,6 +230,11 @@ DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_
   DDMI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "N must be a multiple of 16 in [16,256] (got %d)", N);
   DDMI_REQUIRE(K >= 16 && K <= 256 && K % 16 == 0, "K must be a multiple of 16 in [16,256] (got %d)", K);
   return launch_selftest_umma(a, b, d, N, K, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset) {
+  DDMI_REQUIRE(out != nullptr, "out is NULL");
+  return debug_profile((unsigned long long*)out, reset);
 }
 
 }  // extern "C"

@@ -27,7 +27,7 @@ using namespace umma;
 
 constexpr int TILE = 128;             // coordinates per tile == MMA M
 constexpr int NEPI = 256;             // epilogue / gather threads
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 384;          // 3 warpgroups: 2 x gather/epilogue (208 regs), 1 x {producer, MMA, 2 idle warps} (88 regs); 208*256 + 88*128 == 168*384: setmaxnreg can only hand out what was released
 constexpr int KG_BYTES = TILE * 16;   // one 8-wide K group of an A operand: 128 rows x 16 B
 constexpr int H_BYTES = 32 * KG_BYTES;   // 256-wide activation, one of hi / lo
 constexpr int X_BYTES = 8 * KG_BYTES;    // 64-wide PE features, one of hi / lo
@@ -48,71 +48,107 @@ constexpr int BAR_WFULL = 0, BAR_WEMPTY = 32, BAR_MMADONE = 64, BAR_AREADY = 72,
 constexpr uint32_t IDESC_N256 = idesc_bf16_f32(256);
 constexpr uint32_t IDESC_N16 = idesc_bf16_f32(16);
 
+// Diagnostics: cycle counters of CTA 0 (see ddmi_debug_profile in the header).
+// [0] epilogue thread 0: cycles parked waiting for MMA groups   [1] cycles in epilogue stages
+// [2] cycles in gathers   [3] MMA thread: cycles waiting for operands (a_ready)
+// [4] MMA thread: cycles waiting for weight chunks   [5] MMA thread: total   [6] tiles   [7] spare
+__device__ unsigned long long g_prof[8];
+
 constexpr float kSqrt2 = 1.41421356237309504880f;
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 
 // ---------------------------------------------------------------------------
 // epilogue helpers (one thread = one tile row, 128 of the 256 output columns)
 // ---------------------------------------------------------------------------
-// y[0..31] -> bf16 hi/lo, written as 4 K groups of the 256-wide A operand
-__device__ __forceinline__ void store_act32(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float (&y)[32]) {
+// y[0..31] (16 pairs) -> bf16 hi/lo, written as 4 K groups of the 256-wide A operand
+__device__ __forceinline__ void store_act32(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     uint4 hi, lo;
-    split8(&y[g * 8], hi, lo);
-    uint32_t off = (uint32_t)((col0 / 8 + g) * KG_BYTES + row * 16);
+    split8(&y[g * 4], hi, lo);
+    const uint32_t off = (uint32_t)((col0 / 8 + g) * KG_BYTES + row * 16);
     st_shared_v4(h_hi + off, hi);
     st_shared_v4(h_lo + off, lo);
   }
 }
 
-__device__ __forceinline__ void load_bias32(const float* __restrict__ p, float (&b)[32]) {
+template <int NP>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float2 (&b)[NP]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
-    b[4 * i] = v.x; b[4 * i + 1] = v.y; b[4 * i + 2] = v.z; b[4 * i + 3] = v.w;
+  for (int i = 0; i < NP / 2; ++i) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+    b[2 * i] = make_float2(v.x, v.y);
+    b[2 * i + 1] = make_float2(v.z, v.w);
+  }
+}
+// 16 columns (8 pairs) -> two K groups of the A operand
+__device__ __forceinline__ void store_act16(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[8]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint4 hi, lo;
+    split8(&y[g * 4], hi, lo);
+    const uint32_t off = (uint32_t)((col0 / 8 + g) * KG_BYTES + row * 16);
+    st_shared_v4(h_hi + off, hi);
+    st_shared_v4(h_lo + off, lo);
   }
 }
 
-// MODE 0: H = sqrt2 * lrelu(acc1 + b)                     (conv1 / conv2)
-// MODE 1: H = lrelu(acc1 + b) + acc2 + cs                  (conv3 + skip; res1..3)
+// One epilogue stage for this thread's row and 128 of the 256 columns.  sqrt2 gains are folded into
+// the weights / biases on the host (leaky ReLU is positively homogeneous).  The TMEM load of the
+// next chunk is in flight while the current one is converted.
+// MODE 0: H = lrelu(acc1 + b)                              (conv1 / conv2; 32-column chunks)
+// MODE 1: H = lrelu(acc1 + b) + acc2 + cs                  (conv3 + skip; res1, res2; 16-column chunks)
 // MODE 2: as 1, and acc2 <- H / sqrt2                      (res3: stash res4's identity skip)
 // MODE 3: H = lrelu(acc1 + b) + acc2                       (res4: acc2 holds h3 / sqrt2)
 template <int MODE>
 __device__ __forceinline__ void epilogue(uint32_t tmem, uint32_t h_hi, uint32_t h_lo, int row, int lane_base,
                                          int col_half, const float* __restrict__ bias,
                                          const float* __restrict__ cs) {
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int col0 = col_half * 128 + c * 32;
-    const uint32_t t1 = tmem + ((uint32_t)lane_base << 16) + (uint32_t)col0;
-    float v[32], b[32];
-    tmem_ld32(t1, v);
-    load_bias32(bias + col0, b);
-    if (MODE == 0) {
-      tmem_ld_wait();
+  const uint32_t t0 = tmem + ((uint32_t)lane_base << 16) + (uint32_t)(col_half * 128);
+  if (MODE == 0) {
+    float2 v[2][16];
+    tmem_ld32(t0, v[0]);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = kSqrt2 * lrelu(v[i] + b[i], 0.2f);
-    } else {
-      float s[32];
-      tmem_ld32(t1 + 256, s);
+    for (int c = 0; c < 4; ++c) {
+      const int cur = c & 1, col0 = col_half * 128 + c * 32;
+      float2 b[16];
+      load_vec<16>(bias + col0, b);
       tmem_ld_wait();
+      if (c < 3) tmem_ld32(t0 + (c + 1) * 32, v[cur ^ 1]);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i] + b[i], 0.2f) + s[i];
+      for (int i = 0; i < 16; ++i) v[cur][i] = bias_lrelu_pair(v[cur][i], b[i], 0.2f);
+      store_act32(h_hi, h_lo, row, col0, v[cur]);
+    }
+  } else {
+    float2 v[2][8], s[2][8];
+    tmem_ld16(t0, v[0]);
+    tmem_ld16(t0 + 256, s[0]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int cur = c & 1, col0 = col_half * 128 + c * 16;
+      float2 b[8];
+      load_vec<8>(bias + col0, b);
+      tmem_ld_wait();
+      if (c < 7) {
+        tmem_ld16(t0 + (c + 1) * 16, v[cur ^ 1]);
+        tmem_ld16(t0 + 256 + (c + 1) * 16, s[cur ^ 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[cur][i] = __fadd2_rn(bias_lrelu_pair(v[cur][i], b[i], 0.2f), s[cur][i]);
       if (MODE == 1 || MODE == 2) {
-        load_bias32(cs + col0, b);
+        load_vec<8>(cs + col0, b);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += b[i];
+        for (int i = 0; i < 8; ++i) v[cur][i] = __fadd2_rn(v[cur][i], b[i]);
       }
       if (MODE == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[i] = v[i] * kInvSqrt2;
-        tmem_st32(t1 + 256, s);
+        for (int i = 0; i < 8; ++i) s[cur][i] = __fmul2_rn(v[cur][i], make_float2(kInvSqrt2, kInvSqrt2));
+        tmem_st16(t0 + 256 + c * 16, s[cur]);
       }
+      store_act16(h_hi, h_lo, row, col0, v[cur]);
     }
-    store_act32(h_hi, h_lo, row, col0, v);
+    if (MODE == 2) tmem_st_wait();
   }
-  if (MODE == 2) tmem_st_wait();
 }
 
 // ---------------------------------------------------------------------------
@@ -151,13 +187,17 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
 
   if (warp < 8) {
     // =================== gather + epilogue threads ===================
+    reg_inc<208>();
     const int row = tid & 127;             // tile row == TMEM lane
     const int lane_base = (warp & 3) * 32; // this warp's TMEM lane quadrant
     const int col_half = warp >> 2;        // output columns [128*col_half, +128)
     const int ghalf = tid >> 7;            // gather: channels [32*ghalf, +32)
     uint32_t ph_mma = 0;
+    const bool prof = (blockIdx.x == 0 && tid == 0);
+    long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = 0;
 
     auto gather = [&](long long tile, int s) {
+      const long long g0 = clock64();
       const int b = (int)(tile / tiles_per_item);
       long long gi = (tile % tiles_per_item) * TILE + row;
       if (gi > n - 1) gi = n - 1;
@@ -175,16 +215,21 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         st_shared_v4(x_hi + off, hi);
         st_shared_v4(x_lo + off, lo);
       }
+      p_gather += clock64() - g0;
     };
     auto publish = [&]() {   // make this thread's smem / TMEM writes visible to the MMA warp, then signal
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(b_ardy);
+      p_epi += clock64() - p_t;
     };
     auto wait_mma = [&]() {
+      const long long w0 = clock64();
       mbar_wait(b_mma, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
+      p_t = clock64();
+      p_wait += p_t - w0;
     };
 
     gather(first, 0);
@@ -227,7 +272,14 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       }
       publish();
     }
-  } else if (warp == 8) {
+    if (prof) {
+      atomicAdd(&g_prof[0], (unsigned long long)p_wait);
+      atomicAdd(&g_prof[1], (unsigned long long)(p_epi - p_gather));
+      atomicAdd(&g_prof[2], (unsigned long long)p_gather);
+    }
+  } else {
+   reg_dec<88>();   // the whole third warpgroup (warps 8-11) executes this one instruction
+   if (warp == 8) {
     // =================== weight producer ===================
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
@@ -241,15 +293,21 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         }
       }
     }
-  } else {
+   } else if (warp == 9) {
     // =================== MMA issuer ===================
     if (lane == 0) {
       uint32_t s = 0, ph = 0, ph_a = 0;
       const uint32_t acc1 = tmem, acc2 = tmem + 256;
+      long long q_a = 0, q_w = 0, q_tiles = 0;
+      const long long q_start = clock64();
       // one GEMM segment: acc (+)= A[:, nk*16] * W^T, W K-steps taken from the ring
       auto seg = [&](uint32_t a_hi, uint32_t a_lo, int nk, uint32_t acc, uint32_t first_acc) {
         for (int j = 0; j < nk; ++j) {
-          mbar_wait(bar + BAR_WFULL + 8 * s, ph);
+          if (!mbar_try_wait(bar + BAR_WFULL + 8 * s, ph)) {
+            const long long w0 = clock64();
+            mbar_wait(bar + BAR_WFULL + 8 * s, ph);
+            q_w += clock64() - w0;
+          }
           tc_fence_after();
           const uint32_t wb = wst + s * STAGE_BYTES;
           const uint64_t bhi = smem_desc(wb, 256 * 16, 128), blo = smem_desc(wb + 8192, 256 * 16, 128);
@@ -263,9 +321,11 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         }
       };
       auto wait_a = [&]() {
+        const long long w0 = clock64();
         mbar_wait(b_ardy, ph_a);
         ph_a ^= 1;
         tc_fence_after();
+        q_a += clock64() - w0;
       };
       for (long long tile = first; tile < total_tiles; tile += stride) {
         for (int blk = 0; blk < 4; ++blk) {
@@ -305,9 +365,17 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         mma_commit(bar + BAR_WEMPTY + 8 * s);
         if (++s == NSTAGE) { s = 0; ph ^= 1; }
         mma_commit(b_mma);
+        ++q_tiles;
+      }
+      if (blockIdx.x == 0) {
+        atomicAdd(&g_prof[3], (unsigned long long)q_a);
+        atomicAdd(&g_prof[4], (unsigned long long)q_w);
+        atomicAdd(&g_prof[5], (unsigned long long)(clock64() - q_start));
+        atomicAdd(&g_prof[6], (unsigned long long)q_tiles);
       }
     }
     __syncwarp();
+   }
   }
   tc_fence_before();
   __syncthreads();
@@ -423,6 +491,15 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   const unsigned grid = (unsigned)(total < sms ? total : sms);
   image_umma_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ps, cx, cy, n, (int)tpi, total, (const uint8_t*)gemm, vec, out);
   DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
+
+int debug_profile(unsigned long long* out, int reset) {
+  DDMI_CUDA(cudaMemcpyFromSymbol(out, ummak::g_prof, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {};
+    DDMI_CUDA(cudaMemcpyToSymbol(ummak::g_prof, z, sizeof(z)));
+  }
   return DDMI_OK;
 }
 

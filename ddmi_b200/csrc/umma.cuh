@@ -46,13 +46,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("ddmi_b200: mbarrier watchdog (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: surfaces as a CUDA launch failure
   }
 }
+
+// ---- register re-distribution between warpgroups (setmaxnreg) ---------------------------
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- proxies / fences ---------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async() {  // generic-proxy smem writes -> async proxy (UMMA, bulk copy)
@@ -120,6 +120,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float2 (&v)[16]) {
+  tmem_ld32(taddr, *reinterpret_cast<float (*)[32]>(&v[0]));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -133,23 +136,59 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
       "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float2 (&v)[16]) {
+  tmem_st32(taddr, *reinterpret_cast<const float (*)[32]>(&v[0]));
+}
+// 16-column variants
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(&v[0]);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float2 (&v)[8]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(&v[0]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(r[0]),
+      "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ---- bf16 hi/lo split of 8 consecutive-K fp32 values -> two 16-byte core-matrix rows ---
+// ---- bf16 hi/lo split (packed f32x2 math: cvt.rn.bf16x2 + FFMA2) --------------------------
+// y -> hi = bf16(y), lo = bf16(y - hi); returns the two packed bf16x2 words (x in the low half).
+__device__ __forceinline__ void split_pair(float2 y, uint32_t& hb, uint32_t& lb) {
+  __nv_bfloat162 hp = __float22bfloat162_rn(y);
+  hb = *reinterpret_cast<uint32_t*>(&hp);
+  const float2 hf = make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xFFFF0000u));
+  const float2 r = __ffma2_rn(hf, make_float2(-1.f, -1.f), y);
+  __nv_bfloat162 lp = __float22bfloat162_rn(r);
+  lb = *reinterpret_cast<uint32_t*>(&lp);
+}
+// 8 consecutive-K fp32 values -> two 16-byte core-matrix rows
 __device__ __forceinline__ void split8(const float* y, uint4& hi, uint4& lo) {
   uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 hp = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-    uint32_t hb = *reinterpret_cast<uint32_t*>(&hp);
-    float r0 = y[2 * i] - __uint_as_float(hb << 16);
-    float r1 = y[2 * i + 1] - __uint_as_float(hb & 0xFFFF0000u);
-    __nv_bfloat162 lp = __floats2bfloat162_rn(r0, r1);
-    h[i] = hb;
-    l[i] = *reinterpret_cast<uint32_t*>(&lp);
-  }
+  for (int i = 0; i < 4; ++i) split_pair(make_float2(y[2 * i], y[2 * i + 1]), h[i], l[i]);
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void split8(const float2* y, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pair(y[i], h[i], l[i]);
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// leaky ReLU (slope < 1) of (t + b) on a pair: max(x, slope * x)
+__device__ __forceinline__ float2 bias_lrelu_pair(float2 t, float2 b, float slope) {
+  t = __fadd2_rn(t, b);
+  const float2 u = __fmul2_rn(t, make_float2(slope, slope));
+  return make_float2(fmaxf(t.x, u.x), fmaxf(t.y, u.y));
 }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {

@@ -153,10 +153,11 @@ def fold_image(module, si):
     return {'blocks': blocks, 'Wrgb': Wrgb, 'brgb': p['torgb.bias'].reshape(-1)}
 
 
-def _image_vec(f):
+def _image_vec(f, gain=1.0):
+    """gain: sqrt(2) when the activation gain of conv1 / conv2 is folded into weights + biases."""
     v = []
     for d in f['blocks']:
-        v += [d['b1'], d['b2'], d['b3'], d['cs']]
+        v += [d['b1'] * gain, d['b2'] * gain, d['b3'], d['cs']]
     v += [f['Wrgb'].reshape(-1), f['brgb']]
     return torch.cat(v).to(torch.float32).contiguous()
 
@@ -177,20 +178,20 @@ def pack_image(module, si, precision):
                 segs.append(_seg_fp32(d['Ws'], hk, hk + 64))
         gemm = torch.cat(segs).to(torch.float32).contiguous()
     elif precision == PREC_BF16X3:
-        # consumption order of csrc/decode_umma.cu: per block skip first, then conv1..3
-        eye = torch.eye(256, dtype=torch.float64, device=f['Wrgb'].device)
+        # consumption order of csrc/decode_umma.cu: per block skip first, then conv1..3.
+        # lrelu(x)*sqrt2 == lrelu(x*sqrt2): conv1 / conv2 carry their activation gain in W and b.
+        gain = math.sqrt(2.0)
         for i, d in enumerate(f['blocks']):
             hk = 256 if i > 0 else 0
             if d['Ws'] is not None:
                 if hk: segs.append(umma_kstep_blocks(d['Ws'], 0, hk))
                 segs.append(umma_kstep_blocks(d['Ws'], hk, hk + 64))
-            if hk: segs.append(umma_kstep_blocks(d['W1'], 0, hk))
-            if i < 3: segs.append(umma_kstep_blocks(d['W1'], hk, hk + 64))
-            segs.append(umma_kstep_blocks(d['W2'], 0, 256))
+            if hk: segs.append(umma_kstep_blocks(d['W1'] * gain, 0, hk))
+            if i < 3: segs.append(umma_kstep_blocks(d['W1'] * gain, hk, hk + 64))
+            segs.append(umma_kstep_blocks(d['W2'] * gain, 0, 256))
             segs.append(umma_kstep_blocks(d['W3'], 0, 256))
         segs.append(umma_kstep_blocks(f['Wrgb'], 0, 256, n_pad=16))
-        del eye
-        gemm = torch.cat(segs).contiguous()
+        return Packed(precision, torch.cat(segs).contiguous(), _image_vec(f, gain))
     else:
         raise ValueError(f"unknown precision {precision}")
     return Packed(precision, gemm, _image_vec(f))

@@ -160,6 +160,14 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
 DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_t N, int32_t K,
                        void* stream);
 
+/*
+ * Diagnostics: cycle counters accumulated by CTA 0 of the tcgen05 image kernel since the last
+ * reset (synchronises the device).  out[0] epilogue thread: cycles parked waiting for MMA groups,
+ * [1] cycles in epilogue stages, [2] cycles in plane gathers, [3] MMA thread: cycles waiting for
+ * operands, [4] cycles waiting for weight chunks, [5] MMA thread total, [6] tiles, [7] spare.
+ */
+DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif
