@@ -29,7 +29,8 @@ class Plane(ctypes.Structure):
 class Weights(ctypes.Structure):
     _fields_ = [("precision", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("gemm", ctypes.c_void_p), ("gemm_bytes", ctypes.c_uint64),
-                ("vec", ctypes.c_void_p), ("vec_floats", ctypes.c_uint64)]
+                ("vec", ctypes.c_void_p), ("vec_floats", ctypes.c_uint64),
+                ("program", ctypes.c_void_p), ("program_host", ctypes.c_void_p), ("program_words", ctypes.c_uint64)]
 
 
 def build_library(verbose=False):
@@ -75,7 +76,7 @@ def lib():
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
-        if L.ddmi_abi_version() != 1:
+        if L.ddmi_abi_version() != 2:
             raise RuntimeError("libddmi_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -107,4 +108,8 @@ def weights_struct(packed):
     w.gemm_bytes = packed.gemm.numel() * packed.gemm.element_size()
     w.vec = packed.vec.data_ptr()
     w.vec_floats = packed.vec.numel()
+    if packed.program is not None:
+        w.program = packed.program.data_ptr()
+        w.program_host = packed.program_host.data_ptr()
+        w.program_words = packed.program_host.numel()
     return w

@@ -27,7 +27,7 @@ int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, con
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
 int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
-int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const float*, size_t, float*, cudaStream_t);
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 
@@ -112,8 +112,9 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
   } else if (weights->precision == DDMI_PREC_BF16X3) {
     DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
-    return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm,
-                             weights->gemm_bytes, weights->vec, weights->vec_floats, out, st);
+    return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm, weights->gemm_bytes,
+                             weights->program_host, weights->program_words, weights->program, weights->vec,
+                             weights->vec_floats, out, st);
   }
   set_error("unknown precision %d", weights->precision);
   return DDMI_ERR_UNSUPPORTED;

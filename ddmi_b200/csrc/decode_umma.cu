@@ -1,22 +1,26 @@
 // tcgen05 (5th-gen tensor core) decode kernels: DDMI_PREC_BF16X3.
 //
-// image_umma_kernel -- MLP.forward (models/d2c_vae/mlp.py:34-66) fused end to end:
-// one persistent CTA per SM walks 128-coordinate tiles; per tile
-//   gather   : 3 bilinear plane lookups (align_corners=false, border) per coordinate,
-//              written straight into the MMA A-operand layout as bf16 hi/lo pairs
-//   13 GEMM groups on the tensor core: D[128 x 256] (+)= A[128 x K] * W^T, fp32
-//              accumulators in TMEM, every product as 3 bf16 MMAs
-//              (Ahi*Bhi + Alo*Bhi + Ahi*Blo) so the result carries ~16 mantissa bits
-//   epilogues: TMEM -> registers (tcgen05.ld), bias + leaky-ReLU (the reference's
-//              fused_bias_act op, op/fused_bias_act_kernel.cu:28-47) + residual,
-//              re-split to bf16 hi/lo and written back as the next layer's A operand
-//   ToRGB    : N = 16 MMA, 3 columns stored.
-// Weights stream from L2 through a 4-stage shared-memory ring filled by 1-D bulk
-// async copies (cp.async.bulk + mbarrier complete_tx); the host packs them in the
-// exact consumption order and shared-memory image (ddmi_b200/packing.py).
+// Engine (shared by every decoder family): one persistent CTA per SM walks 128-row tiles.
+//   * warps 0-7  : gather + epilogue ("E" threads; warp w owns TMEM lanes 32*(w%4)..+31)
+//   * warp  8    : weight producer -- one lane streams weight units (<= 16 KB) from L2 into a
+//                  4-slot shared-memory ring with 1-D bulk async copies (cp.async.bulk + mbarrier)
+//   * warp  9    : MMA issuer -- one lane interprets the host-built PROGRAM (packing.py): a list
+//                  of UNIT ops (one 16-wide K step of a 128 x N block = 3 tcgen05.mma: Ahi*Bhi +
+//                  Alo*Bhi + Ahi*Blo, fp32 accumulate in TMEM), WAIT ops (operands ready) and
+//                  COMMIT ops (tcgen05.commit -> the E threads may drain the accumulator).
+//   The program and the weight stream are generated together, so the ring is consumed in exactly
+//   the order it is produced and neither warp knows anything about the network.
 //
-// Warp roles (10 warps): 0-7 gather + epilogue (warp w owns TMEM lanes 32*(w%4).. and
-// column half w/4), 8 weight producer (one lane), 9 MMA issuer (one lane) + TMEM owner.
+// K-split software pipeline: every epilogue thread first drains ALL of its accumulator values
+// into registers (the TMEM accumulator is free again), converts + stores output columns 0-127
+// (= K groups 0-15 of the next layer's A operand), signals barrier A0, then converts columns
+// 128-255 and signals A1.  The program places the next layer's K steps 0-7 (full N = 256) after
+// WAIT A0, so the tensor core is already working while the second half is still being converted.
+//
+// image_umma_kernel -- MLP.forward (models/d2c_vae/mlp.py:34-66): gather of the 3 PE planes
+// (align_corners=false, border) straight into the A-operand layout (bf16 hi/lo), 13 GEMM groups,
+// epilogues = the reference's fused_bias_act (op/fused_bias_act_kernel.cu:28-47) + residuals,
+// ToRGB as an N=16 block.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -25,53 +29,145 @@ namespace ummak {
 
 using namespace umma;
 
-constexpr int TILE = 128;             // coordinates per tile == MMA M
-constexpr int NEPI = 256;             // epilogue / gather threads
-constexpr int NTHREADS = 384;          // 3 warpgroups: 2 x gather/epilogue (208 regs), 1 x {producer, MMA, 2 idle warps} (88 regs); 208*256 + 88*128 == 168*384: setmaxnreg can only hand out what was released
-constexpr int KG_BYTES = TILE * 16;   // one 8-wide K group of an A operand: 128 rows x 16 B
-constexpr int H_BYTES = 32 * KG_BYTES;   // 256-wide activation, one of hi / lo
-constexpr int X_BYTES = 8 * KG_BYTES;    // 64-wide PE features, one of hi / lo
-constexpr int STAGE_BYTES = 16384;    // one K step (16) of a 256-wide layer: hi 8 KB | lo 8 KB
-constexpr int NSTAGE = 4;
-constexpr int CHUNKS_PER_TILE = 233;  // 232 K steps of N = 256, + 1 chunk holding ToRGB's 16 K steps of N = 16
+constexpr int TILE = 128;              // rows per tile == MMA M
+constexpr int NEPI = 256;              // gather / epilogue threads
+constexpr int NTHREADS = 384;          // 3 warpgroups: 2 x E (216 regs), 1 x {producer, MMA, 2 idle warps} (72 regs);
+                                       // 216*256 + 72*128 == 168*384: setmaxnreg only hands out what was released
+constexpr int KG_BYTES = TILE * 16;    // one 8-wide K group of an A operand: 128 rows x 16 B
+constexpr int H_KG = 32;               // 256-wide running activation
+constexpr int SLOT_BYTES = 16384;      // one weight unit: K step of a 256-wide block, [hi 8 KB | lo 8 KB]
+constexpr int NSLOT = 4;
 
-constexpr int OFF_HHI = 0;
-constexpr int OFF_HLO = OFF_HHI + H_BYTES;
-constexpr int OFF_XHI = OFF_HLO + H_BYTES;
-constexpr int OFF_XLO = OFF_XHI + X_BYTES;
-constexpr int OFF_W = OFF_XLO + X_BYTES;
-constexpr int OFF_BAR = OFF_W + NSTAGE * STAGE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
-// barriers (8 B each) at OFF_BAR: w_full[4], w_empty[4], mma_done, a_ready; then the TMEM base address
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 32, BAR_MMADONE = 64, BAR_AREADY = 72, TMEM_SLOT = 80;
+// program op encoding (ddmi_b200/packing.py::UmmaProgram)
+constexpr uint32_t OP_UNIT = 0, OP_WAIT = 1, OP_COMMIT = 2, OP_END = 3;
 
-constexpr uint32_t IDESC_N256 = idesc_bf16_f32(256);
-constexpr uint32_t IDESC_N16 = idesc_bf16_f32(16);
+// barriers, 8 B each, relative to the barrier block
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 64, BAR_MMADONE = 128, BAR_A0 = 136 /* A0..A3: 136,144,152,160 */,
+              TMEM_SLOT = 168;
+constexpr int BAR_BYTES = 192;
 
-// Diagnostics: cycle counters of CTA 0 (see ddmi_debug_profile in the header).
-// [0] epilogue thread 0: cycles parked waiting for MMA groups   [1] cycles in epilogue stages
-// [2] cycles in gathers   [3] MMA thread: cycles waiting for operands (a_ready)
-// [4] MMA thread: cycles waiting for weight chunks   [5] MMA thread: total   [6] tiles   [7] spare
-__device__ unsigned long long g_prof[8];
+template <int XKG>   // K groups of the per-scale feature operand X
+struct Layout {
+  static constexpr int A_BYTES = (2 * H_KG + 2 * XKG) * KG_BYTES;   // [H hi | H lo | X hi | X lo]
+  static constexpr int OFF_RING = A_BYTES;
+  static constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES;
+  static constexpr int KG_HHI = 0, KG_HLO = H_KG, KG_XHI = 2 * H_KG, KG_XLO = 2 * H_KG + XKG;
+};
 
-constexpr float kSqrt2 = 1.41421356237309504880f;
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 
+// Diagnostics: cycle counters of CTA 0 (ddmi_debug_profile).
+// [0] E thread 0: cycles parked waiting for MMA groups   [1] cycles in epilogue stages (excl. gathers)
+// [2] cycles in gathers   [3] MMA thread: cycles waiting for operands   [4] cycles waiting for weights
+// [5] MMA thread total   [6] tiles   [7] spare
+__device__ unsigned long long g_prof[8];
+
 // ---------------------------------------------------------------------------
-// epilogue helpers (one thread = one tile row, 128 of the 256 output columns)
+// engine: producer + MMA issuer (program interpreters)
 // ---------------------------------------------------------------------------
-// y[0..31] (16 pairs) -> bf16 hi/lo, written as 4 K groups of the 256-wide A operand
-__device__ __forceinline__ void store_act32(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[16]) {
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint4 hi, lo;
-    split8(&y[g * 4], hi, lo);
-    const uint32_t off = (uint32_t)((col0 / 8 + g) * KG_BYTES + row * 16);
-    st_shared_v4(h_hi + off, hi);
-    st_shared_v4(h_lo + off, lo);
+__device__ __forceinline__ uint32_t op_n(uint32_t op) {
+  const uint32_t c = (op >> 2) & 3;
+  return c == 0 ? 128u : (c == 2 ? 16u : (c == 3 ? 64u : 256u));
+}
+
+__device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
+                                              uint32_t ring, uint32_t bar, long long ntiles) {
+  uint32_t slot = 0, ph = 0;
+  for (long long t = 0; t < ntiles; ++t) {
+    const uint8_t* src = wstream;
+    for (int pc = 0;; ++pc) {
+      const uint32_t op = __ldg(program + pc);
+      const uint32_t kind = op & 3;
+      if (kind == OP_END) break;
+      if (kind != OP_UNIT) continue;
+      const uint32_t bytes = op_n(op) * 64;
+      const int cnt = (int)((op >> 24) & 31) + 1;
+      for (int j = 0; j < cnt; ++j) {
+        mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar + BAR_WFULL + 8 * slot, bytes);
+          bulk_g2s(ring + slot * SLOT_BYTES, src, bytes, bar + BAR_WFULL + 8 * slot);
+        }
+        src += bytes;
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      }
+    }
   }
 }
 
+// UNIT op = a run of `cnt` consecutive K steps of one 128 x N block; decoded once, then a tight
+// per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.
+__device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
+                                         uint32_t bar, uint32_t tmem, long long ntiles) {
+  uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
+  long long q_a = 0, q_w = 0;
+  const long long q_start = clock64();
+  // descriptors: hi word is constant (SBO = 128 B, version 1); lo word = addr >> 4 | LBO >> 4 << 16
+  constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) | (1ull << 14)) << 32;
+  const uint32_t a_lo32 = (a_base >> 4) | ((KG_BYTES >> 4) << 16);
+  const uint32_t ring_lo32 = ring >> 4;
+  for (long long t = 0; t < ntiles; ++t) {
+    uint32_t op = __ldg(program);
+    for (int pc = 0;; ++pc) {
+      const uint32_t nxt = __ldg(program + pc + 1);   // the table is padded with END ops
+      const uint32_t kind = op & 3;
+      if (kind == OP_UNIT) {
+        const uint32_t n = op_n(op);
+        const uint32_t idesc = idesc_bf16_f32(0) | (n << 14);                     // N >> 3 at bit 17
+        const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
+        uint32_t ahi32 = a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
+        uint32_t alo32 = a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
+        uint32_t accum = (op >> 4) & 1;
+        const int cnt = (int)((op >> 24) & 31) + 1;
+        for (int j = 0; j < cnt; ++j) {
+          const uint32_t fb = bar + BAR_WFULL + 8 * slot;
+          if (!mbar_try_wait(fb, ph)) {
+            const long long w0 = clock64();
+            mbar_wait(fb, ph);
+            q_w += clock64() - w0;
+          }
+          tc_fence_after();
+          const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (n << 16);   // LBO = n * 16 bytes
+          const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + n * 2);          // lo block at + n * 32 bytes
+          const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
+          if (elect_one()) {
+            mma_bf16(acc, ahi, bhi, idesc, accum);
+            mma_bf16(acc, alo, bhi, idesc, 1u);
+            mma_bf16(acc, ahi, blo, idesc, 1u);
+            mma_commit(bar + BAR_WEMPTY + 8 * slot);
+          }
+          accum = 1u;
+          ahi32 += 2 * (KG_BYTES >> 4);
+          alo32 += 2 * (KG_BYTES >> 4);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+        }
+      } else if (kind == OP_WAIT) {
+        const uint32_t i = (op >> 2) & 3;
+        const long long w0 = clock64();
+        mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
+        ph_a ^= 1u << i;
+        tc_fence_after();
+        q_a += clock64() - w0;
+      } else if (kind == OP_COMMIT) {
+        if (elect_one()) mma_commit(bar + BAR_MMADONE);
+      } else {
+        break;
+      }
+      op = nxt;
+    }
+  }
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    atomicAdd(&g_prof[3], (unsigned long long)q_a);
+    atomicAdd(&g_prof[4], (unsigned long long)q_w);
+    atomicAdd(&g_prof[5], (unsigned long long)(clock64() - q_start));
+    atomicAdd(&g_prof[6], (unsigned long long)ntiles);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// epilogue helpers: one thread = one tile row (TMEM lane), 64 columns of one accumulator half
+// ---------------------------------------------------------------------------
 template <int NP>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, float2 (&b)[NP]) {
 #pragma unroll
@@ -81,10 +177,11 @@ __device__ __forceinline__ void load_vec(const float* __restrict__ p, float2 (&b
     b[2 * i + 1] = make_float2(v.z, v.w);
   }
 }
-// 16 columns (8 pairs) -> two K groups of the A operand
-__device__ __forceinline__ void store_act16(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[8]) {
+// NP pairs (2*NP consecutive columns starting at col0) -> bf16 hi/lo K groups of the 256-wide operand
+template <int NP>
+__device__ __forceinline__ void store_act(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[NP]) {
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < NP / 4; ++g) {
     uint4 hi, lo;
     split8(&y[g * 4], hi, lo);
     const uint32_t off = (uint32_t)((col0 / 8 + g) * KG_BYTES + row * 16);
@@ -93,108 +190,105 @@ __device__ __forceinline__ void store_act16(uint32_t h_hi, uint32_t h_lo, int ro
   }
 }
 
-// One epilogue stage for this thread's row and 128 of the 256 columns.  sqrt2 gains are folded into
-// the weights / biases on the host (leaky ReLU is positively homogeneous).  The TMEM load of the
-// next chunk is in flight while the current one is converted.
-// MODE 0: H = lrelu(acc1 + b)                              (conv1 / conv2; 32-column chunks)
-// MODE 1: H = lrelu(acc1 + b) + acc2 + cs                  (conv3 + skip; res1, res2; 16-column chunks)
-// MODE 2: as 1, and acc2 <- H / sqrt2                      (res3: stash res4's identity skip)
-// MODE 3: H = lrelu(acc1 + b) + acc2                       (res4: acc2 holds h3 / sqrt2)
-template <int MODE>
-__device__ __forceinline__ void epilogue(uint32_t tmem, uint32_t h_hi, uint32_t h_lo, int row, int lane_base,
-                                         int col_half, const float* __restrict__ bias,
-                                         const float* __restrict__ cs) {
-  const uint32_t t0 = tmem + ((uint32_t)lane_base << 16) + (uint32_t)(col_half * 128);
-  if (MODE == 0) {
-    float2 v[2][16];
-    tmem_ld32(t0, v[0]);
+// One image epilogue stage for this thread's row.  The 256 output columns are produced in four
+// quarters of 64 (= 4 K steps of the next layer); within a quarter the two warps that share a
+// TMEM lane quadrant take 32 columns each (sub = 0 / 1).  All 128 accumulator values of the
+// thread are drained into registers first (the accumulator is free for the next layer at once),
+// then converted quarter by quarter with `signal(q)` after each.
+// sqrt2 gains are folded into weights / biases on the host.
+// MODE 0: H = lrelu(acc1 + b)                     (conv1 / conv2)
+// MODE 1: H = lrelu(acc1 + b) + acc2 + cs         (conv3 + skip; res1, res2)
+// MODE 2: as 1, and acc2 <- H / sqrt2             (res3: stash res4's identity skip)
+// MODE 3: H = lrelu(acc1 + b) + acc2              (res4: acc2 holds h3 / sqrt2)
+template <int MODE, class Signal>
+__device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, uint32_t h_lo, int row, int sub,
+                                            const float* __restrict__ bias, const float* __restrict__ cs,
+                                            Signal signal) {
+  float2 v[4][16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int cur = c & 1, col0 = col_half * 128 + c * 32;
-      float2 b[16];
-      load_vec<16>(bias + col0, b);
-      tmem_ld_wait();
-      if (c < 3) tmem_ld32(t0 + (c + 1) * 32, v[cur ^ 1]);
+  for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
+  tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[cur][i] = bias_lrelu_pair(v[cur][i], b[i], 0.2f);
-      store_act32(h_hi, h_lo, row, col0, v[cur]);
-    }
-  } else {
-    float2 v[2][8], s[2][8];
-    tmem_ld16(t0, v[0]);
-    tmem_ld16(t0 + 256, s[0]);
+  for (int q = 0; q < 4; ++q) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int cur = c & 1, col0 = col_half * 128 + c * 16;
+    for (int c = 0; c < 2; ++c) {                      // 16-column pieces
+      const int col0 = q * 64 + sub * 32 + c * 16;
+      float2(&y)[8] = *reinterpret_cast<float2(*)[8]>(&v[q][c * 8]);
       float2 b[8];
       load_vec<8>(bias + col0, b);
-      tmem_ld_wait();
-      if (c < 7) {
-        tmem_ld16(t0 + (c + 1) * 16, v[cur ^ 1]);
-        tmem_ld16(t0 + 256 + (c + 1) * 16, s[cur ^ 1]);
-      }
+      if (MODE == 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[cur][i] = __fadd2_rn(bias_lrelu_pair(v[cur][i], b[i], 0.2f), s[cur][i]);
-      if (MODE == 1 || MODE == 2) {
-        load_vec<8>(cs + col0, b);
+        for (int i = 0; i < 8; ++i) y[i] = bias_lrelu_pair(y[i], b[i], 0.2f);
+      } else {
+        float2 s[8];
+        tmem_ld16(tmem_lane + 256 + col0, s);
+        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[cur][i] = __fadd2_rn(v[cur][i], b[i]);
-      }
-      if (MODE == 2) {
+        for (int i = 0; i < 8; ++i) y[i] = __fadd2_rn(bias_lrelu_pair(y[i], b[i], 0.2f), s[i]);
+        if (MODE == 1 || MODE == 2) {
+          load_vec<8>(cs + col0, b);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s[cur][i] = __fmul2_rn(v[cur][i], make_float2(kInvSqrt2, kInvSqrt2));
-        tmem_st16(t0 + 256 + c * 16, s[cur]);
+          for (int i = 0; i < 8; ++i) y[i] = __fadd2_rn(y[i], b[i]);
+        }
+        if (MODE == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] = __fmul2_rn(y[i], make_float2(kInvSqrt2, kInvSqrt2));
+          tmem_st16(tmem_lane + 256 + col0, s);
+        }
       }
-      store_act16(h_hi, h_lo, row, col0, v[cur]);
+      store_act<8>(h_hi, h_lo, row, col0, y);
     }
-    if (MODE == 2) tmem_st_wait();
+    if (MODE == 2 && q == 3) tmem_st_wait();
+    signal(q);
   }
 }
 
 // ---------------------------------------------------------------------------
 // the fused image kernel
 // ---------------------------------------------------------------------------
+using ImgL = Layout<8>;
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
-                  const float* __restrict__ vec, float* __restrict__ out) {
+                  const uint32_t* __restrict__ program, const float* __restrict__ vec, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t h_hi = sbase + OFF_HHI, h_lo = sbase + OFF_HLO;
-  const uint32_t x_hi = sbase + OFF_XHI, x_lo = sbase + OFF_XLO;
-  const uint32_t wst = sbase + OFF_W;
-  const uint32_t bar = sbase + OFF_BAR;
-  const uint32_t b_mma = bar + BAR_MMADONE, b_ardy = bar + BAR_AREADY;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t h_hi = sbase + ImgL::KG_HHI * KG_BYTES, h_lo = sbase + ImgL::KG_HLO * KG_BYTES;
+  const uint32_t x_hi = sbase + ImgL::KG_XHI * KG_BYTES, x_lo = sbase + ImgL::KG_XLO * KG_BYTES;
+  const uint32_t ring = sbase + ImgL::OFF_RING;
+  const uint32_t bar = sbase + ImgL::OFF_BAR;
+  const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int C = 64;
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < NSLOT; ++s) {
       mbar_init(bar + BAR_WFULL + 8 * s, 1);
       mbar_init(bar + BAR_WEMPTY + 8 * s, 1);
     }
-    mbar_init(b_mma, 1);
-    mbar_init(b_ardy, NEPI);
+    mbar_init(bar + BAR_MMADONE, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_A0 + 8 * q, NEPI);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc(bar + TMEM_SLOT, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + TMEM_SLOT);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + ImgL::OFF_BAR + TMEM_SLOT);
 
   const long long first = blockIdx.x, stride = gridDim.x;
+  const long long ntiles = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
 
   if (warp < 8) {
     // =================== gather + epilogue threads ===================
-    reg_inc<208>();
-    const int row = tid & 127;             // tile row == TMEM lane
-    const int lane_base = (warp & 3) * 32; // this warp's TMEM lane quadrant
-    const int col_half = warp >> 2;        // output columns [128*col_half, +128)
-    const int ghalf = tid >> 7;            // gather: channels [32*ghalf, +32)
+    reg_inc<216>();
+    const int row = tid & 127;                          // tile row == TMEM lane
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int sub = warp >> 2;                          // which 32 columns of each 64-column quarter
+    const int ghalf = tid >> 7;                         // gather: channels [32*ghalf, +32)
     uint32_t ph_mma = 0;
     const bool prof = (blockIdx.x == 0 && tid == 0);
-    long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = 0;
+    long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = clock64();
 
     auto gather = [&](long long tile, int s) {
       const long long g0 = clock64();
@@ -217,15 +311,20 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       }
       p_gather += clock64() - g0;
     };
-    auto publish = [&]() {   // make this thread's smem / TMEM writes visible to the MMA warp, then signal
+    // make this thread's smem / TMEM writes visible to the MMA warp, then signal one quarter
+    auto signal = [&](int q) {
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(b_ardy);
-      p_epi += clock64() - p_t;
+      mbar_arrive(bar + BAR_A0 + 8 * q);
+      if (q == 3) p_epi += clock64() - p_t;
+    };
+    auto signal_all = [&]() {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) signal(q);
     };
     auto wait_mma = [&]() {
       const long long w0 = clock64();
-      mbar_wait(b_mma, ph_mma);
+      mbar_wait(bar + BAR_MMADONE, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
       p_t = clock64();
@@ -233,44 +332,42 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     };
 
     gather(first, 0);
-    publish();
+    signal_all();
     for (long long tile = first; tile < total_tiles; tile += stride) {
       const float* bv = vec;
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, bv += 1024) {
-        // conv1 (+ skip into acc2 for blk < 3)
+        // ---- conv1 (+ skip into acc2 for blk < 3)
         wait_mma();
-        epilogue<0>(tmem, h_hi, h_lo, row, lane_base, col_half, bv, nullptr);
-        publish();
+        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, signal);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale)
         if (blk < 2) gather(tile, blk + 1);
         else if (blk == 2 && tile + stride < total_tiles) gather(tile + stride, 0);
-        // conv2
+        // ---- conv2
         wait_mma();
-        epilogue<0>(tmem, h_hi, h_lo, row, lane_base, col_half, bv + 256, nullptr);
-        publish();
-        // conv3 + skip
+        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, signal);
+        // ---- conv3 + skip
         wait_mma();
-        if (blk < 2) epilogue<1>(tmem, h_hi, h_lo, row, lane_base, col_half, bv + 512, bv + 768);
-        else if (blk == 2) epilogue<2>(tmem, h_hi, h_lo, row, lane_base, col_half, bv + 512, bv + 768);
-        else epilogue<3>(tmem, h_hi, h_lo, row, lane_base, col_half, bv + 512, nullptr);
-        publish();
+        if (blk < 2) image_stage<1>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, signal);
+        else if (blk == 2) image_stage<2>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, signal);
+        else image_stage<3>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, signal);
       }
-      // ToRGB: acc1[:, 0:16]
+      // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
-      if (col_half == 0) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)lane_base << 16), v);   // only columns 0..2 are meaningful
+      if (sub == 0) {
+        float2 v[8];
+        tmem_ld16(tmem_lane, v);   // only columns 0..2 are meaningful
         tmem_ld_wait();
         const int b = (int)(tile / tiles_per_item);
         const long long gi = (tile % tiles_per_item) * TILE + row;
         if (gi < n) {
           const float* brgb = vec + 4096 + 768;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) out[((size_t)b * 3 + c) * n + gi] = v[c] + __ldg(brgb + c);
+          out[((size_t)b * 3 + 0) * n + gi] = v[0].x + __ldg(brgb + 0);
+          out[((size_t)b * 3 + 1) * n + gi] = v[0].y + __ldg(brgb + 1);
+          out[((size_t)b * 3 + 2) * n + gi] = v[1].x + __ldg(brgb + 2);
         }
       }
-      publish();
+      signal_all();
     }
     if (prof) {
       atomicAdd(&g_prof[0], (unsigned long long)p_wait);
@@ -278,104 +375,12 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       atomicAdd(&g_prof[2], (unsigned long long)p_gather);
     }
   } else {
-   reg_dec<88>();   // the whole third warpgroup (warps 8-11) executes this one instruction
-   if (warp == 8) {
-    // =================== weight producer ===================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      for (long long tile = first; tile < total_tiles; tile += stride) {
-        const uint8_t* src = wstream;
-        for (int c = 0; c < CHUNKS_PER_TILE; ++c, src += STAGE_BYTES) {
-          mbar_wait(bar + BAR_WEMPTY + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar + BAR_WFULL + 8 * s, STAGE_BYTES);
-          bulk_g2s(wst + s * STAGE_BYTES, src, STAGE_BYTES, bar + BAR_WFULL + 8 * s);
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
-        }
-      }
+    reg_dec<72>();   // the whole third warpgroup (warps 8-11) executes this one instruction
+    if (warp == 8) {
+      producer_loop(program, wstream, ring, bar, ntiles);    // whole warp, one elected lane issues
+    } else if (warp == 9) {
+      mma_loop(program, sbase, ring, bar, tmem, ntiles);     // whole warp, one elected lane issues
     }
-   } else if (warp == 9) {
-    // =================== MMA issuer ===================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0, ph_a = 0;
-      const uint32_t acc1 = tmem, acc2 = tmem + 256;
-      long long q_a = 0, q_w = 0, q_tiles = 0;
-      const long long q_start = clock64();
-      // one GEMM segment: acc (+)= A[:, nk*16] * W^T, W K-steps taken from the ring
-      auto seg = [&](uint32_t a_hi, uint32_t a_lo, int nk, uint32_t acc, uint32_t first_acc) {
-        for (int j = 0; j < nk; ++j) {
-          if (!mbar_try_wait(bar + BAR_WFULL + 8 * s, ph)) {
-            const long long w0 = clock64();
-            mbar_wait(bar + BAR_WFULL + 8 * s, ph);
-            q_w += clock64() - w0;
-          }
-          tc_fence_after();
-          const uint32_t wb = wst + s * STAGE_BYTES;
-          const uint64_t bhi = smem_desc(wb, 256 * 16, 128), blo = smem_desc(wb + 8192, 256 * 16, 128);
-          const uint64_t ahi = smem_desc(a_hi + j * 2 * KG_BYTES, KG_BYTES, 128);
-          const uint64_t alo = smem_desc(a_lo + j * 2 * KG_BYTES, KG_BYTES, 128);
-          mma_bf16(acc, ahi, bhi, IDESC_N256, (j > 0) ? 1u : first_acc);
-          mma_bf16(acc, alo, bhi, IDESC_N256, 1u);
-          mma_bf16(acc, ahi, blo, IDESC_N256, 1u);
-          mma_commit(bar + BAR_WEMPTY + 8 * s);
-          if (++s == NSTAGE) { s = 0; ph ^= 1; }
-        }
-      };
-      auto wait_a = [&]() {
-        const long long w0 = clock64();
-        mbar_wait(b_ardy, ph_a);
-        ph_a ^= 1;
-        tc_fence_after();
-        q_a += clock64() - w0;
-      };
-      for (long long tile = first; tile < total_tiles; tile += stride) {
-        for (int blk = 0; blk < 4; ++blk) {
-          wait_a();
-          if (blk == 0) {
-            seg(x_hi, x_lo, 4, acc2, 0u);
-            seg(x_hi, x_lo, 4, acc1, 0u);
-          } else if (blk < 3) {
-            seg(h_hi, h_lo, 16, acc2, 0u);
-            seg(x_hi, x_lo, 4, acc2, 1u);
-            seg(h_hi, h_lo, 16, acc1, 0u);
-            seg(x_hi, x_lo, 4, acc1, 1u);
-          } else {
-            seg(h_hi, h_lo, 16, acc1, 0u);
-          }
-          mma_commit(b_mma);
-          wait_a();
-          seg(h_hi, h_lo, 16, acc1, 0u);
-          mma_commit(b_mma);
-          wait_a();
-          seg(h_hi, h_lo, 16, acc1, 0u);
-          mma_commit(b_mma);
-        }
-        // ToRGB: one ring chunk = 16 K steps of [hi 512 B | lo 512 B] (N = 16)
-        wait_a();
-        mbar_wait(bar + BAR_WFULL + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t wb = wst + s * STAGE_BYTES;
-        for (int j = 0; j < 16; ++j) {
-          const uint64_t bhi = smem_desc(wb + j * 1024, 16 * 16, 128), blo = smem_desc(wb + j * 1024 + 512, 16 * 16, 128);
-          const uint64_t ahi = smem_desc(h_hi + j * 2 * KG_BYTES, KG_BYTES, 128);
-          const uint64_t alo = smem_desc(h_lo + j * 2 * KG_BYTES, KG_BYTES, 128);
-          mma_bf16(acc1, ahi, bhi, IDESC_N16, j > 0 ? 1u : 0u);
-          mma_bf16(acc1, alo, bhi, IDESC_N16, 1u);
-          mma_bf16(acc1, ahi, blo, IDESC_N16, 1u);
-        }
-        mma_commit(bar + BAR_WEMPTY + 8 * s);
-        if (++s == NSTAGE) { s = 0; ph ^= 1; }
-        mma_commit(b_mma);
-        ++q_tiles;
-      }
-      if (blockIdx.x == 0) {
-        atomicAdd(&g_prof[3], (unsigned long long)q_a);
-        atomicAdd(&g_prof[4], (unsigned long long)q_w);
-        atomicAdd(&g_prof[5], (unsigned long long)(clock64() - q_start));
-        atomicAdd(&g_prof[6], (unsigned long long)q_tiles);
-      }
-    }
-    __syncwarp();
-   }
   }
   tc_fence_before();
   __syncthreads();
@@ -384,9 +389,10 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
 
 // ---------------------------------------------------------------------------
 // bring-up self test: D[128 x N] = A[128 x K] * B[N x K]^T through the same
-// descriptors, split, MMA and TMEM load paths as the decode kernel.
+// descriptors, split, MMA and TMEM load paths as the decode kernels.
 // ---------------------------------------------------------------------------
-constexpr int ST_OFF_AHI = 0, ST_OFF_ALO = H_BYTES, ST_OFF_B = 2 * H_BYTES, ST_OFF_BAR = ST_OFF_B + STAGE_BYTES;
+constexpr int ST_H_BYTES = H_KG * KG_BYTES;
+constexpr int ST_OFF_AHI = 0, ST_OFF_ALO = ST_H_BYTES, ST_OFF_B = 2 * ST_H_BYTES, ST_OFF_BAR = ST_OFF_B + 16384;
 constexpr int ST_SMEM = ST_OFF_BAR + 64;
 
 __global__ void __launch_bounds__(160, 1)
@@ -467,16 +473,33 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
+// Walk a program on the host: number of weight bytes it consumes; -1 if malformed.
+static long long program_stream_bytes(const uint32_t* prog, size_t words) {
+  long long bytes = 0;
+  for (size_t i = 0; i < words; ++i) {
+    const uint32_t kind = prog[i] & 3;
+    if (kind == ummak::OP_END) return (i + 1 < words) ? bytes : -1;   // needs >= 1 END of padding after the first
+    if (kind == ummak::OP_UNIT) {
+      const uint32_t c = (prog[i] >> 2) & 3;
+      bytes += (long long)(c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 16 : 64))) * 64 * (((prog[i] >> 24) & 31) + 1);
+    }
+  }
+  return -1;
+}
+
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
-                      const void* gemm, size_t gemm_bytes, const float* vec, size_t vec_floats, float* out,
+                      const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
+                      const uint32_t* program_dev, const float* vec, size_t vec_floats, float* out,
                       cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
     set_error("tcgen05 image kernel is built for 64-channel planes");
     return DDMI_ERR_UNSUPPORTED;
   }
-  DDMI_REQUIRE(gemm_bytes == (size_t)CHUNKS_PER_TILE * STAGE_BYTES, "packed bf16x3 stream is %zu bytes, expected %zu",
-               gemm_bytes, (size_t)CHUNKS_PER_TILE * STAGE_BYTES);
+  DDMI_REQUIRE(program_host && program_dev && program_words >= 2, "bf16x3 weights carry no MMA program");
+  const long long need = program_stream_bytes(program_host, program_words);
+  DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
+               need, gemm_bytes);
   DDMI_REQUIRE(vec_floats == 4096 + 768 + 3, "packed vec blob is %zu floats, expected 4867", vec_floats);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));
@@ -487,9 +510,10 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
     set_error("n_coords %lld too large for one launch", n);
     return DDMI_ERR_UNSUPPORTED;
   }
-  DDMI_CUDA(cudaFuncSetAttribute(image_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  DDMI_CUDA(cudaFuncSetAttribute(image_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ImgL::SMEM_BYTES));
   const unsigned grid = (unsigned)(total < sms ? total : sms);
-  image_umma_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(ps, cx, cy, n, (int)tpi, total, (const uint8_t*)gemm, vec, out);
+  image_umma_kernel<<<grid, NTHREADS, ImgL::SMEM_BYTES, st>>>(ps, cx, cy, n, (int)tpi, total, (const uint8_t*)gemm,
+                                                              program_dev, vec, out);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

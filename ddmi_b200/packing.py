@@ -15,6 +15,7 @@ Both formats share one ``vec`` blob of fp32 vectors (biases, folded constants,
 the narrow output heads that run in the epilogue).
 """
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -27,6 +28,47 @@ class Packed:
     precision: int
     gemm: torch.Tensor   # flat device tensor (fp32 or int16 bit patterns of bf16)
     vec: torch.Tensor    # flat fp32 device tensor
+    program: torch.Tensor = None        # bf16x3: int32 MMA program (device)
+    program_host: torch.Tensor = None   # same, host copy (validated by the launcher)
+
+
+class UmmaProgram:
+    """Builds the MMA program and the weight stream of a tcgen05 kernel TOGETHER, so the
+    producer warp's ring is consumed in exactly the order it is filled (csrc/decode_umma.cu).
+
+    Op encoding (uint32): bits[1:0] kind (0 UNIT, 1 WAIT, 2 COMMIT, 3 END).
+    UNIT = a run of consecutive 16-wide K steps of one 128-row x N block (3 MMAs per step):
+    [3:2] N code (0:128, 1:256, 2:16, 3:64), [4] accumulate flag of the FIRST step (later steps always
+    accumulate), [7:5] accumulator column / 64, [15:8] first A-hi K group, [23:16] first A-lo K group
+    (K groups = 8 columns x 128 rows = 2 KB, counted from the A region base in shared memory; each
+    step advances both by 2), [28:24] number of steps - 1.
+    WAIT: bits [3:2] select the operand barrier (quarter q of the previous epilogue's output is ready).
+    """
+    NCODE = {128: 0, 256: 1, 16: 2, 64: 3}
+
+    def __init__(self):
+        self.ops = []
+        self.segs = []
+
+    def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None):
+        """acc[:, acc_col:acc_col+N] (+)= A[:, K] @ W.T ; W is (N, K), K zero-padded to 16."""
+        n = W.shape[0] if n_pad is None else n_pad
+        k16 = (W.shape[1] + 15) // 16
+        assert n in self.NCODE and acc_col % 64 == 0 and acc_col + n <= 512
+        assert 1 <= k16 <= 32 and a_hi_kg + 2 * k16 <= 256 and a_lo_kg + 2 * k16 <= 256
+        self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
+                        | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k16 - 1) << 24))
+        self.segs.append(umma_kstep_blocks(W, 0, W.shape[1], n_pad=n_pad))
+
+    def wait(self, which):
+        self.ops.append(1 | (which << 2))
+
+    def commit(self):
+        self.ops.append(2)
+
+    def finish(self, device):
+        ops = torch.tensor(self.ops + [3, 3, 3, 3], dtype=torch.int64).to(torch.int32)
+        return torch.cat(self.segs).contiguous(), ops.to(device), ops.contiguous()
 
 
 # ---------------------------------------------------------------------------
@@ -178,20 +220,63 @@ def pack_image(module, si, precision):
                 segs.append(_seg_fp32(d['Ws'], hk, hk + 64))
         gemm = torch.cat(segs).to(torch.float32).contiguous()
     elif precision == PREC_BF16X3:
-        # consumption order of csrc/decode_umma.cu: per block skip first, then conv1..3.
+        # Program of csrc/decode_umma.cu::image_umma_kernel.  K groups of the A region:
+        # [H hi 0..31 | H lo 32..63 | X hi 64..71 | X lo 72..79]; acc1 = TMEM columns 0..255, acc2 = 256..511.
         # lrelu(x)*sqrt2 == lrelu(x*sqrt2): conv1 / conv2 carry their activation gain in W and b.
+        # Every GEMM group is [WAIT q, K steps over H columns 64q..64q+63] for q = 0..3, then COMMIT: the
+        # previous epilogue drains the whole accumulator, then publishes its output quarter by quarter
+        # (operand barrier q).  acc2 (skip) is only written after WAIT 3 because the previous conv3
+        # epilogue still reads it until then.
         gain = math.sqrt(2.0)
+        HH, HL, XH, XL = 0, 32, 64, 72
+        P = UmmaProgram()
+        # schedule: how many operand quarters must be published before a K run starts
+        #   'quarters' : run q needs barriers 0..q      (finest overlap)
+        #   'halves'   : runs 0,1 need 0..1; runs 2,3 need 0..3
+        #   'serial'   : every run needs all four       (no overlap; reference schedule)
+        sched = os.environ.get('DDMI_B200_SCHEDULE', 'quarters')
+        need = {'quarters': (1, 2, 3, 4), 'halves': (2, 2, 4, 4), 'serial': (4, 4, 4, 4)}[sched]
+        state = {'waited': 0}
+
+        def wait_upto(k):              # emit WAITs so that barriers 0..k-1 have been consumed in this group
+            while state['waited'] < k:
+                P.wait(state['waited'])
+                state['waited'] += 1
+
+        def end_group():
+            wait_upto(4)               # every group consumes each barrier exactly once
+            P.commit()
+            state['waited'] = 0
+
+        def dense256(W, acc, n_pad=None, first=True):          # K = 256 from H
+            for q in range(4):
+                wait_upto(need[q])
+                P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, acc, first and q == 0, n_pad=n_pad)
+
         for i, d in enumerate(f['blocks']):
-            hk = 256 if i > 0 else 0
-            if d['Ws'] is not None:
-                if hk: segs.append(umma_kstep_blocks(d['Ws'], 0, hk))
-                segs.append(umma_kstep_blocks(d['Ws'], hk, hk + 64))
-            if hk: segs.append(umma_kstep_blocks(d['W1'] * gain, 0, hk))
-            if i < 3: segs.append(umma_kstep_blocks(d['W1'] * gain, hk, hk + 64))
-            segs.append(umma_kstep_blocks(d['W2'] * gain, 0, 256))
-            segs.append(umma_kstep_blocks(d['W3'], 0, 256))
-        segs.append(umma_kstep_blocks(f['Wrgb'], 0, 256, n_pad=16))
-        return Packed(precision, torch.cat(segs).contiguous(), _image_vec(f, gain))
+            W1 = d['W1'] * gain
+            if i == 0:                 # x = PE only (K = 64)
+                wait_upto(4)
+                P.block(d['Ws'][:, 0:64], XH, XL, 256, True)
+                P.block(W1[:, 0:64], XH, XL, 0, True)
+            elif i < 3:                # x = [h (256) | PE (64)], conv1 -> acc1, skip -> acc2
+                wait_upto(need[0])     # the accumulator is drained once barrier 0 has completed
+                P.block(W1[:, 256:320], XH, XL, 0, True)
+                dense256(W1, 0, first=False)
+                wait_upto(4)           # acc2 is read by the previous conv3 epilogue until its last quarter
+                P.block(d['Ws'][:, 0:256], HH, HL, 256, True)
+                P.block(d['Ws'][:, 256:320], XH, XL, 256, False)
+            else:
+                dense256(W1, 0)
+            end_group()
+            dense256(d['W2'] * gain, 0)
+            end_group()
+            dense256(d['W3'], 0)
+            end_group()
+        dense256(f['Wrgb'], 0, n_pad=16)   # ToRGB: N = 16 block (3 real rows)
+        end_group()
+        gemm, prog_dev, prog_host = P.finish(f['Wrgb'].device)
+        return Packed(precision, gemm, _image_vec(f, gain), prog_dev, prog_host)
     else:
         raise ValueError(f"unknown precision {precision}")
     return Packed(precision, gemm, _image_vec(f))

@@ -50,7 +50,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 1
+#define DDMI_ABI_VERSION 2
 
 enum {
   DDMI_OK = 0,
@@ -72,10 +72,15 @@ typedef struct {
 typedef struct {
   int32_t precision;   /* DDMI_PREC_* */
   int32_t reserved;
-  const void* gemm;    /* GEMM operands, layout per precision                     */
+  const void* gemm;    /* GEMM operands, layout per precision (device)            */
   uint64_t gemm_bytes;
-  const float* vec;    /* fp32 vectors: biases, folded constants, small heads     */
+  const float* vec;    /* fp32 vectors: biases, folded constants, small heads (device) */
   uint64_t vec_floats;
+  /* DDMI_PREC_BF16X3 only: the MMA program that consumes `gemm`, one
+     copy in device memory for the kernel and one in host memory for validation.     */
+  const uint32_t* program;
+  const uint32_t* program_host;
+  uint64_t program_words;
 } ddmi_weights_t;
 
 DDMI_API int ddmi_abi_version(void);
