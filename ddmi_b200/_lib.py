@@ -18,7 +18,7 @@ PREC_BF16X3 = 1
 EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
     "ddmi_decode_image", "ddmi_decode_occupancy", "ddmi_decode_video",
-    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma", "ddmi_debug_profile",
+    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_debug_profile",
 )
 
 
@@ -73,6 +73,7 @@ def lib():
         L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, i64, i32, vp, i32, f32, f32,
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]
         L.ddmi_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
+        L.ddmi_selftest_umma2.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
@@ -104,6 +105,7 @@ def weights_struct(packed):
     """packed: packing.Packed (precision, gemm tensor, vec tensor)."""
     w = Weights()
     w.precision = packed.precision
+    w.reserved = 1 if getattr(packed, "pair", False) else 0
     w.gemm = packed.gemm.data_ptr()
     w.gemm_bytes = packed.gemm.numel() * packed.gemm.element_size()
     w.vec = packed.vec.data_ptr()

@@ -17,6 +17,13 @@
 // 128-255 and signals A1.  The program places the next layer's K steps 0-7 (full N = 256) after
 // WAIT A0, so the tensor core is already working while the second half is still being converted.
 //
+// CTA pairs (PAIR = 1, the default): two CTAs of a cluster run tcgen05.mma.cta_group::2 (M = 256): each CTA
+// owns its own 128-row tile (A operand, accumulators, epilogue) but only HALF of every weight K step
+// (N/2 rows of B), so the per-CTA shared-memory operand traffic and the L2 -> SM weight stream are cut
+// (the single-CTA kernel is shared-memory-bandwidth bound, profiles/r01_*).  Only the leader CTA's warp 9
+// issues MMAs; the peer's warp 9 forwards "my half of slot s has landed" to the leader; epilogue warps
+// of both CTAs arrive on the leader's operand barriers; tcgen05.commit multicasts to both CTAs.
+//
 // image_umma_kernel -- MLP.forward (models/d2c_vae/mlp.py:34-66): gather of the 3 PE planes
 // (align_corners=false, border) straight into the A-operand layout (bf16 hi/lo), 13 GEMM groups,
 // epilogues = the reference's fused_bias_act (op/fused_bias_act_kernel.cu:28-47) + residuals,
@@ -35,22 +42,22 @@ constexpr int NTHREADS = 384;          // 3 warpgroups: 2 x E (216 regs), 1 x {p
                                        // 216*256 + 72*128 == 168*384: setmaxnreg only hands out what was released
 constexpr int KG_BYTES = TILE * 16;    // one 8-wide K group of an A operand: 128 rows x 16 B
 constexpr int H_KG = 32;               // 256-wide running activation
-constexpr int SLOT_BYTES = 16384;      // one weight unit: K step of a 256-wide block, [hi 8 KB | lo 8 KB]
-constexpr int NSLOT = 4;
+constexpr int RING_BYTES = 65536;      // weight ring: 4 x 16 KB (one K step of a 256-wide block) or, per CTA of a
+                                       // pair, 8 x 8 KB (this CTA's 128 of the 256 rows)
 
 // program op encoding (ddmi_b200/packing.py::UmmaProgram)
 constexpr uint32_t OP_UNIT = 0, OP_WAIT = 1, OP_COMMIT = 2, OP_END = 3;
 
 // barriers, 8 B each, relative to the barrier block
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 64, BAR_MMADONE = 128, BAR_A0 = 136 /* A0..A3: 136,144,152,160 */,
-              TMEM_SLOT = 168;
-constexpr int BAR_BYTES = 192;
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 64, BAR_PFULL = 128 /* leader: the peer's half of slot s landed */,
+              BAR_MMADONE = 192, BAR_A0 = 200 /* A0..A3 */, TMEM_SLOT = 232;
+constexpr int BAR_BYTES = 256;
 
 template <int XKG>   // K groups of the per-scale feature operand X
 struct Layout {
   static constexpr int A_BYTES = (2 * H_KG + 2 * XKG) * KG_BYTES;   // [H hi | H lo | X hi | X lo]
   static constexpr int OFF_RING = A_BYTES;
-  static constexpr int OFF_BAR = OFF_RING + NSLOT * SLOT_BYTES;
+  static constexpr int OFF_BAR = OFF_RING + RING_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES;
   static constexpr int KG_HHI = 0, KG_HLO = H_KG, KG_XHI = 2 * H_KG, KG_XLO = 2 * H_KG + XKG;
 };
@@ -71,8 +78,10 @@ __device__ __forceinline__ uint32_t op_n(uint32_t op) {
   return c == 0 ? 128u : (c == 2 ? 16u : (c == 3 ? 64u : 256u));
 }
 
+template <int PAIR>
 __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
-                                              uint32_t ring, uint32_t bar, long long ntiles) {
+                                              uint32_t ring, uint32_t bar, long long ntiles, uint32_t rank) {
+  constexpr uint32_t NSLOT = PAIR ? 8 : 4, SLOT_BYTES = RING_BYTES / NSLOT;
   uint32_t slot = 0, ph = 0;
   for (long long t = 0; t < ntiles; ++t) {
     const uint8_t* src = wstream;
@@ -81,25 +90,48 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
       const uint32_t kind = op & 3;
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
-      const uint32_t bytes = op_n(op) * 64;
+      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64);    // this CTA's share of one K step
       const int cnt = (int)((op >> 24) & 31) + 1;
       for (int j = 0; j < cnt; ++j) {
         mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(bar + BAR_WFULL + 8 * slot, bytes);
-          bulk_g2s(ring + slot * SLOT_BYTES, src, bytes, bar + BAR_WFULL + 8 * slot);
+          bulk_g2s(ring + slot * SLOT_BYTES, src + rank * bytes, bytes, bar + BAR_WFULL + 8 * slot);
         }
-        src += bytes;
+        src += bytes * (PAIR ? 2 : 1);
         if (++slot == NSLOT) { slot = 0; ph ^= 1; }
       }
     }
   }
 }
 
-// UNIT op = a run of `cnt` consecutive K steps of one 128 x N block; decoded once, then a tight
-// per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.
+// Peer CTA of a pair: tell the leader when this CTA's half of each ring slot has landed.
+__device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ program, uint32_t bar, long long ntiles) {
+  uint32_t slot = 0, ph = 0;
+  const uint32_t leader_pfull = mapa_rank(bar + BAR_PFULL, 0);
+  for (long long t = 0; t < ntiles; ++t) {
+    for (int pc = 0;; ++pc) {
+      const uint32_t op = __ldg(program + pc);
+      const uint32_t kind = op & 3;
+      if (kind == OP_END) break;
+      if (kind != OP_UNIT) continue;
+      const int cnt = (int)((op >> 24) & 31) + 1;
+      for (int j = 0; j < cnt; ++j) {
+        mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
+        if (elect_one()) mbar_arrive_remote(leader_pfull + 8 * slot);
+        if (++slot == 8) { slot = 0; ph ^= 1; }
+      }
+    }
+  }
+}
+
+// UNIT op = a run of `cnt` consecutive K steps of one (128 x PAIR?2:1) x N block; decoded once, then a
+// tight per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.  The whole warp runs the loop
+// (warp-uniform), one elected lane issues.
+template <int PAIR>
 __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
                                          uint32_t bar, uint32_t tmem, long long ntiles) {
+  constexpr uint32_t NSLOT = PAIR ? 8 : 4, SLOT_BYTES = RING_BYTES / NSLOT;
   uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
   long long q_a = 0, q_w = 0;
   const long long q_start = clock64();
@@ -114,7 +146,8 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
       const uint32_t kind = op & 3;
       if (kind == OP_UNIT) {
         const uint32_t n = op_n(op);
-        const uint32_t idesc = idesc_bf16_f32(0) | (n << 14);                     // N >> 3 at bit 17
+        const uint32_t nloc = PAIR ? n / 2 : n;                                   // B rows held by one CTA
+        const uint32_t idesc = (PAIR ? idesc2_bf16_f32(0) : idesc_bf16_f32(0)) | (n << 14);   // N >> 3 at bit 17
         const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
         uint32_t ahi32 = a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
         uint32_t alo32 = a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
@@ -127,15 +160,23 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
             mbar_wait(fb, ph);
             q_w += clock64() - w0;
           }
+          if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
           tc_fence_after();
-          const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (n << 16);   // LBO = n * 16 bytes
-          const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + n * 2);          // lo block at + n * 32 bytes
+          const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
+          const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
           const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
           if (elect_one()) {
-            mma_bf16(acc, ahi, bhi, idesc, accum);
-            mma_bf16(acc, alo, bhi, idesc, 1u);
-            mma_bf16(acc, ahi, blo, idesc, 1u);
-            mma_commit(bar + BAR_WEMPTY + 8 * slot);
+            if (PAIR) {
+              mma2_bf16(acc, ahi, bhi, idesc, accum);
+              mma2_bf16(acc, alo, bhi, idesc, 1u);
+              mma2_bf16(acc, ahi, blo, idesc, 1u);
+              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
+            } else {
+              mma_bf16(acc, ahi, bhi, idesc, accum);
+              mma_bf16(acc, alo, bhi, idesc, 1u);
+              mma_bf16(acc, ahi, blo, idesc, 1u);
+              mma_commit(bar + BAR_WEMPTY + 8 * slot);
+            }
           }
           accum = 1u;
           ahi32 += 2 * (KG_BYTES >> 4);
@@ -150,7 +191,10 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         tc_fence_after();
         q_a += clock64() - w0;
       } else if (kind == OP_COMMIT) {
-        if (elect_one()) mma_commit(bar + BAR_MMADONE);
+        if (elect_one()) {
+          if (PAIR) mma2_commit_mc(bar + BAR_MMADONE, 3);
+          else      mma_commit(bar + BAR_MMADONE);
+        }
       } else {
         break;
       }
@@ -248,6 +292,7 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
 // ---------------------------------------------------------------------------
 using ImgL = Layout<8>;
 
+template <int PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
@@ -258,26 +303,34 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
   const uint32_t x_hi = sbase + ImgL::KG_XHI * KG_BYTES, x_lo = sbase + ImgL::KG_XLO * KG_BYTES;
   const uint32_t ring = sbase + ImgL::OFF_RING;
   const uint32_t bar = sbase + ImgL::OFF_BAR;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int C = 64;
 
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(bar + BAR_WFULL + 8 * s, 1);
       mbar_init(bar + BAR_WEMPTY + 8 * s, 1);
+      mbar_init(bar + BAR_PFULL + 8 * s, 1);
     }
     mbar_init(bar + BAR_MMADONE, 1);
-    for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_A0 + 8 * q, NEPI);
+    for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_A0 + 8 * q, 8 * (1 + PAIR));   // one arrival per E warp (of both CTAs)
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(bar + TMEM_SLOT, 512);
+  if (warp == 9) {
+    if (PAIR) tmem_alloc2(bar + TMEM_SLOT, 512);
+    else tmem_alloc(bar + TMEM_SLOT, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + ImgL::OFF_BAR + TMEM_SLOT);
 
-  const long long first = blockIdx.x, stride = gridDim.x;
-  const long long ntiles = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
+  // work split: CTA (or CTA pair) w of W takes iterations w, w + W, ...; a pair iteration = tiles 2u and 2u + 1
+  const long long nwork = PAIR ? (total_tiles + 1) / 2 : total_tiles;
+  const long long wfirst = PAIR ? blockIdx.x / 2 : blockIdx.x, wstride = PAIR ? gridDim.x / 2 : gridDim.x;
+  const long long ntiles = wfirst < nwork ? (nwork - wfirst + wstride - 1) / wstride : 0;
+  auto tile_of = [&](long long i) { const long long u = wfirst + i * wstride; return PAIR ? 2 * u + rank : u; };
 
   if (warp < 8) {
     // =================== gather + epilogue threads ===================
@@ -286,12 +339,14 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int sub = warp >> 2;                          // which 32 columns of each 64-column quarter
     const int ghalf = tid >> 7;                         // gather: channels [32*ghalf, +32)
+    const uint32_t a_bar = PAIR ? mapa_rank(bar + BAR_A0, 0) : bar + BAR_A0;   // operand barriers live in the leader
     uint32_t ph_mma = 0;
     const bool prof = (blockIdx.x == 0 && tid == 0);
     long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = clock64();
 
     auto gather = [&](long long tile, int s) {
       const long long g0 = clock64();
+      if (tile > total_tiles - 1) tile = total_tiles - 1;   // odd tail of a pair: decode a duplicate, store nothing
       const int b = (int)(tile / tiles_per_item);
       long long gi = (tile % tiles_per_item) * TILE + row;
       if (gi > n - 1) gi = n - 1;
@@ -311,11 +366,12 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       }
       p_gather += clock64() - g0;
     };
-    // make this thread's smem / TMEM writes visible to the MMA warp, then signal one quarter
+    // make this warp's smem / TMEM writes visible to the MMA warp (of the leader CTA), then signal one quarter
     auto signal = [&](int q) {
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(bar + BAR_A0 + 8 * q);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
       if (q == 3) p_epi += clock64() - p_t;
     };
     auto signal_all = [&]() {
@@ -331,9 +387,10 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       p_wait += p_t - w0;
     };
 
-    gather(first, 0);
-    signal_all();
-    for (long long tile = first; tile < total_tiles; tile += stride) {
+    if (ntiles > 0) gather(tile_of(0), 0);
+    if (ntiles > 0) signal_all();
+    for (long long it = 0; it < ntiles; ++it) {
+      const long long tile = tile_of(it);
       const float* bv = vec;
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, bv += 1024) {
@@ -342,7 +399,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, signal);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale)
         if (blk < 2) gather(tile, blk + 1);
-        else if (blk == 2 && tile + stride < total_tiles) gather(tile + stride, 0);
+        else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0);
         // ---- conv2
         wait_mma();
         image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, signal);
@@ -354,7 +411,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       }
       // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
-      if (sub == 0) {
+      if (sub == 0 && tile < total_tiles) {
         float2 v[8];
         tmem_ld16(tmem_lane, v);   // only columns 0..2 are meaningful
         tmem_ld_wait();
@@ -367,24 +424,28 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
           out[((size_t)b * 3 + 2) * n + gi] = v[1].x + __ldg(brgb + 2);
         }
       }
-      signal_all();
+      if (it + 1 < ntiles) signal_all();
     }
     if (prof) {
       atomicAdd(&g_prof[0], (unsigned long long)p_wait);
-      atomicAdd(&g_prof[1], (unsigned long long)(p_epi - p_gather));
+      atomicAdd(&g_prof[1], (unsigned long long)p_epi);
       atomicAdd(&g_prof[2], (unsigned long long)p_gather);
     }
   } else {
     reg_dec<72>();   // the whole third warpgroup (warps 8-11) executes this one instruction
     if (warp == 8) {
-      producer_loop(program, wstream, ring, bar, ntiles);    // whole warp, one elected lane issues
+      producer_loop<PAIR>(program, wstream, ring, bar, ntiles, rank);     // whole warp, one elected lane issues
     } else if (warp == 9) {
-      mma_loop(program, sbase, ring, bar, tmem, ntiles);     // whole warp, one elected lane issues
+      if (rank == 0) mma_loop<PAIR>(program, sbase, ring, bar, tmem, ntiles);
+      else forward_loop(program, bar, ntiles);
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 512);
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 9) {
+    if (PAIR) tmem_dealloc2(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -489,7 +550,7 @@ static long long program_stream_bytes(const uint32_t* prog, size_t words) {
 
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
                       const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
-                      const uint32_t* program_dev, const float* vec, size_t vec_floats, float* out,
+                      const uint32_t* program_dev, const float* vec, size_t vec_floats, float* out, int pair,
                       cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
@@ -510,10 +571,32 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
     set_error("n_coords %lld too large for one launch", n);
     return DDMI_ERR_UNSUPPORTED;
   }
-  DDMI_CUDA(cudaFuncSetAttribute(image_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ImgL::SMEM_BYTES));
-  const unsigned grid = (unsigned)(total < sms ? total : sms);
-  image_umma_kernel<<<grid, NTHREADS, ImgL::SMEM_BYTES, st>>>(ps, cx, cy, n, (int)tpi, total, (const uint8_t*)gemm,
-                                                              program_dev, vec, out);
+  if (pair) {
+    // CTA pairs: a 2-CTA cluster per pair of tiles (weights for the pair are packed [half 0 | half 1] per K step)
+    DDMI_CUDA(cudaFuncSetAttribute(image_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ImgL::SMEM_BYTES));
+    const long long npair_work = (total + 1) / 2;
+    const long long npairs = npair_work < sms / 2 ? npair_work : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * npairs));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = ImgL::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const uint8_t* ws = (const uint8_t*)gemm;
+    const int tpi_i = (int)tpi;
+    DDMI_CUDA(cudaLaunchKernelEx(&cfg, image_umma_kernel<1>, ps, cx, cy, n, tpi_i, total, ws, program_dev, vec, out));
+  } else {
+    DDMI_CUDA(cudaFuncSetAttribute(image_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ImgL::SMEM_BYTES));
+    const unsigned grid = (unsigned)(total < sms ? total : sms);
+    image_umma_kernel<0><<<grid, NTHREADS, ImgL::SMEM_BYTES, st>>>(ps, cx, cy, n, (int)tpi, total, (const uint8_t*)gemm,
+                                                                   program_dev, vec, out);
+  }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

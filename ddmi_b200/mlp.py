@@ -112,7 +112,8 @@ class MLP(_FusedDecoder):
         c = coords.detach().to(device=planes[0].device, dtype=torch.float32).contiguous()
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
         si = float(si)
-        packed = self._packed(('image', prec, si), lambda: packing.pack_image(self, si, prec))
+        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'     # tcgen05 kernel: CTA pairs (cta_group::2) by default
+        packed = self._packed(('image', prec, si, pair), lambda: packing.pack_image(self, si, prec, pair))
         out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
         n = h * w
         cx, cy = c[0, 0], c[0, 1]

@@ -30,6 +30,7 @@ class Packed:
     vec: torch.Tensor    # flat fp32 device tensor
     program: torch.Tensor = None        # bf16x3: int32 MMA program (device)
     program_host: torch.Tensor = None   # same, host copy (validated by the launcher)
+    pair: bool = False                  # bf16x3: stream packed for CTA pairs ([half 0 | half 1] per K step)
 
 
 class UmmaProgram:
@@ -46,9 +47,10 @@ class UmmaProgram:
     """
     NCODE = {128: 0, 256: 1, 16: 2, 64: 3}
 
-    def __init__(self):
+    def __init__(self, pair=False):
         self.ops = []
         self.segs = []
+        self.pair = pair      # CTA pairs: each K step is stored as [rows 0..N/2-1 | rows N/2..N-1]
 
     def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None):
         """acc[:, acc_col:acc_col+N] (+)= A[:, K] @ W.T ; W is (N, K), K zero-padded to 16."""
@@ -58,7 +60,16 @@ class UmmaProgram:
         assert 1 <= k16 <= 32 and a_hi_kg + 2 * k16 <= 256 and a_lo_kg + 2 * k16 <= 256
         self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
                         | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k16 - 1) << 24))
-        self.segs.append(umma_kstep_blocks(W, 0, W.shape[1], n_pad=n_pad))
+        if not self.pair:
+            self.segs.append(umma_kstep_blocks(W, 0, W.shape[1], n_pad=n_pad))
+        else:
+            Wp = W
+            if n != W.shape[0]:
+                Wp = W.new_zeros(n, W.shape[1])
+                Wp[:W.shape[0]] = W
+            halves = [umma_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)], 0, W.shape[1]).reshape(k16, -1)
+                      for h in (0, 1)]
+            self.segs.append(torch.cat(halves, dim=1).reshape(-1))
 
     def wait(self, which):
         self.ops.append(1 | (which << 2))
@@ -204,7 +215,7 @@ def _image_vec(f, gain=1.0):
     return torch.cat(v).to(torch.float32).contiguous()
 
 
-def pack_image(module, si, precision):
+def pack_image(module, si, precision, pair=True):
     f = fold_image(module, si)
     segs = []
     if precision == PREC_FP32:
@@ -229,7 +240,7 @@ def pack_image(module, si, precision):
         # epilogue still reads it until then.
         gain = math.sqrt(2.0)
         HH, HL, XH, XL = 0, 32, 64, 72
-        P = UmmaProgram()
+        P = UmmaProgram(pair=pair)
         # schedule: how many operand quarters must be published before a K run starts
         #   'quarters' : run q needs barriers 0..q      (finest overlap)
         #   'halves'   : runs 0,1 need 0..1; runs 2,3 need 0..3
@@ -276,7 +287,7 @@ def pack_image(module, si, precision):
         dense256(f['Wrgb'], 0, n_pad=16)   # ToRGB: N = 16 block (3 real rows)
         end_group()
         gemm, prog_dev, prog_host = P.finish(f['Wrgb'].device)
-        return Packed(precision, gemm, _image_vec(f, gain), prog_dev, prog_host)
+        return Packed(precision, gemm, _image_vec(f, gain), prog_dev, prog_host, pair)
     else:
         raise ValueError(f"unknown precision {precision}")
     return Packed(precision, gemm, _image_vec(f))

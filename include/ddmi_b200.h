@@ -71,7 +71,7 @@ typedef struct {
 /* Host-folded, packed MLP weights (device memory). */
 typedef struct {
   int32_t precision;   /* DDMI_PREC_* */
-  int32_t reserved;
+  int32_t reserved;    /* bit 0: bf16x3 stream is packed for CTA pairs ([half 0 | half 1] per K step) */
   const void* gemm;    /* GEMM operands, layout per precision (device)            */
   uint64_t gemm_bytes;
   const float* vec;    /* fp32 vectors: biases, folded constants, small heads (device) */
@@ -164,6 +164,13 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
  */
 DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_t N, int32_t K,
                        void* stream);
+
+/*
+ * Same for the CTA-pair path (tcgen05.mma.cta_group::2, M = 256 over a 2-CTA cluster):
+ * a: (256,K), b: (N,K), d: (256,N); CTA r owns rows 128r.. of a / d and rows (N/2)r.. of b.
+ */
+DDMI_API int ddmi_selftest_umma2(const float* a, const float* b, float* d, int32_t N, int32_t K,
+                                 void* stream);
 
 /*
  * Diagnostics: cycle counters accumulated by CTA 0 of the tcgen05 image kernel since the last

@@ -208,3 +208,18 @@ def test_umma_selftest(N, K):
     ref = a.double() @ b.double().t()
     assert float((d.double() - ref).abs().max()) < 2e-3 * float(ref.abs().max())
     assert float((d.double() - ref).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 64), (16, 256), (128, 32)])
+def test_umma2_selftest(N, K):
+    """CTA-pair MMA (cta_group::2): M = 256 across a 2-CTA cluster, B split N/2 per CTA."""
+    from ddmi_b200 import _lib
+    g = torch.Generator().manual_seed(N * 1000 + K + 7)
+    a = torch.randn(256, K, generator=g).to(DEV)
+    b = torch.randn(N, K, generator=g).to(DEV)
+    d = torch.full((256, N), float('nan'), device=DEV)
+    _lib.check(_lib.lib().ddmi_selftest_umma2(a.data_ptr(), b.data_ptr(), d.data_ptr(), N, K,
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    assert float((d.double() - ref).abs().max()) < 1e-3
