@@ -1,0 +1,300 @@
+// Shared tcgen05 engine of the bf16x3 decode kernels (see decode_umma.cu for the design notes):
+// program interpreters (weight producer, MMA issuer, pair forwarder), shared-memory layout,
+// barrier map and the epilogue building blocks.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ddmi {
+namespace ummak {
+
+using namespace umma;
+
+constexpr int TILE = 128;              // rows per tile == MMA M
+constexpr int NEPI = 256;              // gather / epilogue threads
+constexpr int NTHREADS = 384;          // 3 warpgroups: 2 x E (216 regs), 1 x {producer, MMA, 2 idle warps} (72 regs);
+                                       // 216*256 + 72*128 == 168*384: setmaxnreg only hands out what was released
+constexpr int KG_BYTES = TILE * 16;    // one 8-wide K group of an A operand: 128 rows x 16 B
+constexpr int H_KG = 32;               // 256-wide running activation
+// weight ring: RING bytes cut into slots of one K step of a 256-wide block: 16 KB, or 8 KB per CTA of a
+// pair (this CTA's 128 of the 256 rows)
+
+// program op encoding (ddmi_b200/packing.py::UmmaProgram)
+constexpr uint32_t OP_UNIT = 0, OP_WAIT = 1, OP_COMMIT = 2, OP_END = 3;
+
+// barriers, 8 B each, relative to the barrier block
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 64, BAR_PFULL = 128 /* leader: the peer's half of slot s landed */,
+              BAR_MMADONE = 192, BAR_A0 = 200 /* A0..A3 */, TMEM_SLOT = 232;
+constexpr int BAR_BYTES = 256;
+
+template <int XKG, int RING = 65536>   // XKG: K groups of the feature operand region behind H
+struct Layout {
+  static constexpr int A_BYTES = (2 * H_KG + 2 * XKG) * KG_BYTES;   // [H hi | H lo | X hi | X lo]
+  static constexpr int OFF_RING = A_BYTES;
+  static constexpr int RING_BYTES = RING;
+  static constexpr int OFF_BAR = OFF_RING + RING;
+  static constexpr int SMEM_BYTES = OFF_BAR + BAR_BYTES;
+  static constexpr int KG_HHI = 0, KG_HLO = H_KG, KG_XHI = 2 * H_KG, KG_XLO = 2 * H_KG + XKG;
+};
+
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+
+// Diagnostics: cycle counters of CTA 0 (ddmi_debug_profile).
+// [0] E thread 0: cycles parked waiting for MMA groups   [1] cycles in epilogue stages (excl. gathers)
+// [2] cycles in gathers   [3] MMA thread: cycles waiting for operands   [4] cycles waiting for weights
+// [5] MMA thread total   [6] tiles   [7] spare
+__device__ unsigned long long g_prof[8];
+
+// ---------------------------------------------------------------------------
+// engine: producer + MMA issuer (program interpreters)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t op_n(uint32_t op) {
+  const uint32_t c = (op >> 2) & 3;
+  return c == 0 ? 128u : (c == 2 ? 16u : (c == 3 ? 64u : 256u));
+}
+
+template <int PAIR, int RING_BYTES>
+__device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
+                                              uint32_t ring, uint32_t bar, long long ntiles, uint32_t rank) {
+  constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
+  uint32_t slot = 0, ph = 0;
+  for (long long t = 0; t < ntiles; ++t) {
+    const uint8_t* src = wstream;
+    for (int pc = 0;; ++pc) {
+      const uint32_t op = __ldg(program + pc);
+      const uint32_t kind = op & 3;
+      if (kind == OP_END) break;
+      if (kind != OP_UNIT) continue;
+      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64);    // this CTA's share of one K step
+      const int cnt = (int)((op >> 24) & 31) + 1;
+      for (int j = 0; j < cnt; ++j) {
+        mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bar + BAR_WFULL + 8 * slot, bytes);
+          bulk_g2s(ring + slot * SLOT_BYTES, src + rank * bytes, bytes, bar + BAR_WFULL + 8 * slot);
+        }
+        src += bytes * (PAIR ? 2 : 1);
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      }
+    }
+  }
+}
+
+// Peer CTA of a pair: tell the leader when this CTA's half of each ring slot has landed.
+template <int RING_BYTES>
+__device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ program, uint32_t bar, long long ntiles) {
+  constexpr uint32_t NSLOT = RING_BYTES / 8192;
+  uint32_t slot = 0, ph = 0;
+  const uint32_t leader_pfull = mapa_rank(bar + BAR_PFULL, 0);
+  for (long long t = 0; t < ntiles; ++t) {
+    for (int pc = 0;; ++pc) {
+      const uint32_t op = __ldg(program + pc);
+      const uint32_t kind = op & 3;
+      if (kind == OP_END) break;
+      if (kind != OP_UNIT) continue;
+      const int cnt = (int)((op >> 24) & 31) + 1;
+      for (int j = 0; j < cnt; ++j) {
+        mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
+        if (elect_one()) mbar_arrive_remote(leader_pfull + 8 * slot);
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      }
+    }
+  }
+}
+
+// UNIT op = a run of `cnt` consecutive K steps of one (128 x PAIR?2:1) x N block; decoded once, then a
+// tight per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.  The whole warp runs the loop
+// (warp-uniform), one elected lane issues.
+template <int PAIR, int RING_BYTES>
+__device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
+                                         uint32_t bar, uint32_t tmem, long long ntiles) {
+  constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
+  uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
+  long long q_a = 0, q_w = 0;
+  const long long q_start = clock64();
+  // descriptors: hi word is constant (SBO = 128 B, version 1); lo word = addr >> 4 | LBO >> 4 << 16
+  constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) | (1ull << 14)) << 32;
+  const uint32_t a_lo32 = (a_base >> 4) | ((KG_BYTES >> 4) << 16);
+  const uint32_t ring_lo32 = ring >> 4;
+  for (long long t = 0; t < ntiles; ++t) {
+    uint32_t op = __ldg(program);
+    for (int pc = 0;; ++pc) {
+      const uint32_t nxt = __ldg(program + pc + 1);   // the table is padded with END ops
+      const uint32_t kind = op & 3;
+      if (kind == OP_UNIT) {
+        const uint32_t n = op_n(op);
+        const uint32_t nloc = PAIR ? n / 2 : n;                                   // B rows held by one CTA
+        const uint32_t idesc = (PAIR ? idesc2_bf16_f32(0) : idesc_bf16_f32(0)) | (n << 14);   // N >> 3 at bit 17
+        const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
+        uint32_t ahi32 = a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
+        uint32_t alo32 = a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
+        uint32_t accum = (op >> 4) & 1;
+        const int cnt = (int)((op >> 24) & 31) + 1;
+        for (int j = 0; j < cnt; ++j) {
+          const uint32_t fb = bar + BAR_WFULL + 8 * slot;
+          if (!mbar_try_wait(fb, ph)) {
+            const long long w0 = clock64();
+            mbar_wait(fb, ph);
+            q_w += clock64() - w0;
+          }
+          if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
+          tc_fence_after();
+          const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
+          const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
+          const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
+          if (elect_one()) {
+            if (PAIR) {
+              mma2_bf16(acc, ahi, bhi, idesc, accum);
+              mma2_bf16(acc, alo, bhi, idesc, 1u);
+              mma2_bf16(acc, ahi, blo, idesc, 1u);
+              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
+            } else {
+              mma_bf16(acc, ahi, bhi, idesc, accum);
+              mma_bf16(acc, alo, bhi, idesc, 1u);
+              mma_bf16(acc, ahi, blo, idesc, 1u);
+              mma_commit(bar + BAR_WEMPTY + 8 * slot);
+            }
+          }
+          accum = 1u;
+          ahi32 += 2 * (KG_BYTES >> 4);
+          alo32 += 2 * (KG_BYTES >> 4);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+        }
+      } else if (kind == OP_WAIT) {
+        const uint32_t i = (op >> 2) & 3;
+        const long long w0 = clock64();
+        mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
+        ph_a ^= 1u << i;
+        tc_fence_after();
+        q_a += clock64() - w0;
+      } else if (kind == OP_COMMIT) {
+        if (elect_one()) {
+          if (PAIR) mma2_commit_mc(bar + BAR_MMADONE, 3);
+          else      mma_commit(bar + BAR_MMADONE);
+        }
+      } else {
+        break;
+      }
+      op = nxt;
+    }
+  }
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    atomicAdd(&g_prof[3], (unsigned long long)q_a);
+    atomicAdd(&g_prof[4], (unsigned long long)q_w);
+    atomicAdd(&g_prof[5], (unsigned long long)(clock64() - q_start));
+    atomicAdd(&g_prof[6], (unsigned long long)ntiles);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// epilogue helpers: one thread = one tile row (TMEM lane), 64 columns of one accumulator half
+// ---------------------------------------------------------------------------
+template <int NP>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float2 (&b)[NP]) {
+#pragma unroll
+  for (int i = 0; i < NP / 2; ++i) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+    b[2 * i] = make_float2(v.x, v.y);
+    b[2 * i + 1] = make_float2(v.z, v.w);
+  }
+}
+// NP pairs (2*NP consecutive columns starting at col0) -> bf16 hi/lo K groups of the 256-wide operand
+template <int NP>
+__device__ __forceinline__ void store_act(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[NP]) {
+#pragma unroll
+  for (int g = 0; g < NP / 4; ++g) {
+    uint4 hi, lo;
+    split8(&y[g * 4], hi, lo);
+    const uint32_t off = (uint32_t)((col0 / 8 + g) * KG_BYTES + row * 16);
+    st_shared_v4(h_hi + off, hi);
+    st_shared_v4(h_lo + off, lo);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// kernel prologue / epilogue shared by every decoder
+// ---------------------------------------------------------------------------
+// Initialise the barrier block, allocate 512 TMEM columns (warp 9), sync; returns the TMEM base.
+template <int PAIR>
+__device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar) {
+  const uint32_t bar = smem_u32(smem) + off_bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(bar + BAR_WFULL + 8 * s, 1);
+      mbar_init(bar + BAR_WEMPTY + 8 * s, 1);
+      mbar_init(bar + BAR_PFULL + 8 * s, 1);
+    }
+    mbar_init(bar + BAR_MMADONE, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_A0 + 8 * q, 8 * (1 + PAIR));   // one arrival per E warp (of both CTAs)
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    if (PAIR) tmem_alloc2(bar + TMEM_SLOT, 512);
+    else tmem_alloc(bar + TMEM_SLOT, 512);
+  }
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  return *reinterpret_cast<volatile uint32_t*>(smem + off_bar + TMEM_SLOT);
+}
+template <int PAIR>
+__device__ __forceinline__ void engine_end(uint32_t tmem) {
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if ((threadIdx.x >> 5) == 9) {
+    if (PAIR) tmem_dealloc2(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
+}
+// Warps 8..11: weight producer, MMA issuer (leader) / forwarder (peer).
+template <int PAIR, int RING_BYTES>
+__device__ __forceinline__ void engine_service_warps(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
+                                                     uint32_t sbase, uint32_t ring, uint32_t bar, uint32_t tmem,
+                                                     long long ntiles, uint32_t rank) {
+  reg_dec<72>();   // the whole third warpgroup (warps 8-11) executes this one instruction
+  const int warp = threadIdx.x >> 5;
+  if (warp == 8) {
+    producer_loop<PAIR, RING_BYTES>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
+  } else if (warp == 9) {
+    if (rank == 0) mma_loop<PAIR, RING_BYTES>(program, sbase, ring, bar, tmem, ntiles);
+    else forward_loop<RING_BYTES>(program, bar, ntiles);
+  }
+}
+
+// Host: launch a decode kernel as 2-CTA clusters (pair) or plain CTAs.
+template <class Kernel, class... Args>
+static inline cudaError_t launch_engine(Kernel kernel, int pair, unsigned ctas, size_t smem, cudaStream_t st, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// Walk a program on the host: number of weight bytes it consumes; -1 if malformed.
+static inline long long program_stream_bytes(const uint32_t* prog, size_t words) {
+  long long bytes = 0;
+  for (size_t i = 0; i < words; ++i) {
+    const uint32_t kind = prog[i] & 3;
+    if (kind == OP_END) return (i + 1 < words) ? bytes : -1;   // needs >= 1 END of padding after the first
+    if (kind == OP_UNIT) {
+      const uint32_t c = (prog[i] >> 2) & 3;
+      bytes += (long long)(c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 16 : 64))) * 64 * (((prog[i] >> 24) & 31) + 1);
+    }
+  }
+  return -1;
+}
+
+}  // namespace ummak
+}  // namespace ddmi
