@@ -29,6 +29,7 @@ int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, 
 // tcgen05 path (decode_umma.cu)
 int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
+int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 
@@ -137,16 +138,24 @@ DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, 
     return DDMI_ERR_UNSUPPORTED;
   }
   DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  // the Python scalars of normalize_coordinate: double arithmetic, then fp32
+  const float divisor = (float)(1.0 + (double)padding + 10e-6);
+  const float upper = (float)(1.0 - 10e-6);
+  if (weights->precision == DDMI_PREC_BF16X3) {
+    DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
+    DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
+    return launch_occupancy_umma_entry(ps, batch, channels, points, n_points, point_batch_stride, divisor, upper,
+                                       weights->gemm, weights->gemm_bytes, weights->program_host, weights->program_words,
+                                       weights->program, weights->vec, weights->vec_floats, logits,
+                                       weights->reserved & 1, (cudaStream_t)stream);
+  }
   if (weights->precision != DDMI_PREC_FP32) {
-    set_error("occupancy decode: precision %d has no kernel in this build (fp32 only)", weights->precision);
+    set_error("occupancy decode: unknown precision %d", weights->precision);
     return DDMI_ERR_UNSUPPORTED;
   }
   const uint64_t gfl = (64 * 64 + 64 * 256 + 64 * 256) + 2 * ((320 + 320 + 256) * 256) + 2 * 256 * 256;
   rc = check_weights(weights, gfl * sizeof(float), 1856 + 768 + 256 + 1);
   if (rc) return rc;
-  // the Python scalars of normalize_coordinate: double arithmetic, then fp32
-  const float divisor = (float)(1.0 + (double)padding + 10e-6);
-  const float upper = (float)(1.0 - 10e-6);
   return launch_occupancy_fp32(ps, batch, channels, points, n_points, point_batch_stride, divisor, upper,
                                (const float*)weights->gemm, weights->vec, logits, (cudaStream_t)stream);
 }

@@ -29,6 +29,7 @@
 // epilogues = the reference's fused_bias_act (op/fused_bias_act_kernel.cu:28-47) + residuals,
 // ToRGB as an N=16 block.
 #include "umma_engine.cuh"
+#include "decode_umma_occ.cuh"
 
 namespace ddmi {
 namespace ummak {
@@ -340,6 +341,14 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
+}
+
+int launch_occupancy_umma_entry(const PlaneSet& ps, int batch, int C, const float* pts, long long n, long long batch_stride,
+                                float divisor, float upper, const void* gemm, size_t gemm_bytes,
+                                const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
+                                const float* vec, size_t vec_floats, float* logits, int pair, cudaStream_t st) {
+  return launch_occupancy_umma(ps, batch, C, pts, n, batch_stride, divisor, upper, gemm, gemm_bytes, program_host,
+                               program_words, program_dev, vec, vec_floats, logits, pair, st);
 }
 
 int debug_profile(unsigned long long* out, int reset) {

@@ -1,0 +1,307 @@
+// Occupancy decoder (MLP3D.forward, models/d2c_vae/mlp.py:82-111) on the tcgen05 engine.
+//
+// Per 128-point tile: triplane gather (normalize_coordinate + 3 bilinear lookups summed,
+// utils/general_utils.py:71-94,115-131) -> ResnetBlockFC x4 (blocks.py:673-716) -> logit.
+// A ResnetBlockFC needs its input twice: raw for the shortcut, relu'd for fc_0.  The running
+// activation lives once in shared memory, so each block with a shortcut runs in two operand
+// phases: the epilogue keeps h (fp32) in registers, publishes RAW h (shortcut GEMM -> acc2),
+// and after that GEMM committed rewrites the same buffer with relu(h) (fc_0 GEMM -> acc1);
+// fc_1 then accumulates ONTO the shortcut in acc2, so x_s + dx never leaves TMEM.
+// The 64-wide plane features are kept in both forms (Xa raw, Xb relu).
+//
+// vec layout (floats): b0_1[64] b1_1'[256] Wp[3][256] b0_2[256] b1_2[256] b0_3[256] b1_3[256]
+//                      b0_4[256] (b1_3+b1_4)[256] w_out[256] b_out[1]          (b1_1' = b1_1 + net_p.bias)
+#pragma once
+#include "umma_engine.cuh"
+
+namespace ddmi {
+namespace ummak {
+
+using OccL = Layout<16, 32768>;   // X region: [Xa hi 8 | Xb hi 8] [Xa lo 8 | Xb lo 8] K groups; 4 x 8 KB ring slots
+constexpr int OCC_KG_XAH = 64, OCC_KG_XBH = 72, OCC_KG_XAL = 80, OCC_KG_XBL = 88;
+constexpr int OCC_OFF_PART = OccL::OFF_BAR + BAR_BYTES;          // [2][128] fp32 partial logits
+constexpr int OCC_SMEM = OCC_OFF_PART + 1024;
+constexpr int OV_B01 = 0, OV_B11 = 64, OV_WP = 320, OV_B02 = 1088, OV_B12 = 1344, OV_B03 = 1600, OV_B13 = 1856,
+              OV_B04 = 2112, OV_B14 = 2368, OV_WOUT = 2624, OV_BOUT = 2880, OV_TOTAL = 2881;
+
+__device__ __forceinline__ float2 bias_relu_pair(float2 t, float2 b) {
+  t = __fadd2_rn(t, b);
+  return make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f));
+}
+__device__ __forceinline__ float2 relu_pair(float2 t) { return make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)); }
+
+// this thread's 128 values of a 256-wide accumulator: quarter q -> columns [64q + 32 sub, +32)
+__device__ __forceinline__ void drain128(uint32_t tmem_lane, int acc_col, int sub, float2 (&v)[4][16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + acc_col + q * 64 + sub * 32, v[q]);
+  tmem_ld_wait();
+}
+template <int NP>
+__device__ __forceinline__ void add_vec(float2 (&y)[NP], const float* __restrict__ p) {
+  float2 b[NP];
+  load_vec<NP>(p, b);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) y[i] = __fadd2_rn(y[i], b[i]);
+}
+// write one quarter (32 columns of this thread) of the 256-wide operand, optionally relu'd
+template <bool RELU>
+__device__ __forceinline__ void put_quarter(uint32_t h_hi, uint32_t h_lo, int row, int q, int sub, const float2 (&vq)[16]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float2 y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = RELU ? relu_pair(vq[c * 8 + i]) : vq[c * 8 + i];
+    store_act<8>(h_hi, h_lo, row, q * 64 + sub * 32 + c * 16, y);
+  }
+}
+
+template <int PAIR>
+__global__ void __launch_bounds__(NTHREADS, 1)
+occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, long long batch_stride,
+                      int tiles_per_item, long long total_tiles, float divisor, float upper,
+                      const uint8_t* __restrict__ wstream, const uint32_t* __restrict__ program,
+                      const float* __restrict__ vec, float* __restrict__ logits) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
+  const uint32_t ring = sbase + OccL::OFF_RING, bar = sbase + OccL::OFF_BAR;
+  float* part = reinterpret_cast<float*>(smem + OCC_OFF_PART);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  constexpr int C = 64;
+  const uint32_t tmem = engine_begin<PAIR>(smem, OccL::OFF_BAR);
+
+  const long long nwork = PAIR ? (total_tiles + 1) / 2 : total_tiles;
+  const long long wfirst = PAIR ? blockIdx.x / 2 : blockIdx.x, wstride = PAIR ? gridDim.x / 2 : gridDim.x;
+  const long long ntiles = wfirst < nwork ? (nwork - wfirst + wstride - 1) / wstride : 0;
+  auto tile_of = [&](long long i) { const long long u = wfirst + i * wstride; return PAIR ? 2 * u + rank : u; };
+
+  if (warp < 8) {
+    reg_inc<216>();
+    const int row = tid & 127;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int sub = warp >> 2;
+    const int ghalf = tid >> 7;
+    const uint32_t a_bar = PAIR ? mapa_rank(bar + BAR_A0, 0) : bar + BAR_A0;
+    uint32_t ph_mma = 0;
+
+    auto signal = [&](int q) {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
+    };
+    auto signal_all = [&]() {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) signal(q);
+    };
+    auto wait_mma = [&]() {
+      mbar_wait(bar + BAR_MMADONE, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+    };
+    // this thread's query point of a tile (rows past the end replay the last point)
+    auto point_of = [&](long long tile, float (&p)[3]) {
+      if (tile > total_tiles - 1) tile = total_tiles - 1;
+      const int b = (int)(tile / tiles_per_item);
+      long long gi = (tile % tiles_per_item) * TILE + row;
+      if (gi > n - 1) gi = n - 1;
+      const float* pp = pts + (size_t)b * batch_stride + gi * 3;
+      p[0] = __ldg(pp); p[1] = __ldg(pp + 1); p[2] = __ldg(pp + 2);
+      return b;
+    };
+    // triplane 'add' gather of scale s: raw -> Xa, relu -> Xb (32 of the 64 channels per thread)
+    auto gather = [&](long long tile, int s) {
+      float p[3];
+      const int b = point_of(tile, p);
+      const float g0 = occ_normalize(p[0], divisor, upper), g1 = occ_normalize(p[1], divisor, upper),
+                  g2 = occ_normalize(p[2], divisor, upper);
+      const Tap txy = make_tap<true>(g0, g1, ps.h[s], ps.w[s]);
+      const Tap tyz = make_tap<true>(g1, g2, ps.h[3 + s], ps.w[3 + s]);
+      const Tap txz = make_tap<true>(g0, g2, ps.h[6 + s], ps.w[6 + s]);
+      const size_t hw0 = (size_t)ps.h[s] * ps.w[s], hw1 = (size_t)ps.h[3 + s] * ps.w[3 + s],
+                   hw2 = (size_t)ps.h[6 + s] * ps.w[6 + s];
+      const float* b0 = ps.data[s] + ((size_t)b * C + ghalf * 32) * hw0;
+      const float* b1 = ps.data[3 + s] + ((size_t)b * C + ghalf * 32) * hw1;
+      const float* b2 = ps.data[6 + s] + ((size_t)b * C + ghalf * 32) * hw2;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        float y[8], yr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = g * 8 + i;
+          float v = tap_sample(b0 + c * hw0, txy);
+          v = __fadd_rn(v, tap_sample(b1 + c * hw1, tyz));
+          v = __fadd_rn(v, tap_sample(b2 + c * hw2, txz));
+          y[i] = v;
+          yr[i] = fmaxf(v, 0.f);
+        }
+        uint4 hi, lo;
+        const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
+        split8(y, hi, lo);
+        st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
+        st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
+        split8(yr, hi, lo);
+        st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
+        st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
+      }
+    };
+    // relu(acc1 + b) -> H, quarter by quarter (fc_0 epilogue)
+    auto stage_net = [&](const float* __restrict__ b0) {
+      float2 v[4][16];
+      drain128(tmem_lane, 0, sub, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float2 b[16];
+        load_vec<16>(b0 + q * 64 + sub * 32, b);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[q][i] = bias_relu_pair(v[q][i], b[i]);
+        put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]);
+        signal(q);
+      }
+    };
+
+    if (ntiles > 0) {
+      gather(tile_of(0), 0);
+      signal_all();
+    }
+    for (long long it = 0; it < ntiles; ++it) {
+      const long long tile = tile_of(it);
+      // ---- R1.fc_0 (N = 64): net = relu(acc1[:, 0:64] + b0) -> H[:, 0:64]
+      wait_mma();
+      {
+        float2 v[16], b[16];
+        tmem_ld32(tmem_lane + sub * 32, v);
+        load_vec<16>(vec + OV_B01 + sub * 32, b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = bias_relu_pair(v[i], b[i]);
+        store_act<16>(h_hi, h_lo, row, sub * 32, v);
+        signal_all();
+      }
+      // ---- R1 output h1 = acc2 + b1' + net_p(p); R2, R3: two operand phases (raw, then relu)
+#pragma unroll 1
+      for (int blk = 1; blk < 3; ++blk) {
+        wait_mma();
+        float2 v[4][16];
+        drain128(tmem_lane, 256, sub, v);
+        const float* b1 = vec + (blk == 1 ? OV_B11 : OV_B12);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) add_vec<16>(v[q], b1 + q * 64 + sub * 32);
+        if (blk == 1) {   // + net_p(p): 3 FMAs per output, fp32 (mlp.py:103)
+          float p[3];
+          point_of(tile, p);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float2 pk = make_float2(p[k], p[k]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 w[16];
+              load_vec<16>(vec + OV_WP + k * 256 + q * 64 + sub * 32, w);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[q][i] = __ffma2_rn(pk, w[i], v[q][i]);
+            }
+          }
+        }
+        // phase 1: raw h (shortcut operand); the next scale's features are gathered before the last quarter
+        put_quarter<false>(h_hi, h_lo, row, 0, sub, v[0]); signal(0);
+        put_quarter<false>(h_hi, h_lo, row, 1, sub, v[1]); signal(1);
+        put_quarter<false>(h_hi, h_lo, row, 2, sub, v[2]); signal(2);
+        gather(tile, blk);
+        put_quarter<false>(h_hi, h_lo, row, 3, sub, v[3]); signal(3);
+        // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
+        wait_mma();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
+        // fc_0 epilogue
+        wait_mma();
+        stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
+      }
+      // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
+      wait_mma();
+      {
+        float2 v[4][16];
+        drain128(tmem_lane, 256, sub, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          add_vec<16>(v[q], vec + OV_B13 + q * 64 + sub * 32);
+          put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]);
+          signal(q);
+        }
+      }
+      // the plane feature buffers are free now: prefetch the next tile's coarse scale
+      if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
+      // ---- R4.fc_0 epilogue
+      wait_mma();
+      stage_net(vec + OV_B04);
+      // ---- logits = w_out . (acc2 + b1_3 + b1_4) + b_out
+      wait_mma();
+      {
+        float2 v[4][16];
+        drain128(tmem_lane, 256, sub, v);
+        float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          add_vec<16>(v[q], vec + OV_B14 + q * 64 + sub * 32);
+          float2 w[16];
+          load_vec<16>(vec + OV_WOUT + q * 64 + sub * 32, w);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s2 = __ffma2_rn(v[q][i], w[i], s2);
+        }
+        part[sub * 128 + row] = s2.x + s2.y;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 E threads only
+        if (sub == 0 && tile < total_tiles) {
+          const int b = (int)(tile / tiles_per_item);
+          const long long gi = (tile % tiles_per_item) * TILE + row;
+          if (gi < n) logits[(size_t)b * n + gi] = part[row] + part[128 + row] + __ldg(vec + OV_BOUT);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // part[] may be rewritten by the next tile
+      }
+      if (it + 1 < ntiles) signal_all();
+    }
+  } else {
+    engine_service_warps<PAIR, OccL::RING_BYTES>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+  }
+  engine_end<PAIR>(tmem);
+}
+
+}  // namespace ummak
+
+inline int launch_occupancy_umma(const PlaneSet& ps, int batch, int C, const float* pts, long long n, long long batch_stride,
+                                 float divisor, float upper, const void* gemm, size_t gemm_bytes,
+                                 const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
+                                 const float* vec, size_t vec_floats, float* logits, int pair, cudaStream_t st) {
+  using namespace ummak;
+  if (C != 64) {
+    set_error("tcgen05 occupancy kernel is built for 64-channel planes");
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(program_host && program_dev && program_words >= 2, "bf16x3 weights carry no MMA program");
+  const long long need = program_stream_bytes(program_host, program_words);
+  DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
+               need, gemm_bytes);
+  DDMI_REQUIRE(vec_floats == (size_t)OV_TOTAL, "packed vec blob is %zu floats, expected %d", vec_floats, OV_TOTAL);
+  int dev = 0, sms = 0;
+  DDMI_CUDA(cudaGetDevice(&dev));
+  DDMI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long tpi = (n + TILE - 1) / TILE;
+  const long long total = tpi * batch;
+  if (tpi > 2147483647LL) {
+    set_error("n_points %lld too large for one launch", n);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  const uint8_t* ws = (const uint8_t*)gemm;
+  const int tpi_i = (int)tpi;
+  if (pair) {
+    const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
+    DDMI_CUDA(launch_engine(occupancy_umma_kernel<1>, 1, (unsigned)(2 * npairs), OCC_SMEM, st, ps, pts, n, batch_stride,
+                            tpi_i, total, divisor, upper, ws, program_dev, vec, logits));
+  } else {
+    DDMI_CUDA(launch_engine(occupancy_umma_kernel<0>, 0, (unsigned)(total < sms ? total : sms), OCC_SMEM, st, ps, pts, n,
+                            batch_stride, tpi_i, total, divisor, upper, ws, program_dev, vec, logits));
+  }
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
+
+}  // namespace ddmi

@@ -128,6 +128,9 @@ class MLP(_FusedDecoder):
 class MLP3D(_FusedDecoder):
     """Occupancy decoder.  Reference: models/d2c_vae/mlp.py:69-111."""
 
+    _supported = ('fp32', 'bf16x3')
+    _default_precision = 'bf16x3'
+
     def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None):
         super().__init__()
         if (in_ch, latent_dim, out_ch, ch) != (3, 64, 1, 256):
@@ -163,7 +166,8 @@ class MLP3D(_FusedDecoder):
             base = pts.contiguous()
             bstride = n * 3
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
-        packed = self._packed(('occ', prec), lambda: packing.pack_occupancy(self, prec))
+        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'
+        packed = self._packed(('occ', prec, pair), lambda: packing.pack_occupancy(self, prec, pair))
         logits = torch.empty((b, n), device=base.device, dtype=torch.float32)
         with torch.cuda.device(base.device):
             _lib.check(_lib.lib().ddmi_decode_occupancy(

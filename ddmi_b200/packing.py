@@ -315,8 +315,58 @@ def _pack_resnet_chain(p, kx, precision):
     return segs, vec
 
 
-def pack_occupancy(module, precision=PREC_FP32):
+def _pack_occupancy_umma(p, pair):
+    """Program + stream + vec of csrc/decode_umma_occ.cuh.  A-region K groups: H hi 0..31, H lo 32..63,
+    Xa (raw PE) hi 64..71 / lo 80..87, Xb (relu PE) hi 72..79 / lo 88..95; acc1 = TMEM cols 0.., acc2 = 256..
+    Each ResnetBlockFC with a shortcut is three GEMM groups: shortcut on RAW h -> acc2, fc_0 on relu(h) -> acc1,
+    fc_1 on relu(net) accumulated ONTO acc2.  K runs over h follow the epilogue's quarter-by-quarter publication."""
+    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88
+    P = UmmaProgram(pair=pair)
+
+    def wait_all():
+        for q in range(4):
+            P.wait(q)
+
+    def over_h(W, acc, first):
+        for q in range(4):
+            P.wait(q)
+            P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, acc, first and q == 0)
+
+    # R1: x = PE(64)
+    wait_all()
+    P.block(p['net_res1.fc_0.weight'], XBH, XBL, 0, True)                       # N = 64
+    P.commit()
+    wait_all()
+    P.block(p['net_res1.shortcut.weight'], XAH, XAL, 256, True)
+    P.block(p['net_res1.fc_1.weight'], HH, HL, 256, False)                      # K = 64 hidden
+    P.commit()
+    for i in (2, 3):                                                            # x = [h(256) | PE(64)]
+        Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
+        over_h(Ws, 256, True)
+        P.block(Ws[:, 256:320], XAH, XAL, 256, False)                           # PE gathered before quarter 3 is published
+        P.commit()
+        over_h(W0, 0, True)
+        P.block(W0[:, 256:320], XBH, XBL, 0, False)
+        P.commit()
+        over_h(W1, 256, False)                                                  # x_s + dx accumulate in TMEM
+        P.commit()
+    over_h(p['net_res4.fc_0.weight'], 0, True)                                  # R4: identity shortcut stays in acc2
+    P.commit()
+    over_h(p['net_res4.fc_1.weight'], 256, False)
+    P.commit()
+    vec = torch.cat([p['net_res1.fc_0.bias'], p['net_res1.fc_1.bias'] + p['net_p.bias'],
+                     p['net_p.weight'].t().contiguous().reshape(-1),
+                     p['net_res2.fc_0.bias'], p['net_res2.fc_1.bias'], p['net_res3.fc_0.bias'], p['net_res3.fc_1.bias'],
+                     p['net_res4.fc_0.bias'], p['net_res3.fc_1.bias'] + p['net_res4.fc_1.bias'],
+                     p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]).to(torch.float32).contiguous()
+    gemm, prog_dev, prog_host = P.finish(vec.device)
+    return Packed(PREC_BF16X3, gemm, vec, prog_dev, prog_host, pair)
+
+
+def pack_occupancy(module, precision=PREC_FP32, pair=True):
     p = _params64(module)
+    if precision == PREC_BF16X3:
+        return _pack_occupancy_umma(p, pair)
     segs, vec = _pack_resnet_chain(p, 64, precision)
     vec[1] = vec[1] + p['net_p.bias']                       # net_p bias rides on R1.fc_1's
     vec += [p['net_p.weight'].t().contiguous().reshape(-1),  # [3][256]
