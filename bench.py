@@ -225,6 +225,77 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_other(args):
+    """The other BASELINE configs (parity-test cases, not the headline): device-resident throughput only.
+    occupancy = configs[3] (B=32, 128^3 grid + 100k random points), video = configs[2] (B=16, 256x256x16),
+    nerf = configs[4] (B=16 objects, 128x128 rays x 128 samples, composited)."""
+    import numpy as np
+    import ddmi_b200
+    from ddmi_b200 import nerf_helpers as nh
+    torch.set_grad_enabled(False)
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(777)
+    g = torch.Generator().manual_seed(777)
+    kind = args.workload
+    if kind == 'occupancy':
+        B = args.batch if args.batch != 64 else 32
+        m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
+        torch.nn.init.kaiming_uniform_(m.net_res1.fc_1.weight, a=5 ** 0.5)
+        for blk in (m.net_res2, m.net_res3, m.net_res4):
+            torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
+        hdbf = tuple([torch.randn(B, 64, s, s, generator=g).to(dev) for s in (16, 32, 64)] for _ in range(3))
+        pts = torch.cat([1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3),
+                         (torch.rand(100000, 3, generator=g) - 0.5) * 1.1]).to(dev)
+        coords = B * pts.shape[0]
+        fn = lambda: m(pts[None].expand(B, -1, -1), hdbf).logits
+        desc = f"ShapeNet-shape occupancy decode: triplanes 16^2/32^2/64^2 x64ch, 128^3 grid + 100k random points, batch {B}"
+    elif kind == 'video':
+        B = args.batch if args.batch != 64 else 16
+        m = ddmi_b200.MLPVideo(in_ch=2, latent_dim=64, out_ch=3, ch=256).to(dev)
+        for blk in (m.net_res1, m.net_res2, m.net_res3, m.net_res4):
+            torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
+        xy = [torch.randn(B, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
+        yt = [torch.randn(B, 64, 16, s, generator=g).to(dev) for s in (64, 128, 256)]
+        xt = [torch.randn(B, 64, 16, s, generator=g).to(dev) for s in (64, 128, 256)]
+        c = ddmi_b200.convert_to_coord_format_3d(1, 256, 256, 16, hstart=-255 / 256, hend=255 / 256, wstart=-255 / 256,
+                                                 wend=255 / 256, tstart=-15 / 16, tend=15 / 16)
+        c = {k: v.to(dev) for k, v in c.items()}
+        coords = B * 256 * 256 * 16
+        fn = lambda: m(c, (xy, yt, xt))
+        desc = f"SkyTimelapse-shape video decode: xy/yt/xt planes, 256x256x16 volume, batch {B}"
+    else:
+        B = args.batch if args.batch != 64 else 16
+        m = ddmi_b200.MLPNeRF(D=6, W=256, in_channels_xyz=159, skips=[2, 4], in_channels_dir=27).to(dev)
+        fea = {k: torch.randn(B, 32, 64, 64, generator=g).to(dev) for k in ('xy', 'yz', 'xz')}
+        H = W = 128
+        focal = .5 * W / np.tan(.5 * 0.6911112070083618)
+        K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+        ro, rd = nh.get_rays(H, W, K, nh.pose_spherical(40.0, -20, 5)[:3, :4], dev)
+        vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
+        rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(H * W, 1, device=dev),
+                          6. * torch.ones(H * W, 1, device=dev), vd], -1)
+        coords = B * H * W * 128
+        fn = lambda: nh.render_rays_fused(rays, fea, m, 128, True)
+        desc = f"srn-cars-shape NeRF decode: triplane 64^2 x32ch, 128x128 rays x 128 samples, composited, batch {B} objects"
+    for _ in range(args.warmup):
+        fn()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    tf_peak, _, which = peaks()
+    achieved = coords * args.steps * FLOP_PER_COORD[kind] / (ms * 1e-3) / 1e12
+    print(json.dumps({"metric": METRIC, "value": coords * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": {"workload": desc},
+                      "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                                   "frac": achieved / tf_peak, "traffic": None, "peak_source": which}}))
+
+
 def cpu_baseline(res, batch, repeats=1):
     """The oracle port of the reference decoder on the host cores (bounded sample of the same workload)."""
     from oracle import ddmi_oracle as orc   # the checker, timed here as the CPU baseline only
@@ -297,8 +368,12 @@ if __name__ == '__main__':
     ap.add_argument('--cpu-res', type=int, default=512)
     ap.add_argument('--cpu-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='image', choices=['image', 'occupancy', 'video', 'nerf'],
+                    help='image = the headline (BASELINE configs[1]); the others are the parity-case configs, 1 GPU')
     ARGS = ap.parse_args()
     if ARGS.impl == 'reference':
         run_reference(ARGS)
+    elif ARGS.workload != 'image':
+        run_other(ARGS)
     else:
         run_ours(ARGS)

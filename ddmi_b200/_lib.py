@@ -17,7 +17,7 @@ PREC_BF16X3 = 1
 
 EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
-    "ddmi_decode_image", "ddmi_decode_occupancy", "ddmi_decode_video",
+    "ddmi_decode_image", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy", "ddmi_decode_video",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_debug_profile",
 )
 
@@ -65,7 +65,8 @@ def lib():
         L.ddmi_device_info.argtypes = [ctypes.POINTER(i32)] * 3
         L.ddmi_decode_image.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, i64,
                                         ctypes.POINTER(Weights), vp, vp]
-        L.ddmi_decode_occupancy.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, i64, i64, f32,
+        L.ddmi_planes_to_channels_last.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+        L.ddmi_decode_occupancy.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i64, f32,
                                             ctypes.POINTER(Weights), vp, vp]
         L.ddmi_decode_video.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
                                         ctypes.POINTER(Weights), vp, vp]
@@ -77,7 +78,7 @@ def lib():
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
-        if L.ddmi_abi_version() != 2:
+        if L.ddmi_abi_version() != 3:
             raise RuntimeError("libddmi_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -99,6 +100,24 @@ def planes_array(tensors):
         arr[i].height = t.shape[-2]
         arr[i].width = t.shape[-1]
     return arr
+
+
+def planes_channels_last(tensors, stream):
+    """Channels-last copies (B,H,W,C) of contiguous fp32 CUDA planes (B,C,H,W), made by the library's own
+    transpose kernel.  Returns (list of NHWC tensors, ctypes plane array)."""
+    import torch
+    outs = []
+    for t in tensors:
+        b, c, h, w = t.shape
+        o = torch.empty((b, h, w, c), device=t.device, dtype=torch.float32)
+        check(lib().ddmi_planes_to_channels_last(t.data_ptr(), o.data_ptr(), b, c, h, w, stream))
+        outs.append(o)
+    arr = (Plane * len(outs))()
+    for i, o in enumerate(outs):
+        arr[i].data = o.data_ptr()
+        arr[i].height = o.shape[1]
+        arr[i].width = o.shape[2]
+    return outs, arr
 
 
 def weights_struct(packed):

@@ -29,7 +29,8 @@ int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, 
 // tcgen05 path (decode_umma.cu)
 int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
-int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, cudaStream_t);
+int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
+int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 
@@ -122,7 +123,15 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
   return DDMI_ERR_UNSUPPORTED;
 }
 
-DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+DDMI_API int ddmi_planes_to_channels_last(const float* src, float* dst, int32_t batch, int32_t channels, int32_t height,
+                                          int32_t width, void* stream) {
+  DDMI_REQUIRE(src && dst && src != dst, "src / dst is NULL or aliased");
+  DDMI_REQUIRE(batch >= 1 && channels >= 1 && height >= 1 && width >= 1, "empty plane");
+  DDMI_REQUIRE(batch <= 65535, "batch %d too large for one launch", batch);
+  return launch_planes_to_nhwc(src, dst, batch, channels, height * width, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, int32_t channels, int32_t plane_layout,
                           const float* points, int64_t n_points, int64_t point_batch_stride,
                           float padding, const ddmi_weights_t* weights, float* logits, void* stream) {
   PlaneSet ps = {};
@@ -131,6 +140,7 @@ DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, 
   DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
   DDMI_REQUIRE(n_points >= 1, "n_points must be >= 1 (got %lld)", (long long)n_points);
   DDMI_REQUIRE(points && logits, "points / logits is NULL");
+  DDMI_REQUIRE(plane_layout == DDMI_LAYOUT_NCHW || plane_layout == DDMI_LAYOUT_NHWC, "unknown plane_layout %d", plane_layout);
   DDMI_REQUIRE(point_batch_stride == 0 || point_batch_stride >= 3 * n_points,
                "point_batch_stride %lld overlaps items", (long long)point_batch_stride);
   if (channels != 64) {
@@ -147,7 +157,11 @@ DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, 
     return launch_occupancy_umma_entry(ps, batch, channels, points, n_points, point_batch_stride, divisor, upper,
                                        weights->gemm, weights->gemm_bytes, weights->program_host, weights->program_words,
                                        weights->program, weights->vec, weights->vec_floats, logits,
-                                       weights->reserved & 1, (cudaStream_t)stream);
+                                       weights->reserved & 1, plane_layout, (cudaStream_t)stream);
+  }
+  if (plane_layout != DDMI_LAYOUT_NCHW) {
+    set_error("the fp32 occupancy kernel reads NCHW planes only");
+    return DDMI_ERR_UNSUPPORTED;
   }
   if (weights->precision != DDMI_PREC_FP32) {
     set_error("occupancy decode: unknown precision %d", weights->precision);

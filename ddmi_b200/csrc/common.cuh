@@ -89,6 +89,23 @@ __device__ __forceinline__ float tap_sample(const float* __restrict__ ch, const 
   return acc;
 }
 
+// Channels-last variant: 8 consecutive channels of one pixel are two float4 loads.
+// img = base of one (H, W, C) item; c = first channel (multiple of 4).
+__device__ __forceinline__ void tap_sample8_nhwc(const float* __restrict__ img, const Tap& t, int C, int c, float (&out)[8]) {
+  const float4* p00 = reinterpret_cast<const float4*>(img + (size_t)t.o00 * C + c);
+  const float4* p01 = reinterpret_cast<const float4*>(img + (size_t)t.o01 * C + c);
+  const float4* p10 = reinterpret_cast<const float4*>(img + (size_t)t.o10 * C + c);
+  const float4* p11 = reinterpret_cast<const float4*>(img + (size_t)t.o11 * C + c);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float4 a = __ldg(p00 + h), b = __ldg(p01 + h), cc = __ldg(p10 + h), d = __ldg(p11 + h);
+    out[4 * h + 0] = fmaf(d.x, t.w11, fmaf(cc.x, t.w10, fmaf(b.x, t.w01, a.x * t.w00)));
+    out[4 * h + 1] = fmaf(d.y, t.w11, fmaf(cc.y, t.w10, fmaf(b.y, t.w01, a.y * t.w00)));
+    out[4 * h + 2] = fmaf(d.z, t.w11, fmaf(cc.z, t.w10, fmaf(b.z, t.w01, a.z * t.w00)));
+    out[4 * h + 3] = fmaf(d.w, t.w11, fmaf(cc.w, t.w10, fmaf(b.w, t.w01, a.w * t.w00)));
+  }
+}
+
 // normalize_coordinate + sample_plane_feature (utils/general_utils.py:71-94,
 // 115-119): u = p / (1 + padding + 10e-6) + 0.5, clamped to [0, 1 - 10e-6],
 // g = 2u - 1.  `divisor` and `upper` are computed on the host exactly the way

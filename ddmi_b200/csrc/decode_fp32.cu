@@ -566,7 +566,31 @@ __global__ void nerf_composite_kernel(const float* __restrict__ raw, const float
   rgb_map[i * 3 + 0] = cr; rgb_map[i * 3 + 1] = cg; rgb_map[i * 3 + 2] = cb;
 }
 
+// (batch, C, HW) -> (batch, HW, C): channels-last planes for vectorised scattered gathers.
+// One CTA = 32 pixels x all channels of one item, through a padded shared-memory tile.
+__global__ void planes_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][65];
+  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 256 threads: 32 x 8
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    for (int c = ty; c < 64 && c0 + c < C; c += 8)
+      tile[tx][c] = (p0 + tx < HW) ? src[((size_t)b * C + c0 + c) * HW + p0 + tx] : 0.f;
+    __syncthreads();
+    for (int p = ty; p < 32; p += 8)
+      for (int c = tx; c < 64 && c0 + c < C; c += 32)
+        if (p0 + p < HW) dst[((size_t)b * HW + p0 + p) * C + c0 + c] = tile[p][c];
+    __syncthreads();
+  }
+}
+
 }  // namespace fp32
+
+int launch_planes_to_nhwc(const float* src, float* dst, int batch, int C, int HW, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, batch);
+  fp32::planes_to_nhwc_kernel<<<grid, 256, 0, st>>>(src, dst, C, HW);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
 
 // ---------------------------------------------------------------------------
 // host launchers

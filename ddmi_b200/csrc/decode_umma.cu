@@ -346,9 +346,9 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
 int launch_occupancy_umma_entry(const PlaneSet& ps, int batch, int C, const float* pts, long long n, long long batch_stride,
                                 float divisor, float upper, const void* gemm, size_t gemm_bytes,
                                 const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
-                                const float* vec, size_t vec_floats, float* logits, int pair, cudaStream_t st) {
+                                const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, cudaStream_t st) {
   return launch_occupancy_umma(ps, batch, C, pts, n, batch_stride, divisor, upper, gemm, gemm_bytes, program_host,
-                               program_words, program_dev, vec, vec_floats, logits, pair, st);
+                               program_words, program_dev, vec, vec_floats, logits, pair, nhwc, st);
 }
 
 int debug_profile(unsigned long long* out, int reset) {

@@ -55,7 +55,7 @@ __device__ __forceinline__ void put_quarter(uint32_t h_hi, uint32_t h_lo, int ro
   }
 }
 
-template <int PAIR>
+template <int PAIR, int NHWC>   // NHWC: planes are channels-last (batch, H, W, C) -- vectorised scattered gathers
 __global__ void __launch_bounds__(NTHREADS, 1)
 occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, long long batch_stride,
                       int tiles_per_item, long long total_tiles, float divisor, float upper,
@@ -110,40 +110,82 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       p[0] = __ldg(pp); p[1] = __ldg(pp + 1); p[2] = __ldg(pp + 2);
       return b;
     };
-    // triplane 'add' gather of scale s: raw -> Xa, relu -> Xb (32 of the 64 channels per thread)
+    // triplane 'add' gather of scale s: raw -> Xa, relu -> Xb.
+    // NHWC: 8 threads cooperate on one point -- thread (tid & 7) owns K group kg = 8 consecutive channels
+    //   (two float4 per tap), so one warp instruction touches 4 points x 2 cache lines; 4 passes of 32 points.
+    // NCHW: one thread per (point, 32-channel half), scalar loads (layout the VAE decoder emits).
     auto gather = [&](long long tile, int s) {
-      float p[3];
-      const int b = point_of(tile, p);
-      const float g0 = occ_normalize(p[0], divisor, upper), g1 = occ_normalize(p[1], divisor, upper),
-                  g2 = occ_normalize(p[2], divisor, upper);
-      const Tap txy = make_tap<true>(g0, g1, ps.h[s], ps.w[s]);
-      const Tap tyz = make_tap<true>(g1, g2, ps.h[3 + s], ps.w[3 + s]);
-      const Tap txz = make_tap<true>(g0, g2, ps.h[6 + s], ps.w[6 + s]);
+      if (tile > total_tiles - 1) tile = total_tiles - 1;
+      const int b = (int)(tile / tiles_per_item);
+      const long long r0 = (tile % tiles_per_item) * TILE;
       const size_t hw0 = (size_t)ps.h[s] * ps.w[s], hw1 = (size_t)ps.h[3 + s] * ps.w[3 + s],
                    hw2 = (size_t)ps.h[6 + s] * ps.w[6 + s];
-      const float* b0 = ps.data[s] + ((size_t)b * C + ghalf * 32) * hw0;
-      const float* b1 = ps.data[3 + s] + ((size_t)b * C + ghalf * 32) * hw1;
-      const float* b2 = ps.data[6 + s] + ((size_t)b * C + ghalf * 32) * hw2;
+      if (NHWC) {
+        const int kg = tid & 7;
+        const float* b0 = ps.data[s] + (size_t)b * hw0 * C;
+        const float* b1 = ps.data[3 + s] + (size_t)b * hw1 * C;
+        const float* b2 = ps.data[6 + s] + (size_t)b * hw2 * C;
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        float y[8], yr[8];
+        for (int pass = 0; pass < 4; ++pass) {
+          const int prow = pass * 32 + (tid >> 3);
+          long long gi = r0 + prow;
+          if (gi > n - 1) gi = n - 1;
+          const float* pp = pts + (size_t)b * batch_stride + gi * 3;
+          const float g0 = occ_normalize(__ldg(pp), divisor, upper), g1 = occ_normalize(__ldg(pp + 1), divisor, upper),
+                      g2 = occ_normalize(__ldg(pp + 2), divisor, upper);
+          const Tap txy = make_tap<true>(g0, g1, ps.h[s], ps.w[s]);
+          const Tap tyz = make_tap<true>(g1, g2, ps.h[3 + s], ps.w[3 + s]);
+          const Tap txz = make_tap<true>(g0, g2, ps.h[6 + s], ps.w[6 + s]);
+          float y[8], u[8], w[8], yr[8];
+          tap_sample8_nhwc(b0, txy, C, kg * 8, y);
+          tap_sample8_nhwc(b1, tyz, C, kg * 8, u);
+          tap_sample8_nhwc(b2, txz, C, kg * 8, w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = g * 8 + i;
-          float v = tap_sample(b0 + c * hw0, txy);
-          v = __fadd_rn(v, tap_sample(b1 + c * hw1, tyz));
-          v = __fadd_rn(v, tap_sample(b2 + c * hw2, txz));
-          y[i] = v;
-          yr[i] = fmaxf(v, 0.f);
+          for (int i = 0; i < 8; ++i) {
+            y[i] = __fadd_rn(__fadd_rn(y[i], u[i]), w[i]);
+            yr[i] = fmaxf(y[i], 0.f);
+          }
+          uint4 hi, lo;
+          const uint32_t off = (uint32_t)(kg * KG_BYTES + prow * 16);
+          split8(y, hi, lo);
+          st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
+          st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
+          split8(yr, hi, lo);
+          st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
+          st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
         }
-        uint4 hi, lo;
-        const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
-        split8(y, hi, lo);
-        st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
-        st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
-        split8(yr, hi, lo);
-        st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
-        st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
+      } else {
+        float p[3];
+        point_of(tile, p);
+        const float g0 = occ_normalize(p[0], divisor, upper), g1 = occ_normalize(p[1], divisor, upper),
+                    g2 = occ_normalize(p[2], divisor, upper);
+        const Tap txy = make_tap<true>(g0, g1, ps.h[s], ps.w[s]);
+        const Tap tyz = make_tap<true>(g1, g2, ps.h[3 + s], ps.w[3 + s]);
+        const Tap txz = make_tap<true>(g0, g2, ps.h[6 + s], ps.w[6 + s]);
+        const float* b0 = ps.data[s] + ((size_t)b * C + ghalf * 32) * hw0;
+        const float* b1 = ps.data[3 + s] + ((size_t)b * C + ghalf * 32) * hw1;
+        const float* b2 = ps.data[6 + s] + ((size_t)b * C + ghalf * 32) * hw2;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          float y[8], yr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int c = g * 8 + i;
+            float v = tap_sample(b0 + c * hw0, txy);
+            v = __fadd_rn(v, tap_sample(b1 + c * hw1, tyz));
+            v = __fadd_rn(v, tap_sample(b2 + c * hw2, txz));
+            y[i] = v;
+            yr[i] = fmaxf(v, 0.f);
+          }
+          uint4 hi, lo;
+          const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
+          split8(y, hi, lo);
+          st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
+          st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
+          split8(yr, hi, lo);
+          st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
+          st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
+        }
       }
     };
     // relu(acc1 + b) -> H, quarter by quarter (fc_0 epilogue)
@@ -179,6 +221,9 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         store_act<16>(h_hi, h_lo, row, sub * 32, v);
         signal_all();
       }
+      // R1's fc_0 AND shortcut ran in that group, so both feature buffers are free: gather the next scale now,
+      // overlapping R1.fc_1 (every gather sits right after the group that last reads Xa / Xb)
+      gather(tile, 1);
       // ---- R1 output h1 = acc2 + b1' + net_p(p); R2, R3: two operand phases (raw, then relu)
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
@@ -203,19 +248,18 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
             }
           }
         }
-        // phase 1: raw h (shortcut operand); the next scale's features are gathered before the last quarter
-        put_quarter<false>(h_hi, h_lo, row, 0, sub, v[0]); signal(0);
-        put_quarter<false>(h_hi, h_lo, row, 1, sub, v[1]); signal(1);
-        put_quarter<false>(h_hi, h_lo, row, 2, sub, v[2]); signal(2);
-        gather(tile, blk);
-        put_quarter<false>(h_hi, h_lo, row, 3, sub, v[3]); signal(3);
+        // phase 1: raw h (shortcut operand)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
         // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
         wait_mma();
 #pragma unroll
         for (int q = 0; q < 4; ++q) { put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
-        // fc_0 epilogue
+        // fc_0 epilogue; Xa / Xb are free again: gather what comes next while fc_1 runs
         wait_mma();
         stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
+        if (blk == 1) gather(tile, 2);
+        else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
       }
       // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
       wait_mma();
@@ -229,8 +273,6 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
           signal(q);
         }
       }
-      // the plane feature buffers are free now: prefetch the next tile's coarse scale
-      if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
       // ---- R4.fc_0 epilogue
       wait_mma();
       stage_net(vec + OV_B04);
@@ -270,7 +312,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
 inline int launch_occupancy_umma(const PlaneSet& ps, int batch, int C, const float* pts, long long n, long long batch_stride,
                                  float divisor, float upper, const void* gemm, size_t gemm_bytes,
                                  const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
-                                 const float* vec, size_t vec_floats, float* logits, int pair, cudaStream_t st) {
+                                 const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
     set_error("tcgen05 occupancy kernel is built for 64-channel planes");
@@ -292,14 +334,16 @@ inline int launch_occupancy_umma(const PlaneSet& ps, int batch, int C, const flo
   }
   const uint8_t* ws = (const uint8_t*)gemm;
   const int tpi_i = (int)tpi;
-  if (pair) {
-    const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
-    DDMI_CUDA(launch_engine(occupancy_umma_kernel<1>, 1, (unsigned)(2 * npairs), OCC_SMEM, st, ps, pts, n, batch_stride,
-                            tpi_i, total, divisor, upper, ws, program_dev, vec, logits));
-  } else {
-    DDMI_CUDA(launch_engine(occupancy_umma_kernel<0>, 0, (unsigned)(total < sms ? total : sms), OCC_SMEM, st, ps, pts, n,
-                            batch_stride, tpi_i, total, divisor, upper, ws, program_dev, vec, logits));
-  }
+  const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
+  const unsigned ctas = pair ? (unsigned)(2 * npairs) : (unsigned)(total < sms ? total : sms);
+#define DDMI_OCC_LAUNCH(P, L)                                                                                        \
+  DDMI_CUDA(launch_engine(occupancy_umma_kernel<P, L>, P, ctas, OCC_SMEM, st, ps, pts, n, batch_stride, tpi_i, total, \
+                          divisor, upper, ws, program_dev, vec, logits))
+  if (pair && nhwc) { DDMI_OCC_LAUNCH(1, 1); }
+  else if (pair) { DDMI_OCC_LAUNCH(1, 0); }
+  else if (nhwc) { DDMI_OCC_LAUNCH(0, 1); }
+  else { DDMI_OCC_LAUNCH(0, 0); }
+#undef DDMI_OCC_LAUNCH
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

@@ -170,9 +170,16 @@ class MLP3D(_FusedDecoder):
         packed = self._packed(('occ', prec, pair), lambda: packing.pack_occupancy(self, prec, pair))
         logits = torch.empty((b, n), device=base.device, dtype=torch.float32)
         with torch.cuda.device(base.device):
+            st = _stream_ptr(base.device)
+            if prec == _lib.PREC_BF16X3:     # scattered queries: channels-last planes, float4 gathers
+                keep, arr = _lib.planes_channels_last(planes, st)
+                layout = 1
+            else:
+                keep, arr, layout = planes, _lib.planes_array(planes), 0
             _lib.check(_lib.lib().ddmi_decode_occupancy(
-                _lib.planes_array(planes), b, planes[0].shape[1], base.data_ptr(), n, bstride, 0.1,
-                _lib.weights_struct(packed), logits.data_ptr(), _stream_ptr(base.device)))
+                arr, b, planes[0].shape[1], layout, base.data_ptr(), n, bstride, 0.1,
+                _lib.weights_struct(packed), logits.data_ptr(), st))
+            del keep
         return logits
 
     def forward(self, coords, hdbf):

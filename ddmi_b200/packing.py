@@ -332,18 +332,18 @@ def _pack_occupancy_umma(p, pair):
             P.wait(q)
             P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, acc, first and q == 0)
 
-    # R1: x = PE(64)
+    # R1: x = PE(64).  fc_0 and the shortcut share one group so both PE buffers are released together
     wait_all()
     P.block(p['net_res1.fc_0.weight'], XBH, XBL, 0, True)                       # N = 64
+    P.block(p['net_res1.shortcut.weight'], XAH, XAL, 256, True)
     P.commit()
     wait_all()
-    P.block(p['net_res1.shortcut.weight'], XAH, XAL, 256, True)
-    P.block(p['net_res1.fc_1.weight'], HH, HL, 256, False)                      # K = 64 hidden
+    P.block(p['net_res1.fc_1.weight'], HH, HL, 256, False)                      # K = 64 hidden, onto the shortcut
     P.commit()
     for i in (2, 3):                                                            # x = [h(256) | PE(64)]
         Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
         over_h(Ws, 256, True)
-        P.block(Ws[:, 256:320], XAH, XAL, 256, False)                           # PE gathered before quarter 3 is published
+        P.block(Ws[:, 256:320], XAH, XAL, 256, False)
         P.commit()
         over_h(W0, 0, True)
         P.block(W0[:, 256:320], XBH, XBL, 0, False)

@@ -50,7 +50,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 2
+#define DDMI_ABI_VERSION 3
 
 enum {
   DDMI_OK = 0,
@@ -60,6 +60,9 @@ enum {
 };
 
 enum { DDMI_PREC_FP32 = 0, DDMI_PREC_BF16X3 = 1 };
+
+/* plane memory layout: as the reference's VAE decoder emits them, or channels-last */
+enum { DDMI_LAYOUT_NCHW = 0, DDMI_LAYOUT_NHWC = 1 };
 
 /* One positional-embedding plane batch: fp32, contiguous (batch, channels, height, width). */
 typedef struct {
@@ -102,14 +105,23 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
                       const ddmi_weights_t* weights, float* out, void* stream);
 
 /*
+ * (batch, C, H, W) -> (batch, H, W, C).  Scattered queries (3-D points, ray samples) gather all
+ * channels of a texel with float4 loads from the channels-last copy; planes are a few MB per item,
+ * so the one-off re-layout is noise next to the decode.  src / dst: device, distinct.
+ */
+DDMI_API int ddmi_planes_to_channels_last(const float* src, float* dst, int32_t batch, int32_t channels,
+                                          int32_t height, int32_t width, void* stream);
+
+/*
  * Occupancy decode.  planes[a*3+s]: axis a = 0 'xy', 1 'yz', 2 'xz'; scale s =
  * 0..2; each (batch, 64, R_s, R_s).  points: (batch, n_points, 3) fp32 with
  * batch stride `point_batch_stride` floats (0 = the same points for every item).
  * Coordinates are normalised as normalize_coordinate(padding) does, then sampled
  * bilinear / border / align_corners = true and summed over the three axes.
- * logits: (batch, n_points) fp32.
+ * logits: (batch, n_points) fp32.  plane_layout: DDMI_LAYOUT_NCHW (each (batch, 64, R, R)) or
+ * DDMI_LAYOUT_NHWC (each (batch, R, R, 64), tcgen05 kernel only).
  */
-DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, int32_t channels, int32_t plane_layout,
                           const float* points, int64_t n_points, int64_t point_batch_stride,
                           float padding, const ddmi_weights_t* weights, float* logits,
                           void* stream);
