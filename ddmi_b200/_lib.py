@@ -71,14 +71,14 @@ def lib():
         L.ddmi_decode_video.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
                                         ctypes.POINTER(Weights), vp, vp]
         L.ddmi_nerf_mlp.argtypes = [vp, i64, i32, i32, f32, ctypes.POINTER(Weights), vp, vp]
-        L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, i64, i32, vp, i32, f32, f32,
+        L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i32, vp, i32, f32, f32,
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]
         L.ddmi_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_selftest_umma2.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
-        if L.ddmi_abi_version() != 3:
+        if L.ddmi_abi_version() != 4:
             raise RuntimeError("libddmi_b200.so ABI version mismatch")
         _lib = L
     return _lib

@@ -31,6 +31,8 @@ int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, lon
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
+int launch_nerf_composite(const float*, const float*, int, const float*, int, long long, int, int, float*, cudaStream_t);
+int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 
@@ -220,8 +222,8 @@ DDMI_API int ddmi_nerf_mlp(const float* x, int64_t n, int32_t x_stride, int32_t 
                               weights->vec, out, (cudaStream_t)stream);
 }
 
-DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, const float* rays,
-                     int64_t n_rays, int32_t ray_stride, const float* t_vals, int32_t n_samples,
+DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
+                     const float* rays, int64_t n_rays, int32_t ray_stride, const float* t_vals, int32_t n_samples,
                      float plane_extent, float negative_slope, int32_t white_bkgd,
                      const ddmi_weights_t* weights, float* rgb_map, float* raw, void* stream) {
   PlaneSet ps = {};
@@ -237,14 +239,36 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
     return DDMI_ERR_UNSUPPORTED;
   }
   DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  DDMI_REQUIRE(raw == nullptr || ((uintptr_t)raw & 15) == 0, "raw must be 16-byte aligned");
+  if (weights->precision == DDMI_PREC_BF16X3) {
+    // tcgen05 kernel: channels-last planes, CTA pairs; compositing is fused when one tile is one ray
+    if (plane_layout != DDMI_LAYOUT_NHWC || !(weights->reserved & 1)) {
+      set_error("the tcgen05 NeRF kernel needs channels-last planes and pair-packed weights");
+      return DDMI_ERR_UNSUPPORTED;
+    }
+    DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
+    DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
+    const int fuse = n_samples == 128;
+    DDMI_REQUIRE(fuse || raw != nullptr, "n_samples != 128: compositing runs as a second kernel over `raw`; pass the buffer");
+    rc = launch_nerf_umma_entry(ps, batch, channels, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent,
+                                negative_slope, white_bkgd, weights->gemm, weights->gemm_bytes, weights->program_host,
+                                weights->program_words, weights->program, weights->vec, weights->vec_floats, rgb_map, raw,
+                                fuse, (cudaStream_t)stream);
+    if (rc || fuse) return rc;
+    return launch_nerf_composite(raw, rays, ray_stride, t_vals, n_samples, n_rays, batch, white_bkgd, rgb_map,
+                                 (cudaStream_t)stream);
+  }
   if (weights->precision != DDMI_PREC_FP32) {
-    set_error("nerf render: precision %d has no kernel in this build (fp32 only)", weights->precision);
+    set_error("nerf render: unknown precision %d", weights->precision);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  if (plane_layout != DDMI_LAYOUT_NCHW) {
+    set_error("the fp32 NeRF kernel reads NCHW planes only");
     return DDMI_ERR_UNSUPPORTED;
   }
   rc = check_weights(weights, kNerfGemmFloats * sizeof(float), kNerfVecFloats);
   if (rc) return rc;
   DDMI_REQUIRE(raw != nullptr, "the fp32 render kernel composites from `raw`; pass a (batch,n_rays,n_samples,4) buffer");
-  DDMI_REQUIRE(((uintptr_t)raw & 15) == 0, "raw must be 16-byte aligned");
   return launch_nerf_render_fp32(ps, batch, channels, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent,
                                  negative_slope, white_bkgd, (const float*)weights->gemm, weights->vec, rgb_map,
                                  raw, (cudaStream_t)stream);

@@ -664,6 +664,15 @@ int launch_nerf_mlp_fp32(const float* x, long long n, int x_stride, int sigma_on
   return DDMI_OK;
 }
 
+int launch_nerf_composite(const float* raw, const float* rays, int ray_stride, const float* t_vals, int n_samples,
+                          long long n_rays, int batch, int white_bkgd, float* rgb_map, cudaStream_t st) {
+  long long tot = n_rays * batch;
+  fp32::nerf_composite_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(raw, rays, ray_stride, t_vals, n_samples, n_rays,
+                                                                             batch, white_bkgd, rgb_map);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
+
 int launch_nerf_render_fp32(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays,
                             int ray_stride, const float* t_vals, int n_samples, float plane_extent,
                             float slope, int white_bkgd, const float* Wg, const float* vec,

@@ -30,6 +30,7 @@
 // ToRGB as an N=16 block.
 #include "umma_engine.cuh"
 #include "decode_umma_occ.cuh"
+#include "decode_umma_nerf.cuh"
 
 namespace ddmi {
 namespace ummak {
@@ -349,6 +350,15 @@ int launch_occupancy_umma_entry(const PlaneSet& ps, int batch, int C, const floa
                                 const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, cudaStream_t st) {
   return launch_occupancy_umma(ps, batch, C, pts, n, batch_stride, divisor, upper, gemm, gemm_bytes, program_host,
                                program_words, program_dev, vec, vec_floats, logits, pair, nhwc, st);
+}
+
+int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays, int ray_stride,
+                           const float* t_vals, int n_samples, float plane_extent, float slope, int white_bkgd,
+                           const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
+                           const uint32_t* program_dev, const float* vec, size_t vec_floats, float* rgb_map, float* raw,
+                           int fuse, cudaStream_t st) {
+  return launch_nerf_umma(ps, batch, C, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent, slope, white_bkgd, gemm,
+                          gemm_bytes, program_host, program_words, program_dev, vec, vec_floats, rgb_map, raw, fuse, st);
 }
 
 int debug_profile(unsigned long long* out, int reset) {

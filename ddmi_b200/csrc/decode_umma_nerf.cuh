@@ -1,0 +1,324 @@
+// NeRF ray decode (utils/nerf_helpers.py:296-530 render_rays + run_network + raw2outputs, with
+// MLPNeRF.forward models/d2c_vae/mlp.py:241-281) on the tcgen05 engine.
+//
+// One tile = 128 consecutive (ray, sample) rows.  Per tile: sample generation, triplane gather
+// (channels-last planes, align_corners = true), positional embeddings of the un-normalised point
+// (L = 10) written straight into the A-operand layout, the 8-layer MLP (skips re-read the 160-wide
+// [latent | embedding] operand X, which therefore stays resident), the view-direction layer
+// (N = 128 block, its 27-wide embedding reuses X's space once the last skip layer is done), the
+// sigma / rgb heads in the epilogue, and -- when n_samples == 128, i.e. one tile == one ray --
+// the volume compositing with a warp-shuffle product scan, so only 3 floats per ray leave the SM.
+//
+// Shared memory: H (128 KB) + X (80 KB) leave room for a 2-slot weight ring only.
+//
+// vec layout (floats): b1..b6 [6][256] | b_final[256] | b_dir[128] | w_sigma[256] | b_sigma[1] pad[3]
+//                      | w_rgb[3][128] | b_rgb[3]
+#pragma once
+#include "decode_umma_occ.cuh"
+
+namespace ddmi {
+namespace ummak {
+
+using NrfL = Layout<20, 16384>;   // X: 160 columns = 20 K groups (hi) + 20 (lo); 2 x 8 KB ring slots (CTA pairs only)
+constexpr int NRF_KG_XH = 64, NRF_KG_XL = 84;
+constexpr int NV_B = 0, NV_BF = 1536, NV_BD = 1792, NV_WS = 1920, NV_BS = 2176, NV_WRGB = 2180, NV_BRGB = 2564, NV_TOTAL = 2567;
+// scratch inside X's hi region (K groups 68..83), valid once the last skip layer has committed
+constexpr int NRF_SCRATCH = (NRF_KG_XH + 4) * KG_BYTES;
+
+__device__ __forceinline__ float2 lrelu_pair(float2 t, float slope) {
+  return make_float2(fmaxf(t.x, 0.f) + slope * fminf(t.x, 0.f), fmaxf(t.y, 0.f) + slope * fminf(t.y, 0.f));
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
+                 int n_samples, float plane_extent, long long n /* rows per object */, int tiles_per_item,
+                 long long total_tiles, float slope, int white_bkgd, int fuse,
+                 const uint8_t* __restrict__ wstream, const uint32_t* __restrict__ program,
+                 const float* __restrict__ vec, float* __restrict__ rgb_map, float* __restrict__ raw) {
+  constexpr int PAIR = 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
+  const uint32_t x_hi = sbase + NRF_KG_XH * KG_BYTES, x_lo = sbase + NRF_KG_XL * KG_BYTES;
+  const uint32_t ring = sbase + NrfL::OFF_RING, bar = sbase + NrfL::OFF_BAR;
+  float* scratch = reinterpret_cast<float*>(smem + NRF_SCRATCH);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t tmem = engine_begin<PAIR>(smem, NrfL::OFF_BAR);
+
+  const long long nwork = (total_tiles + 1) / 2;
+  const long long wfirst = blockIdx.x / 2, wstride = gridDim.x / 2;
+  const long long ntiles = wfirst < nwork ? (nwork - wfirst + wstride - 1) / wstride : 0;
+  auto tile_of = [&](long long i) { return 2 * (wfirst + i * wstride) + rank; };
+
+  if (warp < 8) {
+    reg_inc<216>();
+    const int row = tid & 127;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int sub = warp >> 2;
+    const int ghalf = tid >> 7;
+    const uint32_t a_bar = mapa_rank(bar + BAR_A0, 0);
+    uint32_t ph_mma = 0;
+
+    auto signal = [&](int q) {
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
+    };
+    auto signal_all = [&]() {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) signal(q);
+    };
+    auto wait_mma = [&]() {
+      mbar_wait(bar + BAR_MMADONE, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+    };
+    // row -> (object, ray, sample); rows past the end replay the last one
+    struct RowInfo { int b; long long ray; int smp; long long gi; };
+    auto row_of = [&](long long tile) {
+      if (tile > total_tiles - 1) tile = total_tiles - 1;
+      RowInfo r;
+      r.b = (int)(tile / tiles_per_item);
+      r.gi = (tile % tiles_per_item) * TILE + row;
+      if (r.gi > n - 1) r.gi = n - 1;
+      r.ray = r.gi / n_samples;
+      r.smp = (int)(r.gi % n_samples);
+      return r;
+    };
+    auto zval = [&](const float* rr, int smp) {   // near * (1 - t) + far * t  (nerf_helpers.py:356-358)
+      const float tv = __ldg(t_vals + smp);
+      return __fadd_rn(__fmul_rn(__ldg(rr + 6), __fsub_rn(1.f, tv)), __fmul_rn(__ldg(rr + 7), tv));
+    };
+    // gamma(p) element e of the 63-wide embedding (Embedder.embed): [p, sin(2^0 p), cos(2^0 p), ...]
+    auto embed_elem = [&](const float (&p)[3], int e, int nmax) {
+      if (e >= nmax) return 0.f;
+      if (e < 3) return p[e];
+      const int l = (e - 3) / 6, r = (e - 3) % 6;
+      const float a = __fmul_rn(p[r % 3], (float)(1 << l));
+      return r < 3 ? sinf(a) : cosf(a);
+    };
+    // X = [latent xy|yz|xz (3 x 32) | gamma(pts) 63 | 0]: this thread fills K groups [10 ghalf, +10) of its row
+    auto build_x = [&](long long tile) {
+      const RowInfo ri = row_of(tile);
+      const float* rr = rays + (size_t)ri.ray * ray_stride;
+      const float z = zval(rr, ri.smp);
+      float p[3], g[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        p[i] = __fadd_rn(__ldg(rr + i), __fmul_rn(__ldg(rr + 3 + i), z));
+        g[i] = __fdiv_rn(p[i], plane_extent);
+      }
+#pragma unroll 1
+      for (int j = ghalf * 10; j < ghalf * 10 + 10; ++j) {
+        float y[8];
+        if (j < 12) {   // plane a = j / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate -> column
+          const int a = j >> 2;
+          const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
+          const Tap tp = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
+          tap_sample8_nhwc(ps.data[a] + (size_t)ri.b * ps.h[a] * ps.w[a] * C, tp, C, (j & 3) * 8, y);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = embed_elem(p, (j - 12) * 8 + i, 63);
+        }
+        uint4 hi, lo;
+        split8(y, hi, lo);
+        const uint32_t off = (uint32_t)(j * KG_BYTES + row * 16);
+        st_shared_v4(x_hi + off, hi);
+        st_shared_v4(x_lo + off, lo);
+      }
+    };
+    // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
+    auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {
+      drain128(tmem_lane, 0, sub, v);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        add_vec<16>(v[q], b + q * 64 + sub * 32);
+        if (act) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[q][i] = lrelu_pair(v[q][i], slope);
+        }
+        put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]);
+        signal(q);
+      }
+    };
+
+    if (ntiles > 0) {
+      build_x(tile_of(0));
+      signal_all();
+    }
+    for (long long it = 0; it < ntiles; ++it) {
+      const long long tile = tile_of(it);
+      const RowInfo ri = row_of(tile);
+      const float* rr = rays + (size_t)ri.ray * ray_stride;
+      float sigma = 0.f;
+      // ---- xyz_encoding_1..6
+#pragma unroll 1
+      for (int l = 0; l < 6; ++l) {
+        wait_mma();
+        float2 v[4][16];
+        stage_act(vec + NV_B + l * 256, true, v);
+        if (l == 5) {
+          // X is dead (the last skip layer committed): view-direction embedding -> X's first 4 K groups,
+          // sigma = w_sigma . h6 + b_sigma (this thread's 128 columns, summed across the two sub-warps below)
+          if (ghalf == 0) {
+            const float vd[3] = {__ldg(rr + 8), __ldg(rr + 9), __ldg(rr + 10)};
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = embed_elem(vd, j * 8 + i, 27);
+              uint4 hi, lo;
+              split8(y, hi, lo);
+              st_shared_v4(x_hi + j * KG_BYTES + row * 16, hi);
+              st_shared_v4(x_lo + j * KG_BYTES + row * 16, lo);
+            }
+          }
+          float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float2 w[16];
+            load_vec<16>(vec + NV_WS + q * 64 + sub * 32, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s2 = __ffma2_rn(v[q][i], w[i], s2);
+          }
+          scratch[sub * 128 + row] = s2.x + s2.y;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          sigma = scratch[row] + scratch[128 + row] + __ldg(vec + NV_BS);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+      // ---- xyz_encoding_final (no activation); the direction embedding written above rides on these signals
+      wait_mma();
+      {
+        float2 v[4][16];
+        stage_act(vec + NV_BF, false, v);
+      }
+      // ---- dir_encoding (N = 128) + rgb head
+      wait_mma();
+      float rgb[3];
+      {
+        float2 v[2][16];
+        tmem_ld32(tmem_lane + sub * 32, v[0]);
+        tmem_ld32(tmem_lane + 64 + sub * 32, v[1]);
+        tmem_ld_wait();
+        float2 acc3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          add_vec<16>(v[q], vec + NV_BD + q * 64 + sub * 32);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[q][i] = lrelu_pair(v[q][i], slope);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float2 w[16];
+            load_vec<16>(vec + NV_WRGB + c * 128 + q * 64 + sub * 32, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc3[c] = __ffma2_rn(v[q][i], w[i], acc3[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) scratch[(c * 2 + sub) * 128 + row] = acc3[c].x + acc3[c].y;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float s = scratch[(c * 2) * 128 + row] + scratch[(c * 2 + 1) * 128 + row] + __ldg(vec + NV_BRGB + c);
+          rgb[c] = 1.f / (1.f + expf(-s));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const bool valid = tile < total_tiles && (tile % tiles_per_item) * TILE + row < n;
+      if (sub == 0) {
+        if (raw != nullptr && valid) {
+          reinterpret_cast<float4*>(raw)[(size_t)ri.b * n + ri.gi] = make_float4(rgb[0], rgb[1], rgb[2], sigma);
+        }
+        if (fuse) {
+          // raw2outputs (nerf_helpers.py:487-530): one tile == one ray, row == sample index
+          const float z0 = zval(rr, ri.smp);
+          float dist = ri.smp + 1 < n_samples ? __fsub_rn(zval(rr, ri.smp + 1), z0) : 1e10f;
+          const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
+          dist = __fmul_rn(dist, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+          const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(softplus20(sigma), dist)));
+          float t = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+          // inclusive product scan over the warp's 32 samples, then across the 4 warps
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t *= u;
+          }
+          float T = __shfl_up_sync(0xffffffffu, t, 1);
+          if (lane == 0) T = 1.f;
+          if (lane == 31) scratch[1024 + warp] = t;
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          for (int w = 0; w < warp; ++w) T *= scratch[1024 + w];
+          const float wgt = alpha * T;
+          float s0 = wgt * rgb[0], s1 = wgt * rgb[1], s2 = wgt * rgb[2], sa = wgt;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          }
+          if (lane == 0) {
+            scratch[1040 + warp * 4 + 0] = s0; scratch[1040 + warp * 4 + 1] = s1;
+            scratch[1040 + warp * 4 + 2] = s2; scratch[1040 + warp * 4 + 3] = sa;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (row == 0 && tile < total_tiles) {
+            float o3[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int w = 0; w < 4; ++w)
+              for (int c = 0; c < 4; ++c) o3[c] += scratch[1040 + w * 4 + c];
+            const float bg = white_bkgd ? 1.f - o3[3] : 0.f;
+            float* dst = rgb_map + ((size_t)ri.b * (n / n_samples) + ri.ray) * 3;
+            dst[0] = o3[0] + bg; dst[1] = o3[1] + bg; dst[2] = o3[2] + bg;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+      }
+      // scratch (inside X) is done with: build the next tile's X, then hand over
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (it + 1 < ntiles) {
+        build_x(tile_of(it + 1));
+        signal_all();
+      }
+    }
+  } else {
+    engine_service_warps<PAIR, NrfL::RING_BYTES>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+  }
+  engine_end<PAIR>(tmem);
+}
+
+}  // namespace ummak
+
+inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays, int ray_stride,
+                            const float* t_vals, int n_samples, float plane_extent, float slope, int white_bkgd,
+                            const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
+                            const uint32_t* program_dev, const float* vec, size_t vec_floats, float* rgb_map, float* raw,
+                            int fuse, cudaStream_t st) {
+  using namespace ummak;
+  DDMI_REQUIRE(program_host && program_dev && program_words >= 2, "bf16x3 weights carry no MMA program");
+  const long long need = program_stream_bytes(program_host, program_words);
+  DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
+               need, gemm_bytes);
+  DDMI_REQUIRE(vec_floats == (size_t)NV_TOTAL, "packed vec blob is %zu floats, expected %d", vec_floats, NV_TOTAL);
+  int dev = 0, sms = 0;
+  DDMI_CUDA(cudaGetDevice(&dev));
+  DDMI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long n = n_rays * n_samples;
+  const long long tpi = (n + TILE - 1) / TILE;
+  const long long total = tpi * batch;
+  if (tpi > 2147483647LL) {
+    set_error("ray set too large for one launch");
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
+  DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NrfL::SMEM_BYTES));
+  nerf_umma_kernel<<<(unsigned)(2 * npairs), NTHREADS, NrfL::SMEM_BYTES, st>>>(
+      ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
+      (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
+
+}  // namespace ddmi

@@ -124,9 +124,12 @@ def _find_module(network_fn):
         "or pass the module itself); an opaque callable cannot be fused")
 
 
-def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False):
+def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False, precision=None):
     """rays (N,11) [o d near far viewdir]; fea = dict of (B,32,R,R) planes.
-    Returns rgb_map (B,N,3) (and raw (B,N,S,4))."""
+    Returns rgb_map (B,N,3) (and raw (B,N,S,4)).  precision: 'bf16x3' (tcgen05 kernel, default; compositing is
+    fused in-kernel when N_samples == 128) or 'fp32' (CUDA-core kernels); env DDMI_B200_PRECISION overrides."""
+    import os
+    precision = precision or module.precision or os.environ.get('DDMI_B200_PRECISION') or 'bf16x3'
     planes = []
     for k in ('xy', 'yz', 'xz'):
         t = fea[k]
@@ -139,13 +142,21 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
     n = rays.shape[0]
     t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)
     rgb = torch.empty((b, n, 3), device=dev, dtype=torch.float32)
-    raw = torch.empty((b, n, N_samples, 4), device=dev, dtype=torch.float32)
-    packed = module.packed_weights()
+    umma = precision == 'bf16x3'
+    need_raw = return_raw or not (umma and N_samples == 128)
+    raw = torch.empty((b, n, N_samples, 4), device=dev, dtype=torch.float32) if need_raw else None
+    packed = module.packed_weights(precision)
     with torch.cuda.device(dev):
+        st = _stream_ptr(dev)
+        if umma:
+            keep, arr = _lib.planes_channels_last(planes, st)
+        else:
+            keep, arr = planes, _lib.planes_array(planes)
         _lib.check(_lib.lib().ddmi_nerf_render(
-            _lib.planes_array(planes), b, planes[0].shape[1], rays.data_ptr(), n, rays.shape[1],
+            arr, b, planes[0].shape[1], 1 if umma else 0, rays.data_ptr(), n, rays.shape[1],
             t_vals.data_ptr(), N_samples, PLANE_EXTENT, module.negative_slope, 1 if white_bkgd else 0,
-            _lib.weights_struct(packed), rgb.data_ptr(), raw.data_ptr(), _stream_ptr(dev)))
+            _lib.weights_struct(packed), rgb.data_ptr(), raw.data_ptr() if raw is not None else None, st))
+        del keep
     return (rgb, raw) if return_raw else rgb
 
 

@@ -386,14 +386,62 @@ def pack_video(module, precision=PREC_FP32):
 # ---------------------------------------------------------------------------
 # NeRF MLP (mlp.py:199-281), D=6, W=256, skips=[2,4], xyz 159, dir 27
 # ---------------------------------------------------------------------------
+def _pack_nerf_umma(p):
+    """Program + stream + vec of csrc/decode_umma_nerf.cuh (CTA pairs).  A-region K groups: H hi 0..31, H lo 32..63,
+    X ([latent 96 | gamma(pts) 63 | 0]) hi 64..83, lo 84..103; the 27-wide direction embedding reuses X's first 4
+    K groups for the last layer.  One accumulator (TMEM columns 0..255)."""
+    HH, HL, XH, XL = 0, 32, 64, 84
+    P = UmmaProgram(pair=True)
+
+    def over_h(W, first, n_pad=None):
+        for q in range(4):
+            P.wait(q)
+            P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 0, first and q == 0, n_pad=n_pad)
+
+    def pad_k(W, k):
+        out = W.new_zeros(W.shape[0], k)
+        out[:, :W.shape[1]] = W
+        return out
+
+    for i in range(6):
+        W = p[f'xyz_encoding_{i + 1}.0.weight']
+        if i == 0:
+            for q in range(4):
+                P.wait(q)
+            P.block(pad_k(W, 160), XH, XL, 0, True)
+        elif i in (2, 4):                      # cat([input_xyz, h]): X part first (ready at once), then h by quarters
+            P.wait(0)
+            P.block(pad_k(W[:, :159], 160), XH, XL, 0, True)
+            for q in range(4):
+                if q:
+                    P.wait(q)
+                P.block(W[:, 159 + 64 * q:159 + 64 * q + 64], HH + 8 * q, HL + 8 * q, 0, False)
+        else:
+            over_h(W, True)
+        P.commit()
+    over_h(p['xyz_encoding_final.weight'], True)
+    P.commit()
+    Wd = p['dir_encoding.0.weight']            # (128, 283) on cat([final, dir27])
+    over_h(Wd[:, :256], True)
+    P.block(pad_k(Wd[:, 256:283], 32), XH, XL, 0, False)
+    P.commit()
+    z3 = torch.zeros(3, dtype=torch.float64, device=Wd.device)
+    vec = torch.cat([p[f'xyz_encoding_{i + 1}.0.bias'] for i in range(6)]
+                    + [p['xyz_encoding_final.bias'], p['dir_encoding.0.bias'], p['sigma.weight'].reshape(-1),
+                       p['sigma.bias'].reshape(-1), z3, p['rgb.0.weight'].reshape(-1), p['rgb.0.bias'].reshape(-1)]
+                    ).to(torch.float32).contiguous()
+    gemm, prog_dev, prog_host = P.finish(vec.device)
+    return Packed(PREC_BF16X3, gemm, vec, prog_dev, prog_host, True)
+
+
 def pack_nerf(module, precision=PREC_FP32):
-    if precision != PREC_FP32:
-        raise ValueError("MLPNeRF is packed for the fp32 kernels only in this build")
     if (module.D, module.W, module.in_channels_xyz, module.in_channels_dir, list(module.skips)) != (6, 256, 159, 27, [2, 4]):
         raise NotImplementedError(
             "the fused NeRF kernel is specialised for D=6, W=256, in_channels_xyz=159, "
             "in_channels_dir=27, skips=[2,4] (configs/d2c-vae/srn_cars.yaml:45-49)")
     p = _params64(module)
+    if precision == PREC_BF16X3:
+        return _pack_nerf_umma(p)
     segs, vec = [], []
     for i in range(6):
         W = p[f'xyz_encoding_{i + 1}.0.weight']

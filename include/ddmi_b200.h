@@ -50,7 +50,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 3
+#define DDMI_ABI_VERSION 4
 
 enum {
   DDMI_OK = 0,
@@ -156,12 +156,13 @@ DDMI_API int ddmi_nerf_mlp(const float* x, int64_t n, int32_t x_stride, int32_t 
  * rows [o(3) d(3) near far viewdir(3)].  t_vals: (n_samples) the caller's
  * linspace(0,1,n_samples).  pts are divided by `plane_extent` (3.5) before
  * sampling (bilinear / border / align_corners = true).
+ * plane_layout: DDMI_LAYOUT_NCHW (fp32 kernel) or DDMI_LAYOUT_NHWC (tcgen05 kernel, each (batch, R, R, 32)).
  * rgb_map: (batch, n_rays, 3).  raw: optional (batch, n_rays, n_samples, 4)
  * model outputs [rgb, sigma] (pass NULL to skip the store when the kernel
  * composites in place; some kernels need it as workspace and then it is required
  * -- the function says so with DDMI_ERR_BAD_ARG).
  */
-DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
                      const float* rays, int64_t n_rays, int32_t ray_stride,
                      const float* t_vals, int32_t n_samples, float plane_extent,
                      float negative_slope, int32_t white_bkgd,

@@ -162,9 +162,11 @@ def test_nerf_mlp_golden(golden_dir):
     assert float((sig[:, 0] - g['out'][:, 3]).abs().max()) < 2e-5
 
 
-def test_nerf_render_golden(golden_dir):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_nerf_render_golden(golden_dir, precision):
     g = _golden(golden_dir, 'nerf_render')
     m = cases.build_module('nerf').to(DEV)
+    m.precision = precision
     res, K, fea, c2w = cases.nerf_inputs()
     e1, _ = nh.get_embedder(10, 0)
     e2, _ = nh.get_embedder(4, 0)
@@ -172,21 +174,43 @@ def test_nerf_render_golden(golden_dir):
     rgb = nh.render(res, res, K, _cuda(fea), None, 0, DEV, chunk=4096, c2w=c2w, verbose=True, retraw=True,
                     hw_idx=None, **kw).cpu()
     assert rgb.shape == g['out'].shape == (res * res, 3)
-    assert float((rgb - g['out']).abs().max()) < 1e-4
+    assert float((rgb - g['out']).abs().max()) < (1e-4 if precision == 'fp32' else TOL)
 
 
-def test_nerf_render_batch_and_ray_subset():
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_nerf_render_batch_and_ray_subset(precision):
     m = cases.build_module('nerf').to(DEV)
     sd = cases.state_dict32(m)
+    tol = 1e-4 if precision == 'fp32' else TOL
     g = torch.Generator().manual_seed(11)
     fea = {k: torch.randn(2, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
     gold_rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][100:165]
-    rgb, raw = nh.render_rays_fused(gold_rays.to(DEV), _cuda(fea), m, 48, True, return_raw=True)
+    rgb, raw = nh.render_rays_fused(gold_rays.to(DEV), _cuda(fea), m, 48, True, return_raw=True, precision=precision)
     for b in range(2):
         fb = {k: v[b:b + 1] for k, v in fea.items()}
         ref, ref_raw = orc.nerf_render_rays(sd, gold_rays, fb, 48, True, return_raw=True)
-        assert float((raw[b].cpu() - ref_raw).abs().max()) < 1e-4
-        assert float((rgb[b].cpu() - ref).abs().max()) < 1e-4
+        assert float((raw[b].cpu() - ref_raw).abs().max()) < tol
+        assert float((rgb[b].cpu() - ref).abs().max()) < tol
+
+
+@pytest.mark.parametrize("n_obj,n_rays", [(1, 37), (3, 64)])
+def test_nerf_render_fused_compositing_128_samples(n_obj, n_rays):
+    """N_samples == 128: one tile == one ray, compositing runs inside the tcgen05 kernel (no raw round trip)."""
+    m = cases.build_module('nerf').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(13)
+    fea = {k: torch.randn(n_obj, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
+    rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][300:300 + n_rays]
+    rgb = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, precision='bf16x3')
+    rgb2, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, return_raw=True, precision='bf16x3')
+    assert float((rgb - rgb2).abs().max()) == 0.0
+    for b in range(n_obj):
+        fb = {k: v[b:b + 1] for k, v in fea.items()}
+        ref, ref_raw = orc.nerf_render_rays(sd, rays, fb, 128, True, return_raw=True)
+        assert float((raw[b].cpu() - ref_raw).abs().max()) < TOL
+        assert float((rgb[b].cpu() - ref).abs().max()) < TOL
+    black = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, False, precision='bf16x3')
+    assert float((rgb - black).min()) >= -1e-6      # the white background only adds (1 - acc) >= 0
 
 
 def test_unsupported_render_options_raise():
