@@ -31,6 +31,7 @@
 #include "umma_engine.cuh"
 #include "decode_umma_occ.cuh"
 #include "decode_umma_nerf.cuh"
+#include "decode_umma_video.cuh"
 
 namespace ddmi {
 namespace ummak {
@@ -359,6 +360,14 @@ int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* ra
                            int fuse, cudaStream_t st) {
   return launch_nerf_umma(ps, batch, C, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent, slope, white_bkgd, gemm,
                           gemm_bytes, program_host, program_words, program_dev, vec, vec_floats, rgb_map, raw, fuse, st);
+}
+
+int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt, int T,
+                            int H, int W, const void* gemm, size_t gemm_bytes, const uint32_t* program_host,
+                            size_t program_words, const uint32_t* program_dev, const float* vec, size_t vec_floats,
+                            float* out, int pair, cudaStream_t st) {
+  return launch_video_umma(ps, batch, C, cxy, cyt, cxt, T, H, W, gemm, gemm_bytes, program_host, program_words, program_dev,
+                           vec, vec_floats, out, pair, st);
 }
 
 int debug_profile(unsigned long long* out, int reset) {

@@ -24,8 +24,13 @@ constexpr uint32_t OP_UNIT = 0, OP_WAIT = 1, OP_COMMIT = 2, OP_END = 3;
 
 // barriers, 8 B each, relative to the barrier block
 constexpr int BAR_WFULL = 0, BAR_WEMPTY = 64, BAR_PFULL = 128 /* leader: the peer's half of slot s landed */,
-              BAR_MMADONE = 192, BAR_A0 = 200 /* A0..A3 */, TMEM_SLOT = 232;
-constexpr int BAR_BYTES = 256;
+              BAR_MMADONE = 192 /* D0..D3: COMMIT targets */, BAR_A0 = 224 /* A0..A7: operand barriers (WAIT ops) */,
+              TMEM_SLOT = 288;
+constexpr int BAR_BYTES = 320;
+// Protocol rule for every mbarrier here: it must never complete two phases before its waiter has consumed the
+// first (a parity wait cannot tell 0 from 2 completed phases).  E threads therefore re-signal operand barrier i
+// only after waiting a COMMIT that follows the previous WAIT i in program order, and the program re-commits
+// done-barrier j only after a WAIT whose signal the E threads issue after consuming the previous COMMIT j.
 
 template <int XKG, int RING = 65536>   // XKG: K groups of the feature operand region behind H
 struct Layout {
@@ -161,16 +166,17 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         }
       } else if (kind == OP_WAIT) {
-        const uint32_t i = (op >> 2) & 3;
+        const uint32_t i = (op >> 2) & 7;
         const long long w0 = clock64();
         mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
         ph_a ^= 1u << i;
         tc_fence_after();
         q_a += clock64() - w0;
       } else if (kind == OP_COMMIT) {
+        const uint32_t db = bar + BAR_MMADONE + 8 * ((op >> 2) & 3);
         if (elect_one()) {
-          if (PAIR) mma2_commit_mc(bar + BAR_MMADONE, 3);
-          else      mma_commit(bar + BAR_MMADONE);
+          if (PAIR) mma2_commit_mc(db, 3);
+          else      mma_commit(db);
         }
       } else {
         break;
@@ -225,8 +231,8 @@ __device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar) {
       mbar_init(bar + BAR_WEMPTY + 8 * s, 1);
       mbar_init(bar + BAR_PFULL + 8 * s, 1);
     }
-    mbar_init(bar + BAR_MMADONE, 1);
-    for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_A0 + 8 * q, 8 * (1 + PAIR));   // one arrival per E warp (of both CTAs)
+    for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_MMADONE + 8 * q, 1);
+    for (int q = 0; q < 8; ++q) mbar_init(bar + BAR_A0 + 8 * q, 8 * (1 + PAIR));   // one arrival per E warp (of both CTAs)
     fence_mbar_init();
   }
   if (warp == 9) {
@@ -266,7 +272,13 @@ __device__ __forceinline__ void engine_service_warps(const uint32_t* __restrict_
 template <class Kernel, class... Args>
 static inline cudaError_t launch_engine(Kernel kernel, int pair, unsigned ctas, size_t smem, cudaStream_t st, Args... args) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  if (e != cudaSuccess) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kernel);
+    fprintf(stderr, "ddmi_b200: cudaFuncSetAttribute(smem=%zu) failed: static smem %zu, regs %d, max dyn %d\n", smem,
+            fa.sharedSizeBytes, fa.numRegs, fa.maxDynamicSharedSizeBytes);
+    return e;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(NTHREADS);

@@ -191,6 +191,9 @@ class MLP3D(_FusedDecoder):
 class MLPVideo(_FusedDecoder):
     """Video decoder.  Reference: models/d2c_vae/mlp.py:114-157."""
 
+    _supported = ('fp32', 'bf16x3')
+    _default_precision = 'bf16x3'
+
     def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None, **ignore_kwargs):
         super().__init__()
         if (latent_dim, out_ch, ch) != (64, 3, 256):
@@ -229,7 +232,8 @@ class MLPVideo(_FusedDecoder):
         if tuple(cyt.shape[1:]) != (2, T, H) or tuple(cxt.shape[1:]) != (2, T, W):
             raise RuntimeError("inconsistent coords grids: expected xy (1,2,H,W), yt (1,2,T,H), xt (1,2,T,W)")
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
-        packed = self._packed(('video', prec), lambda: packing.pack_video(self, prec))
+        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'
+        packed = self._packed(('video', prec, pair), lambda: packing.pack_video(self, prec, pair))
         out = torch.empty((b, self.out_ch, T * H * W), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().ddmi_decode_video(

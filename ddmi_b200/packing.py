@@ -43,7 +43,8 @@ class UmmaProgram:
     accumulate), [7:5] accumulator column / 64, [15:8] first A-hi K group, [23:16] first A-lo K group
     (K groups = 8 columns x 128 rows = 2 KB, counted from the A region base in shared memory; each
     step advances both by 2), [28:24] number of steps - 1.
-    WAIT: bits [3:2] select the operand barrier (quarter q of the previous epilogue's output is ready).
+    WAIT: bits [4:2] select one of 8 operand barriers (e.g. quarter q of the previous epilogue's output is ready).
+    COMMIT: bits [3:2] select one of 4 completion barriers the epilogue threads wait on.
     """
     NCODE = {128: 0, 256: 1, 16: 2, 64: 3}
 
@@ -72,10 +73,12 @@ class UmmaProgram:
             self.segs.append(torch.cat(halves, dim=1).reshape(-1))
 
     def wait(self, which):
+        assert 0 <= which < 8
         self.ops.append(1 | (which << 2))
 
-    def commit(self):
-        self.ops.append(2)
+    def commit(self, which=0):
+        assert 0 <= which < 4
+        self.ops.append(2 | (which << 2))
 
     def finish(self, device):
         ops = torch.tensor(self.ops + [3, 3, 3, 3], dtype=torch.int64).to(torch.int32)
@@ -375,8 +378,78 @@ def pack_occupancy(module, precision=PREC_FP32, pair=True):
                   torch.cat(vec).to(torch.float32).contiguous())
 
 
-def pack_video(module, precision=PREC_FP32):
+def _pack_video_umma(p, pair):
+    """Program + stream + vec of csrc/decode_umma_video.cuh (the protocol is spelled out there).  A-region K groups
+    as for occupancy: H hi 0..31 / lo 32..63, Xa (raw piece) hi 64..71 / lo 80..87, Xb (relu piece) hi 72..79 / lo 88..95.
+    Operand barriers: 0..3 raw-h quarters / R1 pieces / later pieces, 4..7 relu-h and net quarters.
+    Completion barriers: D0 = "accumulators final for this phase", D1 = "piece consumed, Xa / Xb free"."""
+    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88
+    P = UmmaProgram(pair=pair)
+
+    def piece(Ws, W0, col0, first, n0_split):
+        """one 64-wide piece: fc_0 (relu piece, acc1) and shortcut (raw piece, acc2)"""
+        if n0_split:                                   # R1: fc_0 has N = 192 -> a 128 and a 64 block
+            P.block(W0[0:128, col0:col0 + 64], XBH, XBL, 0, first)
+            P.block(W0[128:192, col0:col0 + 64], XBH, XBL, 128, first)
+        else:
+            P.block(W0[:, col0:col0 + 64], XBH, XBL, 0, first)
+        P.block(Ws[:, col0:col0 + 64], XAH, XAL, 256, first)
+
+    # ---- R1: x = [xy | yt | xt] of scale 0
+    Ws, W0, W1 = p['net_res1.shortcut.weight'], p['net_res1.fc_0.weight'], p['net_res1.fc_1.weight']
+    for j in range(3):
+        P.wait(j)
+        piece(Ws, W0, 64 * j, j == 0, True)
+        P.commit(1 if j < 2 else 0)
+    for q in range(3):                                 # fc_1: K = 192 hidden, onto the shortcut
+        P.wait(4 + q)
+        P.block(W1[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 256, False)
+    P.commit(0)
+    # ---- R2, R3: x = [h (256) | xy | yt | xt]
+    for i in (2, 3):
+        Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
+        for q in range(4):                             # shortcut over RAW h
+            P.wait(q)
+            P.block(Ws[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 256, q == 0)
+        P.commit(0)
+        P.wait(4)                                      # relu(h) quarter 0 (+ piece 0, gathered meanwhile)
+        P.block(W0[:, 0:64], HH, HL, 0, True)
+        piece(Ws, W0, 256, False, False)
+        P.commit(1)
+        for q in range(1, 4):
+            P.wait(4 + q)
+            P.block(W0[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 0, False)
+        P.wait(0)
+        piece(Ws, W0, 320, False, False)
+        P.commit(1)
+        P.wait(1)
+        piece(Ws, W0, 384, False, False)
+        P.commit(0)
+        for q in range(4):                             # fc_1 onto the shortcut
+            P.wait(4 + q)
+            P.block(W1[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 256, False)
+        P.commit(0)
+    # ---- R4: identity shortcut (acc2 keeps accumulating)
+    for q in range(4):
+        P.wait(q)
+        P.block(p['net_res4.fc_0.weight'][:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 0, q == 0)
+    P.commit(0)
+    for q in range(4):
+        P.wait(4 + q)
+        P.block(p['net_res4.fc_1.weight'][:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 256, False)
+    P.commit(0)
+    vec = torch.cat([p['net_res1.fc_0.bias'], p['net_res1.fc_1.bias'], p['net_res2.fc_0.bias'], p['net_res2.fc_1.bias'],
+                     p['net_res3.fc_0.bias'], p['net_res3.fc_1.bias'], p['net_res4.fc_0.bias'],
+                     p['net_res3.fc_1.bias'] + p['net_res4.fc_1.bias'], p['net_out.weight'].reshape(-1),
+                     p['net_out.bias'].reshape(-1)]).to(torch.float32).contiguous()
+    gemm, prog_dev, prog_host = P.finish(vec.device)
+    return Packed(PREC_BF16X3, gemm, vec, prog_dev, prog_host, pair)
+
+
+def pack_video(module, precision=PREC_FP32, pair=True):
     p = _params64(module)
+    if precision == PREC_BF16X3:
+        return _pack_video_umma(p, pair)
     segs, vec = _pack_resnet_chain(p, 192, precision)
     vec += [p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]
     return Packed(precision, torch.cat(segs).to(torch.float32).contiguous(),

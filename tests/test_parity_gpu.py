@@ -128,17 +128,21 @@ def test_occupancy_dense_grid_chunks_like_eval_points():
 
 
 # ---------------------------------------------------------------- video
-def test_video_golden(golden_dir):
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_video_golden(golden_dir, precision):
     g = _golden(golden_dir, 'video')
     m = cases.build_module('video').to(DEV)
+    m.precision = precision
     coords, hdbf = cases.video_inputs()
     out = m(_cuda(coords), _cuda(hdbf)).cpu()
     assert out.shape == g['out'].shape
-    assert float((out - g['out']).abs().max()) < 2e-5
+    assert float((out - g['out']).abs().max()) < (2e-5 if precision == 'fp32' else TOL)
 
 
-def test_video_batch_and_anisotropic():
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_video_batch_and_anisotropic(precision):
     m = cases.build_module('video').to(DEV)
+    m.precision = precision
     sd = cases.state_dict32(m)
     g = torch.Generator().manual_seed(9)
     T, H, W = 3, 10, 14
@@ -148,7 +152,7 @@ def test_video_batch_and_anisotropic():
     coords = ddmi_b200.convert_to_coord_format_3d(1, H, W, T, hstart=-.9, hend=.9, wstart=-.8, wend=.8, tstart=-.5, tend=.5)
     ref = orc.video_decode(sd, coords, (xy, yt, xt))
     out = m(_cuda(coords), _cuda((xy, yt, xt))).cpu()
-    assert float((out - ref).abs().max()) < 2e-5
+    assert float((out - ref).abs().max()) < (2e-5 if precision == 'fp32' else TOL)
 
 
 # ---------------------------------------------------------------- nerf
