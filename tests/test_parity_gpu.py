@@ -257,3 +257,74 @@ def test_umma2_selftest(N, K):
     torch.cuda.synchronize()
     ref = a.double() @ b.double().t()
     assert float((d.double() - ref).abs().max()) < 1e-3
+
+
+# ---------------------------------------------------------------- size-independent properties at larger shapes
+def test_image_full_size_cross_check_and_crop_independence():
+    """BASELINE configs[0]-size grid (256^2) and an up-sampled 512^2 grid: the tcgen05 kernel agrees with the fp32
+    CUDA-core kernel to 1e-3, and decoding a crop of the coordinates reproduces the crop of the full decode
+    (results do not depend on how rows fall into tiles / CTA pairs)."""
+    m = cases.build_module('image').to(DEV)
+    g = torch.Generator().manual_seed(21)
+    planes = _cuda([torch.randn(3, 64, s, s, generator=g) for s in (64, 128, 256)])
+    for R in (256, 512):
+        e = (R - 1) / R
+        coords = ddmi_b200.convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(DEV)
+        si = ddmi_b200.get_scale_injection(R)
+        m.precision = 'bf16x3'
+        full = m(coords, hdbf=planes, si=si)
+        m.precision = 'fp32'
+        exact = m(coords, hdbf=planes, si=si)
+        assert float((full - exact).abs().max()) < TOL
+        m.precision = 'bf16x3'
+        crop = m(coords[:, :, 37:101, 5:R - 3], hdbf=planes, si=si)
+        assert torch.equal(crop, full[:, :, 37:101, 5:R - 3])
+        one = m(coords, hdbf=[p[1:2] for p in planes], si=si)
+        assert torch.equal(one[0], full[1])
+
+
+def test_occupancy_full_grid_sign_agreement():
+    """One item on the full 128^3 grid + 100k random points (config C4 per item): tcgen05 vs fp32 kernel."""
+    m = cases.build_module('occupancy').to(DEV)
+    _, hdbf = cases.occupancy_inputs(batch=1, n=1)
+    g = torch.Generator().manual_seed(22)
+    p = torch.cat([1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3),
+                   (torch.rand(100000, 3, generator=g) - 0.5) * 1.1]).to(DEV)
+    c = _cuda(hdbf)
+    m.precision = 'bf16x3'
+    a = m(p[None], c).logits
+    m.precision = 'fp32'
+    b = m(p[None], c).logits
+    assert float((a - b).abs().max()) < TOL
+    assert _sign_agreement(a, b) >= 0.9999
+
+
+def test_video_batch_independence_and_cross_check():
+    m = cases.build_module('video').to(DEV)
+    g = torch.Generator().manual_seed(23)
+    T, R = 8, 64
+    xy = _cuda([torch.randn(3, 64, s, s, generator=g) for s in (16, 32, 64)])
+    yt = _cuda([torch.randn(3, 64, T, s, generator=g) for s in (16, 32, 64)])
+    xt = _cuda([torch.randn(3, 64, T, s, generator=g) for s in (16, 32, 64)])
+    e, et = (R - 1) / R, (T - 1) / T
+    coords = _cuda(ddmi_b200.convert_to_coord_format_3d(1, R, R, T, hstart=-e, hend=e, wstart=-e, wend=e, tstart=-et, tend=et))
+    m.precision = 'bf16x3'
+    full = m(coords, (xy, yt, xt))
+    one = m(coords, ([p[2:3] for p in xy], [p[2:3] for p in yt], [p[2:3] for p in xt]))
+    assert torch.equal(one[0], full[2])
+    m.precision = 'fp32'
+    exact = m(coords, (xy, yt, xt))
+    assert float((full - exact).abs().max()) < TOL
+
+
+def test_nerf_full_view_cross_check():
+    """A full 64x64-ray view at 128 samples (fused compositing) vs the fp32 kernels (separate compositing kernel)."""
+    m = cases.build_module('nerf').to(DEV)
+    res, K, fea, c2w = cases.nerf_inputs(res=64, theta=110.0)
+    ro, rd = nh.get_rays(res, res, K, c2w, 'cpu')
+    vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
+    rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(res * res, 1), 6. * torch.ones(res * res, 1), vd], -1).to(DEV)
+    a = nh.render_rays_fused(rays, _cuda(fea), m, 128, True, precision='bf16x3')
+    b = nh.render_rays_fused(rays, _cuda(fea), m, 128, True, precision='fp32')
+    assert float((a - b).abs().max()) < TOL
+    assert float(a.max() - a.min()) > 0.2
