@@ -135,14 +135,17 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         uint32_t alo32 = a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
         const int cnt = (int)((op >> 24) & 31) + 1;
+        // The barrier probes of K step j+1 are issued right after the MMAs of step j (both probes back to back),
+        // so their ~90-cycle latencies overlap the issue work instead of heading every iteration.
+        bool ready = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
+        if (PAIR) ready = mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && ready;
         for (int j = 0; j < cnt; ++j) {
-          const uint32_t fb = bar + BAR_WFULL + 8 * slot;
-          if (!mbar_try_wait(fb, ph)) {
+          if (!ready) {
             const long long w0 = clock64();
-            mbar_wait(fb, ph);
+            mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
+            if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
             q_w += clock64() - w0;
           }
-          if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
           tc_fence_after();
           const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
           const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
@@ -164,6 +167,10 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           ahi32 += 2 * (KG_BYTES >> 4);
           alo32 += 2 * (KG_BYTES >> 4);
           if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+          if (j + 1 < cnt) {
+            ready = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
+            if (PAIR) ready = mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && ready;
+          }
         }
       } else if (kind == OP_WAIT) {
         const uint32_t i = (op >> 2) & 7;
