@@ -160,6 +160,8 @@ class MLP3D(_FusedDecoder):
         if pts.shape[0] == 1 and b > 1:
             pts = pts.expand(b, -1, -1)
         n = pts.shape[1]
+        if n == 0:                                   # empty query set: nothing to launch (the reference returns (B, 0) too)
+            return torch.empty((b, 0), device=planes[0].device, dtype=torch.float32)
         if pts.stride(0) == 0 or b == 1:
             base, bstride = pts[0].contiguous(), 0
         else:

@@ -328,3 +328,43 @@ def test_nerf_full_view_cross_check():
     b = nh.render_rays_fused(rays, _cuda(fea), m, 128, True, precision='fp32')
     assert float((a - b).abs().max()) < TOL
     assert float(a.max() - a.min()) > 0.2
+
+
+# ---------------------------------------------------------------- ragged / degenerate shapes
+def test_occupancy_empty_and_per_item_points():
+    m = cases.build_module('occupancy').to(DEV)
+    sd = cases.state_dict32(m)
+    pts, hdbf = cases.occupancy_inputs(batch=3, n=130)          # 130 = one full tile + 2 rows; distinct points per item
+    out = m(pts.to(DEV), _cuda(hdbf)).logits.cpu()
+    assert float((out - orc.occupancy_logits(sd, pts, hdbf)).abs().max()) < TOL
+    empty = m(pts[:, :0].to(DEV), _cuda(hdbf)).logits
+    assert tuple(empty.shape) == (3, 0)
+
+
+def test_video_ragged_volume():
+    """W not a multiple of the tile, odd tile count (the pair's second CTA decodes a duplicate and stores nothing)."""
+    m = cases.build_module('video').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(31)
+    T, H, W = 3, 7, 19                                              # 399 voxels -> 4 tiles; x3 items -> 12 tiles... x1 item -> odd
+    xy = [torch.randn(1, 64, 5, 6, generator=g), torch.randn(1, 64, 7, 9, generator=g), torch.randn(1, 64, H, W, generator=g)]
+    yt = [torch.randn(1, 64, 2, 5, generator=g), torch.randn(1, 64, 3, 7, generator=g), torch.randn(1, 64, T, H, generator=g)]
+    xt = [torch.randn(1, 64, 2, 6, generator=g), torch.randn(1, 64, 3, 9, generator=g), torch.randn(1, 64, T, W, generator=g)]
+    coords = ddmi_b200.convert_to_coord_format_3d(1, H, W, T, hstart=-1.2, hend=1.1, wstart=-.9, wend=1.3, tstart=-1, tend=1)
+    ref = orc.video_decode(sd, coords, (xy, yt, xt))
+    out = m(_cuda(coords), _cuda((xy, yt, xt))).cpu()
+    assert out.shape == ref.shape == (1, 3, T, H, W)
+    assert float((out - ref).abs().max()) < TOL
+
+
+@pytest.mark.parametrize("n_samples", [1, 100, 192])
+def test_nerf_sample_counts_that_straddle_tiles(n_samples):
+    m = cases.build_module('nerf').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(33)
+    fea = {k: torch.randn(1, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
+    rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][500:511]
+    rgb, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, n_samples, False, return_raw=True, precision='bf16x3')
+    ref, ref_raw = orc.nerf_render_rays(sd, rays, fea, n_samples, False, return_raw=True)
+    assert float((raw[0].cpu() - ref_raw).abs().max()) < TOL
+    assert float((rgb[0].cpu() - ref).abs().max()) < TOL
