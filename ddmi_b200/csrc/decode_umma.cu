@@ -41,51 +41,71 @@ namespace ummak {
 // TMEM lane quadrant take 32 columns each (sub = 0 / 1).  All 128 accumulator values of the
 // thread are drained into registers first (the accumulator is free for the next layer at once),
 // then converted quarter by quarter with `signal(q)` after each.
+// Bias / skip-constant vectors come from global memory and there is no L1 left beside 224 KB of
+// shared memory, so they are PREFETCHED: quarter 0's before the thread parks on the MMA barrier
+// (StagePrefetch), quarter q+1's while quarter q is converted.
 // sqrt2 gains are folded into weights / biases on the host.
 // MODE 0: H = lrelu(acc1 + b)                     (conv1 / conv2)
 // MODE 1: H = lrelu(acc1 + b) + acc2 + cs         (conv3 + skip; res1, res2)
 // MODE 2: as 1, and acc2 <- H / sqrt2             (res3: stash res4's identity skip)
 // MODE 3: H = lrelu(acc1 + b) + acc2              (res4: acc2 holds h3 / sqrt2)
+struct StagePrefetch {
+  float2 b[16];    // bias of quarter 0 (this thread's 32 columns)
+  float2 c[16];    // skip constant of quarter 0 (MODE 1 / 2)
+};
+template <bool WITH_CS>
+__device__ __forceinline__ void stage_prefetch(StagePrefetch& pf, const float* __restrict__ bias,
+                                               const float* __restrict__ cs, int sub) {
+  load_vec<16>(bias + sub * 32, pf.b);
+  if (WITH_CS) load_vec<16>(cs + sub * 32, pf.c);
+}
+
 template <int MODE, class Signal>
 __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, uint32_t h_lo, int row, int sub,
                                             const float* __restrict__ bias, const float* __restrict__ cs,
-                                            Signal signal) {
+                                            StagePrefetch& pf, Signal signal) {
+  constexpr bool WITH_CS = (MODE == 1 || MODE == 2);
   float2 v[4][16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
   tmem_ld_wait();
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
+    const int col0 = q * 64 + sub * 32;
+    float2 bn[16], cn[16];
+    if (q < 3) {                                        // next quarter's vectors: in flight during this conversion
+      load_vec<16>(bias + col0 + 64, bn);
+      if (WITH_CS) load_vec<16>(cs + col0 + 64, cn);
+    }
+    if (MODE == 0) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {                      // 16-column pieces
-      const int col0 = q * 64 + sub * 32 + c * 16;
-      float2(&y)[8] = *reinterpret_cast<float2(*)[8]>(&v[q][c * 8]);
-      float2 b[8];
-      load_vec<8>(bias + col0, b);
-      if (MODE == 0) {
+      for (int i = 0; i < 16; ++i) v[q][i] = bias_lrelu_pair(v[q][i], pf.b[i], 0.2f);
+    } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = bias_lrelu_pair(y[i], b[i], 0.2f);
-      } else {
+      for (int c = 0; c < 2; ++c) {                    // acc2 in 16-column pieces (TMEM reads are ~50 cycles)
         float2 s[8];
-        tmem_ld16(tmem_lane + 256 + col0, s);
+        tmem_ld16(tmem_lane + 256 + col0 + c * 16, s);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = __fadd2_rn(bias_lrelu_pair(y[i], b[i], 0.2f), s[i]);
-        if (MODE == 1 || MODE == 2) {
-          load_vec<8>(cs + col0, b);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = __fadd2_rn(y[i], b[i]);
+        for (int i = 0; i < 8; ++i) {
+          float2 y = __fadd2_rn(bias_lrelu_pair(v[q][c * 8 + i], pf.b[c * 8 + i], 0.2f), s[i]);
+          if (WITH_CS) y = __fadd2_rn(y, pf.c[c * 8 + i]);
+          v[q][c * 8 + i] = y;
+          if (MODE == 2) s[i] = __fmul2_rn(y, make_float2(kInvSqrt2, kInvSqrt2));
         }
-        if (MODE == 2) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) s[i] = __fmul2_rn(y[i], make_float2(kInvSqrt2, kInvSqrt2));
-          tmem_st16(tmem_lane + 256 + col0, s);
-        }
+        if (MODE == 2) tmem_st16(tmem_lane + 256 + col0 + c * 16, s);
       }
-      store_act<8>(h_hi, h_lo, row, col0, y);
     }
+    store_act<16>(h_hi, h_lo, row, col0, v[q]);
     if (MODE == 2 && q == 3) tmem_st_wait();
     signal(q);
+    if (q < 3) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        pf.b[i] = bn[i];
+        if (WITH_CS) pf.c[i] = cn[i];
+      }
+    }
   }
 }
 
@@ -179,19 +199,24 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, bv += 1024) {
         // ---- conv1 (+ skip into acc2 for blk < 3)
+        StagePrefetch pf;
+        stage_prefetch<false>(pf, bv, nullptr, sub);
         wait_mma();
-        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, signal);
+        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale)
         if (blk < 2) gather(tile, blk + 1);
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0);
         // ---- conv2
+        stage_prefetch<false>(pf, bv + 256, nullptr, sub);
         wait_mma();
-        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, signal);
+        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal);
         // ---- conv3 + skip
+        if (blk < 3) stage_prefetch<true>(pf, bv + 512, bv + 768, sub);
+        else stage_prefetch<false>(pf, bv + 512, nullptr, sub);
         wait_mma();
-        if (blk < 2) image_stage<1>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, signal);
-        else if (blk == 2) image_stage<2>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, signal);
-        else image_stage<3>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, signal);
+        if (blk < 2) image_stage<1>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
+        else if (blk == 2) image_stage<2>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
+        else image_stage<3>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal);
       }
       // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
