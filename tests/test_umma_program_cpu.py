@@ -1,0 +1,137 @@
+"""CPU model of the tcgen05 engine's host contract: the MMA program and the weight stream that
+ddmi_b200/packing.py emit TOGETHER are interpreted here the way csrc/umma_engine.cuh does
+(UNIT = K steps of one 128 x N block read from the stream in order, WAIT / COMMIT = handshakes)
+with the image kernel's epilogue sequence restated in torch.  Running it against the oracle checks,
+without a GPU, that stream order, K-group addressing, accumulator columns, accumulate flags, the
+CTA-pair half split and the folded biases all line up (the GPU tests then only have to prove the
+CUDA side)."""
+import math
+
+import pytest
+import torch
+
+from ddmi_b200 import _lib, packing
+from oracle import cases, ddmi_oracle as orc
+
+torch.set_grad_enabled(False)
+NCODE = {0: 128, 1: 256, 2: 16, 3: 64}
+
+
+def unpack_kstep(words, n, pair):
+    """Inverse of packing.umma_kstep_blocks for ONE K step: int16 words -> (hi + lo) fp32 block (n, 16)."""
+    halves = 2 if pair else 1
+    nloc = n // halves
+    per = 2 * (2 * nloc * 8)                   # hi block + lo block of one half
+    out = torch.zeros(n, 16)
+    for h in range(halves):
+        w = words[h * per:(h + 1) * per].view(torch.bfloat16).float().reshape(2, 2, nloc, 8)   # (hi/lo, kgroup, row, 8)
+        blk = (w[0] + w[1]).permute(1, 0, 2).reshape(nloc, 16)
+        out[h * nloc:(h + 1) * nloc] = blk
+    return out
+
+
+class EngineModel:
+    """A operands as fp32 'K group' columns (8 wide), accumulators as (rows, 512) fp32, like shared memory / TMEM."""
+
+    def __init__(self, packed, rows):
+        self.ops = packed.program_host.tolist()
+        self.stream = packed.gemm.cpu()
+        self.pair = packed.pair
+        self.pos = 0
+        self.pc = 0
+        self.A = torch.zeros(rows, 256 * 8)      # K group g -> columns 8g..8g+7 (hi + lo folded together)
+        self.acc = torch.zeros(rows, 512)
+        self.waits = []
+
+    def split(self, x):                           # what the epilogue writes: bf16 hi + bf16 lo
+        hi = x.to(torch.bfloat16).float()
+        return hi + (x - hi).to(torch.bfloat16).float()
+
+    def write(self, kg, x):                       # x: (rows, 8k) starting at K group kg
+        self.A[:, kg * 8:kg * 8 + x.shape[1]] = self.split(x)
+
+    def run_group(self):
+        """Execute ops up to and including the next COMMIT; returns the waits consumed."""
+        waits = []
+        while True:
+            op = self.ops[self.pc]
+            self.pc += 1
+            kind = op & 3
+            if kind == 1:
+                waits.append((op >> 2) & 7)
+            elif kind == 2:
+                return waits, (op >> 2) & 3
+            elif kind == 3:
+                raise AssertionError("END inside a tile")
+            else:
+                n = NCODE[(op >> 2) & 3]
+                accum, col = (op >> 4) & 1, ((op >> 5) & 7) * 64
+                hi_kg, lo_kg, cnt = (op >> 8) & 0xFF, (op >> 16) & 0xFF, ((op >> 24) & 31) + 1
+                assert lo_kg > hi_kg                      # lo copy lives behind the hi copy of the same operand
+                for j in range(cnt):
+                    words = self.stream[self.pos:self.pos + n * 32]
+                    self.pos += n * 32
+                    W = unpack_kstep(words, n, self.pair)
+                    a = self.A[:, (hi_kg + 2 * j) * 8:(hi_kg + 2 * j) * 8 + 16]
+                    d = a @ W.t()
+                    self.acc[:, col:col + n] = d + (self.acc[:, col:col + n] if (accum or j > 0) else 0)
+
+
+@pytest.mark.parametrize("pair", [True, False])
+def test_image_program_and_stream_reproduce_the_oracle(pair):
+    m = cases.build_module('image')
+    sd = cases.state_dict32(m)
+    coords, planes, si = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=12)
+    ref = orc.image_decode(sd, coords, planes, si)                       # (1,3,12,12)
+    packed = packing.pack_image(m, si, _lib.PREC_BF16X3, pair=pair)
+    vec = packed.vec
+    grid = coords.permute(0, 2, 3, 1)
+    X = [torch.nn.functional.grid_sample(p, grid, padding_mode='border', align_corners=False).permute(0, 2, 3, 1).reshape(-1, 64)
+         for p in planes]
+    E = EngineModel(packed, rows=144)
+    lr = lambda v: torch.nn.functional.leaky_relu(v, 0.2)
+    E.write(64, X[0])                                                    # X region: K groups 64.. (hi), 72.. (lo)
+    for blk in range(4):
+        bv = vec[blk * 1024:(blk + 1) * 1024]
+        waits, done = E.run_group()                                      # conv1 (+ skip)
+        assert sorted(waits) == [0, 1, 2, 3] and done == 0
+        E.write(0, lr(E.acc[:, :256] + bv[:256]))
+        if blk < 2:
+            E.write(64, X[blk + 1])
+        E.run_group()                                                    # conv2
+        E.write(0, lr(E.acc[:, :256] + bv[256:512]))
+        E.run_group()                                                    # conv3
+        h = lr(E.acc[:, :256] + bv[512:768]) + E.acc[:, 256:512] + (bv[768:1024] if blk < 3 else 0)
+        if blk == 2:
+            E.acc[:, 256:512] = h / math.sqrt(2.0)                       # stash res4's identity skip
+        E.write(0, h)
+    E.run_group()                                                        # ToRGB
+    out = (E.acc[:, :3] + vec[4096 + 768:4096 + 771]).t().reshape(1, 3, 12, 12)
+    assert E.ops[E.pc] & 3 == 3 and E.pos == E.stream.numel()            # program and stream end together
+    assert float((out - ref).abs().max()) < 1e-3
+
+
+def test_programs_consume_exactly_their_streams():
+    for packed in (packing.pack_occupancy(cases.build_module('occupancy'), _lib.PREC_BF16X3),
+                   packing.pack_video(cases.build_module('video'), _lib.PREC_BF16X3),
+                   packing.pack_nerf(cases.build_module('nerf'), _lib.PREC_BF16X3)):
+        ops = packed.program_host.tolist()
+        assert ops[-4:] == [3, 3, 3, 3] and all(o & 3 != 3 for o in ops[:-4])
+        need = sum(NCODE[(o >> 2) & 3] * 64 * (((o >> 24) & 31) + 1) for o in ops if o & 3 == 0)
+        assert need == packed.gemm.numel() * 2
+        # every accumulator region is started with accumulate = 0 before it is accumulated into
+        assert any(o & 3 == 0 and not (o >> 4) & 1 for o in ops)
+
+
+def test_operand_barriers_never_run_two_phases_ahead():
+    """Video program: between two WAITs on the same operand barrier there is a COMMIT (the E threads only
+    re-signal a barrier after consuming a commit that follows its previous WAIT) -- the parity-wait safety rule."""
+    ops = packing.pack_video(cases.build_module('video'), _lib.PREC_BF16X3).program_host.tolist()[:-4]
+    ops = ops + ops                                  # two consecutive tiles
+    last_wait = {}
+    for i, o in enumerate(ops):
+        if o & 3 == 1:
+            b = (o >> 2) & 7
+            if b in last_wait:
+                assert any(x & 3 == 2 for x in ops[last_wait[b]:i]), (b, i)
+            last_wait[b] = i
