@@ -9,7 +9,10 @@
 // sigma / rgb heads in the epilogue, and -- when n_samples == 128, i.e. one tile == one ray --
 // the volume compositing with a warp-shuffle product scan, so only 3 floats per ray leave the SM.
 //
-// Shared memory: H (128 KB) + X (80 KB) leave room for a 2-slot weight ring only.
+// X lives in TENSOR memory (columns 256..415 behind the single 256-column accumulator; the MMAs that consume it
+// use the A-from-TMEM form), written with tcgen05.st by the thread that owns the row.  With X in shared memory
+// (80 KB next to H's 128 KB) only a 2-slot weight ring fitted and the MMA phases ran ~1.5x slower than the image
+// kernel's, bound by ring refill latency; now the ring has 8 slots.
 //
 // vec layout (floats): b1..b6 [6][256] | b_final[256] | b_dir[128] | w_sigma[256] | b_sigma[1] pad[3]
 //                      | w_rgb[3][128] | b_rgb[3]
@@ -19,11 +22,11 @@
 namespace ddmi {
 namespace ummak {
 
-using NrfL = Layout<20, 16384>;   // X: 160 columns = 20 K groups (hi) + 20 (lo); 2 x 8 KB ring slots (CTA pairs only)
-constexpr int NRF_KG_XH = 64, NRF_KG_XL = 84;
+using NrfL = Layout<0, 65536>;    // shared memory: H + 8 x 8 KB ring slots (CTA pairs only); X is in tensor memory
+constexpr int NRF_KG_XH = 64, NRF_KG_XL = 84;   // X K groups (4 TMEM columns each): hi 64..83 -> columns 256..335, lo 84..103 -> 336..415
+constexpr int NRF_OFF_SCRATCH = NrfL::OFF_BAR + BAR_BYTES;
+constexpr int NRF_SMEM = NRF_OFF_SCRATCH + 5120;
 constexpr int NV_B = 0, NV_BF = 1536, NV_BD = 1792, NV_WS = 1920, NV_BS = 2176, NV_WRGB = 2180, NV_BRGB = 2564, NV_TOTAL = 2567;
-// scratch inside X's hi region (K groups 68..83), valid once the last skip layer has committed
-constexpr int NRF_SCRATCH = (NRF_KG_XH + 4) * KG_BYTES;
 
 __device__ __forceinline__ float2 lrelu_pair(float2 t, float slope) {
   return make_float2(fmaxf(t.x, 0.f) + slope * fminf(t.x, 0.f), fmaxf(t.y, 0.f) + slope * fminf(t.y, 0.f));
@@ -39,9 +42,8 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
-  const uint32_t x_hi = sbase + NRF_KG_XH * KG_BYTES, x_lo = sbase + NRF_KG_XL * KG_BYTES;
   const uint32_t ring = sbase + NrfL::OFF_RING, bar = sbase + NrfL::OFF_BAR;
-  float* scratch = reinterpret_cast<float*>(smem + NRF_SCRATCH);
+  float* scratch = reinterpret_cast<float*>(smem + NRF_OFF_SCRATCH);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t tmem = engine_begin<PAIR>(smem, NrfL::OFF_BAR);
@@ -124,10 +126,10 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         }
         uint4 hi, lo;
         split8(y, hi, lo);
-        const uint32_t off = (uint32_t)(j * KG_BYTES + row * 16);
-        st_shared_v4(x_hi + off, hi);
-        st_shared_v4(x_lo + off, lo);
+        tmem_st4(tmem_lane + (NRF_KG_XH + j) * 4, hi);
+        tmem_st4(tmem_lane + (NRF_KG_XL + j) * 4, lo);
       }
+      tmem_st_wait();
     };
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
     auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {
@@ -171,9 +173,10 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
               for (int i = 0; i < 8; ++i) y[i] = embed_elem(vd, j * 8 + i, 27);
               uint4 hi, lo;
               split8(y, hi, lo);
-              st_shared_v4(x_hi + j * KG_BYTES + row * 16, hi);
-              st_shared_v4(x_lo + j * KG_BYTES + row * 16, lo);
+              tmem_st4(tmem_lane + (NRF_KG_XH + j) * 4, hi);
+              tmem_st4(tmem_lane + (NRF_KG_XL + j) * 4, lo);
             }
+            tmem_st_wait();
           }
           float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -276,8 +279,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
           asm volatile("bar.sync 2, 128;" ::: "memory");
         }
       }
-      // scratch (inside X) is done with: build the next tile's X, then hand over
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // every MMA that reads X / the direction embedding has committed: build the next tile's X, then hand over
       if (it + 1 < ntiles) {
         build_x(tile_of(it + 1));
         signal_all();
@@ -313,8 +315,8 @@ inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* r
     return DDMI_ERR_UNSUPPORTED;
   }
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
-  DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NrfL::SMEM_BYTES));
-  nerf_umma_kernel<<<(unsigned)(2 * npairs), NTHREADS, NrfL::SMEM_BYTES, st>>>(
+  DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
+  nerf_umma_kernel<<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
       ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
       (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
   DDMI_CUDA(cudaGetLastError());

@@ -280,6 +280,21 @@ __device__ __forceinline__ void mma2_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand in TENSOR MEMORY (each CTA's 128 rows = its TMEM lanes; 16-bit elements packed along K,
+// two per 32-bit column, so a 16-wide K step = 8 columns starting at `a_tmem`).
+__device__ __forceinline__ void mma2_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 4 consecutive 32-bit columns (= one 8-wide K group of a bf16 A operand) per warp
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 // arrive on the mbarrier at this offset in every CTA of `mask` once all prior MMAs of the pair completed
 __device__ __forceinline__ void mma2_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

@@ -131,8 +131,12 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         const uint32_t nloc = PAIR ? n / 2 : n;                                   // B rows held by one CTA
         const uint32_t idesc = (PAIR ? idesc2_bf16_f32(0) : idesc_bf16_f32(0)) | (n << 14);   // N >> 3 at bit 17
         const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
-        uint32_t ahi32 = a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
-        uint32_t alo32 = a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
+        // A operand: K groups of the shared-memory A region, or (bit 29, CTA pairs only) of tensor memory, where one
+        // K group = 4 columns counted from the TMEM base (so K group 64 sits right behind a 256-column accumulator)
+        const bool a_in_tmem = PAIR && ((op >> 29) & 1);
+        const uint32_t a_step = a_in_tmem ? 8u : 2 * (KG_BYTES >> 4);
+        uint32_t ahi32 = a_in_tmem ? tmem + ((op >> 8) & 0xFF) * 4 : a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
+        uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
         const int cnt = (int)((op >> 24) & 31) + 1;
         // The barrier probes of K step j+1 are issued right after the MMAs of step j (both probes back to back),
@@ -151,7 +155,12 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
           const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
           if (elect_one()) {
-            if (PAIR) {
+            if (PAIR && a_in_tmem) {
+              mma2_bf16_ts(acc, ahi32, bhi, idesc, accum);
+              mma2_bf16_ts(acc, alo32, bhi, idesc, 1u);
+              mma2_bf16_ts(acc, ahi32, blo, idesc, 1u);
+              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
+            } else if (PAIR) {
               mma2_bf16(acc, ahi, bhi, idesc, accum);
               mma2_bf16(acc, alo, bhi, idesc, 1u);
               mma2_bf16(acc, ahi, blo, idesc, 1u);
@@ -164,8 +173,8 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
             }
           }
           accum = 1u;
-          ahi32 += 2 * (KG_BYTES >> 4);
-          alo32 += 2 * (KG_BYTES >> 4);
+          ahi32 += a_step;
+          alo32 += a_step;
           if (++slot == NSLOT) { slot = 0; ph ^= 1; }
           if (j + 1 < cnt) {
             ready = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);

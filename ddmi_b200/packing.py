@@ -53,14 +53,16 @@ class UmmaProgram:
         self.segs = []
         self.pair = pair      # CTA pairs: each K step is stored as [rows 0..N/2-1 | rows N/2..N-1]
 
-    def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None):
-        """acc[:, acc_col:acc_col+N] (+)= A[:, K] @ W.T ; W is (N, K), K zero-padded to 16."""
+    def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None, a_in_tmem=False):
+        """acc[:, acc_col:acc_col+N] (+)= A[:, K] @ W.T ; W is (N, K), K zero-padded to 16.  a_in_tmem: the A operand
+        lives in tensor memory (K group g = TMEM columns 4g..4g+3), CTA-pair kernels only (op bit 29)."""
         n = W.shape[0] if n_pad is None else n_pad
         k16 = (W.shape[1] + 15) // 16
         assert n in self.NCODE and acc_col % 64 == 0 and acc_col + n <= 512
         assert 1 <= k16 <= 32 and a_hi_kg + 2 * k16 <= 256 and a_lo_kg + 2 * k16 <= 256
         self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
-                        | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k16 - 1) << 24))
+                        | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k16 - 1) << 24) | ((1 if a_in_tmem else 0) << 29))
+        assert not a_in_tmem or (self.pair and 4 * (a_lo_kg + 2 * k16) <= 512)
         if not self.pair:
             self.segs.append(umma_kstep_blocks(W, 0, W.shape[1], n_pad=n_pad))
         else:
@@ -463,7 +465,7 @@ def _pack_nerf_umma(p):
     """Program + stream + vec of csrc/decode_umma_nerf.cuh (CTA pairs).  A-region K groups: H hi 0..31, H lo 32..63,
     X ([latent 96 | gamma(pts) 63 | 0]) hi 64..83, lo 84..103; the 27-wide direction embedding reuses X's first 4
     K groups for the last layer.  One accumulator (TMEM columns 0..255)."""
-    HH, HL, XH, XL = 0, 32, 64, 84
+    HH, HL, XH, XL = 0, 32, 64, 84        # X K groups live in TENSOR memory: columns 256..335 (hi), 336..415 (lo)
     P = UmmaProgram(pair=True)
 
     def over_h(W, first, n_pad=None):
@@ -481,10 +483,10 @@ def _pack_nerf_umma(p):
         if i == 0:
             for q in range(4):
                 P.wait(q)
-            P.block(pad_k(W, 160), XH, XL, 0, True)
+            P.block(pad_k(W, 160), XH, XL, 0, True, a_in_tmem=True)
         elif i in (2, 4):                      # cat([input_xyz, h]): X part first (ready at once), then h by quarters
             P.wait(0)
-            P.block(pad_k(W[:, :159], 160), XH, XL, 0, True)
+            P.block(pad_k(W[:, :159], 160), XH, XL, 0, True, a_in_tmem=True)
             for q in range(4):
                 if q:
                     P.wait(q)
@@ -496,7 +498,7 @@ def _pack_nerf_umma(p):
     P.commit()
     Wd = p['dir_encoding.0.weight']            # (128, 283) on cat([final, dir27])
     over_h(Wd[:, :256], True)
-    P.block(pad_k(Wd[:, 256:283], 32), XH, XL, 0, False)
+    P.block(pad_k(Wd[:, 256:283], 32), XH, XL, 0, False, a_in_tmem=True)
     P.commit()
     z3 = torch.zeros(3, dtype=torch.float64, device=Wd.device)
     vec = torch.cat([p[f'xyz_encoding_{i + 1}.0.bias'] for i in range(6)]
