@@ -132,18 +132,9 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       tmem_st_wait();
     };
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
-    auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {
-      drain128(tmem_lane, 0, sub, v);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        add_vec<16>(v[q], b + q * 64 + sub * 32);
-        if (act) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[q][i] = lrelu_pair(v[q][i], slope);
-        }
-        put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]);
-        signal(q);
-      }
+    auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {   // waits for the GEMM first
+      const float sl = act ? slope : 1.f;
+      biased_stage(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
     };
 
     if (ntiles > 0) {
@@ -158,7 +149,6 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       // ---- xyz_encoding_1..6
 #pragma unroll 1
       for (int l = 0; l < 6; ++l) {
-        wait_mma();
         float2 v[4][16];
         stage_act(vec + NV_B + l * 256, true, v);
         if (l == 5) {
@@ -193,7 +183,6 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         }
       }
       // ---- xyz_encoding_final (no activation); the direction embedding written above rides on these signals
-      wait_mma();
       {
         float2 v[4][16];
         stage_act(vec + NV_BF, false, v);

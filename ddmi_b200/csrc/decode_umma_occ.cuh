@@ -43,6 +43,46 @@ __device__ __forceinline__ void add_vec(float2 (&y)[NP], const float* __restrict
 #pragma unroll
   for (int i = 0; i < NP; ++i) y[i] = __fadd2_rn(y[i], b[i]);
 }
+// Generic epilogue stage: prefetch quarter 0's bias, park on the MMA barrier (`wait`), drain this thread's values of the
+// accumulator at `acc_col`, then per quarter q < nq: v = f(v + bias) -> H, signal(sig0 + q); the bias of quarter q + 1 is
+// loaded while quarter q is converted (there is no L1 beside ~224 KB of shared memory: an unprefetched bias costs an
+// exposed L2 round trip per stage).  v is left holding the stored values.
+template <class Wait, class Act, class Signal>
+__device__ __forceinline__ void biased_stage(uint32_t tmem_lane, int acc_col, int sub, int row, uint32_t h_hi, uint32_t h_lo,
+                                             const float* __restrict__ bias, int nq, float2 (&v)[4][16], Wait wait, Act act,
+                                             Signal signal, int sig0) {
+  float2 b[16];
+  load_vec<16>(bias + sub * 32, b);
+  wait();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < nq) tmem_ld32(tmem_lane + acc_col + q * 64 + sub * 32, v[q]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q < nq) {
+      float2 bn[16];
+      if (q + 1 < nq) load_vec<16>(bias + (q + 1) * 64 + sub * 32, bn);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[q][i] = act(__fadd2_rn(v[q][i], b[i]));
+      {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float2 y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = v[q][c * 8 + i];
+          store_act<8>(h_hi, h_lo, row, q * 64 + sub * 32 + c * 16, y);
+        }
+      }
+      signal(sig0 + q);
+      if (q + 1 < nq) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b[i] = bn[i];
+      }
+    }
+  }
+}
+
 // write one quarter (32 columns of this thread) of the 256-wide operand, optionally relu'd
 template <bool RELU>
 __device__ __forceinline__ void put_quarter(uint32_t h_hi, uint32_t h_lo, int row, int q, int sub, const float2 (&vq)[16]) {
@@ -188,19 +228,10 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
       }
     };
-    // relu(acc1 + b) -> H, quarter by quarter (fc_0 epilogue)
+    // wait for the fc_0 GEMM, then relu(acc1 + b) -> H, quarter by quarter
     auto stage_net = [&](const float* __restrict__ b0) {
       float2 v[4][16];
-      drain128(tmem_lane, 0, sub, v);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float2 b[16];
-        load_vec<16>(b0 + q * 64 + sub * 32, b);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[q][i] = bias_relu_pair(v[q][i], b[i]);
-        put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]);
-        signal(q);
-      }
+      biased_stage(tmem_lane, 0, sub, row, h_hi, h_lo, b0, 4, v, wait_mma, [](float2 t) { return relu_pair(t); }, signal, 0);
     };
 
     if (ntiles > 0) {
@@ -256,7 +287,6 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
 #pragma unroll
         for (int q = 0; q < 4; ++q) { put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
         // fc_0 epilogue; Xa / Xb are free again: gather what comes next while fc_1 runs
-        wait_mma();
         stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
         if (blk == 1) gather(tile, 2);
         else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
@@ -274,7 +304,6 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
       }
       // ---- R4.fc_0 epilogue
-      wait_mma();
       stage_net(vec + OV_B04);
       // ---- logits = w_out . (acc2 + b1_3 + b1_4) + b_out
       wait_mma();

@@ -106,23 +106,10 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       }
     };
     // net = relu(acc1 + b0) -> H quarters, published on A4..A7 (NQ = number of 64-column quarters: 3 for R1)
-    auto stage_net = [&](const float* __restrict__ b0, int nq) {
+    auto stage_net = [&](const float* __restrict__ b0, int nq) {   // waits completion barrier D0 first
       float2 v[4][16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q < nq) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q < nq) {
-          float2 b[16];
-          load_vec<16>(b0 + q * 64 + sub * 32, b);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[q][i] = bias_relu_pair(v[q][i], b[i]);
-          put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]);
-          signal(4 + q);
-        }
-      }
+      biased_stage(tmem_lane, 0, sub, row, h_hi, h_lo, b0, nq, v, [&]() { wait_done(0); },
+                   [](float2 t) { return relu_pair(t); }, signal, 4);
     };
 
     if (ntiles > 0) gather(tile_of(0), 0, 0);
@@ -134,8 +121,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       gather(tile, 0, 1); signal(1);
       wait_done(1);
       gather(tile, 0, 2); signal(2);
-      wait_done(0);
-      stage_net(vec + VV_B01, 3);      // fc_1 (K = 192) accumulates onto the shortcut in acc2
+      stage_net(vec + VV_B01, 3);      // (waits D0) fc_1 (K = 192) accumulates onto the shortcut in acc2
       // ================= R2, R3: x = [h | X_s] =================
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
@@ -155,7 +141,6 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
         gather(tile, blk, 1); signal(0);
         wait_done(1);
         gather(tile, blk, 2); signal(1);
-        wait_done(0);
         stage_net(vec + (blk == 1 ? VV_B02 : VV_B03), 4);
         // Xa / Xb are free (piece 2 committed): prefetch the next tile's first piece behind R3
         if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
@@ -172,7 +157,6 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
           signal(q);
         }
       }
-      wait_done(0);
       stage_net(vec + VV_B04, 4);
       // ================= out = w_out . lrelu(acc2 + b1_3 + b1_4, 0.2) + b_out =================
       wait_done(0);
