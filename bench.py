@@ -111,6 +111,19 @@ def image_workload(batch, device, pinned=False):
     return planes, grids
 
 
+# per precision: what the tensor pipe executes per algorithmic flop, and how long that takes in units of one bf16 pass
+PREC_INFO = {
+    'bf16x3': {'dtype': "bf16x3 (bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate)",
+               'kernel': "image_umma_kernel<pair, bf16x3>", 'executed': 3.0, 'tensor_time': 3.0,
+               'note': "the bf16x3 split executes 3x that on the tensor pipe"},
+    'f16f8': {'dtype': "f16f8 (fp16 main term + two e4m3 correction terms at the FP8 rate, fp32 accumulate)",
+              'kernel': "image_umma_kernel<pair, f16f8>", 'executed': 3.0, 'tensor_time': 2.0,
+              'note': "the f16f8 split executes 1x that in fp16 + 2x in FP8 (= 2 bf16-pass times) on the tensor pipe"},
+    'fp32': {'dtype': "f32", 'kernel': "fp32::image_kernel", 'executed': 1.0, 'tensor_time': 0.0,
+             'note': "CUDA-core fp32 FMAs"},
+}
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0))
@@ -216,8 +229,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16x3 (bf16 hi/lo split operands, 3 MMAs per product, fp32 accumulate)"
-        if args.precision == 'bf16x3' else "f32",
+        "vs_baseline": None, "dtype": PREC_INFO[args.precision]['dtype'],
         "data": "synthetic",
         "config": {"workload": f"AFHQ-shape image D2C-VAE decode (BASELINE configs[1]): planes 64^2/128^2/256^2 x64ch, "
                                f"query grids {'+'.join(f'{R}x{R}' for R in args.res)}, batch {B} per GPU",
@@ -231,9 +243,11 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                      "frac": achieved / tf_peak, "traffic": traffic, "traffic_note": traffic_note,
                      "peak_source": which + " (bf16 sustained)",
-                     "kernel": "image_umma_kernel" if args.precision == 'bf16x3' else "fp32::image_kernel",
-                     "note": "achieved = ALGORITHMIC flops (1,908,224 / coord, as-written layers); the bf16x3 split "
-                             "executes 3x that on the tensor pipe", "executed_tflops": achieved * (3.0 if args.precision == 'bf16x3' else 1.0),
+                     "kernel": PREC_INFO[args.precision]['kernel'],
+                     "note": "achieved = ALGORITHMIC flops (1,908,224 / coord, as-written layers); "
+                             + PREC_INFO[args.precision]['note'],
+                     "executed_tflops": achieved * PREC_INFO[args.precision]['executed'],
+                     "bf16_equivalent_tensor_time": PREC_INFO[args.precision]['tensor_time'],
                      "avg_launch_ms": {str(n): statistics.mean(t for t, m in launch_ms if m == n) for n in sorted({m for _, m in launch_ms})}},
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -382,7 +396,7 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--res', type=int, nargs='+', default=[1024, 2048])
-    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'fp32'])
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'f16f8', 'fp32'])
     ap.add_argument('--cpu-res', type=int, default=512)
     ap.add_argument('--cpu-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')

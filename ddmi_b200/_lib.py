@@ -14,11 +14,12 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 PREC_FP32 = 0
 PREC_BF16X3 = 1
+PREC_F16F8 = 2
 
 EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
     "ddmi_decode_image", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy", "ddmi_decode_video",
-    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_debug_profile",
+    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
 )
 
 
@@ -75,10 +76,11 @@ def lib():
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]
         L.ddmi_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_selftest_umma2.argtypes = [vp, vp, vp, i32, i32, vp]
+        L.ddmi_selftest_f16f8.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
-        if L.ddmi_abi_version() != 4:
+        if L.ddmi_abi_version() != 5:
             raise RuntimeError("libddmi_b200.so ABI version mismatch")
         _lib = L
     return _lib

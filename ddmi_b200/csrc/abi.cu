@@ -27,7 +27,7 @@ int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, con
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
 int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
-int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, cudaStream_t);
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
@@ -36,6 +36,7 @@ int launch_nerf_composite(const float*, const float*, int, const float*, int, lo
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
+int launch_selftest_f16f8(const float*, const float*, float*, int, int, cudaStream_t);
 
 static int check_planes(const ddmi_plane_t* planes, int count, PlaneSet* ps) {
   DDMI_REQUIRE(planes != nullptr, "planes is NULL");
@@ -115,12 +116,14 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
     if (rc) return rc;
     return launch_image_fp32(ps, batch, channels, coord_x, coord_y, n_coords, (const float*)weights->gemm,
                              weights->vec, out, st);
-  } else if (weights->precision == DDMI_PREC_BF16X3) {
+  } else if (weights->precision == DDMI_PREC_BF16X3 || weights->precision == DDMI_PREC_F16F8) {
     DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
+    const int f16f8 = weights->precision == DDMI_PREC_F16F8;
+    DDMI_REQUIRE(!f16f8 || (weights->reserved & 1), "DDMI_PREC_F16F8 weights must be packed for CTA pairs");
     return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm, weights->gemm_bytes,
                              weights->program_host, weights->program_words, weights->program, weights->vec,
-                             weights->vec_floats, out, weights->reserved & 1, st);
+                             weights->vec_floats, out, weights->reserved & 1, f16f8, st);
   }
   set_error("unknown precision %d", weights->precision);
   return DDMI_ERR_UNSUPPORTED;
@@ -294,6 +297,13 @@ DDMI_API int ddmi_selftest_umma2(const float* a, const float* b, float* d, int32
   DDMI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "N must be a multiple of 16 in [16,256] (got %d)", N);
   DDMI_REQUIRE(K >= 16 && K <= 256 && K % 16 == 0, "K must be a multiple of 16 in [16,256] (got %d)", K);
   return launch_selftest_umma2(a, b, d, N, K, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_selftest_f16f8(const float* a, const float* b, float* d, int32_t N, int32_t K, void* stream) {
+  DDMI_REQUIRE(a && b && d, "a / b / d is NULL");
+  DDMI_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "N must be a multiple of 16 in [16,256] (got %d)", N);
+  DDMI_REQUIRE(K >= 32 && K <= 256 && K % 32 == 0, "K must be a multiple of 32 in [32,256] (got %d)", K);
+  return launch_selftest_f16f8(a, b, d, N, K, (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset) {

@@ -60,7 +60,17 @@ __device__ __forceinline__ void stage_prefetch(StagePrefetch& pf, const float* _
   if (WITH_CS) load_vec<16>(cs + sub * 32, pf.c);
 }
 
-template <int MODE, class Signal>
+// SCHEME 1 (f16f8): the accumulators hold 4096 x the GEMM result; 1/4096 rides in the bias / skip FMAs.
+template <int SCHEME>
+__device__ __forceinline__ float2 image_act(float2 t, float2 b) {
+  if (SCHEME) {
+    t = __ffma2_rn(t, make_float2(kF8InvScale, kF8InvScale), b);
+    const float2 u = __fmul2_rn(t, make_float2(0.2f, 0.2f));
+    return make_float2(fmaxf(t.x, u.x), fmaxf(t.y, u.y));
+  }
+  return bias_lrelu_pair(t, b, 0.2f);
+}
+template <int MODE, int SCHEME, class Signal>
 __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, uint32_t h_lo, int row, int sub,
                                             const float* __restrict__ bias, const float* __restrict__ cs,
                                             StagePrefetch& pf, Signal signal) {
@@ -79,7 +89,7 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
     }
     if (MODE == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[q][i] = bias_lrelu_pair(v[q][i], pf.b[i], 0.2f);
+      for (int i = 0; i < 16; ++i) v[q][i] = image_act<SCHEME>(v[q][i], pf.b[i]);
     } else {
 #pragma unroll
       for (int c = 0; c < 2; ++c) {                    // acc2 in 16-column pieces (TMEM reads are ~50 cycles)
@@ -88,15 +98,18 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float2 y = __fadd2_rn(bias_lrelu_pair(v[q][c * 8 + i], pf.b[c * 8 + i], 0.2f), s[i]);
+          float2 y = image_act<SCHEME>(v[q][c * 8 + i], pf.b[c * 8 + i]);
+          y = SCHEME ? __ffma2_rn(s[i], make_float2(kF8InvScale, kF8InvScale), y) : __fadd2_rn(y, s[i]);
           if (WITH_CS) y = __fadd2_rn(y, pf.c[c * 8 + i]);
           v[q][c * 8 + i] = y;
-          if (MODE == 2) s[i] = __fmul2_rn(y, make_float2(kInvSqrt2, kInvSqrt2));
+          constexpr float kStash = SCHEME ? kInvSqrt2 * kF8Scale : kInvSqrt2;
+          if (MODE == 2) s[i] = __fmul2_rn(y, make_float2(kStash, kStash));
         }
         if (MODE == 2) tmem_st16(tmem_lane + 256 + col0 + c * 16, s);
       }
     }
-    store_act<16>(h_hi, h_lo, row, col0, v[q]);
+    if (SCHEME) store_step_f16f8(h_hi + (col0 / 8) * KG_BYTES + row * 16, h_lo + (col0 / 8) * KG_BYTES + row * 16, KG_BYTES, v[q]);
+    else store_act<16>(h_hi, h_lo, row, col0, v[q]);
     if (MODE == 2 && q == 3) tmem_st_wait();
     signal(q);
     if (q < 3) {
@@ -114,7 +127,7 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
 // ---------------------------------------------------------------------------
 using ImgL = Layout<8>;
 
-template <int PAIR>
+template <int PAIR, int SCHEME>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
@@ -157,16 +170,36 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       const Tap t = make_tap<false>(__ldg(cx + gi), __ldg(cy + gi), ps.h[s], ps.w[s]);
       const size_t hw = (size_t)ps.h[s] * ps.w[s];
       const float* base = ps.data[s] + ((size_t)b * C + ghalf * 32) * hw;
+      if (SCHEME) {
+        // f16f8: this thread's 32 channels = K step `ghalf` of X: fp16 groups 4*ghalf.., FP8 groups [r8 r8 a8 a8] at x_lo
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        float y[8];
+        for (int g = 0; g < 2; ++g) {
+          float2 y[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = tap_sample(base + (size_t)(g * 8 + i) * hw, t);
-        uint4 hi, lo;
-        split8(y, hi, lo);
-        const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
-        st_shared_v4(x_hi + off, hi);
-        st_shared_v4(x_lo + off, lo);
+          for (int i = 0; i < 8; ++i) {
+            y[i].x = tap_sample(base + (size_t)(g * 16 + 2 * i) * hw, t);
+            y[i].y = tap_sample(base + (size_t)(g * 16 + 2 * i + 1) * hw, t);
+          }
+          uint4 a16[2], r8, a8;
+          split16_f16f8(y, a16, r8, a8);
+          const uint32_t off = (uint32_t)(ghalf * 4 * KG_BYTES + row * 16);
+          st_shared_v4(x_hi + off + (2 * g) * KG_BYTES, a16[0]);
+          st_shared_v4(x_hi + off + (2 * g + 1) * KG_BYTES, a16[1]);
+          st_shared_v4(x_lo + off + g * KG_BYTES, r8);
+          st_shared_v4(x_lo + off + (2 + g) * KG_BYTES, a8);
+        }
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = tap_sample(base + (size_t)(g * 8 + i) * hw, t);
+          uint4 hi, lo;
+          split8(y, hi, lo);
+          const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
+          st_shared_v4(x_hi + off, hi);
+          st_shared_v4(x_lo + off, lo);
+        }
       }
       p_gather += clock64() - g0;
     };
@@ -202,21 +235,21 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         StagePrefetch pf;
         stage_prefetch<false>(pf, bv, nullptr, sub);
         wait_mma();
-        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal);
+        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale)
         if (blk < 2) gather(tile, blk + 1);
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0);
         // ---- conv2
         stage_prefetch<false>(pf, bv + 256, nullptr, sub);
         wait_mma();
-        image_stage<0>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal);
+        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal);
         // ---- conv3 + skip
         if (blk < 3) stage_prefetch<true>(pf, bv + 512, bv + 768, sub);
         else stage_prefetch<false>(pf, bv + 512, nullptr, sub);
         wait_mma();
-        if (blk < 2) image_stage<1>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
-        else if (blk == 2) image_stage<2>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
-        else image_stage<3>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal);
+        if (blk < 2) image_stage<1, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
+        else if (blk == 2) image_stage<2, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
+        else image_stage<3, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal);
       }
       // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
@@ -228,9 +261,10 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         const long long gi = (tile % tiles_per_item) * TILE + row;
         if (gi < n) {
           const float* brgb = vec + 4096 + 768;
-          out[((size_t)b * 3 + 0) * n + gi] = v[0].x + __ldg(brgb + 0);
-          out[((size_t)b * 3 + 1) * n + gi] = v[0].y + __ldg(brgb + 1);
-          out[((size_t)b * 3 + 2) * n + gi] = v[1].x + __ldg(brgb + 2);
+          constexpr float kOut = SCHEME ? kF8InvScale : 1.0f;
+          out[((size_t)b * 3 + 0) * n + gi] = v[0].x * kOut + __ldg(brgb + 0);
+          out[((size_t)b * 3 + 1) * n + gi] = v[0].y * kOut + __ldg(brgb + 1);
+          out[((size_t)b * 3 + 2) * n + gi] = v[1].x * kOut + __ldg(brgb + 2);
         }
       }
       if (it + 1 < ntiles) signal_all();
@@ -241,7 +275,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       atomicAdd(&g_prof[2], (unsigned long long)p_gather);
     }
   } else {
-    engine_service_warps<PAIR, ImgL::RING_BYTES>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -334,7 +368,7 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 // ---------------------------------------------------------------------------
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
                       const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
-                      const uint32_t* program_dev, const float* vec, size_t vec_floats, float* out, int pair,
+                      const uint32_t* program_dev, const float* vec, size_t vec_floats, float* out, int pair, int f16f8,
                       cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
@@ -342,9 +376,10 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
     return DDMI_ERR_UNSUPPORTED;
   }
   DDMI_REQUIRE(program_host && program_dev && program_words >= 2, "bf16x3 weights carry no MMA program");
-  const long long need = ummak::program_stream_bytes(program_host, program_words);
+  const long long need = ummak::program_stream_bytes(program_host, program_words, f16f8);
   DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
                need, gemm_bytes);
+  DDMI_REQUIRE(!f16f8 || pair, "the f16f8 image kernel runs as CTA pairs only");
   DDMI_REQUIRE(vec_floats == 4096 + 768 + 3, "packed vec blob is %zu floats, expected 4867", vec_floats);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));
@@ -360,10 +395,14 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   const int tpi_i = (int)tpi;
   if (pair) {
     const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
-    DDMI_CUDA(launch_engine(image_umma_kernel<1>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
-                            total, ws, program_dev, vec, out));
+    if (f16f8)
+      DDMI_CUDA(launch_engine(image_umma_kernel<1, 1>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
+                              total, ws, program_dev, vec, out));
+    else
+      DDMI_CUDA(launch_engine(image_umma_kernel<1, 0>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
+                              total, ws, program_dev, vec, out));
   } else {
-    DDMI_CUDA(launch_engine(image_umma_kernel<0>, 0, (unsigned)(total < sms ? total : sms), ImgL::SMEM_BYTES, st, ps, cx, cy,
+    DDMI_CUDA(launch_engine(image_umma_kernel<0, 0>, 0, (unsigned)(total < sms ? total : sms), ImgL::SMEM_BYTES, st, ps, cx, cy,
                             n, tpi_i, total, ws, program_dev, vec, out));
   }
   DDMI_CUDA(cudaGetLastError());

@@ -8,6 +8,8 @@
 // = 128.  Consecutive K steps are 2 * LBO apart.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 
 namespace ddmi {
@@ -300,6 +302,104 @@ __device__ __forceinline__ void mma2_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(mask)
                : "memory");
+}
+
+}  // namespace umma
+}  // namespace ddmi
+
+// ===========================================================================
+// "f16f8" operand scheme (DDMI_PREC_F16F8): fp16 main term + two FP8 correction terms at twice the MMA rate.
+//   S * (A W^T) ~= a16 (S w16)^T + e4m3(S r) e4m3(W)^T + e4m3(A) e4m3(S s)^T,   S = 4096,
+//   a16 = fp16(A), r = A - a16, w16 = fp16(W), s = W - w16  (|r| <= 2^-12 |A|, so S r is O(A): in FP8 range without
+//   block scaling).  The accumulator holds S times the product; the epilogue multiplies by 1/S in its bias FMA.
+// FP8 operands use the same canonical no-swizzle core-matrix layout: 8 rows x 16 B, i.e. 16 elements per K group,
+// one K = 32 MMA = 2 K groups.
+// ===========================================================================
+namespace ddmi {
+namespace umma {
+
+constexpr float kF8Scale = 4096.0f, kF8InvScale = 1.0f / 4096.0f;
+
+// kind::f16 with fp16 operands (format code 0), D fp32; m = 128 (one CTA) or 256 (pair)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// kind::f8f6f4 with A = B = e4m3 (format code 0), D fp32
+__host__ __device__ constexpr uint32_t idesc_e4m3_f32(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma2_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 16 consecutive-K fp32 values of one row -> half of a K = 32 step of the three A operands:
+// a16[2] (2 K groups of 8 fp16), r8 (1 K group of 16 e4m3: S * (y - a16)), a8 (e4m3(y)).
+__device__ __forceinline__ void split16_f16f8(const float2* y, uint4 (&a16)[2], uint4& r8, uint4& a8) {
+  uint32_t h[8], r[4], a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t rp[2], ap[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 v = y[2 * i + j];
+      const __half2 hp = __float22half2_rn(v);
+      h[2 * i + j] = *reinterpret_cast<const uint32_t*>(&hp);
+      const float2 hf = __half22float2(hp);
+      // S*v - S*hf: both products exact, the difference has <= 13 significant bits -> exact
+      const float2 res = __ffma2_rn(hf, make_float2(-kF8Scale, -kF8Scale), __fmul2_rn(v, make_float2(kF8Scale, kF8Scale)));
+      rp[j] = __nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);
+      ap[j] = __nv_cvt_float2_to_fp8x2(v, __NV_SATFINITE, __NV_E4M3);
+    }
+    r[i] = rp[0] | (rp[1] << 16);
+    a[i] = ap[0] | (ap[1] << 16);
+  }
+  a16[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  a16[1] = make_uint4(h[4], h[5], h[6], h[7]);
+  r8 = make_uint4(r[0], r[1], r[2], r[3]);
+  a8 = make_uint4(a[0], a[1], a[2], a[3]);
+}
+// 32 values = one K = 32 step: a16[4], r8[2], a8[2]
+__device__ __forceinline__ void split32_f16f8(const float2* y, uint4 (&a16)[4], uint4 (&r8)[2], uint4 (&a8)[2]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    uint4 t[2];
+    split16_f16f8(y + 8 * g, t, r8[g], a8[g]);
+    a16[2 * g] = t[0];
+    a16[2 * g + 1] = t[1];
+  }
+}
+__device__ __forceinline__ void split32_f16f8(const float* y, uint4 (&a16)[4], uint4 (&r8)[2], uint4 (&a8)[2]) {
+  float2 t[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) t[i] = make_float2(y[2 * i], y[2 * i + 1]);
+  split32_f16f8(t, a16, r8, a8);
+}
+// Store one K = 32 step of a row: a16_base / f8_base = address of the step's first fp16 / FP8 K group (+ row * 16),
+// kg = K-group stride in bytes.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v);
+__device__ __forceinline__ void store_step_f16f8(uint32_t a16_base, uint32_t f8_base, uint32_t kg, const float2* y) {
+  uint4 a16[4], r8[2], a8[2];
+  split32_f16f8(y, a16, r8, a8);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) st_shared_v4(a16_base + g * kg, a16[g]);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    st_shared_v4(f8_base + g * kg, r8[g]);
+    st_shared_v4(f8_base + (2 + g) * kg, a8[g]);
+  }
 }
 
 }  // namespace umma

@@ -58,10 +58,11 @@ __device__ __forceinline__ uint32_t op_n(uint32_t op) {
   return c == 0 ? 128u : (c == 2 ? 16u : (c == 3 ? 64u : 256u));
 }
 
-template <int PAIR, int RING_BYTES>
+// SCHEME 0: bf16x3 (a step = 16 K columns, 64 B per weight row); SCHEME 1: f16f8 (a step = 32 K columns, 128 B per row)
+template <int PAIR, int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
                                               uint32_t ring, uint32_t bar, long long ntiles, uint32_t rank) {
-  constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
+  constexpr uint32_t SLOT_BYTES = (PAIR ? 8192 : 16384) * (SCHEME ? 2 : 1), NSLOT = RING_BYTES / SLOT_BYTES;
   uint32_t slot = 0, ph = 0;
   for (long long t = 0; t < ntiles; ++t) {
     const uint8_t* src = wstream;
@@ -70,7 +71,7 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
       const uint32_t kind = op & 3;
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
-      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64);    // this CTA's share of one K step
+      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64) * (SCHEME ? 2 : 1);    // this CTA's share of one K step
       const int cnt = (int)((op >> 24) & 31) + 1;
       for (int j = 0; j < cnt; ++j) {
         mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
@@ -86,9 +87,9 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
 }
 
 // Peer CTA of a pair: tell the leader when this CTA's half of each ring slot has landed.
-template <int RING_BYTES>
+template <int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ program, uint32_t bar, long long ntiles) {
-  constexpr uint32_t NSLOT = RING_BYTES / 8192;
+  constexpr uint32_t NSLOT = RING_BYTES / (8192 * (SCHEME ? 2 : 1));
   uint32_t slot = 0, ph = 0;
   const uint32_t leader_pfull = mapa_rank(bar + BAR_PFULL, 0);
   for (long long t = 0; t < ntiles; ++t) {
@@ -110,10 +111,11 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
 // UNIT op = a run of `cnt` consecutive K steps of one (128 x PAIR?2:1) x N block; decoded once, then a
 // tight per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.  The whole warp runs the loop
 // (warp-uniform), one elected lane issues.
-template <int PAIR, int RING_BYTES>
+template <int PAIR, int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
                                          uint32_t bar, uint32_t tmem, long long ntiles) {
-  constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
+  static_assert(SCHEME == 0 || PAIR == 1, "the f16f8 scheme is built for CTA pairs");
+  constexpr uint32_t SLOT_BYTES = (PAIR ? 8192 : 16384) * (SCHEME ? 2 : 1), NSLOT = RING_BYTES / SLOT_BYTES;
   uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
   long long q_a = 0, q_w = 0;
   const long long q_start = clock64();
@@ -129,12 +131,13 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
       if (kind == OP_UNIT) {
         const uint32_t n = op_n(op);
         const uint32_t nloc = PAIR ? n / 2 : n;                                   // B rows held by one CTA
-        const uint32_t idesc = (PAIR ? idesc2_bf16_f32(0) : idesc_bf16_f32(0)) | (n << 14);   // N >> 3 at bit 17
+        const uint32_t idesc = (SCHEME ? idesc_f16_f32(256, 0) : PAIR ? idesc2_bf16_f32(0) : idesc_bf16_f32(0)) | (n << 14);   // N >> 3 at bit 17
+        const uint32_t idesc8 = idesc_e4m3_f32(256, 0) | (n << 14);
         const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
         // A operand: K groups of the shared-memory A region, or (bit 29, CTA pairs only) of tensor memory, where one
         // K group = 4 columns counted from the TMEM base (so K group 64 sits right behind a 256-column accumulator)
         const bool a_in_tmem = PAIR && ((op >> 29) & 1);
-        const uint32_t a_step = a_in_tmem ? 8u : 2 * (KG_BYTES >> 4);
+        const uint32_t a_step = a_in_tmem ? 8u : (SCHEME ? 4 : 2) * (KG_BYTES >> 4);
         uint32_t ahi32 = a_in_tmem ? tmem + ((op >> 8) & 0xFF) * 4 : a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
         uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
@@ -154,7 +157,18 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
           const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
           const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
-          if (elect_one()) {
+          if (SCHEME) {
+            // f16f8: [w16: 4 K groups | w8: 2 | s8: 2] x nloc rows x 16 B;  A: fp16 groups at ahi32, [r8 r8 a8 a8] at alo32
+            const uint64_t ahi2 = kDescHi | (ahi32 + 2 * (KG_BYTES >> 4)), aa8 = kDescHi | (alo32 + 2 * (KG_BYTES >> 4));
+            const uint64_t bhi2 = kDescHi | (wlo + nloc * 2), bw8 = kDescHi | (wlo + nloc * 4), bs8 = kDescHi | (wlo + nloc * 6);
+            if (elect_one()) {
+              mma2_bf16(acc, ahi, bhi, idesc, accum);
+              mma2_bf16(acc, ahi2, bhi2, idesc, 1u);
+              mma2_f8(acc, alo, bw8, idesc8, 1u);
+              mma2_f8(acc, aa8, bs8, idesc8, 1u);
+              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
+            }
+          } else if (elect_one()) {
             if (PAIR && a_in_tmem) {
               mma2_bf16_ts(acc, ahi32, bhi, idesc, accum);
               mma2_bf16_ts(acc, alo32, bhi, idesc, 1u);
@@ -270,17 +284,17 @@ __device__ __forceinline__ void engine_end(uint32_t tmem) {
   }
 }
 // Warps 8..11: weight producer, MMA issuer (leader) / forwarder (peer).
-template <int PAIR, int RING_BYTES>
+template <int PAIR, int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void engine_service_warps(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
                                                      uint32_t sbase, uint32_t ring, uint32_t bar, uint32_t tmem,
                                                      long long ntiles, uint32_t rank) {
   reg_dec<72>();   // the whole third warpgroup (warps 8-11) executes this one instruction
   const int warp = threadIdx.x >> 5;
   if (warp == 8) {
-    producer_loop<PAIR, RING_BYTES>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
+    producer_loop<PAIR, RING_BYTES, SCHEME>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
   } else if (warp == 9) {
-    if (rank == 0) mma_loop<PAIR, RING_BYTES>(program, sbase, ring, bar, tmem, ntiles);
-    else forward_loop<RING_BYTES>(program, bar, ntiles);
+    if (rank == 0) mma_loop<PAIR, RING_BYTES, SCHEME>(program, sbase, ring, bar, tmem, ntiles);
+    else forward_loop<RING_BYTES, SCHEME>(program, bar, ntiles);
   }
 }
 
@@ -311,14 +325,14 @@ static inline cudaError_t launch_engine(Kernel kernel, int pair, unsigned ctas, 
 }
 
 // Walk a program on the host: number of weight bytes it consumes; -1 if malformed.
-static inline long long program_stream_bytes(const uint32_t* prog, size_t words) {
+static inline long long program_stream_bytes(const uint32_t* prog, size_t words, int f16f8 = 0) {
   long long bytes = 0;
   for (size_t i = 0; i < words; ++i) {
     const uint32_t kind = prog[i] & 3;
     if (kind == OP_END) return (i + 1 < words) ? bytes : -1;   // needs >= 1 END of padding after the first
     if (kind == OP_UNIT) {
       const uint32_t c = (prog[i] >> 2) & 3;
-      bytes += (long long)(c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 16 : 64))) * 64 * (((prog[i] >> 24) & 31) + 1);
+      bytes += (long long)(c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 16 : 64))) * (f16f8 ? 128 : 64) * (((prog[i] >> 24) & 31) + 1);
     }
   }
   return -1;

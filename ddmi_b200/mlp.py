@@ -16,7 +16,7 @@ from torch import nn
 from . import _lib, packing
 from .blocks import ResnetBlockFC, SinusoidalPosEmb, StyledResBlock, ToRGB
 
-_PREC = {'fp32': _lib.PREC_FP32, 'bf16x3': _lib.PREC_BF16X3}
+_PREC = {'fp32': _lib.PREC_FP32, 'bf16x3': _lib.PREC_BF16X3, 'f16f8': _lib.PREC_F16F8}
 
 
 def _resolve_precision(name, supported, default):
@@ -79,7 +79,7 @@ class _FusedDecoder(nn.Module):
 class MLP(_FusedDecoder):
     """Image decoder.  Reference: models/d2c_vae/mlp.py:12-66."""
 
-    _supported = ('fp32', 'bf16x3')
+    _supported = ('fp32', 'bf16x3', 'f16f8')
     _default_precision = 'bf16x3'
 
     def __init__(self, *, in_ch=2, latent_dim=64, out_ch=3, ch=256, precision=None):
@@ -113,6 +113,7 @@ class MLP(_FusedDecoder):
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
         si = float(si)
         pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'     # tcgen05 kernel: CTA pairs (cta_group::2) by default
+        pair = pair or prec == _lib.PREC_F16F8                      # the f16f8 kernel exists for pairs only
         packed = self._packed(('image', prec, si, pair), lambda: packing.pack_image(self, si, prec, pair))
         out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
         n = h * w

@@ -10,6 +10,8 @@ order and format a kernel family streams them:
   (``W[:, seg].T``), K padded to a multiple of 16 with zero rows.
 * ``PREC_BF16X3`` : per 16-wide K step a ``[hi | lo]`` pair of bf16 blocks in the
   tcgen05 shared-memory "core matrix" order, in consumption order.
+* ``PREC_F16F8``  : per 32-wide K step ``[fp16(S W) | e4m3(W) | e4m3(S W - fp16(S W))]``
+  (S = 4096) in the same core-matrix order (csrc/umma.cuh, "f16f8" scheme).
 
 Both formats share one ``vec`` blob of fp32 vectors (biases, folded constants,
 the narrow output heads that run in the epilogue).
@@ -20,7 +22,7 @@ from dataclasses import dataclass
 
 import torch
 
-from ._lib import PREC_BF16X3, PREC_FP32
+from ._lib import PREC_BF16X3, PREC_F16F8, PREC_FP32
 
 
 @dataclass
@@ -48,17 +50,31 @@ class UmmaProgram:
     """
     NCODE = {128: 0, 256: 1, 16: 2, 64: 3}
 
-    def __init__(self, pair=False):
+    def __init__(self, pair=False, scheme='bf16x3'):
         self.ops = []
         self.segs = []
         self.pair = pair      # CTA pairs: each K step is stored as [rows 0..N/2-1 | rows N/2..N-1]
+        # 'f16f8': a step is 32 wide (2 fp16 MMAs + 2 e4m3 MMAs); [15:8] = first fp16 K group (advances 4 per step),
+        # [23:16] = first K group of the step's FP8 operands [r8 r8 a8 a8] (advances 4 per step); pairs only.
+        self.scheme = scheme
+        assert scheme in ('bf16x3', 'f16f8') and (scheme == 'bf16x3' or pair)
 
     def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None, a_in_tmem=False):
         """acc[:, acc_col:acc_col+N] (+)= A[:, K] @ W.T ; W is (N, K), K zero-padded to 16.  a_in_tmem: the A operand
         lives in tensor memory (K group g = TMEM columns 4g..4g+3), CTA-pair kernels only (op bit 29)."""
         n = W.shape[0] if n_pad is None else n_pad
-        k16 = (W.shape[1] + 15) // 16
         assert n in self.NCODE and acc_col % 64 == 0 and acc_col + n <= 512
+        if self.scheme == 'f16f8':
+            k32 = (W.shape[1] + 31) // 32
+            assert not a_in_tmem and 1 <= k32 <= 32 and a_hi_kg + 4 * k32 <= 256 and a_lo_kg + 4 * k32 <= 256
+            self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
+                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k32 - 1) << 24))
+            Wp = W.new_zeros(n, 32 * k32)
+            Wp[:W.shape[0], :W.shape[1]] = W
+            halves = [f16f8_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)]).reshape(k32, -1) for h in (0, 1)]
+            self.segs.append(torch.cat(halves, dim=1).reshape(-1))
+            return
+        k16 = (W.shape[1] + 15) // 16
         assert 1 <= k16 <= 32 and a_hi_kg + 2 * k16 <= 256 and a_lo_kg + 2 * k16 <= 256
         self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
                         | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k16 - 1) << 24) | ((1 if a_in_tmem else 0) << 29))
@@ -85,6 +101,29 @@ class UmmaProgram:
     def finish(self, device):
         ops = torch.tensor(self.ops + [3, 3, 3, 3], dtype=torch.int64).to(torch.int32)
         return torch.cat(self.segs).contiguous(), ops.to(device), ops.contiguous()
+
+
+F8_SCALE = 4096.0
+
+
+def f16f8_kstep_blocks(W):
+    """Pack W (N, K), K a multiple of 32, for the f16f8 tcgen05 kernels: a flat uint8 tensor, per 32-wide K step
+    [fp16(S W): 4 K groups x N rows x 8 halves | e4m3(W): 2 K groups x N rows x 16 bytes | e4m3(S W - fp16(S W)): same].
+    Raises if a weight does not fit fp16 after scaling (|W| >= 16)."""
+    W = W.to(torch.float32)
+    n, k = W.shape
+    assert k % 32 == 0
+    ws = W * F8_SCALE
+    if float(ws.abs().max()) > 65504.0:
+        raise ValueError("f16f8 packing: |weight| * 4096 exceeds the fp16 range; use precision='bf16x3'")
+    w16 = ws.to(torch.float16)
+    res = ws - w16.to(torch.float32)
+    w8 = W.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    s8 = res.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+    p16 = w16.reshape(n, k // 32, 4, 8).permute(1, 2, 0, 3).contiguous().view(torch.uint8).reshape(k // 32, -1)
+    p8 = [t.reshape(n, k // 32, 2, 16).permute(1, 2, 0, 3).contiguous().view(torch.uint8).reshape(k // 32, -1)
+          for t in (w8, s8)]
+    return torch.cat([p16] + p8, dim=1).reshape(-1)
 
 
 # ---------------------------------------------------------------------------
@@ -235,8 +274,9 @@ def pack_image(module, si, precision, pair=True):
                 if hk: segs.append(_seg_fp32(d['Ws'], 0, hk))
                 segs.append(_seg_fp32(d['Ws'], hk, hk + 64))
         gemm = torch.cat(segs).to(torch.float32).contiguous()
-    elif precision == PREC_BF16X3:
-        # Program of csrc/decode_umma.cu::image_umma_kernel.  K groups of the A region:
+    elif precision in (PREC_BF16X3, PREC_F16F8):
+        # Program of csrc/decode_umma.cu::image_umma_kernel.  (PREC_F16F8: same program and K-group numbers -- a
+        # 64-column quarter is two 32-wide steps, its fp16 groups are 8q.., its FP8 groups 32 + 8q..)  K groups of the A region:
         # [H hi 0..31 | H lo 32..63 | X hi 64..71 | X lo 72..79]; acc1 = TMEM columns 0..255, acc2 = 256..511.
         # lrelu(x)*sqrt2 == lrelu(x*sqrt2): conv1 / conv2 carry their activation gain in W and b.
         # Every GEMM group is [WAIT q, K steps over H columns 64q..64q+63] for q = 0..3, then COMMIT: the
@@ -245,7 +285,7 @@ def pack_image(module, si, precision, pair=True):
         # epilogue still reads it until then.
         gain = math.sqrt(2.0)
         HH, HL, XH, XL = 0, 32, 64, 72
-        P = UmmaProgram(pair=pair)
+        P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
         # schedule: how many operand quarters must be published before a K run starts
         #   'quarters' : run q needs barriers 0..q      (finest overlap)
         #   'halves'   : runs 0,1 need 0..1; runs 2,3 need 0..3

@@ -33,6 +33,9 @@
  *   DDMI_PREC_FP32    fp32 CUDA-core kernels (exact-arithmetic path)
  *   DDMI_PREC_BF16X3  tcgen05 tensor-core kernels, bf16 hi/lo split operands,
  *                     3 MMAs per product, fp32 accumulation in TMEM
+ *   DDMI_PREC_F16F8   tcgen05 kernels, fp16 main term + two FP8 (e4m3) correction terms at twice
+ *                     the MMA rate: 2/3 of the tensor-pipe time of BF16X3 at ~2e-4 max-abs error
+ *                     (CTA pairs only; image decode only in this build)
  */
 #ifndef DDMI_B200_H
 #define DDMI_B200_H
@@ -50,7 +53,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 4
+#define DDMI_ABI_VERSION 5
 
 enum {
   DDMI_OK = 0,
@@ -59,7 +62,7 @@ enum {
   DDMI_ERR_CUDA = 3          /* CUDA runtime error (launch, attribute, no device)    */
 };
 
-enum { DDMI_PREC_FP32 = 0, DDMI_PREC_BF16X3 = 1 };
+enum { DDMI_PREC_FP32 = 0, DDMI_PREC_BF16X3 = 1, DDMI_PREC_F16F8 = 2 };
 
 /* plane memory layout: as the reference's VAE decoder emits them, or channels-last */
 enum { DDMI_LAYOUT_NCHW = 0, DDMI_LAYOUT_NHWC = 1 };
@@ -183,6 +186,13 @@ DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_
  * a: (256,K), b: (N,K), d: (256,N); CTA r owns rows 128r.. of a / d and rows (N/2)r.. of b.
  */
 DDMI_API int ddmi_selftest_umma2(const float* a, const float* b, float* d, int32_t N, int32_t K,
+                                 void* stream);
+
+/*
+ * Same shapes as ddmi_selftest_umma through the DDMI_PREC_F16F8 operand scheme (one fp16 kind::f16 term + two
+ * kind::f8f6f4 e4m3 correction terms into one accumulator); K a multiple of 32.
+ */
+DDMI_API int ddmi_selftest_f16f8(const float* a, const float* b, float* d, int32_t N, int32_t K,
                                  void* stream);
 
 /*

@@ -42,7 +42,7 @@ def test_device_is_blackwell():
 
 
 # ---------------------------------------------------------------- image
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 @pytest.mark.parametrize("tag,kw", [("image_96", dict(batch=2, sizes=(16, 32, 64), res=96)),
                                     ("image_native", dict(batch=1, sizes=(8, 16, 32), res=32))])
 def test_image_golden(golden_dir, tag, kw, precision):
@@ -56,7 +56,7 @@ def test_image_golden(golden_dir, tag, kw, precision):
     assert err < (2e-5 if precision == 'fp32' else TOL), err
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_image_ragged_and_scattered_coords(precision):
     """n_coords not a multiple of the tile; out-of-range coords hit the border clamp."""
     m = cases.build_module('image').to(DEV)
@@ -257,6 +257,31 @@ def test_umma2_selftest(N, K):
     torch.cuda.synchronize()
     ref = a.double() @ b.double().t()
     assert float((d.double() - ref).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 64), (16, 256), (128, 32)])
+def test_f16f8_selftest(N, K):
+    """fp16 main term + two e4m3 correction terms (kind::f8f6f4) into one accumulator: checked against the exact
+    product and, tightly, against a torch emulation of the same operand rounding."""
+    from ddmi_b200 import _lib
+    g = torch.Generator().manual_seed(N * 1000 + K + 13)
+    a = torch.randn(128, K, generator=g)
+    b = torch.randn(N, K, generator=g) * 0.1
+    d = torch.full((128, N), float('nan'), device=DEV)
+    ad, bd = a.to(DEV), b.to(DEV)
+    _lib.check(_lib.lib().ddmi_selftest_f16f8(ad.data_ptr(), bd.data_ptr(), d.data_ptr(), N, K,
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    S = 4096.0
+    q8 = lambda x: x.clamp(-448, 448).to(torch.float8_e4m3fn).double()
+    a16 = a.to(torch.float16)
+    w16 = (b * S).to(torch.float16)
+    emu = (a16.double() @ w16.double().t() + q8((a - a16.float()) * S) @ q8(b).t()
+           + q8(a) @ q8(b * S - w16.float()).t()) / S
+    ref = a.double() @ b.double().t()
+    got = d.double().cpu()
+    assert float((got - emu).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
 
 
 # ---------------------------------------------------------------- size-independent properties at larger shapes

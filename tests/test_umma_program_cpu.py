@@ -77,13 +77,73 @@ class EngineModel:
                     self.acc[:, col:col + n] = d + (self.acc[:, col:col + n] if (accum or j > 0) else 0)
 
 
-@pytest.mark.parametrize("pair", [True, False])
-def test_image_program_and_stream_reproduce_the_oracle(pair):
+class EngineModelF16F8(EngineModel):
+    """The f16f8 scheme (csrc/umma.cuh): a UNIT step is 32 wide; the A region holds fp16 K groups (8 wide) at
+    [15:8] and per step four FP8 K groups [r8 r8 a8 a8] (16 wide) at [23:16]; the stream holds per step and CTA half
+    [fp16(S W) | e4m3(W) | e4m3(S W - fp16(S W))]; accumulators hold S x the product."""
+    S = 4096.0
+
+    def __init__(self, packed, rows):
+        super().__init__(packed, rows)
+        assert self.pair
+        self.A16 = torch.zeros(rows, 256 * 8)     # fp16 K group g -> columns 8g..
+        self.A8 = torch.zeros(rows, 256 * 16)     # FP8 K group g -> columns 16g..
+
+    @staticmethod
+    def q8(x):
+        return x.clamp(-448, 448).to(torch.float8_e4m3fn).float()
+
+    def write(self, kg, x):                       # kg: fp16 K group of the first column (0 = H, 64 = X)
+        f8 = {0: 32, 64: 72}[kg]
+        a16 = x.to(torch.float16).float()
+        self.A16[:, kg * 8:kg * 8 + x.shape[1]] = a16
+        r8, a8 = self.q8((x - a16) * self.S), self.q8(x)
+        for s in range(x.shape[1] // 32):
+            base = (f8 + 4 * s) * 16
+            self.A8[:, base:base + 32] = r8[:, 32 * s:32 * s + 32]
+            self.A8[:, base + 32:base + 64] = a8[:, 32 * s:32 * s + 32]
+
+    def run_group(self):
+        waits = []
+        while True:
+            op = self.ops[self.pc]
+            self.pc += 1
+            kind = op & 3
+            if kind == 1:
+                waits.append((op >> 2) & 7)
+            elif kind == 2:
+                return waits, (op >> 2) & 3
+            elif kind == 3:
+                raise AssertionError("END inside a tile")
+            else:
+                n = NCODE[(op >> 2) & 3]
+                nloc = n // 2
+                accum, col = (op >> 4) & 1, ((op >> 5) & 7) * 64
+                kg16, kg8, cnt = (op >> 8) & 0xFF, (op >> 16) & 0xFF, ((op >> 24) & 31) + 1
+                for j in range(cnt):
+                    W16, W8, S8 = torch.zeros(n, 32), torch.zeros(n, 32), torch.zeros(n, 32)
+                    for h in range(2):
+                        b = self.stream[self.pos:self.pos + nloc * 128]
+                        self.pos += nloc * 128
+                        rows = slice(h * nloc, (h + 1) * nloc)
+                        W16[rows] = b[:nloc * 64].view(torch.float16).float().reshape(4, nloc, 8).permute(1, 0, 2).reshape(nloc, 32)
+                        W8[rows] = b[nloc * 64:nloc * 96].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
+                        S8[rows] = b[nloc * 96:].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
+                    a16 = self.A16[:, (kg16 + 4 * j) * 8:(kg16 + 4 * j) * 8 + 32]
+                    r8 = self.A8[:, (kg8 + 4 * j) * 16:(kg8 + 4 * j) * 16 + 32]
+                    a8 = self.A8[:, (kg8 + 4 * j + 2) * 16:(kg8 + 4 * j + 2) * 16 + 32]
+                    d = (a16 @ W16.t() + r8 @ W8.t() + a8 @ S8.t()) / self.S
+                    self.acc[:, col:col + n] = d + (self.acc[:, col:col + n] if (accum or j > 0) else 0)
+
+
+@pytest.mark.parametrize("pair,scheme", [(True, 'bf16x3'), (False, 'bf16x3'), (True, 'f16f8')])
+def test_image_program_and_stream_reproduce_the_oracle(pair, scheme):
     m = cases.build_module('image')
     sd = cases.state_dict32(m)
     coords, planes, si = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=12)
     ref = orc.image_decode(sd, coords, planes, si)                       # (1,3,12,12)
-    packed = packing.pack_image(m, si, _lib.PREC_BF16X3, pair=pair)
+    packed = packing.pack_image(m, si, _lib.PREC_F16F8 if scheme == 'f16f8' else _lib.PREC_BF16X3, pair=pair)
+    EngineModel = EngineModelF16F8 if scheme == 'f16f8' else globals()['EngineModel']
     vec = packed.vec
     grid = coords.permute(0, 2, 3, 1)
     X = [torch.nn.functional.grid_sample(p, grid, padding_mode='border', align_corners=False).permute(0, 2, 3, 1).reshape(-1, 64)
@@ -108,7 +168,7 @@ def test_image_program_and_stream_reproduce_the_oracle(pair):
     E.run_group()                                                        # ToRGB
     out = (E.acc[:, :3] + vec[4096 + 768:4096 + 771]).t().reshape(1, 3, 12, 12)
     assert E.ops[E.pc] & 3 == 3 and E.pos == E.stream.numel()            # program and stream end together
-    assert float((out - ref).abs().max()) < 1e-3
+    assert float((out - ref).abs().max()) < 1e-3                         # (the model keeps acc / S; the kernel keeps acc)
 
 
 def test_programs_consume_exactly_their_streams():
