@@ -307,8 +307,9 @@ def run_other(args):
         rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(H * W, 1, device=dev),
                           6. * torch.ones(H * W, 1, device=dev), vd], -1)
         coords = B * H * W * 128
-        fn = lambda: nh.render_rays_fused(rays, fea, m, 128, True)
+        fn = lambda: nh.render_rays_fused(rays, fea, m, 128, True, precision=args.precision)
         desc = f"srn-cars-shape NeRF decode: triplane 64^2 x32ch, 128x128 rays x 128 samples, composited, batch {B} objects"
+    m.precision = args.precision
     for _ in range(args.warmup):
         fn()
     torch.cuda.synchronize()
@@ -323,7 +324,8 @@ def run_other(args):
     achieved = coords * args.steps * FLOP_PER_COORD[kind] / (ms * 1e-3) / 1e12
     print(json.dumps({"metric": METRIC, "value": coords * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "data": "synthetic", "config": {"workload": desc},
+                      "scaling": "weak", "vs_baseline": None, "dtype": PREC_INFO[args.precision]['dtype'], "data": "synthetic",
+                      "config": {"workload": desc, "precision": args.precision},
                       "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                                    "frac": achieved / tf_peak, "traffic": None, "peak_source": which}}))
 

@@ -29,9 +29,9 @@ int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, 
 // tcgen05 path (decode_umma.cu)
 int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
-int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
+int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
-int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, cudaStream_t);
+int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
 int launch_nerf_composite(const float*, const float*, int, const float*, int, long long, int, int, float*, cudaStream_t);
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
@@ -157,13 +157,14 @@ DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, 
   // the Python scalars of normalize_coordinate: double arithmetic, then fp32
   const float divisor = (float)(1.0 + (double)padding + 10e-6);
   const float upper = (float)(1.0 - 10e-6);
-  if (weights->precision == DDMI_PREC_BF16X3) {
+  if (weights->precision == DDMI_PREC_BF16X3 || weights->precision == DDMI_PREC_F16F8) {
     DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
     return launch_occupancy_umma_entry(ps, batch, channels, points, n_points, point_batch_stride, divisor, upper,
                                        weights->gemm, weights->gemm_bytes, weights->program_host, weights->program_words,
                                        weights->program, weights->vec, weights->vec_floats, logits,
-                                       weights->reserved & 1, plane_layout, (cudaStream_t)stream);
+                                       weights->reserved & 1, plane_layout, weights->precision == DDMI_PREC_F16F8,
+                                       (cudaStream_t)stream);
   }
   if (plane_layout != DDMI_LAYOUT_NCHW) {
     set_error("the fp32 occupancy kernel reads NCHW planes only");
@@ -195,12 +196,13 @@ DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int3
     return DDMI_ERR_UNSUPPORTED;
   }
   DDMI_REQUIRE(weights != nullptr, "weights is NULL");
-  if (weights->precision == DDMI_PREC_BF16X3) {
+  if (weights->precision == DDMI_PREC_BF16X3 || weights->precision == DDMI_PREC_F16F8) {
     DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
     return launch_video_umma_entry(ps, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W, weights->gemm,
                                    weights->gemm_bytes, weights->program_host, weights->program_words, weights->program,
-                                   weights->vec, weights->vec_floats, out, weights->reserved & 1, (cudaStream_t)stream);
+                                   weights->vec, weights->vec_floats, out, weights->reserved & 1,
+                                   weights->precision == DDMI_PREC_F16F8, (cudaStream_t)stream);
   }
   if (weights->precision != DDMI_PREC_FP32) {
     set_error("video decode: unknown precision %d", weights->precision);

@@ -376,7 +376,7 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
     return DDMI_ERR_UNSUPPORTED;
   }
   DDMI_REQUIRE(program_host && program_dev && program_words >= 2, "bf16x3 weights carry no MMA program");
-  const long long need = ummak::program_stream_bytes(program_host, program_words, f16f8);
+  const long long need = ummak::program_stream_bytes(program_host, program_words);
   DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
                need, gemm_bytes);
   DDMI_REQUIRE(!f16f8 || pair, "the f16f8 image kernel runs as CTA pairs only");
@@ -412,9 +412,10 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
 int launch_occupancy_umma_entry(const PlaneSet& ps, int batch, int C, const float* pts, long long n, long long batch_stride,
                                 float divisor, float upper, const void* gemm, size_t gemm_bytes,
                                 const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
-                                const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, cudaStream_t st) {
+                                const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, int f16f8,
+                                cudaStream_t st) {
   return launch_occupancy_umma(ps, batch, C, pts, n, batch_stride, divisor, upper, gemm, gemm_bytes, program_host,
-                               program_words, program_dev, vec, vec_floats, logits, pair, nhwc, st);
+                               program_words, program_dev, vec, vec_floats, logits, pair, nhwc, f16f8, st);
 }
 
 int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays, int ray_stride,
@@ -429,9 +430,9 @@ int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* ra
 int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt, int T,
                             int H, int W, const void* gemm, size_t gemm_bytes, const uint32_t* program_host,
                             size_t program_words, const uint32_t* program_dev, const float* vec, size_t vec_floats,
-                            float* out, int pair, cudaStream_t st) {
+                            float* out, int pair, int f16f8, cudaStream_t st) {
   return launch_video_umma(ps, batch, C, cxy, cyt, cxt, T, H, W, gemm, gemm_bytes, program_host, program_words, program_dev,
-                           vec, vec_floats, out, pair, st);
+                           vec, vec_floats, out, pair, f16f8, st);
 }
 
 int debug_profile(unsigned long long* out, int reset) {

@@ -134,7 +134,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
     auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {   // waits for the GEMM first
       const float sl = act ? slope : 1.f;
-      biased_stage(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
+      biased_stage<0>(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
     };
 
     if (ntiles > 0) {
@@ -198,7 +198,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         float2 acc3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          add_vec<16>(v[q], vec + NV_BD + q * 64 + sub * 32);
+          add_vec<0, 16>(v[q], vec + NV_BD + q * 64 + sub * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[q][i] = lrelu_pair(v[q][i], slope);
 #pragma unroll

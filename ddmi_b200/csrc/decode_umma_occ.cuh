@@ -36,18 +36,19 @@ __device__ __forceinline__ void drain128(uint32_t tmem_lane, int acc_col, int su
   for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + acc_col + q * 64 + sub * 32, v[q]);
   tmem_ld_wait();
 }
-template <int NP>
+// y <- accumulator values (de-scaled) + vector
+template <int SCHEME, int NP>
 __device__ __forceinline__ void add_vec(float2 (&y)[NP], const float* __restrict__ p) {
   float2 b[NP];
   load_vec<NP>(p, b);
 #pragma unroll
-  for (int i = 0; i < NP; ++i) y[i] = __fadd2_rn(y[i], b[i]);
+  for (int i = 0; i < NP; ++i) y[i] = acc_plus<SCHEME>(y[i], b[i]);
 }
 // Generic epilogue stage: prefetch quarter 0's bias, park on the MMA barrier (`wait`), drain this thread's values of the
 // accumulator at `acc_col`, then per quarter q < nq: v = f(v + bias) -> H, signal(sig0 + q); the bias of quarter q + 1 is
 // loaded while quarter q is converted (there is no L1 beside ~224 KB of shared memory: an unprefetched bias costs an
 // exposed L2 round trip per stage).  v is left holding the stored values.
-template <class Wait, class Act, class Signal>
+template <int SCHEME, class Wait, class Act, class Signal>
 __device__ __forceinline__ void biased_stage(uint32_t tmem_lane, int acc_col, int sub, int row, uint32_t h_hi, uint32_t h_lo,
                                              const float* __restrict__ bias, int nq, float2 (&v)[4][16], Wait wait, Act act,
                                              Signal signal, int sig0) {
@@ -64,14 +65,14 @@ __device__ __forceinline__ void biased_stage(uint32_t tmem_lane, int acc_col, in
       float2 bn[16];
       if (q + 1 < nq) load_vec<16>(bias + (q + 1) * 64 + sub * 32, bn);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[q][i] = act(__fadd2_rn(v[q][i], b[i]));
+      for (int i = 0; i < 16; ++i) v[q][i] = act(acc_plus<SCHEME>(v[q][i], b[i]));
       {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float2 y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] = v[q][c * 8 + i];
-          store_act<8>(h_hi, h_lo, row, q * 64 + sub * 32 + c * 16, y);
+          store16<SCHEME>(h_hi, h_lo, row, q * 64 + sub * 32 + c * 16, y);
         }
       }
       signal(sig0 + q);
@@ -84,18 +85,18 @@ __device__ __forceinline__ void biased_stage(uint32_t tmem_lane, int acc_col, in
 }
 
 // write one quarter (32 columns of this thread) of the 256-wide operand, optionally relu'd
-template <bool RELU>
+template <bool RELU, int SCHEME>
 __device__ __forceinline__ void put_quarter(uint32_t h_hi, uint32_t h_lo, int row, int q, int sub, const float2 (&vq)[16]) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     float2 y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = RELU ? relu_pair(vq[c * 8 + i]) : vq[c * 8 + i];
-    store_act<8>(h_hi, h_lo, row, q * 64 + sub * 32 + c * 16, y);
+    store16<SCHEME>(h_hi, h_lo, row, q * 64 + sub * 32 + c * 16, y);
   }
 }
 
-template <int PAIR, int NHWC>   // NHWC: planes are channels-last (batch, H, W, C) -- vectorised scattered gathers
+template <int PAIR, int NHWC, int SCHEME>   // NHWC: planes are channels-last (batch, H, W, C) -- vectorised scattered gathers
 __global__ void __launch_bounds__(NTHREADS, 1)
 occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, long long batch_stride,
                       int tiles_per_item, long long total_tiles, float divisor, float upper,
@@ -104,6 +105,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
+  const uint32_t xa_hi = sbase + OCC_KG_XAH * KG_BYTES, xa_lo = sbase + OCC_KG_XAL * KG_BYTES;
+  const uint32_t xb_hi = sbase + OCC_KG_XBH * KG_BYTES, xb_lo = sbase + OCC_KG_XBL * KG_BYTES;
   const uint32_t ring = sbase + OccL::OFF_RING, bar = sbase + OccL::OFF_BAR;
   float* part = reinterpret_cast<float*>(smem + OCC_OFF_PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -185,14 +188,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
             y[i] = __fadd_rn(__fadd_rn(y[i], u[i]), w[i]);
             yr[i] = fmaxf(y[i], 0.f);
           }
-          uint4 hi, lo;
-          const uint32_t off = (uint32_t)(kg * KG_BYTES + prow * 16);
-          split8(y, hi, lo);
-          st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
-          st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
-          split8(yr, hi, lo);
-          st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
-          st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
+          store8<SCHEME>(xa_hi, xa_lo, prow, kg, y);
+          store8<SCHEME>(xb_hi, xb_lo, prow, kg, yr);
         }
       } else {
         float p[3];
@@ -217,21 +214,15 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
             y[i] = v;
             yr[i] = fmaxf(v, 0.f);
           }
-          uint4 hi, lo;
-          const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
-          split8(y, hi, lo);
-          st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
-          st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
-          split8(yr, hi, lo);
-          st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
-          st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
+          store8<SCHEME>(xa_hi, xa_lo, row, ghalf * 4 + g, y);
+          store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g, yr);
         }
       }
     };
     // wait for the fc_0 GEMM, then relu(acc1 + b) -> H, quarter by quarter
     auto stage_net = [&](const float* __restrict__ b0) {
       float2 v[4][16];
-      biased_stage(tmem_lane, 0, sub, row, h_hi, h_lo, b0, 4, v, wait_mma, [](float2 t) { return relu_pair(t); }, signal, 0);
+      biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b0, 4, v, wait_mma, [](float2 t) { return relu_pair(t); }, signal, 0);
     };
 
     if (ntiles > 0) {
@@ -248,8 +239,14 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         load_vec<16>(vec + OV_B01 + sub * 32, b);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = bias_relu_pair(v[i], b[i]);
-        store_act<16>(h_hi, h_lo, row, sub * 32, v);
+        for (int i = 0; i < 16; ++i) v[i] = relu_pair(acc_plus<SCHEME>(v[i], b[i]));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float2 y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = v[c * 8 + i];
+          store16<SCHEME>(h_hi, h_lo, row, sub * 32 + c * 16, y);
+        }
         signal_all();
       }
       // R1's fc_0 AND shortcut ran in that group, so both feature buffers are free: gather the next scale now,
@@ -263,7 +260,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         drain128(tmem_lane, 256, sub, v);
         const float* b1 = vec + (blk == 1 ? OV_B11 : OV_B12);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) add_vec<16>(v[q], b1 + q * 64 + sub * 32);
+        for (int q = 0; q < 4; ++q) add_vec<SCHEME, 16>(v[q], b1 + q * 64 + sub * 32);
         if (blk == 1) {   // + net_p(p): 3 FMAs per output, fp32 (mlp.py:103)
           float p[3];
           point_of(tile, p);
@@ -281,11 +278,11 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
         // phase 1: raw h (shortcut operand)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
+        for (int q = 0; q < 4; ++q) { put_quarter<false, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
         // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
         wait_mma();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
+        for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
         // fc_0 epilogue; Xa / Xb are free again: gather what comes next while fc_1 runs
         stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
         if (blk == 1) gather(tile, 2);
@@ -298,8 +295,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         drain128(tmem_lane, 256, sub, v);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          add_vec<16>(v[q], vec + OV_B13 + q * 64 + sub * 32);
-          put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]);
+          add_vec<SCHEME, 16>(v[q], vec + OV_B13 + q * 64 + sub * 32);
+          put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]);
           signal(q);
         }
       }
@@ -313,7 +310,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          add_vec<16>(v[q], vec + OV_B14 + q * 64 + sub * 32);
+          add_vec<SCHEME, 16>(v[q], vec + OV_B14 + q * 64 + sub * 32);
           float2 w[16];
           load_vec<16>(vec + OV_WOUT + q * 64 + sub * 32, w);
 #pragma unroll
@@ -331,7 +328,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       if (it + 1 < ntiles) signal_all();
     }
   } else {
-    engine_service_warps<PAIR, OccL::RING_BYTES>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, OccL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -341,8 +338,10 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
 inline int launch_occupancy_umma(const PlaneSet& ps, int batch, int C, const float* pts, long long n, long long batch_stride,
                                  float divisor, float upper, const void* gemm, size_t gemm_bytes,
                                  const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
-                                 const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, cudaStream_t st) {
+                                 const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, int f16f8,
+                                 cudaStream_t st) {
   using namespace ummak;
+  DDMI_REQUIRE(!f16f8 || pair, "the f16f8 occupancy kernel runs as CTA pairs only");
   if (C != 64) {
     set_error("tcgen05 occupancy kernel is built for 64-channel planes");
     return DDMI_ERR_UNSUPPORTED;
@@ -365,13 +364,15 @@ inline int launch_occupancy_umma(const PlaneSet& ps, int batch, int C, const flo
   const int tpi_i = (int)tpi;
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
   const unsigned ctas = pair ? (unsigned)(2 * npairs) : (unsigned)(total < sms ? total : sms);
-#define DDMI_OCC_LAUNCH(P, L)                                                                                        \
-  DDMI_CUDA(launch_engine(occupancy_umma_kernel<P, L>, P, ctas, OCC_SMEM, st, ps, pts, n, batch_stride, tpi_i, total, \
+#define DDMI_OCC_LAUNCH(P, L, S)                                                                                        \
+  DDMI_CUDA(launch_engine(occupancy_umma_kernel<P, L, S>, P, ctas, OCC_SMEM, st, ps, pts, n, batch_stride, tpi_i, total, \
                           divisor, upper, ws, program_dev, vec, logits))
-  if (pair && nhwc) { DDMI_OCC_LAUNCH(1, 1); }
-  else if (pair) { DDMI_OCC_LAUNCH(1, 0); }
-  else if (nhwc) { DDMI_OCC_LAUNCH(0, 1); }
-  else { DDMI_OCC_LAUNCH(0, 0); }
+  if (f16f8 && nhwc) { DDMI_OCC_LAUNCH(1, 1, 1); }
+  else if (f16f8) { DDMI_OCC_LAUNCH(1, 0, 1); }
+  else if (pair && nhwc) { DDMI_OCC_LAUNCH(1, 1, 0); }
+  else if (pair) { DDMI_OCC_LAUNCH(1, 0, 0); }
+  else if (nhwc) { DDMI_OCC_LAUNCH(0, 1, 0); }
+  else { DDMI_OCC_LAUNCH(0, 0, 0); }
 #undef DDMI_OCC_LAUNCH
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;

@@ -30,7 +30,7 @@ constexpr int VID_SMEM = VidL::OFF_BAR + BAR_BYTES;
 constexpr int VV_B01 = 0, VV_B11 = 192, VV_B02 = 448, VV_B12 = 704, VV_B03 = 960, VV_B13 = 1216, VV_B04 = 1472,
               VV_B14 = 1728, VV_WOUT = 1984, VV_BOUT = 2752, VV_TOTAL = 2755;
 
-template <int PAIR>
+template <int PAIR, int SCHEME>
 __global__ void __launch_bounds__(NTHREADS, 1)
 video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __restrict__ cyt,
                   const float* __restrict__ cxt, int T, int Hh, int Ww, int tiles_per_item, long long total_tiles,
@@ -39,6 +39,8 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
+  const uint32_t xa_hi = sbase + OCC_KG_XAH * KG_BYTES, xa_lo = sbase + OCC_KG_XAL * KG_BYTES;
+  const uint32_t xb_hi = sbase + OCC_KG_XBH * KG_BYTES, xb_lo = sbase + OCC_KG_XBL * KG_BYTES;
   const uint32_t ring = sbase + VidL::OFF_RING, bar = sbase + VidL::OFF_BAR;
   float* part = reinterpret_cast<float*>(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -95,20 +97,14 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
           y[i] = tap_sample(base + (size_t)(g * 8 + i) * hw, tp);
           yr[i] = fmaxf(y[i], 0.f);
         }
-        uint4 hi, lo;
-        const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
-        split8(y, hi, lo);
-        st_shared_v4(sbase + OCC_KG_XAH * KG_BYTES + off, hi);
-        st_shared_v4(sbase + OCC_KG_XAL * KG_BYTES + off, lo);
-        split8(yr, hi, lo);
-        st_shared_v4(sbase + OCC_KG_XBH * KG_BYTES + off, hi);
-        st_shared_v4(sbase + OCC_KG_XBL * KG_BYTES + off, lo);
+        store8<SCHEME>(xa_hi, xa_lo, row, ghalf * 4 + g, y);
+        store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g, yr);
       }
     };
     // net = relu(acc1 + b0) -> H quarters, published on A4..A7 (NQ = number of 64-column quarters: 3 for R1)
     auto stage_net = [&](const float* __restrict__ b0, int nq) {   // waits completion barrier D0 first
       float2 v[4][16];
-      biased_stage(tmem_lane, 0, sub, row, h_hi, h_lo, b0, nq, v, [&]() { wait_done(0); },
+      biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b0, nq, v, [&]() { wait_done(0); },
                    [](float2 t) { return relu_pair(t); }, signal, 4);
     };
 
@@ -130,13 +126,13 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
         drain128(tmem_lane, 256, sub, v);
         const float* b1 = vec + (blk == 1 ? VV_B11 : VV_B12);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) add_vec<16>(v[q], b1 + q * 64 + sub * 32);
+        for (int q = 0; q < 4; ++q) add_vec<SCHEME, 16>(v[q], b1 + q * 64 + sub * 32);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<false>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }      // raw h
+        for (int q = 0; q < 4; ++q) { put_quarter<false, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }      // raw h
         gather(tile, blk, 0);                                                                              // overlaps the shortcut GEMM
         wait_done(0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]); signal(4 + q); }   // relu(h) (+ piece 0)
+        for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(4 + q); }   // relu(h) (+ piece 0)
         wait_done(1);
         gather(tile, blk, 1); signal(0);
         wait_done(1);
@@ -152,8 +148,8 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
         drain128(tmem_lane, 256, sub, v);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          add_vec<16>(v[q], vec + VV_B13 + q * 64 + sub * 32);
-          put_quarter<true>(h_hi, h_lo, row, q, sub, v[q]);
+          add_vec<SCHEME, 16>(v[q], vec + VV_B13 + q * 64 + sub * 32);
+          put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]);
           signal(q);
         }
       }
@@ -166,7 +162,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
         float2 a3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          add_vec<16>(v[q], vec + VV_B14 + q * 64 + sub * 32);
+          add_vec<SCHEME, 16>(v[q], vec + VV_B14 + q * 64 + sub * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float2 u = __fmul2_rn(v[q][i], make_float2(0.2f, 0.2f));
@@ -196,7 +192,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       }
     }
   } else {
-    engine_service_warps<PAIR, VidL::RING_BYTES>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, VidL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -206,8 +202,9 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
 inline int launch_video_umma(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt,
                              int T, int H, int W, const void* gemm, size_t gemm_bytes, const uint32_t* program_host,
                              size_t program_words, const uint32_t* program_dev, const float* vec, size_t vec_floats,
-                             float* out, int pair, cudaStream_t st) {
+                             float* out, int pair, int f16f8, cudaStream_t st) {
   using namespace ummak;
+  DDMI_REQUIRE(!f16f8 || pair, "the f16f8 video kernel runs as CTA pairs only");
   if (C != 64) {
     set_error("tcgen05 video kernel is built for 64-channel planes");
     return DDMI_ERR_UNSUPPORTED;
@@ -230,11 +227,14 @@ inline int launch_video_umma(const PlaneSet& ps, int batch, int C, const float* 
   const uint8_t* ws = (const uint8_t*)gemm;
   const int tpi_i = (int)tpi;
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
-  if (pair) {
-    DDMI_CUDA(launch_engine(video_umma_kernel<1>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
+  if (f16f8) {
+    DDMI_CUDA(launch_engine(video_umma_kernel<1, 1>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
+                            total, ws, program_dev, vec, out));
+  } else if (pair) {
+    DDMI_CUDA(launch_engine(video_umma_kernel<1, 0>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
                             total, ws, program_dev, vec, out));
   } else {
-    DDMI_CUDA(launch_engine(video_umma_kernel<0>, 0, (unsigned)(total < sms ? total : sms), VID_SMEM, st, ps, cxy, cyt, cxt, T,
+    DDMI_CUDA(launch_engine(video_umma_kernel<0, 0>, 0, (unsigned)(total < sms ? total : sms), VID_SMEM, st, ps, cxy, cyt, cxt, T,
                             H, W, tpi_i, total, ws, program_dev, vec, out));
   }
   DDMI_CUDA(cudaGetLastError());

@@ -345,6 +345,9 @@ __device__ __forceinline__ void mma2_f8(uint32_t d_tmem, uint64_t adesc, uint64_
       : "memory");
 }
 
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, const uint2& v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 // 16 consecutive-K fp32 values of one row -> half of a K = 32 step of the three A operands:
 // a16[2] (2 K groups of 8 fp16), r8 (1 K group of 16 e4m3: S * (y - a16)), a8 (e4m3(y)).
 __device__ __forceinline__ void split16_f16f8(const float2* y, uint4 (&a16)[2], uint4& r8, uint4& a8) {
@@ -355,9 +358,10 @@ __device__ __forceinline__ void split16_f16f8(const float2* y, uint4 (&a16)[2], 
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const float2 v = y[2 * i + j];
-      const __half2 hp = __float22half2_rn(v);
-      h[2 * i + j] = *reinterpret_cast<const uint32_t*>(&hp);
-      const float2 hf = __half22float2(hp);
+      uint32_t hb;   // saturating: |v| > 65504 clamps (large but finite error) instead of turning into inf / NaN
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(v.y), "f"(v.x));
+      h[2 * i + j] = hb;
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hb));
       // S*v - S*hf: both products exact, the difference has <= 13 significant bits -> exact
       const float2 res = __ffma2_rn(hf, make_float2(-kF8Scale, -kF8Scale), __fmul2_rn(v, make_float2(kF8Scale, kF8Scale)));
       rp[j] = __nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);

@@ -58,11 +58,10 @@ __device__ __forceinline__ uint32_t op_n(uint32_t op) {
   return c == 0 ? 128u : (c == 2 ? 16u : (c == 3 ? 64u : 256u));
 }
 
-// SCHEME 0: bf16x3 (a step = 16 K columns, 64 B per weight row); SCHEME 1: f16f8 (a step = 32 K columns, 128 B per row)
-template <int PAIR, int RING_BYTES, int SCHEME = 0>
+template <int PAIR, int RING_BYTES>
 __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
                                               uint32_t ring, uint32_t bar, long long ntiles, uint32_t rank) {
-  constexpr uint32_t SLOT_BYTES = (PAIR ? 8192 : 16384) * (SCHEME ? 2 : 1), NSLOT = RING_BYTES / SLOT_BYTES;
+  constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
   uint32_t slot = 0, ph = 0;
   for (long long t = 0; t < ntiles; ++t) {
     const uint8_t* src = wstream;
@@ -71,7 +70,7 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
       const uint32_t kind = op & 3;
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
-      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64) * (SCHEME ? 2 : 1);    // this CTA's share of one K step
+      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64);    // this CTA's share of one K step
       const int cnt = (int)((op >> 24) & 31) + 1;
       for (int j = 0; j < cnt; ++j) {
         mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
@@ -87,9 +86,9 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
 }
 
 // Peer CTA of a pair: tell the leader when this CTA's half of each ring slot has landed.
-template <int RING_BYTES, int SCHEME = 0>
+template <int RING_BYTES>
 __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ program, uint32_t bar, long long ntiles) {
-  constexpr uint32_t NSLOT = RING_BYTES / (8192 * (SCHEME ? 2 : 1));
+  constexpr uint32_t NSLOT = RING_BYTES / 8192;
   uint32_t slot = 0, ph = 0;
   const uint32_t leader_pfull = mapa_rank(bar + BAR_PFULL, 0);
   for (long long t = 0; t < ntiles; ++t) {
@@ -111,11 +110,14 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
 // UNIT op = a run of `cnt` consecutive K steps of one (128 x PAIR?2:1) x N block; decoded once, then a
 // tight per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.  The whole warp runs the loop
 // (warp-uniform), one elected lane issues.
+// SCHEME 1 (f16f8, pairs only): same 16-wide steps, slots and A-operand stepping, but a step is TWO MMAs: the fp16 main
+// term (a16 x w16, K = 16) and one K = 32 e4m3 correction MMA -- r8 x w8 on even steps, a8 x s8 on odd steps of a
+// 32-wide pair (the A region keeps [r8 r8 a8 a8] K groups per pair, the slot [w16: 2 K groups | w8 or s8: 2 K groups]).
 template <int PAIR, int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
                                          uint32_t bar, uint32_t tmem, long long ntiles) {
   static_assert(SCHEME == 0 || PAIR == 1, "the f16f8 scheme is built for CTA pairs");
-  constexpr uint32_t SLOT_BYTES = (PAIR ? 8192 : 16384) * (SCHEME ? 2 : 1), NSLOT = RING_BYTES / SLOT_BYTES;
+  constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
   uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
   long long q_a = 0, q_w = 0;
   const long long q_start = clock64();
@@ -137,7 +139,7 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         // A operand: K groups of the shared-memory A region, or (bit 29, CTA pairs only) of tensor memory, where one
         // K group = 4 columns counted from the TMEM base (so K group 64 sits right behind a 256-column accumulator)
         const bool a_in_tmem = PAIR && ((op >> 29) & 1);
-        const uint32_t a_step = a_in_tmem ? 8u : (SCHEME ? 4 : 2) * (KG_BYTES >> 4);
+        const uint32_t a_step = a_in_tmem ? 8u : 2 * (KG_BYTES >> 4);
         uint32_t ahi32 = a_in_tmem ? tmem + ((op >> 8) & 0xFF) * 4 : a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
         uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
@@ -158,14 +160,9 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
           const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
           if (SCHEME) {
-            // f16f8: [w16: 4 K groups | w8: 2 | s8: 2] x nloc rows x 16 B;  A: fp16 groups at ahi32, [r8 r8 a8 a8] at alo32
-            const uint64_t ahi2 = kDescHi | (ahi32 + 2 * (KG_BYTES >> 4)), aa8 = kDescHi | (alo32 + 2 * (KG_BYTES >> 4));
-            const uint64_t bhi2 = kDescHi | (wlo + nloc * 2), bw8 = kDescHi | (wlo + nloc * 4), bs8 = kDescHi | (wlo + nloc * 6);
             if (elect_one()) {
-              mma2_bf16(acc, ahi, bhi, idesc, accum);
-              mma2_bf16(acc, ahi2, bhi2, idesc, 1u);
-              mma2_f8(acc, alo, bw8, idesc8, 1u);
-              mma2_f8(acc, aa8, bs8, idesc8, 1u);
+              mma2_bf16(acc, ahi, bhi, idesc, accum);     // kind::f16, fp16 formats (idesc)
+              mma2_f8(acc, alo, blo, idesc8, 1u);         // K = 32: the step pair's r8 x w8 (even) / a8 x s8 (odd)
               mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
             }
           } else if (elect_one()) {
@@ -247,6 +244,64 @@ __device__ __forceinline__ void store_act(uint32_t h_hi, uint32_t h_lo, int row,
   }
 }
 
+// SCHEME-generic epilogue pieces (SCHEME 0: bf16x3, h_hi / h_lo = bases of the bf16 hi / lo K groups of an operand
+// region; SCHEME 1: f16f8, h_hi = base of its fp16 K groups, h_lo = base of its FP8 K groups [r8 r8 a8 a8] per 32 columns,
+// and accumulators hold 4096 x the GEMM result).
+template <int SCHEME>
+__device__ __forceinline__ float2 acc_plus(float2 acc, float2 b) {   // accumulator value (de-scaled) + b
+  return SCHEME ? __ffma2_rn(acc, make_float2(kF8InvScale, kF8InvScale), b) : __fadd2_rn(acc, b);
+}
+// 16 consecutive columns starting at col0 (a multiple of 16)
+template <int SCHEME>
+__device__ __forceinline__ void store16(uint32_t h_hi, uint32_t h_lo, int row, int col0, const float2 (&y)[8]) {
+  if (SCHEME) {
+    uint4 a16[2], r8, a8;
+    split16_f16f8(y, a16, r8, a8);
+    const uint32_t o16 = (uint32_t)((col0 / 8) * KG_BYTES + row * 16);
+    const uint32_t o8 = (uint32_t)(((col0 / 32) * 4 + ((col0 / 16) & 1)) * KG_BYTES + row * 16);
+    st_shared_v4(h_hi + o16, a16[0]);
+    st_shared_v4(h_hi + o16 + KG_BYTES, a16[1]);
+    st_shared_v4(h_lo + o8, r8);
+    st_shared_v4(h_lo + o8 + 2 * KG_BYTES, a8);
+  } else {
+    store_act<8>(h_hi, h_lo, row, col0, y);
+  }
+}
+// 8 consecutive columns = K group kg of the region (gathers: one thread owns 8 channels at a time)
+template <int SCHEME>
+__device__ __forceinline__ void store8(uint32_t h_hi, uint32_t h_lo, int row, int kg, const float (&y)[8]) {
+  if (SCHEME) {
+    uint32_t h[4], r[2], a[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      uint32_t rp[2], ap[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 v = make_float2(y[4 * i + 2 * j], y[4 * i + 2 * j + 1]);
+        uint32_t hb;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(v.y), "f"(v.x));
+        h[2 * i + j] = hb;
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hb));
+        const float2 res = __ffma2_rn(hf, make_float2(-kF8Scale, -kF8Scale), __fmul2_rn(v, make_float2(kF8Scale, kF8Scale)));
+        rp[j] = __nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);
+        ap[j] = __nv_cvt_float2_to_fp8x2(v, __NV_SATFINITE, __NV_E4M3);
+      }
+      r[i] = rp[0] | (rp[1] << 16);
+      a[i] = ap[0] | (ap[1] << 16);
+    }
+    st_shared_v4(h_hi + (uint32_t)(kg * KG_BYTES + row * 16), make_uint4(h[0], h[1], h[2], h[3]));
+    const uint32_t o8 = (uint32_t)(((kg >> 2) * 4 + ((kg >> 1) & 1)) * KG_BYTES + row * 16 + (kg & 1) * 8);
+    st_shared_v2(h_lo + o8, make_uint2(r[0], r[1]));
+    st_shared_v2(h_lo + o8 + 2 * KG_BYTES, make_uint2(a[0], a[1]));
+  } else {
+    uint4 hi, lo;
+    split8(y, hi, lo);
+    const uint32_t off = (uint32_t)(kg * KG_BYTES + row * 16);
+    st_shared_v4(h_hi + off, hi);
+    st_shared_v4(h_lo + off, lo);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // kernel prologue / epilogue shared by every decoder
 // ---------------------------------------------------------------------------
@@ -291,10 +346,10 @@ __device__ __forceinline__ void engine_service_warps(const uint32_t* __restrict_
   reg_dec<72>();   // the whole third warpgroup (warps 8-11) executes this one instruction
   const int warp = threadIdx.x >> 5;
   if (warp == 8) {
-    producer_loop<PAIR, RING_BYTES, SCHEME>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
+    producer_loop<PAIR, RING_BYTES>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
   } else if (warp == 9) {
     if (rank == 0) mma_loop<PAIR, RING_BYTES, SCHEME>(program, sbase, ring, bar, tmem, ntiles);
-    else forward_loop<RING_BYTES, SCHEME>(program, bar, ntiles);
+    else forward_loop<RING_BYTES>(program, bar, ntiles);
   }
 }
 
@@ -325,14 +380,14 @@ static inline cudaError_t launch_engine(Kernel kernel, int pair, unsigned ctas, 
 }
 
 // Walk a program on the host: number of weight bytes it consumes; -1 if malformed.
-static inline long long program_stream_bytes(const uint32_t* prog, size_t words, int f16f8 = 0) {
+static inline long long program_stream_bytes(const uint32_t* prog, size_t words) {
   long long bytes = 0;
   for (size_t i = 0; i < words; ++i) {
     const uint32_t kind = prog[i] & 3;
     if (kind == OP_END) return (i + 1 < words) ? bytes : -1;   // needs >= 1 END of padding after the first
     if (kind == OP_UNIT) {
       const uint32_t c = (prog[i] >> 2) & 3;
-      bytes += (long long)(c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 16 : 64))) * (f16f8 ? 128 : 64) * (((prog[i] >> 24) & 31) + 1);
+      bytes += (long long)(c == 0 ? 128 : (c == 1 ? 256 : (c == 2 ? 16 : 64))) * 64 * (((prog[i] >> 24) & 31) + 1);
     }
   }
   return -1;

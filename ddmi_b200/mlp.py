@@ -129,7 +129,7 @@ class MLP(_FusedDecoder):
 class MLP3D(_FusedDecoder):
     """Occupancy decoder.  Reference: models/d2c_vae/mlp.py:69-111."""
 
-    _supported = ('fp32', 'bf16x3')
+    _supported = ('fp32', 'bf16x3', 'f16f8')
     _default_precision = 'bf16x3'
 
     def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None):
@@ -169,12 +169,12 @@ class MLP3D(_FusedDecoder):
             base = pts.contiguous()
             bstride = n * 3
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
-        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'
+        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0' or prec == _lib.PREC_F16F8
         packed = self._packed(('occ', prec, pair), lambda: packing.pack_occupancy(self, prec, pair))
         logits = torch.empty((b, n), device=base.device, dtype=torch.float32)
         with torch.cuda.device(base.device):
             st = _stream_ptr(base.device)
-            if prec == _lib.PREC_BF16X3:     # scattered queries: channels-last planes, float4 gathers
+            if prec != _lib.PREC_FP32:       # scattered queries: channels-last planes, float4 gathers
                 keep, arr = _lib.planes_channels_last(planes, st)
                 layout = 1
             else:
@@ -194,7 +194,7 @@ class MLP3D(_FusedDecoder):
 class MLPVideo(_FusedDecoder):
     """Video decoder.  Reference: models/d2c_vae/mlp.py:114-157."""
 
-    _supported = ('fp32', 'bf16x3')
+    _supported = ('fp32', 'bf16x3', 'f16f8')
     _default_precision = 'bf16x3'
 
     def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None, **ignore_kwargs):
@@ -235,7 +235,7 @@ class MLPVideo(_FusedDecoder):
         if tuple(cyt.shape[1:]) != (2, T, H) or tuple(cxt.shape[1:]) != (2, T, W):
             raise RuntimeError("inconsistent coords grids: expected xy (1,2,H,W), yt (1,2,T,H), xt (1,2,T,W)")
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
-        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'
+        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0' or prec == _lib.PREC_F16F8
         packed = self._packed(('video', prec, pair), lambda: packing.pack_video(self, prec, pair))
         out = torch.empty((b, self.out_ch, T * H * W), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):

@@ -10,8 +10,9 @@ order and format a kernel family streams them:
   (``W[:, seg].T``), K padded to a multiple of 16 with zero rows.
 * ``PREC_BF16X3`` : per 16-wide K step a ``[hi | lo]`` pair of bf16 blocks in the
   tcgen05 shared-memory "core matrix" order, in consumption order.
-* ``PREC_F16F8``  : per 32-wide K step ``[fp16(S W) | e4m3(W) | e4m3(S W - fp16(S W))]``
-  (S = 4096) in the same core-matrix order (csrc/umma.cuh, "f16f8" scheme).
+* ``PREC_F16F8``  : per 16-wide K step ``[fp16(S W) | FP8 block of the step's 32-wide pair]``
+  (S = 4096; even step: ``e4m3(W)``, odd step: ``e4m3(S W - fp16(S W))``) in the same
+  core-matrix order and slot size (csrc/umma.cuh, "f16f8" scheme).
 
 Both formats share one ``vec`` blob of fp32 vectors (biases, folded constants,
 the narrow output heads that run in the epilogue).
@@ -54,8 +55,9 @@ class UmmaProgram:
         self.ops = []
         self.segs = []
         self.pair = pair      # CTA pairs: each K step is stored as [rows 0..N/2-1 | rows N/2..N-1]
-        # 'f16f8': a step is 32 wide (2 fp16 MMAs + 2 e4m3 MMAs); [15:8] = first fp16 K group (advances 4 per step),
-        # [23:16] = first K group of the step's FP8 operands [r8 r8 a8 a8] (advances 4 per step); pairs only.
+        # 'f16f8': same 16-wide steps, always in 32-wide pairs (fp16 MMA + one K = 32 e4m3 MMA each: r8 x w8 on the even
+        # step, a8 x s8 on the odd one); [15:8] = first fp16 K group, [23:16] = first K group of the FP8 operands
+        # [r8 r8 a8 a8] per pair -- both advance 2 per step like the bf16 hi / lo groups; pairs only.
         self.scheme = scheme
         assert scheme in ('bf16x3', 'f16f8') and (scheme == 'bf16x3' or pair)
 
@@ -66,12 +68,12 @@ class UmmaProgram:
         assert n in self.NCODE and acc_col % 64 == 0 and acc_col + n <= 512
         if self.scheme == 'f16f8':
             k32 = (W.shape[1] + 31) // 32
-            assert not a_in_tmem and 1 <= k32 <= 32 and a_hi_kg + 4 * k32 <= 256 and a_lo_kg + 4 * k32 <= 256
+            assert not a_in_tmem and 1 <= k32 <= 16 and a_hi_kg + 4 * k32 <= 256 and a_lo_kg + 4 * k32 <= 256
             self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
-                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((k32 - 1) << 24))
+                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((2 * k32 - 1) << 24))
             Wp = W.new_zeros(n, 32 * k32)
             Wp[:W.shape[0], :W.shape[1]] = W
-            halves = [f16f8_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)]).reshape(k32, -1) for h in (0, 1)]
+            halves = [f16f8_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)]).reshape(2 * k32, -1) for h in (0, 1)]
             self.segs.append(torch.cat(halves, dim=1).reshape(-1))
             return
         k16 = (W.shape[1] + 15) // 16
@@ -107,8 +109,9 @@ F8_SCALE = 4096.0
 
 
 def f16f8_kstep_blocks(W):
-    """Pack W (N, K), K a multiple of 32, for the f16f8 tcgen05 kernels: a flat uint8 tensor, per 32-wide K step
-    [fp16(S W): 4 K groups x N rows x 8 halves | e4m3(W): 2 K groups x N rows x 16 bytes | e4m3(S W - fp16(S W)): same].
+    """Pack W (N, K), K a multiple of 32, for the f16f8 tcgen05 kernels: a flat uint8 tensor, per 16-wide K step
+    [fp16(S W[:, step]): 2 K groups x N rows x 8 halves | FP8: 2 K groups x N rows x 16 bytes], where the FP8 block
+    covers the 32-wide PAIR the step belongs to: e4m3(W) on the even step, e4m3(S W - fp16(S W)) on the odd step.
     Raises if a weight does not fit fp16 after scaling (|W| >= 16)."""
     W = W.to(torch.float32)
     n, k = W.shape
@@ -120,10 +123,10 @@ def f16f8_kstep_blocks(W):
     res = ws - w16.to(torch.float32)
     w8 = W.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
     s8 = res.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
-    p16 = w16.reshape(n, k // 32, 4, 8).permute(1, 2, 0, 3).contiguous().view(torch.uint8).reshape(k // 32, -1)
-    p8 = [t.reshape(n, k // 32, 2, 16).permute(1, 2, 0, 3).contiguous().view(torch.uint8).reshape(k // 32, -1)
-          for t in (w8, s8)]
-    return torch.cat([p16] + p8, dim=1).reshape(-1)
+    p16 = w16.reshape(n, k // 16, 2, 8).permute(1, 2, 0, 3).contiguous().view(torch.uint8).reshape(k // 32, 2, -1)
+    p8 = torch.stack([t.reshape(n, k // 32, 2, 16).permute(1, 2, 0, 3).contiguous().view(torch.uint8).reshape(k // 32, -1)
+                      for t in (w8, s8)], dim=1)                      # (pairs, even / odd step, bytes)
+    return torch.cat([p16, p8], dim=2).reshape(-1)
 
 
 # ---------------------------------------------------------------------------
@@ -360,13 +363,13 @@ def _pack_resnet_chain(p, kx, precision):
     return segs, vec
 
 
-def _pack_occupancy_umma(p, pair):
+def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3):
     """Program + stream + vec of csrc/decode_umma_occ.cuh.  A-region K groups: H hi 0..31, H lo 32..63,
     Xa (raw PE) hi 64..71 / lo 80..87, Xb (relu PE) hi 72..79 / lo 88..95; acc1 = TMEM cols 0.., acc2 = 256..
     Each ResnetBlockFC with a shortcut is three GEMM groups: shortcut on RAW h -> acc2, fc_0 on relu(h) -> acc1,
     fc_1 on relu(net) accumulated ONTO acc2.  K runs over h follow the epilogue's quarter-by-quarter publication."""
-    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88
-    P = UmmaProgram(pair=pair)
+    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
+    P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
     def wait_all():
         for q in range(4):
@@ -405,13 +408,13 @@ def _pack_occupancy_umma(p, pair):
                      p['net_res4.fc_0.bias'], p['net_res3.fc_1.bias'] + p['net_res4.fc_1.bias'],
                      p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]).to(torch.float32).contiguous()
     gemm, prog_dev, prog_host = P.finish(vec.device)
-    return Packed(PREC_BF16X3, gemm, vec, prog_dev, prog_host, pair)
+    return Packed(precision, gemm, vec, prog_dev, prog_host, pair)
 
 
 def pack_occupancy(module, precision=PREC_FP32, pair=True):
     p = _params64(module)
-    if precision == PREC_BF16X3:
-        return _pack_occupancy_umma(p, pair)
+    if precision in (PREC_BF16X3, PREC_F16F8):
+        return _pack_occupancy_umma(p, pair, precision)
     segs, vec = _pack_resnet_chain(p, 64, precision)
     vec[1] = vec[1] + p['net_p.bias']                       # net_p bias rides on R1.fc_1's
     vec += [p['net_p.weight'].t().contiguous().reshape(-1),  # [3][256]
@@ -420,13 +423,13 @@ def pack_occupancy(module, precision=PREC_FP32, pair=True):
                   torch.cat(vec).to(torch.float32).contiguous())
 
 
-def _pack_video_umma(p, pair):
+def _pack_video_umma(p, pair, precision=PREC_BF16X3):
     """Program + stream + vec of csrc/decode_umma_video.cuh (the protocol is spelled out there).  A-region K groups
     as for occupancy: H hi 0..31 / lo 32..63, Xa (raw piece) hi 64..71 / lo 80..87, Xb (relu piece) hi 72..79 / lo 88..95.
     Operand barriers: 0..3 raw-h quarters / R1 pieces / later pieces, 4..7 relu-h and net quarters.
     Completion barriers: D0 = "accumulators final for this phase", D1 = "piece consumed, Xa / Xb free"."""
-    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88
-    P = UmmaProgram(pair=pair)
+    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
+    P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
     def piece(Ws, W0, col0, first, n0_split):
         """one 64-wide piece: fc_0 (relu piece, acc1) and shortcut (raw piece, acc2)"""
@@ -485,13 +488,13 @@ def _pack_video_umma(p, pair):
                      p['net_res3.fc_1.bias'] + p['net_res4.fc_1.bias'], p['net_out.weight'].reshape(-1),
                      p['net_out.bias'].reshape(-1)]).to(torch.float32).contiguous()
     gemm, prog_dev, prog_host = P.finish(vec.device)
-    return Packed(PREC_BF16X3, gemm, vec, prog_dev, prog_host, pair)
+    return Packed(precision, gemm, vec, prog_dev, prog_host, pair)
 
 
 def pack_video(module, precision=PREC_FP32, pair=True):
     p = _params64(module)
-    if precision == PREC_BF16X3:
-        return _pack_video_umma(p, pair)
+    if precision in (PREC_BF16X3, PREC_F16F8):
+        return _pack_video_umma(p, pair, precision)
     segs, vec = _pack_resnet_chain(p, 192, precision)
     vec += [p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]
     return Packed(precision, torch.cat(segs).to(torch.float32).contiguous(),

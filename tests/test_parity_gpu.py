@@ -85,7 +85,7 @@ def test_image_style_cache_tracks_si_and_weights():
 
 
 # ---------------------------------------------------------------- occupancy
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_occupancy_golden(golden_dir, precision):
     g = _golden(golden_dir, 'occupancy')
     m = cases.build_module('occupancy').to(DEV)
@@ -98,7 +98,7 @@ def test_occupancy_golden(golden_dir, precision):
     assert _sign_agreement(out, g['out']) >= 0.9999
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_occupancy_shared_points_and_single_point(precision):
     m = cases.build_module('occupancy').to(DEV)
     m.precision = precision
@@ -128,7 +128,7 @@ def test_occupancy_dense_grid_chunks_like_eval_points():
 
 
 # ---------------------------------------------------------------- video
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_video_golden(golden_dir, precision):
     g = _golden(golden_dir, 'video')
     m = cases.build_module('video').to(DEV)
@@ -139,7 +139,7 @@ def test_video_golden(golden_dir, precision):
     assert float((out - g['out']).abs().max()) < (2e-5 if precision == 'fp32' else TOL)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_video_batch_and_anisotropic(precision):
     m = cases.build_module('video').to(DEV)
     m.precision = precision
@@ -285,7 +285,8 @@ def test_f16f8_selftest(N, K):
 
 
 # ---------------------------------------------------------------- size-independent properties at larger shapes
-def test_image_full_size_cross_check_and_crop_independence():
+@pytest.mark.parametrize("scheme", ["bf16x3", "f16f8"])
+def test_image_full_size_cross_check_and_crop_independence(scheme):
     """BASELINE configs[0]-size grid (256^2) and an up-sampled 512^2 grid: the tcgen05 kernel agrees with the fp32
     CUDA-core kernel to 1e-3, and decoding a crop of the coordinates reproduces the crop of the full decode
     (results do not depend on how rows fall into tiles / CTA pairs)."""
@@ -296,12 +297,14 @@ def test_image_full_size_cross_check_and_crop_independence():
         e = (R - 1) / R
         coords = ddmi_b200.convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(DEV)
         si = ddmi_b200.get_scale_injection(R)
-        m.precision = 'bf16x3'
+        m.precision = scheme
         full = m(coords, hdbf=planes, si=si)
         m.precision = 'fp32'
         exact = m(coords, hdbf=planes, si=si)
-        assert float((full - exact).abs().max()) < TOL
-        m.precision = 'bf16x3'
+        err = float((full - exact).abs().max())
+        print(f"image {R}x{R} {scheme} vs fp32 kernel: max abs {err:.3e}")
+        assert err < TOL
+        m.precision = scheme
         crop = m(coords[:, :, 37:101, 5:R - 3], hdbf=planes, si=si)
         assert torch.equal(crop, full[:, :, 37:101, 5:R - 3])
         one = m(coords, hdbf=[p[1:2] for p in planes], si=si)

@@ -78,9 +78,9 @@ class EngineModel:
 
 
 class EngineModelF16F8(EngineModel):
-    """The f16f8 scheme (csrc/umma.cuh): a UNIT step is 32 wide; the A region holds fp16 K groups (8 wide) at
-    [15:8] and per step four FP8 K groups [r8 r8 a8 a8] (16 wide) at [23:16]; the stream holds per step and CTA half
-    [fp16(S W) | e4m3(W) | e4m3(S W - fp16(S W))]; accumulators hold S x the product."""
+    """The f16f8 scheme (csrc/umma.cuh): 16-wide steps in 32-wide pairs; the A region holds fp16 K groups (8 wide) at
+    [15:8] and per pair four FP8 K groups [r8 r8 a8 a8] (16 wide) at [23:16]; the stream holds per step and CTA half
+    [fp16(S W) | e4m3(W) (even step) or e4m3(S W - fp16(S W)) (odd step) of the pair]; accumulators hold S x the product."""
     S = 4096.0
 
     def __init__(self, packed, rows):
@@ -120,19 +120,18 @@ class EngineModelF16F8(EngineModel):
                 nloc = n // 2
                 accum, col = (op >> 4) & 1, ((op >> 5) & 7) * 64
                 kg16, kg8, cnt = (op >> 8) & 0xFF, (op >> 16) & 0xFF, ((op >> 24) & 31) + 1
+                assert cnt % 2 == 0                                     # steps come in 32-wide pairs
                 for j in range(cnt):
-                    W16, W8, S8 = torch.zeros(n, 32), torch.zeros(n, 32), torch.zeros(n, 32)
+                    W16, F8 = torch.zeros(n, 16), torch.zeros(n, 32)
                     for h in range(2):
-                        b = self.stream[self.pos:self.pos + nloc * 128]
-                        self.pos += nloc * 128
+                        b = self.stream[self.pos:self.pos + nloc * 64]
+                        self.pos += nloc * 64
                         rows = slice(h * nloc, (h + 1) * nloc)
-                        W16[rows] = b[:nloc * 64].view(torch.float16).float().reshape(4, nloc, 8).permute(1, 0, 2).reshape(nloc, 32)
-                        W8[rows] = b[nloc * 64:nloc * 96].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
-                        S8[rows] = b[nloc * 96:].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
-                    a16 = self.A16[:, (kg16 + 4 * j) * 8:(kg16 + 4 * j) * 8 + 32]
-                    r8 = self.A8[:, (kg8 + 4 * j) * 16:(kg8 + 4 * j) * 16 + 32]
-                    a8 = self.A8[:, (kg8 + 4 * j + 2) * 16:(kg8 + 4 * j + 2) * 16 + 32]
-                    d = (a16 @ W16.t() + r8 @ W8.t() + a8 @ S8.t()) / self.S
+                        W16[rows] = b[:nloc * 32].view(torch.float16).float().reshape(2, nloc, 8).permute(1, 0, 2).reshape(nloc, 16)
+                        F8[rows] = b[nloc * 32:].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
+                    a16 = self.A16[:, (kg16 + 2 * j) * 8:(kg16 + 2 * j) * 8 + 16]
+                    a8 = self.A8[:, (kg8 + 2 * j) * 16:(kg8 + 2 * j) * 16 + 32]     # even step: r8, odd step: a8
+                    d = (a16 @ W16.t() + a8 @ F8.t()) / self.S
                     self.acc[:, col:col + n] = d + (self.acc[:, col:col + n] if (accum or j > 0) else 0)
 
 
@@ -174,11 +173,15 @@ def test_image_program_and_stream_reproduce_the_oracle(pair, scheme):
 def test_programs_consume_exactly_their_streams():
     for packed in (packing.pack_occupancy(cases.build_module('occupancy'), _lib.PREC_BF16X3),
                    packing.pack_video(cases.build_module('video'), _lib.PREC_BF16X3),
-                   packing.pack_nerf(cases.build_module('nerf'), _lib.PREC_BF16X3)):
+                   packing.pack_nerf(cases.build_module('nerf'), _lib.PREC_BF16X3),
+                   packing.pack_occupancy(cases.build_module('occupancy'), _lib.PREC_F16F8),
+                   packing.pack_video(cases.build_module('video'), _lib.PREC_F16F8)):
         ops = packed.program_host.tolist()
         assert ops[-4:] == [3, 3, 3, 3] and all(o & 3 != 3 for o in ops[:-4])
         need = sum(NCODE[(o >> 2) & 3] * 64 * (((o >> 24) & 31) + 1) for o in ops if o & 3 == 0)
-        assert need == packed.gemm.numel() * 2
+        assert need == packed.gemm.numel() * packed.gemm.element_size()
+        if packed.precision == _lib.PREC_F16F8:     # 16-wide steps come in 32-wide pairs
+            assert all((((o >> 24) & 31) + 1) % 2 == 0 for o in ops if o & 3 == 0)
         # every accumulator region is started with accumulate = 0 before it is accumulated into
         assert any(o & 3 == 0 and not (o >> 4) & 1 for o in ops)
 
