@@ -33,7 +33,7 @@ int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long lo
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
 int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
 int launch_nerf_composite(const float*, const float*, int, const float*, int, long long, int, int, float*, cudaStream_t);
-int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, cudaStream_t);
+int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_selftest_f16f8(const float*, const float*, float*, int, int, cudaStream_t);
@@ -253,7 +253,7 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
   }
   DDMI_REQUIRE(weights != nullptr, "weights is NULL");
   DDMI_REQUIRE(raw == nullptr || ((uintptr_t)raw & 15) == 0, "raw must be 16-byte aligned");
-  if (weights->precision == DDMI_PREC_BF16X3) {
+  if (weights->precision == DDMI_PREC_BF16X3 || weights->precision == DDMI_PREC_F16F8) {
     // tcgen05 kernel: channels-last planes, CTA pairs; compositing is fused when one tile is one ray
     if (plane_layout != DDMI_LAYOUT_NHWC || !(weights->reserved & 1)) {
       set_error("the tcgen05 NeRF kernel needs channels-last planes and pair-packed weights");
@@ -266,7 +266,7 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
     rc = launch_nerf_umma_entry(ps, batch, channels, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent,
                                 negative_slope, white_bkgd, weights->gemm, weights->gemm_bytes, weights->program_host,
                                 weights->program_words, weights->program, weights->vec, weights->vec_floats, rgb_map, raw,
-                                fuse, (cudaStream_t)stream);
+                                fuse, weights->precision == DDMI_PREC_F16F8, (cudaStream_t)stream);
     if (rc || fuse) return rc;
     return launch_nerf_composite(raw, rays, ray_stride, t_vals, n_samples, n_rays, batch, white_bkgd, rgb_map,
                                  (cudaStream_t)stream);

@@ -141,7 +141,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int C = 64;
-  const uint32_t tmem = engine_begin<PAIR>(smem, ImgL::OFF_BAR);
+  const uint32_t tmem = engine_begin<PAIR, SCHEME>(smem, ImgL::OFF_BAR);
 
   // work split: CTA (or CTA pair) w of W takes iterations w, w + W, ...; a pair iteration = tiles 2u and 2u + 1
   const long long nwork = PAIR ? (total_tiles + 1) / 2 : total_tiles;
@@ -275,7 +275,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       atomicAdd(&g_prof[2], (unsigned long long)p_gather);
     }
   } else {
-    engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME, 0>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -422,9 +422,9 @@ int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* ra
                            const float* t_vals, int n_samples, float plane_extent, float slope, int white_bkgd,
                            const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                            const uint32_t* program_dev, const float* vec, size_t vec_floats, float* rgb_map, float* raw,
-                           int fuse, cudaStream_t st) {
+                           int fuse, int f16f8, cudaStream_t st) {
   return launch_nerf_umma(ps, batch, C, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent, slope, white_bkgd, gemm,
-                          gemm_bytes, program_host, program_words, program_dev, vec, vec_floats, rgb_map, raw, fuse, st);
+                          gemm_bytes, program_host, program_words, program_dev, vec, vec_floats, rgb_map, raw, fuse, f16f8, st);
 }
 
 int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt, int T,

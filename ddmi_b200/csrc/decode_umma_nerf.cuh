@@ -32,6 +32,27 @@ __device__ __forceinline__ float2 lrelu_pair(float2 t, float slope) {
   return make_float2(fmaxf(t.x, 0.f) + slope * fminf(t.x, 0.f), fmaxf(t.y, 0.f) + slope * fminf(t.y, 0.f));
 }
 
+// K group j (8 columns of X) of this thread's row -> tensor memory.  SCHEME 1: fp16 group at XH + j, and 8 bytes each of
+// the pair's r8 / a8 groups ([r8 r8 a8 a8] per 32 columns behind XL; 8 bytes = 2 TMEM columns)
+template <int SCHEME>
+__device__ __forceinline__ void x_store8(uint32_t tmem_lane, int j, const float (&y)[8]) {
+  if (SCHEME) {
+    uint4 a16;
+    uint2 r8, a8;
+    split8_f16f8(y, a16, r8, a8);
+    tmem_st4(tmem_lane + (NRF_KG_XH + j) * 4, a16);
+    const uint32_t c8 = (uint32_t)((NRF_KG_XL + (j >> 2) * 4) * 4 + (j & 3) * 2);
+    tmem_st2(tmem_lane + c8, r8);
+    tmem_st2(tmem_lane + c8 + 8, a8);
+  } else {
+    uint4 hi, lo;
+    split8(y, hi, lo);
+    tmem_st4(tmem_lane + (NRF_KG_XH + j) * 4, hi);
+    tmem_st4(tmem_lane + (NRF_KG_XL + j) * 4, lo);
+  }
+}
+
+template <int SCHEME>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
                  int n_samples, float plane_extent, long long n /* rows per object */, int tiles_per_item,
@@ -46,7 +67,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
   float* scratch = reinterpret_cast<float*>(smem + NRF_OFF_SCRATCH);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t tmem = engine_begin<PAIR>(smem, NrfL::OFF_BAR);
+  const uint32_t tmem = engine_begin<PAIR, SCHEME>(smem, NrfL::OFF_BAR);
 
   const long long nwork = (total_tiles + 1) / 2;
   const long long wfirst = blockIdx.x / 2, wstride = gridDim.x / 2;
@@ -124,17 +145,14 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] = embed_elem(p, (j - 12) * 8 + i, 63);
         }
-        uint4 hi, lo;
-        split8(y, hi, lo);
-        tmem_st4(tmem_lane + (NRF_KG_XH + j) * 4, hi);
-        tmem_st4(tmem_lane + (NRF_KG_XL + j) * 4, lo);
+        x_store8<SCHEME>(tmem_lane, j, y);
       }
       tmem_st_wait();
     };
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
     auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {   // waits for the GEMM first
       const float sl = act ? slope : 1.f;
-      biased_stage<0>(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
+      biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
     };
 
     if (ntiles > 0) {
@@ -161,10 +179,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
               float y[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) y[i] = embed_elem(vd, j * 8 + i, 27);
-              uint4 hi, lo;
-              split8(y, hi, lo);
-              tmem_st4(tmem_lane + (NRF_KG_XH + j) * 4, hi);
-              tmem_st4(tmem_lane + (NRF_KG_XL + j) * 4, lo);
+              x_store8<SCHEME>(tmem_lane, j, y);
             }
             tmem_st_wait();
           }
@@ -198,7 +213,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         float2 acc3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          add_vec<0, 16>(v[q], vec + NV_BD + q * 64 + sub * 32);
+          add_vec<SCHEME, 16>(v[q], vec + NV_BD + q * 64 + sub * 32);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[q][i] = lrelu_pair(v[q][i], slope);
 #pragma unroll
@@ -275,7 +290,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       }
     }
   } else {
-    engine_service_warps<PAIR, NrfL::RING_BYTES>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, NrfL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -286,7 +301,7 @@ inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* r
                             const float* t_vals, int n_samples, float plane_extent, float slope, int white_bkgd,
                             const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                             const uint32_t* program_dev, const float* vec, size_t vec_floats, float* rgb_map, float* raw,
-                            int fuse, cudaStream_t st) {
+                            int fuse, int f16f8, cudaStream_t st) {
   using namespace ummak;
   DDMI_REQUIRE(program_host && program_dev && program_words >= 2, "bf16x3 weights carry no MMA program");
   const long long need = program_stream_bytes(program_host, program_words);
@@ -304,10 +319,17 @@ inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* r
     return DDMI_ERR_UNSUPPORTED;
   }
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
-  DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
-  nerf_umma_kernel<<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
-      ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
-      (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
+  if (f16f8) {
+    DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
+    nerf_umma_kernel<1><<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
+        ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
+        (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
+  } else {
+    DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
+    nerf_umma_kernel<0><<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
+        ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
+        (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
+  }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

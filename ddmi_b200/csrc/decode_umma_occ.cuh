@@ -112,7 +112,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int C = 64;
-  const uint32_t tmem = engine_begin<PAIR>(smem, OccL::OFF_BAR);
+  const uint32_t tmem = engine_begin<PAIR, SCHEME>(smem, OccL::OFF_BAR);
 
   const long long nwork = PAIR ? (total_tiles + 1) / 2 : total_tiles;
   const long long wfirst = PAIR ? blockIdx.x / 2 : blockIdx.x, wstride = PAIR ? gridDim.x / 2 : gridDim.x;
@@ -328,7 +328,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       if (it + 1 < ntiles) signal_all();
     }
   } else {
-    engine_service_warps<PAIR, OccL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, OccL::RING_BYTES, SCHEME, 0>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }

@@ -47,7 +47,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int C = 64;
   const long long n = (long long)T * Hh * Ww;
-  const uint32_t tmem = engine_begin<PAIR>(smem, VidL::OFF_BAR);
+  const uint32_t tmem = engine_begin<PAIR, SCHEME>(smem, VidL::OFF_BAR);
 
   const long long nwork = PAIR ? (total_tiles + 1) / 2 : total_tiles;
   const long long wfirst = PAIR ? blockIdx.x / 2 : blockIdx.x, wstride = PAIR ? gridDim.x / 2 : gridDim.x;
@@ -192,7 +192,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       }
     }
   } else {
-    engine_service_warps<PAIR, VidL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, VidL::RING_BYTES, SCHEME, 0>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }

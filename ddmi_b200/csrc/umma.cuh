@@ -297,6 +297,9 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint2& v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v.x), "r"(v.y) : "memory");
+}
 // arrive on the mbarrier at this offset in every CTA of `mask` once all prior MMAs of the pair completed
 __device__ __forceinline__ void mma2_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -345,8 +348,41 @@ __device__ __forceinline__ void mma2_f8(uint32_t d_tmem, uint64_t adesc, uint64_
       : "memory");
 }
 
+// 8 consecutive-K fp32 values -> a16 (8 halves), r8 / a8 (8 bytes each)
+__device__ __forceinline__ void split8_f16f8(const float (&y)[8], uint4& a16, uint2& r8, uint2& a8) {
+  uint32_t h[4], r[2], a[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint32_t rp[2], ap[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float2 v = make_float2(y[4 * i + 2 * j], y[4 * i + 2 * j + 1]);
+      uint32_t hb;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(v.y), "f"(v.x));
+      h[2 * i + j] = hb;
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hb));
+      const float2 res = __ffma2_rn(hf, make_float2(-kF8Scale, -kF8Scale), __fmul2_rn(v, make_float2(kF8Scale, kF8Scale)));
+      rp[j] = __nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);
+      ap[j] = __nv_cvt_float2_to_fp8x2(v, __NV_SATFINITE, __NV_E4M3);
+    }
+    r[i] = rp[0] | (rp[1] << 16);
+    a[i] = ap[0] | (ap[1] << 16);
+  }
+  a16 = make_uint4(h[0], h[1], h[2], h[3]);
+  r8 = make_uint2(r[0], r[1]);
+  a8 = make_uint2(a[0], a[1]);
+}
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, const uint2& v) {
   asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+// kind::f8f6f4 with the A operand in tensor memory (8-bit elements packed along K, four per 32-bit column: K = 32 = 8 columns)
+__device__ __forceinline__ void mma2_f8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // 16 consecutive-K fp32 values of one row -> half of a K = 32 step of the three A operands:
 // a16[2] (2 K groups of 8 fp16), r8 (1 K group of 16 e4m3: S * (y - a16)), a8 (e4m3(y)).

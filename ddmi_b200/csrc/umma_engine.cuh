@@ -58,7 +58,10 @@ __device__ __forceinline__ uint32_t op_n(uint32_t op) {
   return c == 0 ? 128u : (c == 2 ? 16u : (c == 3 ? 64u : 256u));
 }
 
-template <int PAIR, int RING_BYTES>
+// SCHEME 1 (f16f8): the ring is managed in PAIRS of slots (one 32-wide K step pair = 4 MMAs): one empty barrier (the odd
+// slot's), one full barrier (the even slot's), one expect_tx and two bulk copies per pair -- at 256 tensor cycles per slot
+// a per-slot handshake (each a ~90-cycle barrier round trip) barely keeps the ring full.
+template <int PAIR, int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
                                               uint32_t ring, uint32_t bar, long long ntiles, uint32_t rank) {
   constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
@@ -72,21 +75,36 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
       if (kind != OP_UNIT) continue;
       const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64);    // this CTA's share of one K step
       const int cnt = (int)((op >> 24) & 31) + 1;
-      for (int j = 0; j < cnt; ++j) {
-        mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(bar + BAR_WFULL + 8 * slot, bytes);
-          bulk_g2s(ring + slot * SLOT_BYTES, src + rank * bytes, bytes, bar + BAR_WFULL + 8 * slot);
+      if (SCHEME) {
+        for (int j = 0; j < cnt; j += 2) {
+          const uint32_t full = bar + BAR_WFULL + 8 * slot;
+          mbar_wait(bar + BAR_WEMPTY + 8 * slot + 8, ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(full, 2 * bytes);
+            bulk_g2s(ring + slot * SLOT_BYTES, src + rank * bytes, bytes, full);
+            bulk_g2s(ring + (slot + 1) * SLOT_BYTES, src + (2 + rank) * bytes, bytes, full);
+          }
+          src += bytes * 4;
+          slot += 2;
+          if (slot == NSLOT) { slot = 0; ph ^= 1; }
         }
-        src += bytes * (PAIR ? 2 : 1);
-        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      } else {
+        for (int j = 0; j < cnt; ++j) {
+          mbar_wait(bar + BAR_WEMPTY + 8 * slot, ph ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar + BAR_WFULL + 8 * slot, bytes);
+            bulk_g2s(ring + slot * SLOT_BYTES, src + rank * bytes, bytes, bar + BAR_WFULL + 8 * slot);
+          }
+          src += bytes * (PAIR ? 2 : 1);
+          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+        }
       }
     }
   }
 }
 
 // Peer CTA of a pair: tell the leader when this CTA's half of each ring slot has landed.
-template <int RING_BYTES>
+template <int RING_BYTES, int SCHEME = 0>
 __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ program, uint32_t bar, long long ntiles) {
   constexpr uint32_t NSLOT = RING_BYTES / 8192;
   uint32_t slot = 0, ph = 0;
@@ -98,10 +116,11 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
       const int cnt = (int)((op >> 24) & 31) + 1;
-      for (int j = 0; j < cnt; ++j) {
+      for (int j = 0; j < cnt; j += SCHEME ? 2 : 1) {
         mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
         if (elect_one()) mbar_arrive_remote(leader_pfull + 8 * slot);
-        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+        slot += SCHEME ? 2 : 1;
+        if (slot == NSLOT) { slot = 0; ph ^= 1; }
       }
     }
   }
@@ -113,7 +132,10 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
 // SCHEME 1 (f16f8, pairs only): same 16-wide steps, slots and A-operand stepping, but a step is TWO MMAs: the fp16 main
 // term (a16 x w16, K = 16) and one K = 32 e4m3 correction MMA -- r8 x w8 on even steps, a8 x s8 on odd steps of a
 // 32-wide pair (the A region keeps [r8 r8 a8 a8] K groups per pair, the slot [w16: 2 K groups | w8 or s8: 2 K groups]).
-template <int PAIR, int RING_BYTES, int SCHEME = 0>
+// Steps are issued a PAIR per iteration (4 MMAs = 512 tensor cycles, 2 barrier probes, 1 commit): the issue loop's fixed
+// cost per iteration (probe round trips, descriptor moves to uniform registers, commit) is ~300-400 cycles.
+// TS: the kernel uses A-from-TMEM units (op bit 29); compiled out otherwise to keep the loop small.
+template <int PAIR, int RING_BYTES, int SCHEME = 0, int TS = 1>
 __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
                                          uint32_t bar, uint32_t tmem, long long ntiles) {
   static_assert(SCHEME == 0 || PAIR == 1, "the f16f8 scheme is built for CTA pairs");
@@ -138,12 +160,55 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
         // A operand: K groups of the shared-memory A region, or (bit 29, CTA pairs only) of tensor memory, where one
         // K group = 4 columns counted from the TMEM base (so K group 64 sits right behind a 256-column accumulator)
-        const bool a_in_tmem = PAIR && ((op >> 29) & 1);
+        const bool a_in_tmem = PAIR && TS && ((op >> 29) & 1);
         const uint32_t a_step = a_in_tmem ? 8u : 2 * (KG_BYTES >> 4);
         uint32_t ahi32 = a_in_tmem ? tmem + ((op >> 8) & 0xFF) * 4 : a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
         uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
         const int cnt = (int)((op >> 24) & 31) + 1;
+        if (SCHEME) {
+          auto probe = [&]() {      // the pair's full barriers live at its even slot
+            const bool r = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
+            return mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && r;
+          };
+          bool ready = probe();
+          for (int j = 0; j < cnt; j += 2) {
+            if (!ready) {
+              const long long w0 = clock64();
+              mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
+              mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
+              q_w += clock64() - w0;
+            }
+            tc_fence_after();
+            const uint32_t w0lo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
+            const uint32_t w1lo = w0lo + (SLOT_BYTES >> 4);
+            // slot: [w16: 2 K groups | FP8: 2 K groups] x nloc rows x 16 B
+            const uint64_t b16_0 = kDescHi | w0lo, b8_0 = kDescHi | (w0lo + nloc * 2);
+            const uint64_t b16_1 = kDescHi | w1lo, b8_1 = kDescHi | (w1lo + nloc * 2);
+            if (elect_one()) {
+              if (a_in_tmem) {
+                mma2_bf16_ts(acc, ahi32, b16_0, idesc, accum);          // kind::f16 with fp16 formats (idesc)
+                mma2_bf16_ts(acc, ahi32 + a_step, b16_1, idesc, 1u);
+                mma2_f8_ts(acc, alo32, b8_0, idesc8, 1u);               // r8 x w8
+                mma2_f8_ts(acc, alo32 + a_step, b8_1, idesc8, 1u);      // a8 x s8
+              } else {
+                mma2_bf16(acc, kDescHi | ahi32, b16_0, idesc, accum);
+                mma2_bf16(acc, kDescHi | (ahi32 + a_step), b16_1, idesc, 1u);
+                mma2_f8(acc, kDescHi | alo32, b8_0, idesc8, 1u);
+                mma2_f8(acc, kDescHi | (alo32 + a_step), b8_1, idesc8, 1u);
+              }
+              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot + 8, 3);       // releases the slot pair
+            }
+            accum = 1u;
+            ahi32 += 2 * a_step;
+            alo32 += 2 * a_step;
+            slot += 2;
+            if (slot == NSLOT) { slot = 0; ph ^= 1; }
+            if (j + 2 < cnt) ready = probe();
+          }
+          op = nxt;
+          continue;
+        }
         // The barrier probes of K step j+1 are issued right after the MMAs of step j (both probes back to back),
         // so their ~90-cycle latencies overlap the issue work instead of heading every iteration.
         bool ready = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
@@ -159,13 +224,7 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
           const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
           const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
-          if (SCHEME) {
-            if (elect_one()) {
-              mma2_bf16(acc, ahi, bhi, idesc, accum);     // kind::f16, fp16 formats (idesc)
-              mma2_f8(acc, alo, blo, idesc8, 1u);         // K = 32: the step pair's r8 x w8 (even) / a8 x s8 (odd)
-              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
-            }
-          } else if (elect_one()) {
+          if (elect_one()) {
             if (PAIR && a_in_tmem) {
               mma2_bf16_ts(acc, ahi32, bhi, idesc, accum);
               mma2_bf16_ts(acc, alo32, bhi, idesc, 1u);
@@ -271,28 +330,13 @@ __device__ __forceinline__ void store16(uint32_t h_hi, uint32_t h_lo, int row, i
 template <int SCHEME>
 __device__ __forceinline__ void store8(uint32_t h_hi, uint32_t h_lo, int row, int kg, const float (&y)[8]) {
   if (SCHEME) {
-    uint32_t h[4], r[2], a[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint32_t rp[2], ap[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const float2 v = make_float2(y[4 * i + 2 * j], y[4 * i + 2 * j + 1]);
-        uint32_t hb;
-        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hb) : "f"(v.y), "f"(v.x));
-        h[2 * i + j] = hb;
-        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hb));
-        const float2 res = __ffma2_rn(hf, make_float2(-kF8Scale, -kF8Scale), __fmul2_rn(v, make_float2(kF8Scale, kF8Scale)));
-        rp[j] = __nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);
-        ap[j] = __nv_cvt_float2_to_fp8x2(v, __NV_SATFINITE, __NV_E4M3);
-      }
-      r[i] = rp[0] | (rp[1] << 16);
-      a[i] = ap[0] | (ap[1] << 16);
-    }
-    st_shared_v4(h_hi + (uint32_t)(kg * KG_BYTES + row * 16), make_uint4(h[0], h[1], h[2], h[3]));
+    uint4 a16;
+    uint2 r8, a8;
+    split8_f16f8(y, a16, r8, a8);
+    st_shared_v4(h_hi + (uint32_t)(kg * KG_BYTES + row * 16), a16);
     const uint32_t o8 = (uint32_t)(((kg >> 2) * 4 + ((kg >> 1) & 1)) * KG_BYTES + row * 16 + (kg & 1) * 8);
-    st_shared_v2(h_lo + o8, make_uint2(r[0], r[1]));
-    st_shared_v2(h_lo + o8 + 2 * KG_BYTES, make_uint2(a[0], a[1]));
+    st_shared_v2(h_lo + o8, r8);
+    st_shared_v2(h_lo + o8 + 2 * KG_BYTES, a8);
   } else {
     uint4 hi, lo;
     split8(y, hi, lo);
@@ -306,7 +350,7 @@ __device__ __forceinline__ void store8(uint32_t h_hi, uint32_t h_lo, int row, in
 // kernel prologue / epilogue shared by every decoder
 // ---------------------------------------------------------------------------
 // Initialise the barrier block, allocate 512 TMEM columns (warp 9), sync; returns the TMEM base.
-template <int PAIR>
+template <int PAIR, int SCHEME = 0>
 __device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar) {
   const uint32_t bar = smem_u32(smem) + off_bar;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -339,17 +383,17 @@ __device__ __forceinline__ void engine_end(uint32_t tmem) {
   }
 }
 // Warps 8..11: weight producer, MMA issuer (leader) / forwarder (peer).
-template <int PAIR, int RING_BYTES, int SCHEME = 0>
+template <int PAIR, int RING_BYTES, int SCHEME = 0, int TS = 1>
 __device__ __forceinline__ void engine_service_warps(const uint32_t* __restrict__ program, const uint8_t* __restrict__ wstream,
                                                      uint32_t sbase, uint32_t ring, uint32_t bar, uint32_t tmem,
                                                      long long ntiles, uint32_t rank) {
   reg_dec<72>();   // the whole third warpgroup (warps 8-11) executes this one instruction
   const int warp = threadIdx.x >> 5;
   if (warp == 8) {
-    producer_loop<PAIR, RING_BYTES>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
+    producer_loop<PAIR, RING_BYTES, SCHEME>(program, wstream, ring, bar, ntiles, rank);   // whole warp, one elected lane issues
   } else if (warp == 9) {
-    if (rank == 0) mma_loop<PAIR, RING_BYTES, SCHEME>(program, sbase, ring, bar, tmem, ntiles);
-    else forward_loop<RING_BYTES>(program, bar, ntiles);
+    if (rank == 0) mma_loop<PAIR, RING_BYTES, SCHEME, TS>(program, sbase, ring, bar, tmem, ntiles);
+    else forward_loop<RING_BYTES, SCHEME>(program, bar, ntiles);
   }
 }
 

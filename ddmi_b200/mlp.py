@@ -275,8 +275,8 @@ class MLPNeRF(_FusedDecoder):
         return float(self.dir_encoding[1].negative_slope)
 
     def packed_weights(self, precision=None):
-        """precision: 'fp32' (MLPNeRF.forward on given rows) or 'bf16x3' (fused tcgen05 ray render)."""
-        prec = _resolve_precision(precision or self.precision, ('fp32', 'bf16x3'), self._default_precision)
+        """precision: 'fp32' (MLPNeRF.forward on given rows) or 'bf16x3' / 'f16f8' (fused tcgen05 ray render)."""
+        prec = _resolve_precision(precision or self.precision, ('fp32', 'bf16x3', 'f16f8'), self._default_precision)
         return self._packed(('nerf', prec), lambda: packing.pack_nerf(self, prec))
 
     def forward(self, x, sigma_only=False):

@@ -127,7 +127,8 @@ def _find_module(network_fn):
 def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False, precision=None):
     """rays (N,11) [o d near far viewdir]; fea = dict of (B,32,R,R) planes.
     Returns rgb_map (B,N,3) (and raw (B,N,S,4)).  precision: 'bf16x3' (tcgen05 kernel, default; compositing is
-    fused in-kernel when N_samples == 128) or 'fp32' (CUDA-core kernels); env DDMI_B200_PRECISION overrides."""
+    fused in-kernel when N_samples == 128), 'f16f8' (same kernel, fp16 + FP8-correction operands) or 'fp32'
+    (CUDA-core kernels); env DDMI_B200_PRECISION overrides."""
     import os
     precision = precision or module.precision or os.environ.get('DDMI_B200_PRECISION') or 'bf16x3'
     planes = []
@@ -142,7 +143,7 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
     n = rays.shape[0]
     t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)
     rgb = torch.empty((b, n, 3), device=dev, dtype=torch.float32)
-    umma = precision == 'bf16x3'
+    umma = precision in ('bf16x3', 'f16f8')
     need_raw = return_raw or not (umma and N_samples == 128)
     raw = torch.empty((b, n, N_samples, 4), device=dev, dtype=torch.float32) if need_raw else None
     packed = module.packed_weights(precision)

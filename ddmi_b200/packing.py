@@ -68,9 +68,10 @@ class UmmaProgram:
         assert n in self.NCODE and acc_col % 64 == 0 and acc_col + n <= 512
         if self.scheme == 'f16f8':
             k32 = (W.shape[1] + 31) // 32
-            assert not a_in_tmem and 1 <= k32 <= 16 and a_hi_kg + 4 * k32 <= 256 and a_lo_kg + 4 * k32 <= 256
+            assert 1 <= k32 <= 16 and a_hi_kg + 4 * k32 <= 256 and a_lo_kg + 4 * k32 <= 256
+            assert not a_in_tmem or 4 * (a_lo_kg + 4 * k32) <= 512
             self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
-                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((2 * k32 - 1) << 24))
+                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((2 * k32 - 1) << 24) | ((1 if a_in_tmem else 0) << 29))
             Wp = W.new_zeros(n, 32 * k32)
             Wp[:W.shape[0], :W.shape[1]] = W
             halves = [f16f8_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)]).reshape(2 * k32, -1) for h in (0, 1)]
@@ -504,12 +505,12 @@ def pack_video(module, precision=PREC_FP32, pair=True):
 # ---------------------------------------------------------------------------
 # NeRF MLP (mlp.py:199-281), D=6, W=256, skips=[2,4], xyz 159, dir 27
 # ---------------------------------------------------------------------------
-def _pack_nerf_umma(p):
+def _pack_nerf_umma(p, precision=PREC_BF16X3):
     """Program + stream + vec of csrc/decode_umma_nerf.cuh (CTA pairs).  A-region K groups: H hi 0..31, H lo 32..63,
     X ([latent 96 | gamma(pts) 63 | 0]) hi 64..83, lo 84..103; the 27-wide direction embedding reuses X's first 4
     K groups for the last layer.  One accumulator (TMEM columns 0..255)."""
     HH, HL, XH, XL = 0, 32, 64, 84        # X K groups live in TENSOR memory: columns 256..335 (hi), 336..415 (lo)
-    P = UmmaProgram(pair=True)
+    P = UmmaProgram(pair=True, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
     def over_h(W, first, n_pad=None):
         for q in range(4):
@@ -549,7 +550,7 @@ def _pack_nerf_umma(p):
                        p['sigma.bias'].reshape(-1), z3, p['rgb.0.weight'].reshape(-1), p['rgb.0.bias'].reshape(-1)]
                     ).to(torch.float32).contiguous()
     gemm, prog_dev, prog_host = P.finish(vec.device)
-    return Packed(PREC_BF16X3, gemm, vec, prog_dev, prog_host, True)
+    return Packed(precision, gemm, vec, prog_dev, prog_host, True)
 
 
 def pack_nerf(module, precision=PREC_FP32):
@@ -558,8 +559,8 @@ def pack_nerf(module, precision=PREC_FP32):
             "the fused NeRF kernel is specialised for D=6, W=256, in_channels_xyz=159, "
             "in_channels_dir=27, skips=[2,4] (configs/d2c-vae/srn_cars.yaml:45-49)")
     p = _params64(module)
-    if precision == PREC_BF16X3:
-        return _pack_nerf_umma(p)
+    if precision in (PREC_BF16X3, PREC_F16F8):
+        return _pack_nerf_umma(p, precision)
     segs, vec = [], []
     for i in range(6):
         W = p[f'xyz_encoding_{i + 1}.0.weight']

@@ -166,7 +166,7 @@ def test_nerf_mlp_golden(golden_dir):
     assert float((sig[:, 0] - g['out'][:, 3]).abs().max()) < 2e-5
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_nerf_render_golden(golden_dir, precision):
     g = _golden(golden_dir, 'nerf_render')
     m = cases.build_module('nerf').to(DEV)
@@ -181,7 +181,7 @@ def test_nerf_render_golden(golden_dir, precision):
     assert float((rgb - g['out']).abs().max()) < (1e-4 if precision == 'fp32' else TOL)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_nerf_render_batch_and_ray_subset(precision):
     m = cases.build_module('nerf').to(DEV)
     sd = cases.state_dict32(m)

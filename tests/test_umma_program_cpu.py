@@ -175,7 +175,8 @@ def test_programs_consume_exactly_their_streams():
                    packing.pack_video(cases.build_module('video'), _lib.PREC_BF16X3),
                    packing.pack_nerf(cases.build_module('nerf'), _lib.PREC_BF16X3),
                    packing.pack_occupancy(cases.build_module('occupancy'), _lib.PREC_F16F8),
-                   packing.pack_video(cases.build_module('video'), _lib.PREC_F16F8)):
+                   packing.pack_video(cases.build_module('video'), _lib.PREC_F16F8),
+                   packing.pack_nerf(cases.build_module('nerf'), _lib.PREC_F16F8)):
         ops = packed.program_host.tolist()
         assert ops[-4:] == [3, 3, 3, 3] and all(o & 3 != 3 for o in ops[:-4])
         need = sum(NCODE[(o >> 2) & 3] * 64 * (((o >> 24) & 31) + 1) for o in ops if o & 3 == 0)
