@@ -216,8 +216,9 @@ def run_ours(args):
         return
     tf_peak, hbm_peak, which = peaks()
     traffic, traffic_note = None, None
-    tp = os.path.join(ROOT, 'profiles', 'r01b_image_traffic.json')
-    if os.path.exists(tp) and args.precision == 'bf16x3':
+    tp = os.path.join(ROOT, 'profiles', {'bf16x3': 'r01b_image_traffic.json', 'f16f8': 'r01e_image_traffic_f16f8.json'}
+                      .get(args.precision, 'none'))
+    if os.path.exists(tp):
         t = json.load(open(tp))
         traffic = t['dram_bytes_read'] + t['dram_bytes_write']
         traffic_note = (f"ncu dram bytes of ONE profiled launch ({t['launch']}): {traffic} B vs {t['algorithmic_bytes']} B "
@@ -398,7 +399,7 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--res', type=int, nargs='+', default=[1024, 2048])
-    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'f16f8', 'fp32'])
+    ap.add_argument('--precision', default='f16f8', choices=['f16f8', 'bf16x3', 'fp32'])
     ap.add_argument('--cpu-res', type=int, default=512)
     ap.add_argument('--cpu-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -8,6 +8,7 @@ instead of silently detaching (the reference back-props through this path during
 training; that is out of scope).
 """
 import os
+import warnings
 
 import torch
 from torch import distributions as dist
@@ -69,6 +70,18 @@ class _FusedDecoder(nn.Module):
             entries[key] = builder()
         return entries[key]
 
+    def _packed_auto(self, prec, key_of, build_of):
+        """Packed weights for `prec`.  When f16f8 is only the DEFAULT (neither the module nor DDMI_B200_PRECISION asked
+        for it) and a weight does not fit its fp16 range, fall back to bf16x3 with a warning; an explicit request raises."""
+        try:
+            return prec, self._packed(key_of(prec), lambda: build_of(prec))
+        except packing.F16F8RangeError:
+            if self.precision or os.environ.get('DDMI_B200_PRECISION'):
+                raise
+            warnings.warn("ddmi_b200: a weight exceeds the f16f8 operand range (|w| >= 16); using precision='bf16x3'")
+            prec = _lib.PREC_BF16X3
+            return prec, self._packed(key_of(prec), lambda: build_of(prec))
+
     def _check_device(self, t):
         dev = next(self.parameters()).device
         if not t.is_cuda or dev != t.device:
@@ -80,7 +93,7 @@ class MLP(_FusedDecoder):
     """Image decoder.  Reference: models/d2c_vae/mlp.py:12-66."""
 
     _supported = ('fp32', 'bf16x3', 'f16f8')
-    _default_precision = 'bf16x3'
+    _default_precision = 'f16f8'
 
     def __init__(self, *, in_ch=2, latent_dim=64, out_ch=3, ch=256, precision=None):
         super().__init__()
@@ -112,9 +125,10 @@ class MLP(_FusedDecoder):
         c = coords.detach().to(device=planes[0].device, dtype=torch.float32).contiguous()
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
         si = float(si)
-        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'     # tcgen05 kernel: CTA pairs (cta_group::2) by default
-        pair = pair or prec == _lib.PREC_F16F8                      # the f16f8 kernel exists for pairs only
-        packed = self._packed(('image', prec, si, pair), lambda: packing.pack_image(self, si, prec, pair))
+        env_pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'     # tcgen05 kernels: CTA pairs (cta_group::2) by default
+        pair_of = lambda pr: env_pair or pr == _lib.PREC_F16F8          # the f16f8 kernels exist for pairs only
+        prec, packed = self._packed_auto(prec, lambda pr: ('image', pr, si, pair_of(pr)),
+                                         lambda pr: packing.pack_image(self, si, pr, pair_of(pr)))
         out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
         n = h * w
         cx, cy = c[0, 0], c[0, 1]
@@ -130,7 +144,7 @@ class MLP3D(_FusedDecoder):
     """Occupancy decoder.  Reference: models/d2c_vae/mlp.py:69-111."""
 
     _supported = ('fp32', 'bf16x3', 'f16f8')
-    _default_precision = 'bf16x3'
+    _default_precision = 'f16f8'
 
     def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None):
         super().__init__()
@@ -169,8 +183,10 @@ class MLP3D(_FusedDecoder):
             base = pts.contiguous()
             bstride = n * 3
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
-        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0' or prec == _lib.PREC_F16F8
-        packed = self._packed(('occ', prec, pair), lambda: packing.pack_occupancy(self, prec, pair))
+        env_pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'
+        pair_of = lambda pr: env_pair or pr == _lib.PREC_F16F8
+        prec, packed = self._packed_auto(prec, lambda pr: ('occ', pr, pair_of(pr)),
+                                         lambda pr: packing.pack_occupancy(self, pr, pair_of(pr)))
         logits = torch.empty((b, n), device=base.device, dtype=torch.float32)
         with torch.cuda.device(base.device):
             st = _stream_ptr(base.device)
@@ -195,7 +211,7 @@ class MLPVideo(_FusedDecoder):
     """Video decoder.  Reference: models/d2c_vae/mlp.py:114-157."""
 
     _supported = ('fp32', 'bf16x3', 'f16f8')
-    _default_precision = 'bf16x3'
+    _default_precision = 'f16f8'
 
     def __init__(self, *, in_ch, latent_dim, out_ch, ch=256, precision=None, **ignore_kwargs):
         super().__init__()
@@ -235,8 +251,10 @@ class MLPVideo(_FusedDecoder):
         if tuple(cyt.shape[1:]) != (2, T, H) or tuple(cxt.shape[1:]) != (2, T, W):
             raise RuntimeError("inconsistent coords grids: expected xy (1,2,H,W), yt (1,2,T,H), xt (1,2,T,W)")
         prec = _resolve_precision(self.precision, self._supported, self._default_precision)
-        pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0' or prec == _lib.PREC_F16F8
-        packed = self._packed(('video', prec, pair), lambda: packing.pack_video(self, prec, pair))
+        env_pair = os.environ.get('DDMI_B200_CTA_PAIR', '1') != '0'
+        pair_of = lambda pr: env_pair or pr == _lib.PREC_F16F8
+        prec, packed = self._packed_auto(prec, lambda pr: ('video', pr, pair_of(pr)),
+                                         lambda pr: packing.pack_video(self, pr, pair_of(pr)))
         out = torch.empty((b, self.out_ch, T * H * W), device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().ddmi_decode_video(

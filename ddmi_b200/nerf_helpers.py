@@ -126,11 +126,22 @@ def _find_module(network_fn):
 
 def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False, precision=None):
     """rays (N,11) [o d near far viewdir]; fea = dict of (B,32,R,R) planes.
-    Returns rgb_map (B,N,3) (and raw (B,N,S,4)).  precision: 'bf16x3' (tcgen05 kernel, default; compositing is
-    fused in-kernel when N_samples == 128), 'f16f8' (same kernel, fp16 + FP8-correction operands) or 'fp32'
-    (CUDA-core kernels); env DDMI_B200_PRECISION overrides."""
+    Returns rgb_map (B,N,3) (and raw (B,N,S,4)).  precision: 'f16f8' (tcgen05 kernel, fp16 + FP8-correction operands;
+    the default) or 'bf16x3' (same kernel, bf16 hi/lo operands) -- compositing is fused in-kernel when N_samples == 128
+    -- or 'fp32' (CUDA-core kernels); env DDMI_B200_PRECISION overrides the default."""
     import os
-    precision = precision or module.precision or os.environ.get('DDMI_B200_PRECISION') or 'bf16x3'
+    import warnings
+    from . import packing
+    explicit = precision or module.precision or os.environ.get('DDMI_B200_PRECISION')
+    precision = explicit or 'f16f8'
+    try:
+        packed = module.packed_weights(precision)
+    except packing.F16F8RangeError:
+        if explicit:
+            raise
+        warnings.warn("ddmi_b200: a weight exceeds the f16f8 operand range (|w| >= 16); using precision='bf16x3'")
+        precision = 'bf16x3'
+        packed = module.packed_weights(precision)
     planes = []
     for k in ('xy', 'yz', 'xz'):
         t = fea[k]
@@ -146,7 +157,6 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
     umma = precision in ('bf16x3', 'f16f8')
     need_raw = return_raw or not (umma and N_samples == 128)
     raw = torch.empty((b, n, N_samples, 4), device=dev, dtype=torch.float32) if need_raw else None
-    packed = module.packed_weights(precision)
     with torch.cuda.device(dev):
         st = _stream_ptr(dev)
         if umma:

@@ -109,6 +109,10 @@ class UmmaProgram:
 F8_SCALE = 4096.0
 
 
+class F16F8RangeError(ValueError):
+    """A weight does not fit fp16 after the 2^12 scaling of the f16f8 scheme (|w| >= 16)."""
+
+
 def f16f8_kstep_blocks(W):
     """Pack W (N, K), K a multiple of 32, for the f16f8 tcgen05 kernels: a flat uint8 tensor, per 16-wide K step
     [fp16(S W[:, step]): 2 K groups x N rows x 8 halves | FP8: 2 K groups x N rows x 16 bytes], where the FP8 block
@@ -119,7 +123,7 @@ def f16f8_kstep_blocks(W):
     assert k % 32 == 0
     ws = W * F8_SCALE
     if float(ws.abs().max()) > 65504.0:
-        raise ValueError("f16f8 packing: |weight| * 4096 exceeds the fp16 range; use precision='bf16x3'")
+        raise F16F8RangeError("f16f8 packing: |weight| * 4096 exceeds the fp16 range; use precision='bf16x3'")
     w16 = ws.to(torch.float16)
     res = ws - w16.to(torch.float32)
     w8 = W.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)

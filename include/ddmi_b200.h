@@ -34,8 +34,9 @@
  *   DDMI_PREC_BF16X3  tcgen05 tensor-core kernels, bf16 hi/lo split operands,
  *                     3 MMAs per product, fp32 accumulation in TMEM
  *   DDMI_PREC_F16F8   tcgen05 kernels, fp16 main term + two FP8 (e4m3) correction terms at twice
- *                     the MMA rate: 2/3 of the tensor-pipe time of BF16X3 at ~2e-4 max-abs error
- *                     (CTA pairs only; image decode only in this build)
+ *                     the MMA rate: 2/3 of the tensor-pipe time of BF16X3 at ~1e-4 max-abs error
+ *                     (all four decoders; CTA-pair kernels only, weights must be pair-packed;
+ *                     |weight| < 16, activations saturate at 65504)
  */
 #ifndef DDMI_B200_H
 #define DDMI_B200_H
@@ -77,12 +78,12 @@ typedef struct {
 /* Host-folded, packed MLP weights (device memory). */
 typedef struct {
   int32_t precision;   /* DDMI_PREC_* */
-  int32_t reserved;    /* bit 0: bf16x3 stream is packed for CTA pairs ([half 0 | half 1] per K step) */
+  int32_t reserved;    /* bit 0: tcgen05 stream is packed for CTA pairs ([half 0 | half 1] per K step) */
   const void* gemm;    /* GEMM operands, layout per precision (device)            */
   uint64_t gemm_bytes;
   const float* vec;    /* fp32 vectors: biases, folded constants, small heads (device) */
   uint64_t vec_floats;
-  /* DDMI_PREC_BF16X3 only: the MMA program that consumes `gemm`, one
+  /* DDMI_PREC_BF16X3 / DDMI_PREC_F16F8: the MMA program that consumes `gemm`, one
      copy in device memory for the kernel and one in host memory for validation.     */
   const uint32_t* program;
   const uint32_t* program_host;

@@ -147,3 +147,24 @@ def test_coord_helpers():
     assert ddmi_b200.get_scale_injection(1024) == 0.25
     g = ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (2, 3, 4))
     assert tuple(g.shape) == (24, 3) and float(g[1, 2] - g[0, 2]) > 0 and float(g[1, 0] - g[0, 0]) == 0
+
+
+def test_f16f8_default_falls_back_to_bf16x3_on_out_of_range_weights():
+    """f16f8 packs fp16(4096 W): a weight >= 16 cannot be represented.  As the DEFAULT precision that silently would be
+    wrong, so the module falls back to bf16x3 (with a warning); an explicit f16f8 request raises."""
+    import warnings
+    import pytest
+    from ddmi_b200 import _lib, packing
+    from oracle import cases
+    m = cases.build_module('occupancy')
+    with torch.no_grad():
+        m.net_res2.fc_0.weight[3, 5] = 17.0
+    key_of = lambda pr: ('occ', pr, True)
+    build_of = lambda pr: packing.pack_occupancy(m, pr, True)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        prec, packed = m._packed_auto(_lib.PREC_F16F8, key_of, build_of)
+    assert prec == _lib.PREC_BF16X3 and packed.precision == _lib.PREC_BF16X3 and len(w) == 1
+    m.precision = 'f16f8'
+    with pytest.raises(packing.F16F8RangeError):
+        m._packed_auto(_lib.PREC_F16F8, key_of, build_of)

@@ -34,7 +34,8 @@ def launches(path, title, cmd, out):
 
 
 def full(rep, title, cmd, notes, out):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    raw = open(rep).read() if rep.endswith('.csv') else \
+        subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     H, U, V = rows[0], rows[1], rows[2]
     o = [f"# {title}", f"command: {cmd}", "", "| metric | unit | value |", "|---|---|---|"]
@@ -47,14 +48,18 @@ def full(rep, title, cmd, notes, out):
 
 
 if __name__ == '__main__':
-    launches('gpurun_out/launches_r01b.csv', 'ncu launch list, round 1, final kernel (CTA-pair tcgen05 engine)',
-             'ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline',
-             'profiles/r01b_launches_bench.md')
-    full('gpurun_out/prof_image_umma_r01b.ncu-rep', 'ncu --set full, image_umma_kernel<PAIR=1>, round 1 final',
+    # round 1, final (f16f8 default): produced by tools/gpu_evidence.sh
+    launches('gpurun_out/r01e_launches_bench.csv', 'ncu launch list, round 1 final (f16f8 operand scheme, CTA-pair tcgen05 engine)',
+             'ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline',
+             'profiles/r01e_launches_bench.md')
+    full('gpurun_out/r01e_image_f16f8_raw.csv', 'ncu --set full, image_umma_kernel<PAIR=1, SCHEME=f16f8>, round 1 final',
          'ncu --set full --clock-control none --import-source on -k regex:image_umma -s 1 -c 1 python bench.py --batch 8 --res 1024 --steps 1 --warmup 1 --no-cpu-baseline',
-         ['workload of the captured launch: batch 8 @ 1024x1024 = 8,388,608 coords = 65,536 tiles of 128, 74 CTA pairs (148 CTAs)'],
-         'profiles/r01b_image_umma_full.md')
-    full('gpurun_out/prof_occ_umma_r01.ncu-rep', 'ncu --set full, occupancy_umma_kernel<PAIR=1,NHWC=1>, round 1',
-         'ncu --set full --clock-control none --import-source on -k regex:occupancy_umma -s 1 -c 1 python bench.py --workload occupancy --batch 4 --steps 1 --warmup 1',
-         ['workload of the captured launch: batch 4 x (128^3 grid + 100k random points) = 8,788,608 coords'],
-         'profiles/r01_occupancy_umma_full.md')
+         ['workload of the captured launch: batch 8 @ 1024x1024 = 8,388,608 coords = 65,536 tiles of 128, 74 CTA pairs (148 CTAs)',
+          'algorithmic DRAM bytes: planes once (176.2 MB) + 12 B/coord out (100.7 MB) = 276.8 MB'],
+         'profiles/r01e_image_umma_full.md')
+    for w, note in (('occupancy', 'batch 32 x (128^3 grid + 100k random points) = 70,308,864 points'),
+                    ('video', 'batch 16 x 256x256x16 = 16,777,216 voxels'),
+                    ('nerf', 'batch 16 objects x 128x128 rays x 128 samples = 33,554,432 samples, compositing fused')):
+        full(f'gpurun_out/r01e_{w}_f16f8_raw.csv', f'ncu --set full, {w}_umma_kernel (f16f8), round 1 final',
+             f'ncu --set full --clock-control none -k regex:{w}_umma -s 1 -c 1 python bench.py --workload {w} --steps 1 --warmup 1',
+             ['workload of the captured launch: ' + note], f'profiles/r01e_{w}_umma_full.md')
