@@ -144,7 +144,7 @@ def run_ours(args):
     def step():
         outs = []
         for c, si, R in grids:
-            outs.append(mlp(c, hdbf=planes, si=si))
+            outs.append(mlp(c, hdbf=planes, si=si, store=args.store))
         return outs
 
     def barrier():
@@ -164,7 +164,7 @@ def run_ours(args):
         for c, si, R in grids:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = mlp(c, hdbf=planes, si=si)
+            out = mlp(c, hdbf=planes, si=si, store=args.store)
             e1.record()
             evs.append((e0, e1, B * R * R))
             del out
@@ -175,9 +175,12 @@ def run_ours(args):
     launch_ms = [(a.elapsed_time(b), n) for a, b, n in evs]
 
     # ---- end to end through the public API with host buffers ----
-    out_host = [torch.empty((B, 3, R, R), dtype=torch.float32).pin_memory() for _, _, R in grids]
+    if args.store == 'u8':
+        out_host = [torch.empty((B, R, R, 3), dtype=torch.uint8).pin_memory() for _, _, R in grids]
+    else:
+        out_host = [torch.empty((B, 3, R, R), dtype=torch.float32).pin_memory() for _, _, R in grids]
     h2d = sum(p.numel() * 4 for p in host_planes)            # the step's latents are uploaded once
-    d2h = sum(o.numel() * 4 for o in out_host)
+    d2h = sum(o.numel() * o.element_size() for o in out_host)
     copy_stream = torch.cuda.Stream(device=dev)
     up_stream = torch.cuda.Stream(device=dev)
     CH = max(1, min(args.e2e_chunk, B))                      # batch items per pipelined chunk
@@ -201,7 +204,7 @@ def run_ours(args):
             for t in dp:
                 t.record_stream(main)
             for i, (c, si, R) in enumerate(grids):
-                o = mlp(c, hdbf=dp, si=si)
+                o = mlp(c, hdbf=dp, si=si, store=args.store)
                 copy_stream.wait_stream(main)
                 with torch.cuda.stream(copy_stream):
                     out_host[i][a:b].copy_(o, non_blocking=True)
@@ -249,6 +252,8 @@ def run_ours(args):
         "config": {"workload": f"AFHQ-shape image D2C-VAE decode (BASELINE configs[1]): planes 64^2/128^2/256^2 x64ch, "
                                f"query grids {'+'.join(f'{R}x{R}' for R in args.res)}, batch {B} per GPU",
                    "coords_per_step_per_gpu": coords_per_step, "precision": args.precision,
+                   "store": args.store + {"f32": " (the reference's output: (B,3,h,w) fp32)", "clamp": " (clamp(-1,1) fused)",
+                                           "u8": " (uint8 (B,h,w,3) = trunc((clamp(x,-1,1)+1)*127.5) fused: the callers' epilogue)"}[args.store],
                    "l2": "inputs larger than L2 (planes %.2f GB per GPU; no flush)" % (sum(p.numel() * 4 for p in planes) / 1e9),
                    "sharding": "batch items per rank, no collective"},
         "e2e": {"value": coords_per_step * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
@@ -414,6 +419,7 @@ if __name__ == '__main__':
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--res', type=int, nargs='+', default=[1024, 2048])
+    ap.add_argument('--store', default='f32', choices=['f32', 'clamp', 'u8'], help='output store mode of the image decoder')
     ap.add_argument('--e2e-chunk', type=int, default=8, help='batch items per pipelined chunk of the e2e leg')
     ap.add_argument('--precision', default='f16f8', choices=['f16f8', 'bf16x3', 'fp32'])
     ap.add_argument('--cpu-res', type=int, default=512)

@@ -15,10 +15,13 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 PREC_FP32 = 0
 PREC_BF16X3 = 1
 PREC_F16F8 = 2
+STORE_F32, STORE_F32_CLAMP, STORE_U8_CHANNELS_LAST = 0, 1, 2
+STORE_MODES = {None: 0, 'f32': 0, 'clamp': 1, 'u8': 2}
 
 EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
-    "ddmi_decode_image", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy", "ddmi_decode_video",
+    "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
+    "ddmi_decode_video", "ddmi_decode_video_store",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
 )
 
@@ -66,11 +69,15 @@ def lib():
         L.ddmi_device_info.argtypes = [ctypes.POINTER(i32)] * 3
         L.ddmi_decode_image.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, i64,
                                         ctypes.POINTER(Weights), vp, vp]
+        L.ddmi_decode_image_store.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, i64,
+                                              ctypes.POINTER(Weights), i32, vp, vp]
         L.ddmi_planes_to_channels_last.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.ddmi_decode_occupancy.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i64, f32,
                                             ctypes.POINTER(Weights), vp, vp]
         L.ddmi_decode_video.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
                                         ctypes.POINTER(Weights), vp, vp]
+        L.ddmi_decode_video_store.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
+                                              ctypes.POINTER(Weights), i32, vp, vp]
         L.ddmi_nerf_mlp.argtypes = [vp, i64, i32, i32, f32, ctypes.POINTER(Weights), vp, vp]
         L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i32, vp, i32, f32, f32,
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]
@@ -80,7 +87,7 @@ def lib():
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
-        if L.ddmi_abi_version() != 5:
+        if L.ddmi_abi_version() != 6:
             raise RuntimeError("libddmi_b200.so ABI version mismatch")
         _lib = L
     return _lib

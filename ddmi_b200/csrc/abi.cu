@@ -21,17 +21,17 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // fp32 CUDA-core path (decode_fp32.cu)
-int launch_image_fp32(const PlaneSet&, int, int, const float*, const float*, long long, const float*, const float*, float*, cudaStream_t);
+int launch_image_fp32(const PlaneSet&, int, int, const float*, const float*, long long, const float*, const float*, void*, int, cudaStream_t);
 int launch_occupancy_fp32(const PlaneSet&, int, int, const float*, long long, long long, float, float, const float*, const float*, float*, cudaStream_t);
-int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const float*, const float*, float*, cudaStream_t);
+int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const float*, const float*, void*, int, cudaStream_t);
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
 int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
-int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
-int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, cudaStream_t);
+int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, cudaStream_t);
 int launch_nerf_composite(const float*, const float*, int, const float*, int, long long, int, int, float*, cudaStream_t);
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
@@ -97,6 +97,13 @@ DDMI_API int ddmi_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_
 DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
                       const float* coord_x, const float* coord_y, int64_t n_coords,
                       const ddmi_weights_t* weights, float* out, void* stream) {
+  return ddmi_decode_image_store(planes, batch, channels, coord_x, coord_y, n_coords, weights, DDMI_STORE_F32, out, stream);
+}
+
+DDMI_API int ddmi_decode_image_store(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                                     const float* coord_x, const float* coord_y, int64_t n_coords,
+                                     const ddmi_weights_t* weights, int32_t store, void* out, void* stream) {
+  DDMI_REQUIRE(store >= DDMI_STORE_F32 && store <= DDMI_STORE_U8_CHANNELS_LAST, "unknown store mode %d", store);
   PlaneSet ps = {};
   int rc = check_planes(planes, 3, &ps);
   if (rc) return rc;
@@ -115,7 +122,7 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
     rc = check_weights(weights, kfl * 256 * sizeof(float), 4096 + 768 + 3);
     if (rc) return rc;
     return launch_image_fp32(ps, batch, channels, coord_x, coord_y, n_coords, (const float*)weights->gemm,
-                             weights->vec, out, st);
+                             weights->vec, out, store, st);
   } else if (weights->precision == DDMI_PREC_BF16X3 || weights->precision == DDMI_PREC_F16F8) {
     DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
@@ -123,7 +130,7 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
     DDMI_REQUIRE(!f16f8 || (weights->reserved & 1), "DDMI_PREC_F16F8 weights must be packed for CTA pairs");
     return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm, weights->gemm_bytes,
                              weights->program_host, weights->program_words, weights->program, weights->vec,
-                             weights->vec_floats, out, weights->reserved & 1, f16f8, st);
+                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, st);
   }
   set_error("unknown precision %d", weights->precision);
   return DDMI_ERR_UNSUPPORTED;
@@ -185,6 +192,15 @@ DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int3
                       const float* coords_xy, const float* coords_yt, const float* coords_xt,
                       int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, float* out,
                       void* stream) {
+  return ddmi_decode_video_store(planes, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W, weights,
+                                 DDMI_STORE_F32, out, stream);
+}
+
+DDMI_API int ddmi_decode_video_store(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                                     const float* coords_xy, const float* coords_yt, const float* coords_xt,
+                                     int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, int32_t store,
+                                     void* out, void* stream) {
+  DDMI_REQUIRE(store >= DDMI_STORE_F32 && store <= DDMI_STORE_U8_CHANNELS_LAST, "unknown store mode %d", store);
   PlaneSet ps = {};
   int rc = check_planes(planes, 9, &ps);
   if (rc) return rc;
@@ -201,7 +217,7 @@ DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int3
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
     return launch_video_umma_entry(ps, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W, weights->gemm,
                                    weights->gemm_bytes, weights->program_host, weights->program_words, weights->program,
-                                   weights->vec, weights->vec_floats, out, weights->reserved & 1,
+                                   weights->vec, weights->vec_floats, out, store, weights->reserved & 1,
                                    weights->precision == DDMI_PREC_F16F8, (cudaStream_t)stream);
   }
   if (weights->precision != DDMI_PREC_FP32) {
@@ -212,7 +228,7 @@ DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int3
   rc = check_weights(weights, gfl * sizeof(float), 448 + 3 * 512 + 768 + 3);
   if (rc) return rc;
   return launch_video_fp32(ps, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W,
-                           (const float*)weights->gemm, weights->vec, out, (cudaStream_t)stream);
+                           (const float*)weights->gemm, weights->vec, out, store, (cudaStream_t)stream);
 }
 
 static const uint64_t kNerfGemmFloats =

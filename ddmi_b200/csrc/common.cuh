@@ -117,6 +117,20 @@ __device__ __forceinline__ float occ_normalize(float p, float divisor, float upp
   return __fsub_rn(__fmul_rn(2.f, u), 1.f);
 }
 
+// Output store modes of the image / video decoders (DDMI_STORE_* in ddmi_b200.h): channel c (of 3) of coordinate gi of
+// item b, n coordinates per item.  0: (b, 3, n) fp32 as the reference returns it; 1: the same, clamp(v, -1, 1)
+// (evals/eval.py:162,226); 2: uint8((clamp(v,-1,1) + 1) * 127.5) channels-last (b, n, 3) -- the reference's
+// `rearrange((fake.clamp(-1,1) + 1) * 127.5, 'b c t h w -> b t h w c').type(torch.uint8)` (evals/eval.py:289,336-337),
+// fp32 ops in that order, truncating cast.
+__device__ __forceinline__ void store_rgb(void* out, int store, size_t b, long long n, long long gi, int c, float v) {
+  if (store != 0) v = fminf(fmaxf(v, -1.f), 1.f);
+  if (store == 2)
+    reinterpret_cast<unsigned char*>(out)[((size_t)b * n + gi) * 3 + c] =
+        (unsigned char)__float2uint_rz(__fmul_rn(__fadd_rn(v, 1.f), 127.5f));
+  else
+    reinterpret_cast<float*>(out)[((size_t)b * 3 + c) * n + gi] = v;
+}
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // torch.nn.functional.softplus (beta = 1, threshold = 20)

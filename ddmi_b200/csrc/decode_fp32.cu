@@ -130,7 +130,7 @@ constexpr size_t IMG_SMEM = (size_t)(2 * TM * HS + TM * IMG_XS + 2 * WBUF) * siz
 __global__ void __launch_bounds__(NT, 1)
 image_kernel(PlaneSet ps, int C, const float* __restrict__ cx, const float* __restrict__ cy,
              long long n, int tiles_per_item, const float* __restrict__ Wg,
-             const float* __restrict__ vec, float* __restrict__ out) {
+             const float* __restrict__ vec, void* __restrict__ out, int store) {
   extern __shared__ float4 smem4[];
   float* H = reinterpret_cast<float*>(smem4);
   float* Hn = H + TM * HS;
@@ -196,7 +196,7 @@ image_kernel(PlaneSet ps, int C, const float* __restrict__ cx, const float* __re
   if (c < 3 && n0 + r < n) {
     float s = 0.f;
     for (int k = 0; k < 256; ++k) s = fmaf(H[r * HS + k], __ldg(wrgb + c * 256 + k), s);
-    out[((size_t)b * 3 + c) * n + n0 + r] = s + __ldg(wrgb + 768 + c);
+    store_rgb(out, store, b, n, n0 + r, c, s + __ldg(wrgb + 768 + c));
   }
 }
 
@@ -332,7 +332,7 @@ constexpr size_t VID_SMEM = (size_t)(2 * TM * HS + TM * (VID_KX + 4) + 2 * WBUF)
 __global__ void __launch_bounds__(NT, 1)
 video_kernel(PlaneSet ps, int C, const float* __restrict__ cxy, const float* __restrict__ cyt,
              const float* __restrict__ cxt, int T, int Hh, int Ww, int tiles_per_item,
-             const float* __restrict__ Wg, const float* __restrict__ vec, float* __restrict__ out) {
+             const float* __restrict__ Wg, const float* __restrict__ vec, void* __restrict__ out, int store) {
   extern __shared__ float4 smem4[];
   float* H = reinterpret_cast<float*>(smem4);
   float* Hn = H + TM * HS;
@@ -370,7 +370,7 @@ video_kernel(PlaneSet ps, int C, const float* __restrict__ cxy, const float* __r
   if (c < 3 && n0 + r < n) {
     float s = 0.f;
     for (int k = 0; k < 256; ++k) s = fmaf(lrelu(H[r * HS + k], 0.2f), __ldg(tail + c * 256 + k), s);
-    out[((size_t)b * 3 + c) * n + n0 + r] = s + __ldg(tail + 768 + c);
+    store_rgb(out, store, b, n, n0 + r, c, s + __ldg(tail + 768 + c));
   }
 }
 
@@ -610,13 +610,13 @@ static int check_grid(long long tiles) {
 }
 
 int launch_image_fp32(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy,
-                      long long n, const float* Wg, const float* vec, float* out, cudaStream_t st) {
+                      long long n, const float* Wg, const float* vec, void* out, int store, cudaStream_t st) {
   long long tpi = (n + fp32::TM - 1) / fp32::TM;
   int rc = check_grid(tpi * batch);
   if (rc) return rc;
   rc = set_smem(fp32::image_kernel, fp32::IMG_SMEM);
   if (rc) return rc;
-  fp32::image_kernel<<<(unsigned)(tpi * batch), fp32::NT, fp32::IMG_SMEM, st>>>(ps, C, cx, cy, n, (int)tpi, Wg, vec, out);
+  fp32::image_kernel<<<(unsigned)(tpi * batch), fp32::NT, fp32::IMG_SMEM, st>>>(ps, C, cx, cy, n, (int)tpi, Wg, vec, out, store);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }
@@ -637,7 +637,7 @@ int launch_occupancy_fp32(const PlaneSet& ps, int batch, int C, const float* pts
 
 int launch_video_fp32(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt,
                       const float* cxt, int T, int H, int W, const float* Wg, const float* vec,
-                      float* out, cudaStream_t st) {
+                      void* out, int store, cudaStream_t st) {
   long long n = (long long)T * H * W;
   long long tpi = (n + fp32::TM - 1) / fp32::TM;
   int rc = check_grid(tpi * batch);
@@ -645,7 +645,7 @@ int launch_video_fp32(const PlaneSet& ps, int batch, int C, const float* cxy, co
   rc = set_smem(fp32::video_kernel, fp32::VID_SMEM);
   if (rc) return rc;
   fp32::video_kernel<<<(unsigned)(tpi * batch), fp32::NT, fp32::VID_SMEM, st>>>(
-      ps, C, cxy, cyt, cxt, T, H, W, (int)tpi, Wg, vec, out);
+      ps, C, cxy, cyt, cxt, T, H, W, (int)tpi, Wg, vec, out, store);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

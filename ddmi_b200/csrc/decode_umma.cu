@@ -131,7 +131,7 @@ template <int PAIR, int SCHEME>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
-                  const uint32_t* __restrict__ program, const float* __restrict__ vec, float* __restrict__ out) {
+                  const uint32_t* __restrict__ program, const float* __restrict__ vec, void* __restrict__ out, int store) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase + ImgL::KG_HHI * KG_BYTES, h_lo = sbase + ImgL::KG_HLO * KG_BYTES;
@@ -262,9 +262,9 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         if (gi < n) {
           const float* brgb = vec + 4096 + 768;
           constexpr float kOut = SCHEME ? kF8InvScale : 1.0f;
-          out[((size_t)b * 3 + 0) * n + gi] = v[0].x * kOut + __ldg(brgb + 0);
-          out[((size_t)b * 3 + 1) * n + gi] = v[0].y * kOut + __ldg(brgb + 1);
-          out[((size_t)b * 3 + 2) * n + gi] = v[1].x * kOut + __ldg(brgb + 2);
+          store_rgb(out, store, b, n, gi, 0, v[0].x * kOut + __ldg(brgb + 0));
+          store_rgb(out, store, b, n, gi, 1, v[0].y * kOut + __ldg(brgb + 1));
+          store_rgb(out, store, b, n, gi, 2, v[1].x * kOut + __ldg(brgb + 2));
         }
       }
       if (it + 1 < ntiles) signal_all();
@@ -368,8 +368,8 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 // ---------------------------------------------------------------------------
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
                       const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
-                      const uint32_t* program_dev, const float* vec, size_t vec_floats, float* out, int pair, int f16f8,
-                      cudaStream_t st) {
+                      const uint32_t* program_dev, const float* vec, size_t vec_floats, void* out, int store, int pair,
+                      int f16f8, cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
     set_error("tcgen05 image kernel is built for 64-channel planes");
@@ -397,13 +397,13 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
     const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
     if (f16f8)
       DDMI_CUDA(launch_engine(image_umma_kernel<1, 1>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
-                              total, ws, program_dev, vec, out));
+                              total, ws, program_dev, vec, out, store));
     else
       DDMI_CUDA(launch_engine(image_umma_kernel<1, 0>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
-                              total, ws, program_dev, vec, out));
+                              total, ws, program_dev, vec, out, store));
   } else {
     DDMI_CUDA(launch_engine(image_umma_kernel<0, 0>, 0, (unsigned)(total < sms ? total : sms), ImgL::SMEM_BYTES, st, ps, cx, cy,
-                            n, tpi_i, total, ws, program_dev, vec, out));
+                            n, tpi_i, total, ws, program_dev, vec, out, store));
   }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
@@ -430,9 +430,9 @@ int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* ra
 int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt, int T,
                             int H, int W, const void* gemm, size_t gemm_bytes, const uint32_t* program_host,
                             size_t program_words, const uint32_t* program_dev, const float* vec, size_t vec_floats,
-                            float* out, int pair, int f16f8, cudaStream_t st) {
+                            void* out, int store, int pair, int f16f8, cudaStream_t st) {
   return launch_video_umma(ps, batch, C, cxy, cyt, cxt, T, H, W, gemm, gemm_bytes, program_host, program_words, program_dev,
-                           vec, vec_floats, out, pair, f16f8, st);
+                           vec, vec_floats, out, store, pair, f16f8, st);
 }
 
 int debug_profile(unsigned long long* out, int reset) {

@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __restrict__ cyt,
                   const float* __restrict__ cxt, int T, int Hh, int Ww, int tiles_per_item, long long total_tiles,
                   const uint8_t* __restrict__ wstream, const uint32_t* __restrict__ program,
-                  const float* __restrict__ vec, float* __restrict__ out) {
+                  const float* __restrict__ vec, void* __restrict__ out, int store) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
@@ -185,7 +185,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
           if (gi < n) {
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-              out[((size_t)b * 3 + c) * n + gi] = part[(c * 2) * 128 + row] + part[(c * 2 + 1) * 128 + row] + __ldg(vec + VV_BOUT + c);
+              store_rgb(out, store, b, n, gi, c, part[(c * 2) * 128 + row] + part[(c * 2 + 1) * 128 + row] + __ldg(vec + VV_BOUT + c));
           }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -202,7 +202,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
 inline int launch_video_umma(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt,
                              int T, int H, int W, const void* gemm, size_t gemm_bytes, const uint32_t* program_host,
                              size_t program_words, const uint32_t* program_dev, const float* vec, size_t vec_floats,
-                             float* out, int pair, int f16f8, cudaStream_t st) {
+                             void* out, int store, int pair, int f16f8, cudaStream_t st) {
   using namespace ummak;
   DDMI_REQUIRE(!f16f8 || pair, "the f16f8 video kernel runs as CTA pairs only");
   if (C != 64) {
@@ -229,13 +229,13 @@ inline int launch_video_umma(const PlaneSet& ps, int batch, int C, const float* 
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
   if (f16f8) {
     DDMI_CUDA(launch_engine(video_umma_kernel<1, 1>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
-                            total, ws, program_dev, vec, out));
+                            total, ws, program_dev, vec, out, store));
   } else if (pair) {
     DDMI_CUDA(launch_engine(video_umma_kernel<1, 0>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
-                            total, ws, program_dev, vec, out));
+                            total, ws, program_dev, vec, out, store));
   } else {
     DDMI_CUDA(launch_engine(video_umma_kernel<0, 0>, 0, (unsigned)(total < sms ? total : sms), VID_SMEM, st, ps, cxy, cyt, cxt, T,
-                            H, W, tpi_i, total, ws, program_dev, vec, out));
+                            H, W, tpi_i, total, ws, program_dev, vec, out, store));
   }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;

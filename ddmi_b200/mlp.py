@@ -29,6 +29,12 @@ def _resolve_precision(name, supported, default):
     return _PREC[name]
 
 
+def _store_mode(store):
+    if store not in _lib.STORE_MODES:
+        raise ValueError(f"store must be one of None, 'f32', 'clamp', 'u8' (got {store!r})")
+    return _lib.STORE_MODES[store]
+
+
 def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -111,9 +117,12 @@ class MLP(_FusedDecoder):
         self.torgb = ToRGB(ch, out_ch, ch)
         self._init_fused(precision)
 
-    def forward(self, coords, hdbf, si=1):
+    def forward(self, coords, hdbf, si=1, store=None):
         """coords (1,2,h,w) in [-1,1]; hdbf = 3 planes (b,64,S,S) coarse->fine;
-        returns (b,3,h,w).  mlp.py:34-66."""
+        returns (b,3,h,w).  mlp.py:34-66.
+        store (extension, the epilogue the reference's callers apply -- fused into the kernel's output stage):
+        None / 'f32' -> the reference's value; 'clamp' -> .clamp(-1, 1) (evals/eval.py:162,226);
+        'u8' -> ((x.clamp(-1,1) + 1) * 127.5).type(torch.uint8) channels-last, (b,h,w,3) (evals/eval.py:289,336-337)."""
         assert hdbf is not None and len(hdbf) == 3
         self._guard_grad(*hdbf)
         planes = [_as_plane(t, f'hdbf[{i}]') for i, t in enumerate(hdbf)]
@@ -129,14 +138,18 @@ class MLP(_FusedDecoder):
         pair_of = lambda pr: env_pair or pr == _lib.PREC_F16F8          # the f16f8 kernels exist for pairs only
         prec, packed = self._packed_auto(prec, lambda pr: ('image', pr, si, pair_of(pr)),
                                          lambda pr: packing.pack_image(self, si, pr, pair_of(pr)))
-        out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
+        mode = _store_mode(store)
+        if mode == _lib.STORE_U8_CHANNELS_LAST:
+            out = torch.empty((b, h, w, 3), device=c.device, dtype=torch.uint8)
+        else:
+            out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
         n = h * w
         cx, cy = c[0, 0], c[0, 1]
         with torch.cuda.device(c.device):
             wst = _lib.weights_struct(packed)
-            _lib.check(_lib.lib().ddmi_decode_image(
+            _lib.check(_lib.lib().ddmi_decode_image_store(
                 _lib.planes_array(planes), b, planes[0].shape[1], cx.data_ptr(), cy.data_ptr(), n,
-                wst, out.data_ptr(), _stream_ptr(c.device)))
+                wst, mode, out.data_ptr(), _stream_ptr(c.device)))
         return out
 
 
@@ -228,10 +241,12 @@ class MLPVideo(_FusedDecoder):
         self.net_out = nn.Linear(ch, out_ch)
         self._init_fused(precision)
 
-    def forward(self, coords, hdbf):
+    def forward(self, coords, hdbf, store=None):
         """coords = {'xy':(1,2,H,W),'xt':(1,2,T,W),'yt':(1,2,T,H)}; hdbf =
         (xy, yt, xt) 3-lists; returns (b,3,t,h,w) with t,h,w taken from the
-        finest planes exactly as the reference does (mlp.py:135-136,155-156)."""
+        finest planes exactly as the reference does (mlp.py:135-136,155-156).
+        store (extension, see MLP.forward): 'clamp' -> clamp(-1,1); 'u8' -> uint8 frames (b,t,h,w,3), the
+        `rearrange((fake.clamp(-1,1) + 1) * 127.5, 'b c t h w -> b t h w c').type(torch.uint8)` of evals/eval.py:336-337."""
         assert len(hdbf) == 3
         xy_hdbf, yt_hdbf, xt_hdbf = hdbf
         assert len(xy_hdbf) == 3 and len(yt_hdbf) == 3 and len(xt_hdbf) == 3
@@ -255,12 +270,15 @@ class MLPVideo(_FusedDecoder):
         pair_of = lambda pr: env_pair or pr == _lib.PREC_F16F8
         prec, packed = self._packed_auto(prec, lambda pr: ('video', pr, pair_of(pr)),
                                          lambda pr: packing.pack_video(self, pr, pair_of(pr)))
-        out = torch.empty((b, self.out_ch, T * H * W), device=dev, dtype=torch.float32)
+        mode = _store_mode(store)
+        u8 = mode == _lib.STORE_U8_CHANNELS_LAST
+        out = torch.empty((b, T * H * W, self.out_ch) if u8 else (b, self.out_ch, T * H * W), device=dev,
+                          dtype=torch.uint8 if u8 else torch.float32)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().ddmi_decode_video(
+            _lib.check(_lib.lib().ddmi_decode_video_store(
                 _lib.planes_array(planes), b, planes[0].shape[1], cxy.data_ptr(), cyt.data_ptr(),
-                cxt.data_ptr(), T, H, W, _lib.weights_struct(packed), out.data_ptr(), _stream_ptr(dev)))
-        return out.reshape(b, self.out_ch, t, h, w)
+                cxt.data_ptr(), T, H, W, _lib.weights_struct(packed), mode, out.data_ptr(), _stream_ptr(dev)))
+        return out.reshape(b, t, h, w, self.out_ch) if u8 else out.reshape(b, self.out_ch, t, h, w)
 
 
 class MLPNeRF(_FusedDecoder):

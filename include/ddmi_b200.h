@@ -54,7 +54,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 5
+#define DDMI_ABI_VERSION 6
 
 enum {
   DDMI_OK = 0,
@@ -64,6 +64,12 @@ enum {
 };
 
 enum { DDMI_PREC_FP32 = 0, DDMI_PREC_BF16X3 = 1, DDMI_PREC_F16F8 = 2 };
+/* Output store modes of the image / video decoders (the epilogues the reference's callers apply to the decoded signal):
+ *   DDMI_STORE_F32               (batch, 3, n) fp32, the value the reference's forward returns
+ *   DDMI_STORE_F32_CLAMP         same layout, clamp(x, -1, 1)                  evals/eval.py:162,226, tools/ldm/image.py:246
+ *   DDMI_STORE_U8_CHANNELS_LAST  (batch, n, 3) uint8 = trunc((clamp(x,-1,1) + 1) * 127.5), i.e. image (b,h,w,c) / video
+ *                                (b,t,h,w,c): rearrange(...).type(torch.uint8) of evals/eval.py:289,336-337          */
+enum { DDMI_STORE_F32 = 0, DDMI_STORE_F32_CLAMP = 1, DDMI_STORE_U8_CHANNELS_LAST = 2 };
 
 /* plane memory layout: as the reference's VAE decoder emits them, or channels-last */
 enum { DDMI_LAYOUT_NCHW = 0, DDMI_LAYOUT_NHWC = 1 };
@@ -108,6 +114,11 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
                       const float* coord_x, const float* coord_y, int64_t n_coords,
                       const ddmi_weights_t* weights, float* out, void* stream);
 
+/* ddmi_decode_image with an output store mode (DDMI_STORE_*); `out` is float* or uint8_t* accordingly. */
+DDMI_API int ddmi_decode_image_store(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                            const float* coord_x, const float* coord_y, int64_t n_coords,
+                            const ddmi_weights_t* weights, int32_t store, void* out, void* stream);
+
 /*
  * (batch, C, H, W) -> (batch, H, W, C).  Scattered queries (3-D points, ray samples) gather all
  * channels of a texel with float4 loads from the channels-last copy; planes are a few MB per item,
@@ -142,6 +153,12 @@ DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int3
                       const float* coords_xy, const float* coords_yt, const float* coords_xt,
                       int32_t T, int32_t H, int32_t W,
                       const ddmi_weights_t* weights, float* out, void* stream);
+
+/* ddmi_decode_video with an output store mode (DDMI_STORE_*); `out` is float* or uint8_t* accordingly. */
+DDMI_API int ddmi_decode_video_store(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                            const float* coords_xy, const float* coords_yt, const float* coords_xt,
+                            int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, int32_t store,
+                            void* out, void* stream);
 
 /*
  * NeRF MLP on pre-embedded rows.  x: (n, 186) = [latent 96 | embed(pts) 63 |

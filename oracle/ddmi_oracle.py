@@ -222,3 +222,18 @@ def nerf_render_rays(sd, rays, fea, n_samples, white_bkgd=True, slope=1.0, retur
     if white_bkgd:
         rgb = rgb + (1. - weights.sum(-1))[..., None]
     return (rgb, raw) if return_raw else rgb
+
+
+# ---------------------------------------------------------------------------
+# caller epilogues of the decoded image / video signal
+# ---------------------------------------------------------------------------
+def store_clamp(x):
+    """`fake.clamp(-1., 1.)` -- evals/eval.py:162,226; tools/ldm/image.py:246."""
+    return x.clamp(-1., 1.)
+
+
+def store_u8_channels_last(x):
+    """`rearrange((fake.clamp(-1,1) + 1) * 127.5, 'b c t h w -> b t h w c').type(torch.uint8)` -- evals/eval.py:289,336-337
+    (for images the same with 'b c h w -> b h w c')."""
+    y = ((x.clamp(-1, 1) + 1) * 127.5)
+    return y.movedim(1, -1).contiguous().type(torch.uint8)

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ddmi_abi_version() == 5
+    assert L.ddmi_abi_version() == 6
     assert L.ddmi_status_string(1).decode() == 'bad argument'
 
 

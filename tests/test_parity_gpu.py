@@ -84,6 +84,28 @@ def test_image_style_cache_tracks_si_and_weights():
     assert float((c - b - 1.0).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("precision", ["fp32", "f16f8"])
+def test_image_store_modes(precision):
+    """Caller epilogues fused into the output stage: clamp is bit-exact against clamping the kernel's own fp32 output, the uint8
+    channels-last mode bit-exact against the reference's expression applied to it, and within 1 LSB of the reference's result."""
+    m = cases.build_module('image').to(DEV)
+    m.precision = precision
+    coords, planes, si = cases.image_inputs(batch=2, sizes=(16, 32, 64), res=96)
+    planes = [p * 3.0 for p in planes]                                  # push part of the signal outside [-1, 1]
+    ref = orc.image_decode(cases.state_dict32(m), coords, planes, si)
+    f32 = m(coords.to(DEV), hdbf=_cuda(planes), si=si).cpu()
+    assert float((f32.abs() > 1).float().mean()) > 0.01                  # the clamp matters on this input
+    clamped = m(coords.to(DEV), hdbf=_cuda(planes), si=si, store='clamp').cpu()
+    assert torch.equal(clamped, orc.store_clamp(f32))
+    u8 = m(coords.to(DEV), hdbf=_cuda(planes), si=si, store='u8').cpu()
+    assert u8.dtype == torch.uint8 and u8.shape == (2, 96, 96, 3)
+    assert torch.equal(u8, orc.store_u8_channels_last(f32))
+    d = (u8.int() - orc.store_u8_channels_last(ref).int()).abs()
+    assert int(d.max()) <= 1 and float((d == 0).float().mean()) > 0.99
+    with pytest.raises(ValueError):
+        m(coords.to(DEV), hdbf=_cuda(planes), si=si, store='u16')
+
+
 # ---------------------------------------------------------------- occupancy
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_occupancy_golden(golden_dir, precision):
@@ -153,6 +175,24 @@ def test_video_batch_and_anisotropic(precision):
     ref = orc.video_decode(sd, coords, (xy, yt, xt))
     out = m(_cuda(coords), _cuda((xy, yt, xt))).cpu()
     assert float((out - ref).abs().max()) < (2e-5 if precision == 'fp32' else TOL)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16f8"])
+def test_video_store_modes(precision):
+    m = cases.build_module('video').to(DEV)
+    m.precision = precision
+    coords, hdbf = cases.video_inputs()
+    hdbf = tuple([p * 4.0 for p in axis] for axis in hdbf)
+    ref = orc.video_decode(cases.state_dict32(m), coords, hdbf)
+    f32 = m(_cuda(coords), _cuda(hdbf)).cpu()
+    clamped = m(_cuda(coords), _cuda(hdbf), store='clamp').cpu()
+    assert torch.equal(clamped, orc.store_clamp(f32))
+    u8 = m(_cuda(coords), _cuda(hdbf), store='u8').cpu()
+    b, c, t, h, w = f32.shape
+    assert u8.dtype == torch.uint8 and u8.shape == (b, t, h, w, c)
+    assert torch.equal(u8, orc.store_u8_channels_last(f32))
+    d = (u8.int() - orc.store_u8_channels_last(ref).int()).abs()
+    assert int(d.max()) <= 1 and float((d == 0).float().mean()) > 0.99
 
 
 # ---------------------------------------------------------------- nerf
