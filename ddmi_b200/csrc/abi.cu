@@ -25,15 +25,15 @@ int launch_image_fp32(const PlaneSet&, int, int, const float*, const float*, lon
 int launch_occupancy_fp32(const PlaneSet&, int, int, const float*, long long, long long, float, float, const float*, const float*, float*, cudaStream_t);
 int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const float*, const float*, void*, int, cudaStream_t);
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
-int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
+int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
 int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
 int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, cudaStream_t);
-int launch_nerf_composite(const float*, const float*, int, const float*, int, long long, int, int, float*, cudaStream_t);
-int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
+int launch_nerf_composite(const float*, const float*, int, const float*, int, int, long long, int, int, float*, cudaStream_t);
+int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_selftest_f16f8(const float*, const float*, float*, int, int, cudaStream_t);
@@ -251,16 +251,37 @@ DDMI_API int ddmi_nerf_mlp(const float* x, int64_t n, int32_t x_stride, int32_t 
                               weights->vec, out, (cudaStream_t)stream);
 }
 
+static int nerf_render_impl(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
+                            const float* rays, int64_t n_rays, int32_t ray_stride, const float* t_vals, int z_stride,
+                            int32_t n_samples, float plane_extent, float negative_slope, int32_t white_bkgd,
+                            const ddmi_weights_t* weights, float* rgb_map, float* raw, void* stream);
+
 DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
                      const float* rays, int64_t n_rays, int32_t ray_stride, const float* t_vals, int32_t n_samples,
                      float plane_extent, float negative_slope, int32_t white_bkgd,
                      const ddmi_weights_t* weights, float* rgb_map, float* raw, void* stream) {
+  return nerf_render_impl(planes, batch, channels, plane_layout, rays, n_rays, ray_stride, t_vals, 0, n_samples, plane_extent,
+                          negative_slope, white_bkgd, weights, rgb_map, raw, stream);
+}
+
+DDMI_API int ddmi_nerf_render_z(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
+                       const float* rays, int64_t n_rays, int32_t ray_stride, const float* z_vals, int32_t n_samples,
+                       float plane_extent, float negative_slope, int32_t white_bkgd,
+                       const ddmi_weights_t* weights, float* rgb_map, float* raw, void* stream) {
+  return nerf_render_impl(planes, batch, channels, plane_layout, rays, n_rays, ray_stride, z_vals, n_samples, n_samples,
+                          plane_extent, negative_slope, white_bkgd, weights, rgb_map, raw, stream);
+}
+
+static int nerf_render_impl(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
+                            const float* rays, int64_t n_rays, int32_t ray_stride, const float* t_vals, int z_stride,
+                            int32_t n_samples, float plane_extent, float negative_slope, int32_t white_bkgd,
+                            const ddmi_weights_t* weights, float* rgb_map, float* raw, void* stream) {
   PlaneSet ps = {};
   int rc = check_planes(planes, 3, &ps);
   if (rc) return rc;
   DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
   DDMI_REQUIRE(n_rays >= 1 && n_samples >= 1, "empty ray set (%lld rays x %d samples)", (long long)n_rays, n_samples);
-  DDMI_REQUIRE(rays && t_vals && rgb_map, "rays / t_vals / rgb_map is NULL");
+  DDMI_REQUIRE(rays && t_vals && rgb_map, "rays / t_vals (z_vals) / rgb_map is NULL");
   DDMI_REQUIRE(ray_stride >= 11, "ray rows need [o d near far viewdir] = 11 floats (stride %d)", ray_stride);
   DDMI_REQUIRE(plane_extent > 0.f, "plane_extent must be positive");
   if (channels != 32) {
@@ -279,12 +300,12 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
     const int fuse = n_samples == 128;
     DDMI_REQUIRE(fuse || raw != nullptr, "n_samples != 128: compositing runs as a second kernel over `raw`; pass the buffer");
-    rc = launch_nerf_umma_entry(ps, batch, channels, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent,
+    rc = launch_nerf_umma_entry(ps, batch, channels, rays, n_rays, ray_stride, t_vals, z_stride, n_samples, plane_extent,
                                 negative_slope, white_bkgd, weights->gemm, weights->gemm_bytes, weights->program_host,
                                 weights->program_words, weights->program, weights->vec, weights->vec_floats, rgb_map, raw,
                                 fuse, weights->precision == DDMI_PREC_F16F8, (cudaStream_t)stream);
     if (rc || fuse) return rc;
-    return launch_nerf_composite(raw, rays, ray_stride, t_vals, n_samples, n_rays, batch, white_bkgd, rgb_map,
+    return launch_nerf_composite(raw, rays, ray_stride, t_vals, z_stride, n_samples, n_rays, batch, white_bkgd, rgb_map,
                                  (cudaStream_t)stream);
   }
   if (weights->precision != DDMI_PREC_FP32) {
@@ -298,7 +319,7 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
   rc = check_weights(weights, kNerfGemmFloats * sizeof(float), kNerfVecFloats);
   if (rc) return rc;
   DDMI_REQUIRE(raw != nullptr, "the fp32 render kernel composites from `raw`; pass a (batch,n_rays,n_samples,4) buffer");
-  return launch_nerf_render_fp32(ps, batch, channels, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent,
+  return launch_nerf_render_fp32(ps, batch, channels, rays, n_rays, ray_stride, t_vals, z_stride, n_samples, plane_extent,
                                  negative_slope, white_bkgd, (const float*)weights->gemm, weights->vec, rgb_map,
                                  raw, (cudaStream_t)stream);
 }

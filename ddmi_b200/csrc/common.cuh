@@ -117,6 +117,14 @@ __device__ __forceinline__ float occ_normalize(float p, float divisor, float upp
   return __fsub_rn(__fmul_rn(2.f, u), 1.f);
 }
 
+// Depth of sample `smp` on ray `ray`: z_stride == 0 -> near * (1 - t) + far * t from the shared t table (nerf_helpers.py:356-358,
+// perturb = 0, lindisp = False); z_stride = n_samples -> the caller's per-ray table (stratified `perturb`, `lindisp`: :359-380).
+__device__ __forceinline__ float nerf_z(const float* __restrict__ zt, int z_stride, long long ray, int smp, float near, float far) {
+  if (z_stride) return __ldg(zt + (size_t)ray * z_stride + smp);
+  const float tv = __ldg(zt + smp);
+  return __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, tv)), __fmul_rn(far, tv));
+}
+
 // Output store modes of the image / video decoders (DDMI_STORE_* in ddmi_b200.h): channel c (of 3) of coordinate gi of
 // item b, n coordinates per item.  0: (b, 3, n) fp32 as the reference returns it; 1: the same, clamp(v, -1, 1)
 // (evals/eval.py:162,226); 2: uint8((clamp(v,-1,1) + 1) * 127.5) channels-last (b, n, 3) -- the reference's

@@ -387,7 +387,7 @@ constexpr size_t NRF_SMEM = (size_t)(2 * TM * HS + TM * NRF_XS + TM * NRF_DS + 2
 template <bool kFused>
 __global__ void __launch_bounds__(NT, 1)
 nerf_kernel(PlaneSet ps, int C, const float* __restrict__ xin, int x_stride, int sigma_only,
-            const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
+            const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals, int z_stride,
             int n_samples, float plane_extent, long long n /* rows per object */,
             int tiles_per_item, float slope, const float* __restrict__ Wg,
             const float* __restrict__ vec, float* __restrict__ out) {
@@ -410,9 +410,7 @@ nerf_kernel(PlaneSet ps, int C, const float* __restrict__ xin, int x_stride, int
     const long long ray = gi / n_samples;
     const int smp = (int)(gi % n_samples);
     const float* rr = rays + (size_t)ray * ray_stride;
-    const float tv = __ldg(t_vals + smp);
-    const float near = __ldg(rr + 6), far = __ldg(rr + 7);
-    const float z = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, tv)), __fmul_rn(far, tv));
+    const float z = nerf_z(t_vals, z_stride, ray, smp, __ldg(rr + 6), __ldg(rr + 7));
     float p[3], g[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -527,7 +525,7 @@ nerf_kernel(PlaneSet ps, int C, const float* __restrict__ xin, int x_stride, int
 
 // raw2outputs (utils/nerf_helpers.py:487-530), raw_noise_std = 0.  One thread per ray.
 __global__ void nerf_composite_kernel(const float* __restrict__ raw, const float* __restrict__ rays,
-                                      int ray_stride, const float* __restrict__ t_vals, int n_samples,
+                                      int ray_stride, const float* __restrict__ t_vals, int z_stride, int n_samples,
                                       long long n_rays, int batch, int white_bkgd,
                                       float* __restrict__ rgb_map) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -539,13 +537,11 @@ __global__ void nerf_composite_kernel(const float* __restrict__ raw, const float
   const float dn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
   const float4* rw = reinterpret_cast<const float4*>(raw) + (size_t)i * n_samples;
   float T = 1.f, acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-  float tv = __ldg(t_vals);
-  float z = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, tv)), __fmul_rn(far, tv));
+  float z = nerf_z(t_vals, z_stride, ray, 0, near, far);
   for (int s = 0; s < n_samples; ++s) {
     float dist;
     if (s + 1 < n_samples) {
-      float tn = __ldg(t_vals + s + 1);
-      float zn = __fadd_rn(__fmul_rn(near, __fsub_rn(1.f, tn)), __fmul_rn(far, tn));
+      float zn = nerf_z(t_vals, z_stride, ray, s + 1, near, far);
       dist = __fsub_rn(zn, z);
       z = zn;
     } else {
@@ -659,22 +655,22 @@ int launch_nerf_mlp_fp32(const float* x, long long n, int x_stride, int sigma_on
   if (rc) return rc;
   PlaneSet ps = {};
   fp32::nerf_kernel<false><<<(unsigned)tpi, fp32::NT, fp32::NRF_SMEM, st>>>(
-      ps, 32, x, x_stride, sigma_only, nullptr, 0, nullptr, 1, 1.f, n, (int)tpi, slope, Wg, vec, out);
+      ps, 32, x, x_stride, sigma_only, nullptr, 0, nullptr, 0, 1, 1.f, n, (int)tpi, slope, Wg, vec, out);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }
 
-int launch_nerf_composite(const float* raw, const float* rays, int ray_stride, const float* t_vals, int n_samples,
+int launch_nerf_composite(const float* raw, const float* rays, int ray_stride, const float* t_vals, int z_stride, int n_samples,
                           long long n_rays, int batch, int white_bkgd, float* rgb_map, cudaStream_t st) {
   long long tot = n_rays * batch;
-  fp32::nerf_composite_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(raw, rays, ray_stride, t_vals, n_samples, n_rays,
+  fp32::nerf_composite_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(raw, rays, ray_stride, t_vals, z_stride, n_samples, n_rays,
                                                                              batch, white_bkgd, rgb_map);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }
 
 int launch_nerf_render_fp32(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays,
-                            int ray_stride, const float* t_vals, int n_samples, float plane_extent,
+                            int ray_stride, const float* t_vals, int z_stride, int n_samples, float plane_extent,
                             float slope, int white_bkgd, const float* Wg, const float* vec,
                             float* rgb_map, float* raw, cudaStream_t st) {
   long long n = n_rays * n_samples;
@@ -684,12 +680,12 @@ int launch_nerf_render_fp32(const PlaneSet& ps, int batch, int C, const float* r
   rc = set_smem(fp32::nerf_kernel<true>, fp32::NRF_SMEM);
   if (rc) return rc;
   fp32::nerf_kernel<true><<<(unsigned)(tpi * batch), fp32::NT, fp32::NRF_SMEM, st>>>(
-      ps, C, nullptr, 0, 0, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, slope,
+      ps, C, nullptr, 0, 0, rays, ray_stride, t_vals, z_stride, n_samples, plane_extent, n, (int)tpi, slope,
       Wg, vec, raw);
   DDMI_CUDA(cudaGetLastError());
   long long tot = n_rays * batch;
   fp32::nerf_composite_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(
-      raw, rays, ray_stride, t_vals, n_samples, n_rays, batch, white_bkgd, rgb_map);
+      raw, rays, ray_stride, t_vals, z_stride, n_samples, n_rays, batch, white_bkgd, rgb_map);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

@@ -419,11 +419,11 @@ int launch_occupancy_umma_entry(const PlaneSet& ps, int batch, int C, const floa
 }
 
 int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays, int ray_stride,
-                           const float* t_vals, int n_samples, float plane_extent, float slope, int white_bkgd,
+                           const float* t_vals, int z_stride, int n_samples, float plane_extent, float slope, int white_bkgd,
                            const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                            const uint32_t* program_dev, const float* vec, size_t vec_floats, float* rgb_map, float* raw,
                            int fuse, int f16f8, cudaStream_t st) {
-  return launch_nerf_umma(ps, batch, C, rays, n_rays, ray_stride, t_vals, n_samples, plane_extent, slope, white_bkgd, gemm,
+  return launch_nerf_umma(ps, batch, C, rays, n_rays, ray_stride, t_vals, z_stride, n_samples, plane_extent, slope, white_bkgd, gemm,
                           gemm_bytes, program_host, program_words, program_dev, vec, vec_floats, rgb_map, raw, fuse, f16f8, st);
 }
 

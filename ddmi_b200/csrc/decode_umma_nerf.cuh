@@ -55,7 +55,7 @@ __device__ __forceinline__ void x_store8(uint32_t tmem_lane, int j, const float 
 template <int SCHEME>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
-                 int n_samples, float plane_extent, long long n /* rows per object */, int tiles_per_item,
+                 int z_stride, int n_samples, float plane_extent, long long n /* rows per object */, int tiles_per_item,
                  long long total_tiles, float slope, int white_bkgd, int fuse,
                  const uint8_t* __restrict__ wstream, const uint32_t* __restrict__ program,
                  const float* __restrict__ vec, float* __restrict__ rgb_map, float* __restrict__ raw) {
@@ -110,9 +110,8 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       r.smp = (int)(r.gi % n_samples);
       return r;
     };
-    auto zval = [&](const float* rr, int smp) {   // near * (1 - t) + far * t  (nerf_helpers.py:356-358)
-      const float tv = __ldg(t_vals + smp);
-      return __fadd_rn(__fmul_rn(__ldg(rr + 6), __fsub_rn(1.f, tv)), __fmul_rn(__ldg(rr + 7), tv));
+    auto zval = [&](const float* rr, long long ray, int smp) {   // nerf_helpers.py:356-380 (common.cuh::nerf_z)
+      return nerf_z(t_vals, z_stride, ray, smp, __ldg(rr + 6), __ldg(rr + 7));
     };
     // gamma(p) element e of the 63-wide embedding (Embedder.embed): [p, sin(2^0 p), cos(2^0 p), ...]
     auto embed_elem = [&](const float (&p)[3], int e, int nmax) {
@@ -126,7 +125,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     auto build_x = [&](long long tile) {
       const RowInfo ri = row_of(tile);
       const float* rr = rays + (size_t)ri.ray * ray_stride;
-      const float z = zval(rr, ri.smp);
+      const float z = zval(rr, ri.ray, ri.smp);
       float p[3], g[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -241,8 +240,8 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         }
         if (fuse) {
           // raw2outputs (nerf_helpers.py:487-530): one tile == one ray, row == sample index
-          const float z0 = zval(rr, ri.smp);
-          float dist = ri.smp + 1 < n_samples ? __fsub_rn(zval(rr, ri.smp + 1), z0) : 1e10f;
+          const float z0 = zval(rr, ri.ray, ri.smp);
+          float dist = ri.smp + 1 < n_samples ? __fsub_rn(zval(rr, ri.ray, ri.smp + 1), z0) : 1e10f;
           const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
           dist = __fmul_rn(dist, sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
           const float alpha = __fsub_rn(1.f, expf(-__fmul_rn(softplus20(sigma), dist)));
@@ -298,7 +297,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
 }  // namespace ummak
 
 inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* rays, long long n_rays, int ray_stride,
-                            const float* t_vals, int n_samples, float plane_extent, float slope, int white_bkgd,
+                            const float* t_vals, int z_stride, int n_samples, float plane_extent, float slope, int white_bkgd,
                             const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                             const uint32_t* program_dev, const float* vec, size_t vec_floats, float* rgb_map, float* raw,
                             int fuse, int f16f8, cudaStream_t st) {
@@ -322,12 +321,12 @@ inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* r
   if (f16f8) {
     DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
     nerf_umma_kernel<1><<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
-        ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
+        ps, C, rays, ray_stride, t_vals, z_stride, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
         (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
   } else {
     DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
     nerf_umma_kernel<0><<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
-        ps, C, rays, ray_stride, t_vals, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
+        ps, C, rays, ray_stride, t_vals, z_stride, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
         (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
   }
   DDMI_CUDA(cudaGetLastError());

@@ -7,9 +7,12 @@ sample generation, triplane gather, positional embedding, MLPNeRF and
 ``raw2outputs`` compositing (nerf_helpers.py:296-530) -- is one call into the
 C ABI (``ddmi_nerf_render``).  Ray generation stays host-side tensor plumbing.
 
-Out of scope here and rejected loudly (SURVEY.md §8f "next" row 4): stratified
-``perturb``, hierarchical ``N_importance`` / ``sample_pdf``, ``raw_noise_std``,
-``ndc`` rays, ``lindisp``, ``c2w_staticcam``.
+Stratified ``perturb`` and ``lindisp`` are supported by handing the kernel a per-ray
+depth table computed here exactly as the reference does (nerf_helpers.py:356-380, same
+torch ops and the same CPU ``torch.rand`` draw, so a seeded run reproduces the
+reference's samples).  Rejected loudly: hierarchical ``N_importance`` (the reference's
+branch, :402-431, reuses the coarse pass's plane coordinates for the enlarged sample set
+and cannot run), ``raw_noise_std`` (random), ``ndc`` rays, ``c2w_staticcam``.
 """
 import math
 
@@ -124,7 +127,30 @@ def _find_module(network_fn):
         "or pass the module itself); an opaque callable cannot be fused")
 
 
-def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False, precision=None):
+def sample_depths(rays, N_samples, perturb=0., lindisp=False):
+    """z_vals (N_rays, N_samples) of the reference's render_rays (nerf_helpers.py:353-380), op for op: linear in depth or
+    (lindisp) in disparity, then optionally stratified: one uniform draw per interval from ``torch.rand`` on the CPU generator,
+    as the reference does, moved to the rays' device."""
+    n = rays.shape[0]
+    bounds = torch.reshape(rays[..., 6:8], [-1, 1, 2])
+    near, far = bounds[..., 0], bounds[..., 1]
+    t_vals = torch.linspace(0., 1., steps=N_samples).to(near.device)
+    if not lindisp:
+        z_vals = near * (1. - t_vals) + far * (t_vals)
+    else:
+        z_vals = 1. / (1. / near * (1. - t_vals) + 1. / far * (t_vals))
+    z_vals = z_vals.expand([n, N_samples])
+    if perturb > 0.:
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], -1)
+        lower = torch.cat([z_vals[..., :1], mids], -1)
+        t_rand = torch.rand(z_vals.shape).to(near.device)
+        z_vals = lower + (upper - lower) * t_rand
+    return z_vals.contiguous()
+
+
+def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False, precision=None, perturb=0.,
+                      lindisp=False):
     """rays (N,11) [o d near far viewdir]; fea = dict of (B,32,R,R) planes.
     Returns rgb_map (B,N,3) (and raw (B,N,S,4)).  precision: 'f16f8' (tcgen05 kernel, fp16 + FP8-correction operands;
     the default) or 'bf16x3' (same kernel, bf16 hi/lo operands) -- compositing is fused in-kernel when N_samples == 128
@@ -152,7 +178,11 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
     b = planes[0].shape[0]
     rays = rays.detach().to(device=dev, dtype=torch.float32).contiguous()
     n = rays.shape[0]
-    t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)
+    per_ray = bool(lindisp) or (perturb is not None and perturb > 0.)
+    if per_ray:      # the kernel reads a (N_rays, N_samples) depth table instead of near * (1 - t) + far * t
+        t_vals = sample_depths(rays, N_samples, perturb or 0., lindisp).to(torch.float32)
+    else:
+        t_vals = torch.linspace(0., 1., steps=N_samples).to(dev)
     rgb = torch.empty((b, n, 3), device=dev, dtype=torch.float32)
     umma = precision in ('bf16x3', 'f16f8')
     need_raw = return_raw or not (umma and N_samples == 128)
@@ -163,7 +193,8 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
             keep, arr = _lib.planes_channels_last(planes, st)
         else:
             keep, arr = planes, _lib.planes_array(planes)
-        _lib.check(_lib.lib().ddmi_nerf_render(
+        entry = _lib.lib().ddmi_nerf_render_z if per_ray else _lib.lib().ddmi_nerf_render
+        _lib.check(entry(
             arr, b, planes[0].shape[1], 1 if umma else 0, rays.data_ptr(), n, rays.shape[1],
             t_vals.data_ptr(), N_samples, PLANE_EXTENT, module.negative_slope, 1 if white_bkgd else 0,
             _lib.weights_struct(packed), rgb.data_ptr(), raw.data_ptr() if raw is not None else None, st))
@@ -184,8 +215,7 @@ def render(H, W, K, fea, pose, idx, device, chunk=1024 * 32, rays=None, c2w=None
         raise NotImplementedError("ndc rays / c2w_staticcam are outside the fused decode path")
     if not use_viewdirs:
         raise NotImplementedError("the fused NeRF kernel is built for use_viewdirs=True (in_channels_dir=27)")
-    for key, bad in (('perturb', lambda v: v and v > 0), ('N_importance', lambda v: v and v > 0),
-                     ('raw_noise_std', lambda v: v and v > 0), ('lindisp', bool)):
+    for key, bad in (('N_importance', lambda v: v and v > 0), ('raw_noise_std', lambda v: v and v > 0)):
         if bad(kwargs.get(key, 0)):
             raise NotImplementedError(f"render(): {key}={kwargs[key]!r} is outside the fused decode path "
                                       "(SURVEY.md §8f row 4)")
@@ -204,5 +234,6 @@ def render(H, W, K, fea, pose, idx, device, chunk=1024 * 32, rays=None, c2w=None
     hw_idx = kwargs.get('hw_idx')
     if hw_idx is not None:
         ray_batch = ray_batch[hw_idx]
-    rgb = render_rays_fused(ray_batch, fea, module, N_samples, bool(kwargs.get('white_bkgd', False)))
+    rgb = render_rays_fused(ray_batch, fea, module, N_samples, bool(kwargs.get('white_bkgd', False)),
+                            perturb=float(kwargs.get('perturb', 0.) or 0.), lindisp=bool(kwargs.get('lindisp', False)))
     return rgb[0] if rgb.shape[0] == 1 else rgb

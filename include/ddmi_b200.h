@@ -191,6 +191,17 @@ DDMI_API int ddmi_nerf_render(const ddmi_plane_t planes[3], int32_t batch, int32
                      void* stream);
 
 /*
+ * Same with per-ray sample depths: z_vals (n_rays, n_samples) fp32 (device), shared by all batch items, replaces
+ * near * (1 - t) + far * t.  This is how the host side passes the reference's stratified `perturb` samples and `lindisp`
+ * spacing (utils/nerf_helpers.py:359-380); compositing uses the same table for its distances (:487-495).
+ */
+DDMI_API int ddmi_nerf_render_z(const ddmi_plane_t planes[3], int32_t batch, int32_t channels, int32_t plane_layout,
+                       const float* rays, int64_t n_rays, int32_t ray_stride,
+                       const float* z_vals, int32_t n_samples, float plane_extent,
+                       float negative_slope, int32_t white_bkgd, const ddmi_weights_t* weights,
+                       float* rgb_map, float* raw, void* stream);
+
+/*
  * Bring-up self test of the tcgen05 path: one 128 x N x K bf16 GEMM through the
  * same descriptors / TMEM epilogue the decode kernels use.  a: (128,K) fp32,
  * b: (N,K) fp32 (device); d: (128,N) fp32 = a * b^T computed with the bf16x3

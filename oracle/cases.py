@@ -93,6 +93,7 @@ def video_inputs(batch=1, T=4, sizes=(8, 16, 32), seed=SEED):
     return coords, (xy, yt, xt)
 
 
+NERF_PERTURB_SEED = 4242     # torch.manual_seed before a stratified (perturb > 0) render: fixes the CPU torch.rand draw
 NERF_CFG = {'model': {'TN': {'netchunk': 40000, 'peturb': 0, 'N_importance': 0, 'N_samples': 64,
                              'use_viewdirs': True, 'white_bkgd': True, 'raw_noise_std': 0}}}
 

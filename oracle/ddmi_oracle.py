@@ -198,13 +198,28 @@ def embed(x, multires):
     return torch.cat(out, -1)
 
 
-def nerf_render_rays(sd, rays, fea, n_samples, white_bkgd=True, slope=1.0, return_raw=False):
-    """render_rays + run_network + raw2outputs (perturb=0, N_importance=0,
-    raw_noise_std=0).  rays (N,11) [o d near far viewdir]; fea planes (1,32,R,R)."""
+def nerf_sample_depths(rays, n_samples, perturb=0., lindisp=False):
+    """z_vals of render_rays (utils/nerf_helpers.py:356-380): linear in depth or (lindisp) disparity, optionally
+    stratified with one torch.rand draw per interval."""
+    dt = rays.dtype
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    t = torch.linspace(0., 1., steps=n_samples).to(dt)
+    z = near * (1. - t) + far * t if not lindisp else 1. / (1. / near * (1. - t) + 1. / far * t)
+    z = z.expand(rays.shape[0], n_samples)
+    if perturb > 0.:
+        mids = .5 * (z[:, 1:] + z[:, :-1])
+        upper = torch.cat([mids, z[:, -1:]], -1)
+        lower = torch.cat([z[:, :1], mids], -1)
+        z = lower + (upper - lower) * torch.rand(z.shape).to(dt)
+    return z
+
+
+def nerf_render_rays(sd, rays, fea, n_samples, white_bkgd=True, slope=1.0, return_raw=False, perturb=0., lindisp=False):
+    """render_rays + run_network + raw2outputs (N_importance=0, raw_noise_std=0).
+    rays (N,11) [o d near far viewdir]; fea planes (1,32,R,R)."""
     dt = rays.dtype
     o, d, near, far, vd = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8], rays[:, 8:11]
-    t = torch.linspace(0., 1., steps=n_samples).to(dt)
-    z = near * (1. - t) + far * t                                   # (N,S)
+    z = nerf_sample_depths(rays, n_samples, perturb, lindisp)       # (N,S)
     pts = o[:, None, :] + d[:, None, :] * z[:, :, None]             # (N,S,3)
     npts = pts / 3.5
     lat = torch.cat((_gs(fea['xy'], npts[:, :, :2][None], True),

@@ -1,7 +1,8 @@
 """Generate tests/golden/*.pt by running the REFERENCE itself (build container only).
 
-Run:  python oracle/make_golden.py          (needs /root/reference, nvcc + ninja for the
-                                             reference's JIT ops; ~2 min the first time)
+Run:  python oracle/make_golden.py [names]  (needs /root/reference, nvcc + ninja for the
+                                             reference's JIT ops; ~2 min the first time;
+                                             names = fixtures to (re)write, default all)
 Imports models/d2c_vae/mlp.py and utils/nerf_helpers.py from /root/reference with the
 two CPU shims of SURVEY.md Appendix A (imageio stub; CPU restatement of
 fused_leaky_relu, semantics from op/fused_bias_act_kernel.cu:28-47), loads the
@@ -39,7 +40,13 @@ os.makedirs(OUT, exist_ok=True)
 torch.set_grad_enabled(False)
 
 
+ONLY = set(sys.argv[1:])     # optional: names of the fixtures to (re)write; default all
+
+
 def save(name, out, inputs, extra=None):
+    if ONLY and name not in ONLY:
+        print(f'{name}: not selected, left untouched')
+        return
     d = {'out': out.float().contiguous(), 'input_checksum': cases.checksum(inputs)}
     d.update(extra or {})
     torch.save(d, os.path.join(OUT, name + '.pt'))
@@ -109,4 +116,16 @@ rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(res * re
 o2 = orc.nerf_render_rays(sd, rays, fea, 64, True)
 print(f'  oracle-vs-reference nerf_render: {float((rgb - o2).abs().max()):.3e}; rgb range {float(rgb.min()):.3f}..{float(rgb.max()):.3f}')
 save('nerf_render', rgb, list(fea.values()) + list(sd.values()), {'rays': rays})
+
+# stratified sampling (perturb = 1: the training-time setting, one torch.rand draw on the CPU generator) and lindisp
+for tag, extra in (('nerf_render_perturb', dict(perturb=1.0)), ('nerf_render_lindisp', dict(lindisp=True)),
+                   ('nerf_render_perturb_lindisp', dict(perturb=1.0, lindisp=True))):
+    kw2 = dict(kw)
+    kw2.update(extra)
+    torch.manual_seed(cases.NERF_PERTURB_SEED)
+    rgb = rnh.render(res, res, K, fea, None, 0, 'cpu', chunk=4096, c2w=c2w, verbose=True, retraw=True, hw_idx=None, **kw2)
+    torch.manual_seed(cases.NERF_PERTURB_SEED)
+    o2 = orc.nerf_render_rays(sd, rays, fea, 64, True, perturb=extra.get('perturb', 0.), lindisp=extra.get('lindisp', False))
+    print(f'  oracle-vs-reference {tag}: {float((rgb - o2).abs().max()):.3e}')
+    save(tag, rgb, list(fea.values()) + list(sd.values()), {'rays': rays})
 print('done')

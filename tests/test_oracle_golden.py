@@ -81,6 +81,22 @@ def test_nerf_render(golden_dir):
     assert float(g['out'].max() - g['out'].min()) > 0.3   # the fixture is not degenerate
 
 
+@pytest.mark.parametrize("tag,perturb,lindisp", [("nerf_render_perturb", 1.0, False), ("nerf_render_lindisp", 0., True),
+                                                 ("nerf_render_perturb_lindisp", 1.0, True)])
+def test_nerf_render_stratified_and_lindisp(golden_dir, tag, perturb, lindisp):
+    """perturb > 0 draws torch.rand(z_vals.shape) on the CPU generator (utils/nerf_helpers.py:370): seeded like the
+    generator script, the oracle reproduces the reference's samples."""
+    g = _load(golden_dir, tag)
+    sd = cases.state_dict32(cases.build_module('nerf'))
+    res, K, fea, c2w = cases.nerf_inputs()
+    _check_inputs(g, list(fea.values()) + list(sd.values()))
+    torch.manual_seed(cases.NERF_PERTURB_SEED)
+    out = orc.nerf_render_rays(sd, g['rays'], fea, 64, True, perturb=perturb, lindisp=lindisp)
+    assert float((out - g['out']).abs().max()) < 1e-5
+    plain = _load(golden_dir, 'nerf_render')['out']
+    assert float((g['out'] - plain).abs().max()) > 1e-3      # the option changes the image
+
+
 def test_oracle_fp64_agrees():
     """fp64 evaluation of the oracle bounds the fp32 reference's own rounding noise."""
     sd = cases.state_dict32(cases.build_module('occupancy'))

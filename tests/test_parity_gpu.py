@@ -263,9 +263,44 @@ def test_unsupported_render_options_raise():
     e1, _ = nh.get_embedder(10, 0)
     e2, _ = nh.get_embedder(4, 0)
     kw = nh.get_render_kwargs(cases.NERF_CFG, m, e1, e2)
-    kw['perturb'] = 1.0
-    with pytest.raises(NotImplementedError):
-        nh.render(res, res, K, _cuda(fea), None, 0, DEV, c2w=c2w, **kw)
+    for key, val in (('N_importance', 64), ('raw_noise_std', 1.0)):
+        kw2 = dict(kw)
+        kw2[key] = val
+        with pytest.raises(NotImplementedError):
+            nh.render(res, res, K, _cuda(fea), None, 0, DEV, c2w=c2w, **kw2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
+@pytest.mark.parametrize("tag,perturb,lindisp", [("nerf_render_perturb", 1.0, False), ("nerf_render_lindisp", 0., True),
+                                                 ("nerf_render_perturb_lindisp", 1.0, True)])
+def test_nerf_render_stratified_and_lindisp_golden(golden_dir, tag, perturb, lindisp, precision):
+    """render(..., perturb=1 / lindisp=True): the host side builds the reference's per-ray depth table (same CPU torch.rand
+    draw under the same seed) and the kernels read it through ddmi_nerf_render_z."""
+    g = _golden(golden_dir, tag)
+    m = cases.build_module('nerf').to(DEV)
+    m.precision = precision
+    res, K, fea, c2w = cases.nerf_inputs()
+    e1, _ = nh.get_embedder(10, 0)
+    e2, _ = nh.get_embedder(4, 0)
+    kw = nh.get_render_kwargs(cases.NERF_CFG, m, e1, e2)
+    kw.update(perturb=perturb, lindisp=lindisp)
+    torch.manual_seed(cases.NERF_PERTURB_SEED)
+    rgb = nh.render(res, res, K, _cuda(fea), None, 0, DEV, chunk=4096, c2w=c2w, **kw).cpu()
+    assert float((rgb - g['out']).abs().max()) < (1e-4 if precision == 'fp32' else TOL)
+
+
+def test_nerf_stratified_fused_compositing_128_samples():
+    """per-ray depth table + in-kernel compositing (N_samples == 128) against the oracle on the same draw."""
+    m = cases.build_module('nerf').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(17)
+    fea = {k: torch.randn(1, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
+    rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][500:541]
+    torch.manual_seed(5)
+    rgb = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, perturb=1.0)
+    torch.manual_seed(5)
+    ref = orc.nerf_render_rays(sd, rays, fea, 128, True, perturb=1.0)
+    assert float((rgb[0].cpu() - ref).abs().max()) < TOL
 
 
 # ---------------------------------------------------------------- tcgen05 bring-up
