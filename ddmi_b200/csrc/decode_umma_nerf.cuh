@@ -121,7 +121,9 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       const float a = __fmul_rn(p[r % 3], (float)(1 << l));
       return r < 3 ? sinf(a) : cosf(a);
     };
-    // X = [latent xy|yz|xz (3 x 32) | gamma(pts) 63 | 0]: this thread fills K groups [10 ghalf, +10) of its row
+    // X = [latent xy|yz|xz (3 x 32) | gamma(pts) 63 | 0] = 12 gathered + 8 embedding K groups per row, split evenly over the
+    // row's two threads: gathers [6 ghalf, +6), embedding groups [12 + 4 ghalf, +4).  The gathers are L2-latency bound (there
+    // is no L1 beside ~200 KB of shared memory), so the 24 float4 loads of three K groups are issued before any is consumed.
     auto build_x = [&](long long tile) {
       const RowInfo ri = row_of(tile);
       const float* rr = rays + (size_t)ri.ray * ray_stride;
@@ -133,17 +135,43 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         g[i] = __fdiv_rn(p[i], plane_extent);
       }
 #pragma unroll 1
-      for (int j = ghalf * 10; j < ghalf * 10 + 10; ++j) {
-        float y[8];
-        if (j < 12) {   // plane a = j / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate -> column
-          const int a = j >> 2;
-          const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
-          const Tap tp = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
-          tap_sample8_nhwc(ps.data[a] + (size_t)ri.b * ps.h[a] * ps.w[a] * C, tp, C, (j & 3) * 8, y);
-        } else {
+      for (int bb = 0; bb < 2; ++bb) {
+        float4 q[3][8];
+        Tap tp[3];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = embed_elem(p, (j - 12) * 8 + i, 63);
+        for (int u = 0; u < 3; ++u) {   // plane a = j / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate -> column
+          const int j = ghalf * 6 + bb * 3 + u, a = j >> 2;
+          const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
+          tp[u] = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
+          const float* img = ps.data[a] + (size_t)ri.b * ps.h[a] * ps.w[a] * C + (j & 3) * 8;
+          const int o[4] = {tp[u].o00, tp[u].o01, tp[u].o10, tp[u].o11};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4* pp = reinterpret_cast<const float4*>(img + (size_t)o[t] * C);
+            q[u][2 * t] = __ldg(pp);
+            q[u][2 * t + 1] = __ldg(pp + 1);
+          }
         }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const float w[4] = {tp[u].w00, tp[u].w01, tp[u].w10, tp[u].w11};
+          float y[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {   // same FMA order as common.cuh::tap_sample8_nhwc
+            const float4 a0 = q[u][h], b0 = q[u][2 + h], c0 = q[u][4 + h], d0 = q[u][6 + h];
+            y[4 * h + 0] = fmaf(d0.x, w[3], fmaf(c0.x, w[2], fmaf(b0.x, w[1], a0.x * w[0])));
+            y[4 * h + 1] = fmaf(d0.y, w[3], fmaf(c0.y, w[2], fmaf(b0.y, w[1], a0.y * w[0])));
+            y[4 * h + 2] = fmaf(d0.z, w[3], fmaf(c0.z, w[2], fmaf(b0.z, w[1], a0.z * w[0])));
+            y[4 * h + 3] = fmaf(d0.w, w[3], fmaf(c0.w, w[2], fmaf(b0.w, w[1], a0.w * w[0])));
+          }
+          x_store8<SCHEME>(tmem_lane, ghalf * 6 + bb * 3 + u, y);
+        }
+      }
+#pragma unroll 1
+      for (int j = 12 + ghalf * 4; j < 16 + ghalf * 4; ++j) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = embed_elem(p, (j - 12) * 8 + i, 63);
         x_store8<SCHEME>(tmem_lane, j, y);
       }
       tmem_st_wait();

@@ -7,7 +7,7 @@ from ddmi_b200 import _lib
 kind = sys.argv[1]
 buf = (ctypes.c_uint64 * 8)()
 class A: pass
-a = A(); a.workload = kind; a.batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4; a.steps = 1; a.warmup = 1
+a = A(); a.workload = kind; a.batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4; a.steps = 1; a.warmup = 1; a.precision = os.environ.get("DDMI_B200_PRECISION", "f16f8")
 import io, contextlib
 bench.ARGS = a
 with contextlib.redirect_stdout(io.StringIO()):
