@@ -161,7 +161,10 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     const bool prof = (blockIdx.x == 0 && tid == 0);
     long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = clock64();
 
-    auto gather = [&](long long tile, int s) {
+    // `part` 0 / 1 = first / second 16 of this thread's 32 channels (-1: both): the two halves are issued in two different
+    // idle windows of the epilogue threads (after the conv1 and after the conv2 epilogue, while conv2 / conv3 run on the
+    // tensor core), so the L2-latency-bound gather delays neither epilogue by much
+    auto gather = [&](long long tile, int s, int part) {
       const long long g0 = clock64();
       if (tile > total_tiles - 1) tile = total_tiles - 1;   // odd tail of a pair: decode a duplicate, store nothing
       const int b = (int)(tile / tiles_per_item);
@@ -173,7 +176,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       if (SCHEME) {
         // f16f8: this thread's 32 channels = K step `ghalf` of X: fp16 groups 4*ghalf.., FP8 groups [r8 r8 a8 a8] at x_lo
 #pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
+        for (int g = (part == 1 ? 1 : 0); g < (part == 0 ? 1 : 2); ++g) {
           float2 y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -190,7 +193,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         }
       } else {
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
+        for (int g = (part == 1 ? 2 : 0); g < (part == 0 ? 2 : 4); ++g) {
           float y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) y[i] = tap_sample(base + (size_t)(g * 8 + i) * hw, t);
@@ -224,7 +227,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       p_wait += p_t - w0;
     };
 
-    if (ntiles > 0) gather(tile_of(0), 0);
+    if (ntiles > 0) gather(tile_of(0), 0, -1);
     if (ntiles > 0) signal_all();
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
@@ -236,13 +239,15 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         stage_prefetch<false>(pf, bv, nullptr, sub);
         wait_mma();
         image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal);
-        // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale)
-        if (blk < 2) gather(tile, blk + 1);
-        else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0);
+        // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale), first half of the channels
+        if (blk < 2) gather(tile, blk + 1, 0);
+        else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
         // ---- conv2
         stage_prefetch<false>(pf, bv + 256, nullptr, sub);
         wait_mma();
         image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal);
+        if (blk < 2) gather(tile, blk + 1, 1);                                   // second half, under conv3's GEMM
+        else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 1);
         // ---- conv3 + skip
         if (blk < 3) stage_prefetch<true>(pf, bv + 512, bv + 768, sub);
         else stage_prefetch<false>(pf, bv + 512, nullptr, sub);
