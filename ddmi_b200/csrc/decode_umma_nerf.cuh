@@ -179,7 +179,12 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
     auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {   // waits for the GEMM first
       const float sl = act ? slope : 1.f;
-      biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
+      // nn.LeakyReLU(True) has negative_slope = 1.0: the reference's activation is the identity -- do not spend
+      // 4 instructions per pair evaluating it
+      if (sl == 1.f)
+        biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [](float2 t) { return t; }, signal, 0);
+      else
+        biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b, 4, v, wait_mma, [sl](float2 t) { return lrelu_pair(t, sl); }, signal, 0);
     };
 
     if (ntiles > 0) {
@@ -242,7 +247,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         for (int q = 0; q < 2; ++q) {
           add_vec<SCHEME, 16>(v[q], vec + NV_BD + q * 64 + sub * 32);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[q][i] = lrelu_pair(v[q][i], slope);
+          for (int i = 0; i < 16; ++i) v[q][i] = slope == 1.f ? v[q][i] : lrelu_pair(v[q][i], slope);
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float2 w[16];

@@ -289,6 +289,26 @@ def test_nerf_render_stratified_and_lindisp_golden(golden_dir, tag, perturb, lin
     assert float((rgb - g['out']).abs().max()) < (1e-4 if precision == 'fp32' else TOL)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
+def test_nerf_render_with_a_real_leaky_slope(precision):
+    """The reference's nn.LeakyReLU(True) has slope 1.0 (identity), which the tcgen05 kernel special-cases; a module whose
+    activations really leak (slope 0.2) goes through the general path."""
+    m = cases.build_module('nerf').to(DEV)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.LeakyReLU):
+            mod.negative_slope = 0.2
+    assert m.negative_slope == 0.2
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(23)
+    fea = {k: torch.randn(1, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
+    rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][40:81]
+    rgb, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, return_raw=True, precision=precision)
+    ref, ref_raw = orc.nerf_render_rays(sd, rays, fea, 128, True, slope=0.2, return_raw=True)
+    tol = 1e-4 if precision == 'fp32' else TOL
+    assert float((raw[0].cpu() - ref_raw).abs().max()) < tol
+    assert float((rgb[0].cpu() - ref).abs().max()) < tol
+
+
 def test_nerf_stratified_fused_compositing_128_samples():
     """per-ray depth table + in-kernel compositing (N_samples == 128) against the oracle on the same draw."""
     m = cases.build_module('nerf').to(DEV)
