@@ -52,6 +52,34 @@ __device__ __forceinline__ void x_store8(uint32_t tmem_lane, int j, const float 
   }
 }
 
+// gamma(p), L = 10 (Embedder.embed, nerf_helpers.py:82-112): [p, sin(2^0 p), cos(2^0 p), ..., sin(2^9 p), cos(2^9 p)] = 63 values
+// (+ one zero pad).  Elements [32 HALF, +32) with compile-time indexing; sin and cos of one argument share a sincosf.
+// LEVELS = 10, N = 32: one half of gamma(pts); LEVELS = 4, N = 16: one half of gamma(viewdir) (27 values + 5 zero pads).
+template <int HALF, int LEVELS, int N>
+__device__ __forceinline__ void embed_half(const float (&p)[3], float (&y)[N]) {
+  constexpr int E0 = N * HALF;
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = 0.f;                  // covers the pad elements
+  if (HALF == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) y[a] = p[a];
+  }
+#pragma unroll
+  for (int l = 0; l < LEVELS; ++l) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int es = 3 + 6 * l + a, ec = es + 3;            // element indices of sin / cos (compile-time after unrolling)
+      const bool ns = es >= E0 && es < E0 + N, nc = ec >= E0 && ec < E0 + N;
+      if (ns || nc) {
+        float sv, cv;
+        sincosf(__fmul_rn(p[a], (float)(1 << l)), &sv, &cv);
+        if (ns) y[es - E0] = sv;
+        if (nc) y[ec - E0] = cv;
+      }
+    }
+  }
+}
+
 template <int SCHEME>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
@@ -113,14 +141,6 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     auto zval = [&](const float* rr, long long ray, int smp) {   // nerf_helpers.py:356-380 (common.cuh::nerf_z)
       return nerf_z(t_vals, z_stride, ray, smp, __ldg(rr + 6), __ldg(rr + 7));
     };
-    // gamma(p) element e of the 63-wide embedding (Embedder.embed): [p, sin(2^0 p), cos(2^0 p), ...]
-    auto embed_elem = [&](const float (&p)[3], int e, int nmax) {
-      if (e >= nmax) return 0.f;
-      if (e < 3) return p[e];
-      const int l = (e - 3) / 6, r = (e - 3) % 6;
-      const float a = __fmul_rn(p[r % 3], (float)(1 << l));
-      return r < 3 ? sinf(a) : cosf(a);
-    };
     // X = [latent xy|yz|xz (3 x 32) | gamma(pts) 63 | 0] = 12 gathered + 8 embedding K groups per row, split evenly over the
     // row's two threads: gathers [6 ghalf, +6), embedding groups [12 + 4 ghalf, +4).  The gathers are L2-latency bound (there
     // is no L1 beside ~200 KB of shared memory), so the 24 float4 loads of three K groups are issued before any is consumed.
@@ -167,12 +187,16 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
           x_store8<SCHEME>(tmem_lane, ghalf * 6 + bb * 3 + u, y);
         }
       }
-#pragma unroll 1
-      for (int j = 12 + ghalf * 4; j < 16 + ghalf * 4; ++j) {
-        float y[8];
+      {
+        float e[32];
+        if (ghalf == 0) embed_half<0, 10, 32>(p, e); else embed_half<1, 10, 32>(p, e);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) y[i] = embed_elem(p, (j - 12) * 8 + i, 63);
-        x_store8<SCHEME>(tmem_lane, j, y);
+        for (int jj = 0; jj < 4; ++jj) {
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = e[jj * 8 + i];
+          x_store8<SCHEME>(tmem_lane, 12 + ghalf * 4 + jj, y);
+        }
       }
       tmem_st_wait();
     };
@@ -204,14 +228,16 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         if (l == 5) {
           // X is dead (the last skip layer committed): view-direction embedding -> X's first 4 K groups,
           // sigma = w_sigma . h6 + b_sigma (this thread's 128 columns, summed across the two sub-warps below)
-          if (ghalf == 0) {
+          {   // 2 of the 4 K groups per thread of the row
             const float vd[3] = {__ldg(rr + 8), __ldg(rr + 9), __ldg(rr + 10)};
-#pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
+            float e[16];
+            if (ghalf == 0) embed_half<0, 4, 16>(vd, e); else embed_half<1, 4, 16>(vd, e);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
               float y[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) y[i] = embed_elem(vd, j * 8 + i, 27);
-              x_store8<SCHEME>(tmem_lane, j, y);
+              for (int i = 0; i < 8; ++i) y[i] = e[jj * 8 + i];
+              x_store8<SCHEME>(tmem_lane, 2 * ghalf + jj, y);
             }
             tmem_st_wait();
           }
