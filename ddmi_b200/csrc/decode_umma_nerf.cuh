@@ -268,6 +268,12 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         tmem_ld32(tmem_lane + sub * 32, v[0]);
         tmem_ld32(tmem_lane + 64 + sub * 32, v[1]);
         tmem_ld_wait();
+        // Every MMA of this tile has committed and its last accumulator is in registers: build the next tile's X and hand
+        // over NOW, so that the rgb head and the compositing below run under the next tile's first GEMM.
+        if (it + 1 < ntiles) {
+          build_x(tile_of(it + 1));
+          signal_all();
+        }
         float2 acc3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
@@ -340,11 +346,6 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
           }
           asm volatile("bar.sync 2, 128;" ::: "memory");
         }
-      }
-      // every MMA that reads X / the direction embedding has committed: build the next tile's X, then hand over
-      if (it + 1 < ntiles) {
-        build_x(tile_of(it + 1));
-        signal_all();
       }
     }
   } else {
