@@ -96,6 +96,33 @@ __device__ __forceinline__ void put_quarter(uint32_t h_hi, uint32_t h_lo, int ro
   }
 }
 
+// Block-output stage: h = acc (de-scaled) + bias [+ extra], published quarter by quarter (raw or relu'd) on barriers
+// sig0..sig0+3; v keeps h (fp32) for a later phase.  Like biased_stage, quarter 0's bias is loaded before the thread parks on
+// the MMA barrier and quarter q + 1's while quarter q is converted (an unprefetched vector is an exposed L2 round trip).
+template <int SCHEME, bool RELU, class Wait, class Extra, class Signal>
+__device__ __forceinline__ void output_stage(uint32_t tmem_lane, int acc_col, int sub, int row, uint32_t h_hi, uint32_t h_lo,
+                                             const float* __restrict__ bias, float2 (&v)[4][16], Wait wait, Extra extra,
+                                             Signal signal, int sig0) {
+  float2 b[16];
+  load_vec<16>(bias + sub * 32, b);
+  wait();
+  drain128(tmem_lane, acc_col, sub, v);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float2 bn[16];
+    if (q < 3) load_vec<16>(bias + (q + 1) * 64 + sub * 32, bn);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[q][i] = acc_plus<SCHEME>(v[q][i], b[i]);
+    extra(q, v[q]);
+    put_quarter<RELU, SCHEME>(h_hi, h_lo, row, q, sub, v[q]);
+    signal(sig0 + q);
+    if (q < 3) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) b[i] = bn[i];
+    }
+  }
+}
+
 template <int PAIR, int NHWC, int SCHEME>   // NHWC: planes are channels-last (batch, H, W, C) -- vectorised scattered gathers
 __global__ void __launch_bounds__(NTHREADS, 1)
 occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, long long batch_stride,
@@ -255,30 +282,24 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       // ---- R1 output h1 = acc2 + b1' + net_p(p); R2, R3: two operand phases (raw, then relu)
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
-        wait_mma();
         float2 v[4][16];
-        drain128(tmem_lane, 256, sub, v);
         const float* b1 = vec + (blk == 1 ? OV_B11 : OV_B12);
+        float p[3] = {0.f, 0.f, 0.f};
+        if (blk == 1) point_of(tile, p);
+        // phase 1: raw h (shortcut operand); R1's output also takes + net_p(p): 3 FMAs per output, fp32 (mlp.py:103)
+        output_stage<SCHEME, false>(tmem_lane, 256, sub, row, h_hi, h_lo, b1, v, wait_mma,
+                                    [&](int q, float2 (&vq)[16]) {
+                                      if (blk != 1) return;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) add_vec<SCHEME, 16>(v[q], b1 + q * 64 + sub * 32);
-        if (blk == 1) {   // + net_p(p): 3 FMAs per output, fp32 (mlp.py:103)
-          float p[3];
-          point_of(tile, p);
+                                      for (int k = 0; k < 3; ++k) {
+                                        const float2 pk = make_float2(p[k], p[k]);
+                                        float2 w[16];
+                                        load_vec<16>(vec + OV_WP + k * 256 + q * 64 + sub * 32, w);
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float2 pk = make_float2(p[k], p[k]);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float2 w[16];
-              load_vec<16>(vec + OV_WP + k * 256 + q * 64 + sub * 32, w);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[q][i] = __ffma2_rn(pk, w[i], v[q][i]);
-            }
-          }
-        }
-        // phase 1: raw h (shortcut operand)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<false, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
+                                        for (int i = 0; i < 16; ++i) vq[i] = __ffma2_rn(pk, w[i], vq[i]);
+                                      }
+                                    },
+                                    signal, 0);
         // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
         wait_mma();
 #pragma unroll
@@ -289,16 +310,10 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
       }
       // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
-      wait_mma();
       {
         float2 v[4][16];
-        drain128(tmem_lane, 256, sub, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          add_vec<SCHEME, 16>(v[q], vec + OV_B13 + q * 64 + sub * 32);
-          put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]);
-          signal(q);
-        }
+        output_stage<SCHEME, true>(tmem_lane, 256, sub, row, h_hi, h_lo, vec + OV_B13, v, wait_mma,
+                                   [](int, float2 (&)[16]) {}, signal, 0);
       }
       // ---- R4.fc_0 epilogue
       stage_net(vec + OV_B04);

@@ -121,14 +121,9 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       // ================= R2, R3: x = [h | X_s] =================
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
-        wait_done(0);
         float2 v[4][16];
-        drain128(tmem_lane, 256, sub, v);
-        const float* b1 = vec + (blk == 1 ? VV_B11 : VV_B12);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) add_vec<SCHEME, 16>(v[q], b1 + q * 64 + sub * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<false, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }      // raw h
+        output_stage<SCHEME, false>(tmem_lane, 256, sub, row, h_hi, h_lo, vec + (blk == 1 ? VV_B11 : VV_B12), v,
+                                    [&]() { wait_done(0); }, [](int, float2 (&)[16]) {}, signal, 0);               // raw h
         gather(tile, blk, 0);                                                                              // overlaps the shortcut GEMM
         wait_done(0);
 #pragma unroll
@@ -142,16 +137,10 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
         if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
       }
       // ================= R4: identity shortcut, acc2 keeps accumulating =================
-      wait_done(0);
       {
         float2 v[4][16];
-        drain128(tmem_lane, 256, sub, v);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          add_vec<SCHEME, 16>(v[q], vec + VV_B13 + q * 64 + sub * 32);
-          put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]);
-          signal(q);
-        }
+        output_stage<SCHEME, true>(tmem_lane, 256, sub, row, h_hi, h_lo, vec + VV_B13, v, [&]() { wait_done(0); },
+                                   [](int, float2 (&)[16]) {}, signal, 0);
       }
       stage_net(vec + VV_B04, 4);
       // ================= out = w_out . lrelu(acc2 + b1_3 + b1_4, 0.2) + b_out =================
