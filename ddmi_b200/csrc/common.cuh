@@ -89,6 +89,22 @@ __device__ __forceinline__ float tap_sample(const float* __restrict__ ch, const 
   return acc;
 }
 
+// NCH consecutive channels of an NCHW plane at one tap: all 4 * NCH loads are issued before any is consumed, so a thread
+// pays one L2 round trip per call instead of one per few channels (the kernels keep no L1 beside their shared memory).
+template <int NCH>
+__device__ __forceinline__ void tap_sample_n(const float* __restrict__ ch0, size_t hw, const Tap& t, float (&out)[NCH]) {
+  float v[NCH][4];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const float* ch = ch0 + (size_t)c * hw;
+    v[c][0] = __ldg(ch + t.o00); v[c][1] = __ldg(ch + t.o01);
+    v[c][2] = __ldg(ch + t.o10); v[c][3] = __ldg(ch + t.o11);
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)   // same order as tap_sample
+    out[c] = fmaf(v[c][3], t.w11, fmaf(v[c][2], t.w10, fmaf(v[c][1], t.w01, v[c][0] * t.w00)));
+}
+
 // Channels-last variant: 8 consecutive channels of one pixel are two float4 loads.
 // img = base of one (H, W, C) item; c = first channel (multiple of 4).
 __device__ __forceinline__ void tap_sample8_nhwc(const float* __restrict__ img, const Tap& t, int C, int c, float (&out)[8]) {

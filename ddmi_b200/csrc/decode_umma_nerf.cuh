@@ -261,10 +261,12 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         stage_act(vec + NV_BF, false, v);
       }
       // ---- dir_encoding (N = 128) + rgb head
-      wait_mma();
       float rgb[3];
       {
-        float2 v[2][16];
+        float2 v[2][16], bd[2][16];
+        load_vec<16>(vec + NV_BD + sub * 32, bd[0]);          // before parking on the barrier (L2 round trip under the GEMM)
+        load_vec<16>(vec + NV_BD + 64 + sub * 32, bd[1]);
+        wait_mma();
         tmem_ld32(tmem_lane + sub * 32, v[0]);
         tmem_ld32(tmem_lane + 64 + sub * 32, v[1]);
         tmem_ld_wait();
@@ -277,9 +279,11 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         float2 acc3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          add_vec<SCHEME, 16>(v[q], vec + NV_BD + q * 64 + sub * 32);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[q][i] = slope == 1.f ? v[q][i] : lrelu_pair(v[q][i], slope);
+          for (int i = 0; i < 16; ++i) {
+            v[q][i] = acc_plus<SCHEME>(v[q][i], bd[q][i]);
+            v[q][i] = slope == 1.f ? v[q][i] : lrelu_pair(v[q][i], slope);
+          }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             float2 w[16];

@@ -259,11 +259,11 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
       // ---- R1.fc_0 (N = 64): net = relu(acc1[:, 0:64] + b0) -> H[:, 0:64]
-      wait_mma();
       {
         float2 v[16], b[16];
+        load_vec<16>(vec + OV_B01 + sub * 32, b);      // before parking on the barrier: the L2 round trip overlaps the GEMM
+        wait_mma();
         tmem_ld32(tmem_lane + sub * 32, v);
-        load_vec<16>(vec + OV_B01 + sub * 32, b);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = relu_pair(acc_plus<SCHEME>(v[i], b[i]));
@@ -317,26 +317,34 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       }
       // ---- R4.fc_0 epilogue
       stage_net(vec + OV_B04);
-      // ---- logits = w_out . (acc2 + b1_3 + b1_4) + b_out
-      wait_mma();
+      // ---- logits = w_out . (acc2 + b1_3 + b1_4) + b_out   (vectors prefetched like in the other stages)
       {
-        float2 v[4][16];
+        float2 v[4][16], b[16], w[16];
+        load_vec<16>(vec + OV_B14 + sub * 32, b);
+        load_vec<16>(vec + OV_WOUT + sub * 32, w);
+        wait_mma();
         drain128(tmem_lane, 256, sub, v);
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          add_vec<SCHEME, 16>(v[q], vec + OV_B14 + q * 64 + sub * 32);
-          float2 w[16];
-          load_vec<16>(vec + OV_WOUT + q * 64 + sub * 32, w);
+          float2 bn[16], wn[16];
+          if (q < 3) {
+            load_vec<16>(vec + OV_B14 + (q + 1) * 64 + sub * 32, bn);
+            load_vec<16>(vec + OV_WOUT + (q + 1) * 64 + sub * 32, wn);
+          }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s2 = __ffma2_rn(v[q][i], w[i], s2);
+          for (int i = 0; i < 16; ++i) s2 = __ffma2_rn(acc_plus<SCHEME>(v[q][i], b[i]), w[i], s2);
+          if (q < 3) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { b[i] = bn[i]; w[i] = wn[i]; }
+          }
         }
         part[sub * 128 + row] = s2.x + s2.y;
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 256 E threads only
         if (sub == 0 && tile < total_tiles) {
-          const int b = (int)(tile / tiles_per_item);
+          const int item = (int)(tile / tiles_per_item);
           const long long gi = (tile % tiles_per_item) * TILE + row;
-          if (gi < n) logits[(size_t)b * n + gi] = part[row] + part[128 + row] + __ldg(vec + OV_BOUT);
+          if (gi < n) logits[(size_t)item * n + gi] = part[row] + part[128 + row] + __ldg(vec + OV_BOUT);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // part[] may be rewritten by the next tile
       }

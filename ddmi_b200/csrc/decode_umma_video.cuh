@@ -90,15 +90,20 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       const size_t hw = (size_t)ps.h[pi] * ps.w[pi];
       const float* base = ps.data[pi] + ((size_t)b * C + ghalf * 32) * hw;
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        float y[8], yr[8];
+      for (int g2 = 0; g2 < 2; ++g2) {          // 16 channels per round trip (64 loads in flight per thread)
+        float y16[16];
+        tap_sample_n<16>(base + (size_t)(g2 * 16) * hw, hw, tp, y16);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          y[i] = tap_sample(base + (size_t)(g * 8 + i) * hw, tp);
-          yr[i] = fmaxf(y[i], 0.f);
+        for (int g = 0; g < 2; ++g) {
+          float y[8], yr[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            y[i] = y16[g * 8 + i];
+            yr[i] = fmaxf(y[i], 0.f);
+          }
+          store8<SCHEME>(xa_hi, xa_lo, row, ghalf * 4 + g2 * 2 + g, y);
+          store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g2 * 2 + g, yr);
         }
-        store8<SCHEME>(xa_hi, xa_lo, row, ghalf * 4 + g, y);
-        store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g, yr);
       }
     };
     // net = relu(acc1 + b0) -> H quarters, published on A4..A7 (NQ = number of 64-column quarters: 3 for R1)
