@@ -1,9 +1,10 @@
-// tcgen05 (5th-gen tensor core) decode kernels: DDMI_PREC_BF16X3.
+// tcgen05 (5th-gen tensor core) decode kernels: DDMI_PREC_BF16X3 and DDMI_PREC_F16F8 (template SCHEME; umma.cuh describes the
+// f16f8 operand scheme: an fp16 main MMA + one e4m3 correction MMA per 16-wide K step, issued a 32-wide step pair at a time).
 //
 // Engine (shared by every decoder family): one persistent CTA per SM walks 128-row tiles.
 //   * warps 0-7  : gather + epilogue ("E" threads; warp w owns TMEM lanes 32*(w%4)..+31)
-//   * warp  8    : weight producer -- one lane streams weight units (<= 16 KB) from L2 into a
-//                  4-slot shared-memory ring with 1-D bulk async copies (cp.async.bulk + mbarrier)
+//   * warp  8    : weight producer -- one lane streams weight units (8 KB per CTA of a pair) from L2 into a
+//                  shared-memory ring (4 or 8 slots) with 1-D bulk async copies (cp.async.bulk + mbarrier)
 //   * warp  9    : MMA issuer -- one lane interprets the host-built PROGRAM (packing.py): a list
 //                  of UNIT ops (one 16-wide K step of a 128 x N block = 3 tcgen05.mma: Ahi*Bhi +
 //                  Alo*Bhi + Ahi*Blo, fp32 accumulate in TMEM), WAIT ops (operands ready) and
@@ -12,10 +13,10 @@
 //   the order it is produced and neither warp knows anything about the network.
 //
 // K-split software pipeline: every epilogue thread first drains ALL of its accumulator values
-// into registers (the TMEM accumulator is free again), converts + stores output columns 0-127
-// (= K groups 0-15 of the next layer's A operand), signals barrier A0, then converts columns
-// 128-255 and signals A1.  The program places the next layer's K steps 0-7 (full N = 256) after
-// WAIT A0, so the tensor core is already working while the second half is still being converted.
+// into registers (the TMEM accumulator is free again), then converts + stores the 256 output columns
+// in four quarters (= 4 K steps each of the next layer's A operand), signalling operand barrier A_q
+// after each.  The program places the next layer's K steps of quarter q (full N = 256) after WAIT q,
+// so the tensor core is already working while the later quarters are still being converted.
 //
 // CTA pairs (PAIR = 1, the default): two CTAs of a cluster run tcgen05.mma.cta_group::2 (M = 256): each CTA
 // owns its own 128-row tile (A operand, accumulators, epilogue) but only HALF of every weight K step

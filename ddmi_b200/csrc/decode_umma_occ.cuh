@@ -24,10 +24,6 @@ constexpr int OCC_SMEM = OCC_OFF_PART + 1024;
 constexpr int OV_B01 = 0, OV_B11 = 64, OV_WP = 320, OV_B02 = 1088, OV_B12 = 1344, OV_B03 = 1600, OV_B13 = 1856,
               OV_B04 = 2112, OV_B14 = 2368, OV_WOUT = 2624, OV_BOUT = 2880, OV_TOTAL = 2881;
 
-__device__ __forceinline__ float2 bias_relu_pair(float2 t, float2 b) {
-  t = __fadd2_rn(t, b);
-  return make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f));
-}
 __device__ __forceinline__ float2 relu_pair(float2 t) { return make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)); }
 
 // this thread's 128 values of a 256-wide accumulator: quarter q -> columns [64q + 32 sub, +32)
