@@ -271,6 +271,32 @@ def run_ours(args):
                      "bf16_equivalent_tensor_time": PREC_INFO[args.precision]['tensor_time'],
                      "avg_launch_ms": {str(n): statistics.mean(t for t, m in launch_ms if m == n) for n in sorted({m for _, m in launch_ms})}},
     }
+    if world == 1:
+        # Self-check of the measured kernel (not timed): the same module on a sample of the workload (4 items @ 256x256) through
+        # the exact-arithmetic fp32 CUDA-core kernels; and, for context, the other tensor-core operand scheme's throughput.
+        c0, si0, _ = grids[0]
+        cs = torch.nn.functional.interpolate(c0, size=(256, 256), mode='bilinear', align_corners=True)
+        sample = [p[:4] for p in planes]
+        mlp.precision = args.precision
+        got = mlp(cs, hdbf=sample, si=si0)
+        mlp.precision = 'fp32'
+        exact = mlp(cs, hdbf=sample, si=si0)
+        line["parity"] = {"max_abs_vs_fp32_kernel": float((got - exact).abs().max()), "tolerance": 1e-3,
+                          "sample": "4 items @ 256x256, same planes and weights"}
+        other = {'f16f8': 'bf16x3', 'bf16x3': 'f16f8'}.get(args.precision)
+        if other:
+            mlp.precision = other
+            step()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                step()
+            a1.record()
+            torch.cuda.synchronize()
+            line["other_precision"] = {"precision": other, "value": coords_per_step * 2 / (a0.elapsed_time(a1) * 1e-3),
+                                       "unit": UNIT, "steps": 2}
+        mlp.precision = args.precision
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_res, args.cpu_batch)
     print(json.dumps(line))
