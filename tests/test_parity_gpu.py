@@ -491,3 +491,41 @@ def test_nerf_sample_counts_that_straddle_tiles(n_samples):
     ref, ref_raw = orc.nerf_render_rays(sd, rays, fea, n_samples, False, return_raw=True)
     assert float((raw[0].cpu() - ref_raw).abs().max()) < TOL
     assert float((rgb[0].cpu() - ref).abs().max()) < TOL
+
+
+# ---------------------------------------------------------------- run-to-run determinism (protocol races would show here)
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+def test_repeated_decodes_are_bit_identical(precision):
+    """Many tiles per CTA pair on every SM, decoded three times: the producer / issuer / epilogue hand-shakes (mbarriers, ring
+    re-use, TMEM re-use) leave no room for timing-dependent results, so the outputs must be bit-identical."""
+    g = torch.Generator().manual_seed(31)
+    m = cases.build_module('image').to(DEV)
+    m.precision = precision
+    planes = _cuda([torch.randn(6, 64, s, s, generator=g) for s in (32, 64, 128)])
+    R = 384
+    e = (R - 1) / R
+    coords = ddmi_b200.convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(DEV)
+    outs = [m(coords, hdbf=planes, si=0.5) for _ in range(3)]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+    mo = cases.build_module('occupancy').to(DEV)
+    mo.precision = precision
+    pts, hdbf = cases.occupancy_inputs(batch=3, n=150001)
+    lo = [mo(pts.to(DEV), _cuda(hdbf)).logits for _ in range(3)]
+    assert torch.equal(lo[0], lo[1]) and torch.equal(lo[0], lo[2])
+
+    mv = cases.build_module('video').to(DEV)
+    mv.precision = precision
+    T, H, W = 5, 96, 160
+    xy = [torch.randn(2, 64, H // s, W // s, generator=g) for s in (4, 2, 1)]
+    yt = [torch.randn(2, 64, T, H // s, generator=g) for s in (4, 2, 1)]
+    xt = [torch.randn(2, 64, T, W // s, generator=g) for s in (4, 2, 1)]
+    cv = ddmi_b200.convert_to_coord_format_3d(1, H, W, T, hstart=-.9, hend=.9, wstart=-.9, wend=.9, tstart=-.8, tend=.8)
+    vo = [mv(_cuda(cv), _cuda((xy, yt, xt))) for _ in range(3)]
+    assert torch.equal(vo[0], vo[1]) and torch.equal(vo[0], vo[2])
+
+    mn = cases.build_module('nerf').to(DEV)
+    fea = _cuda({k: torch.randn(2, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')})
+    rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'].to(DEV).repeat(3, 1)
+    ro = [nh.render_rays_fused(rays, fea, mn, 128, True, precision=precision) for _ in range(3)]
+    assert torch.equal(ro[0], ro[1]) and torch.equal(ro[0], ro[2])
