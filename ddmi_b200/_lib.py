@@ -9,9 +9,11 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libddmi_b200.so")
+# DDMI_B200_LIB: dev tools point this at libddmi_b200_prof.so (the build with in-kernel counters, `make prof`)
+LIB_PATH = os.environ.get("DDMI_B200_LIB") or os.path.join(_HERE, "libddmi_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 7
 PREC_FP32 = 0
 PREC_BF16X3 = 1
 PREC_F16F8 = 2
@@ -23,6 +25,7 @@ EXPORTS = (
     "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
     "ddmi_decode_video", "ddmi_decode_video_store",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
+    "ddmi_debug_trace", "ddmi_debug_microbench",
 )
 
 
@@ -86,9 +89,11 @@ def lib():
         L.ddmi_selftest_umma2.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_selftest_f16f8.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
+        L.ddmi_debug_trace.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32, ctypes.POINTER(i32), i32]
+        L.ddmi_debug_microbench.argtypes = [i32, i32, vp, vp, vp, vp]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync
-        if L.ddmi_abi_version() != 6:
+        if L.ddmi_abi_version() != ABI_VERSION:
             raise RuntimeError("libddmi_b200.so ABI version mismatch")
         _lib = L
     return _lib

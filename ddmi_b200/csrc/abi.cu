@@ -35,6 +35,8 @@ int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float
 int launch_nerf_composite(const float*, const float*, int, const float*, int, int, long long, int, int, float*, cudaStream_t);
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
+int debug_trace(unsigned long long*, int, int*, int);
+int launch_microbench(int, int, const float*, unsigned long long*, float*, cudaStream_t);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_selftest_f16f8(const float*, const float*, float*, int, int, cudaStream_t);
 
@@ -348,6 +350,17 @@ DDMI_API int ddmi_selftest_f16f8(const float* a, const float* b, float* d, int32
 DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset) {
   DDMI_REQUIRE(out != nullptr, "out is NULL");
   return debug_profile((unsigned long long*)out, reset);
+}
+
+DDMI_API int ddmi_debug_trace(uint64_t* out, int32_t capacity, int32_t* count, int32_t reset) {
+  DDMI_REQUIRE(out != nullptr && count != nullptr && capacity >= 1, "out / count is NULL or capacity < 1");
+  return debug_trace((unsigned long long*)out, capacity, count, reset);
+}
+
+DDMI_API int ddmi_debug_microbench(int32_t mode, int32_t iters, const float* seed, uint64_t* out_dev, float* sink_dev, void* stream) {
+  DDMI_REQUIRE(mode >= 0 && mode <= 6 && iters >= 1, "mode must be 0..6 and iters >= 1");
+  DDMI_REQUIRE(seed && out_dev && sink_dev, "seed (1024 floats) / out_dev (2 x u64) / sink_dev (256 floats) is NULL");
+  return launch_microbench(mode, iters, seed, (unsigned long long*)out_dev, sink_dev, (cudaStream_t)stream);
 }
 
 }  // extern "C"

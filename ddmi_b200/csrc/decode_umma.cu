@@ -74,12 +74,13 @@ __device__ __forceinline__ float2 image_act(float2 t, float2 b) {
 template <int MODE, int SCHEME, class Signal>
 __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, uint32_t h_lo, int row, int sub,
                                             const float* __restrict__ bias, const float* __restrict__ cs,
-                                            StagePrefetch& pf, Signal signal) {
+                                            StagePrefetch& pf, Signal signal, bool tr = false) {
   constexpr bool WITH_CS = (MODE == 1 || MODE == 2);
   float2 v[4][16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
   tmem_ld_wait();
+  trace(tr, 0x03);                                      // accumulator drained
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int col0 = q * 64 + sub * 32;
@@ -159,14 +160,16 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     const int ghalf = tid >> 7;                         // gather: channels [32*ghalf, +32)
     const uint32_t a_bar = PAIR ? mapa_rank(bar + BAR_A0, 0) : bar + BAR_A0;   // operand barriers live in the leader
     uint32_t ph_mma = 0;
-    const bool prof = (blockIdx.x == 0 && tid == 0);
-    long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = clock64();
+    const bool prof = DDMI_PROFILE && (blockIdx.x == 0 && tid == 0);
+    bool tr = false;                                    // this thread traces the current tile iteration (profiling build)
+    long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = prof_clock();
 
     // `part` 0 / 1 = first / second 16 of this thread's 32 channels (-1: both): the two halves are issued in two different
     // idle windows of the epilogue threads (after the conv1 and after the conv2 epilogue, while conv2 / conv3 run on the
     // tensor core), so the L2-latency-bound gather delays neither epilogue by much
     auto gather = [&](long long tile, int s, int part) {
-      const long long g0 = clock64();
+      const long long g0 = prof_clock();
+      trace(tr, 0x20);
       if (tile > total_tiles - 1) tile = total_tiles - 1;   // odd tail of a pair: decode a duplicate, store nothing
       const int b = (int)(tile / tiles_per_item);
       long long gi = (tile % tiles_per_item) * TILE + row;
@@ -205,7 +208,8 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
           st_shared_v4(x_lo + off, lo);
         }
       }
-      p_gather += clock64() - g0;
+      p_gather += prof_clock() - g0;
+      trace(tr, 0x21);
     };
     // make this warp's smem / TMEM writes visible to the MMA warp (of the leader CTA), then signal one quarter
     auto signal = [&](int q) {
@@ -213,18 +217,21 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
-      if (q == 3) p_epi += clock64() - p_t;
+      trace(tr, 0x10 + q);
+      if (q == 3) p_epi += prof_clock() - p_t;
     };
     auto signal_all = [&]() {
 #pragma unroll
       for (int q = 0; q < 4; ++q) signal(q);
     };
     auto wait_mma = [&]() {
-      const long long w0 = clock64();
+      const long long w0 = prof_clock();
+      trace(tr, 0x01);
       mbar_wait(bar + BAR_MMADONE, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
-      p_t = clock64();
+      trace(tr, 0x02);
+      p_t = prof_clock();
       p_wait += p_t - w0;
     };
 
@@ -233,29 +240,30 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
       const float* bv = vec;
+      tr = prof && it == kTraceIter;
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, bv += 1024) {
         // ---- conv1 (+ skip into acc2 for blk < 3)
         StagePrefetch pf;
         stage_prefetch<false>(pf, bv, nullptr, sub);
         wait_mma();
-        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal);
+        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal, tr);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale), first half of the channels
         if (blk < 2) gather(tile, blk + 1, 0);
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
         // ---- conv2
         stage_prefetch<false>(pf, bv + 256, nullptr, sub);
         wait_mma();
-        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal);
+        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal, tr);
         if (blk < 2) gather(tile, blk + 1, 1);                                   // second half, under conv3's GEMM
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 1);
         // ---- conv3 + skip
         if (blk < 3) stage_prefetch<true>(pf, bv + 512, bv + 768, sub);
         else stage_prefetch<false>(pf, bv + 512, nullptr, sub);
         wait_mma();
-        if (blk < 2) image_stage<1, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
-        else if (blk == 2) image_stage<2, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal);
-        else image_stage<3, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal);
+        if (blk < 2) image_stage<1, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, tr);
+        else if (blk == 2) image_stage<2, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, tr);
+        else image_stage<3, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal, tr);
       }
       // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
@@ -276,9 +284,9 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       if (it + 1 < ntiles) signal_all();
     }
     if (prof) {
-      atomicAdd(&g_prof[0], (unsigned long long)p_wait);
-      atomicAdd(&g_prof[1], (unsigned long long)p_epi);
-      atomicAdd(&g_prof[2], (unsigned long long)p_gather);
+      prof_add(0, p_wait);
+      prof_add(1, p_epi);
+      prof_add(2, p_gather);
     }
   } else {
     engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME, 0>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
@@ -439,6 +447,20 @@ int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* c
                             void* out, int store, int pair, int f16f8, cudaStream_t st) {
   return launch_video_umma(ps, batch, C, cxy, cyt, cxt, T, H, W, gemm, gemm_bytes, program_host, program_words, program_dev,
                            vec, vec_floats, out, store, pair, f16f8, st);
+}
+
+int debug_trace(unsigned long long* out, int cap, int* n, int reset) {
+  unsigned int cnt = 0;
+  DDMI_CUDA(cudaMemcpyFromSymbol(&cnt, ummak::g_trace_n, sizeof(cnt)));
+  if (cnt > (unsigned)ummak::kTraceCap) cnt = ummak::kTraceCap;
+  if ((int)cnt > cap) cnt = cap;
+  if (cnt) DDMI_CUDA(cudaMemcpyFromSymbol(out, ummak::g_trace, sizeof(unsigned long long) * cnt));
+  *n = (int)cnt;
+  if (reset) {
+    const unsigned int z = 0;
+    DDMI_CUDA(cudaMemcpyToSymbol(ummak::g_trace_n, &z, sizeof(z)));
+  }
+  return DDMI_OK;
 }
 
 int debug_profile(unsigned long long* out, int reset) {

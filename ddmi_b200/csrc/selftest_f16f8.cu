@@ -61,7 +61,7 @@ selftest_f16f8_kernel(const float* __restrict__ a, const float* __restrict__ b, 
       }
     }
   }
-  const uint32_t id16 = idesc_f16_f32(128, N), id8 = idesc_e4m3_f32(128, N);
+  const uint32_t id16 = idesc_f16_f32(128, N), id8 = idesc_f8_f32(128, N);
   uint32_t ph = 0;
   for (int s = 0; s < K / 32; ++s) {
     if (tid < 128) {

@@ -44,11 +44,31 @@ struct Layout {
 
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 
-// Diagnostics: cycle counters of CTA 0 (ddmi_debug_profile).
+// Diagnostics (ddmi_debug_profile / ddmi_debug_trace): compiled in only with -DDDMI_PROFILE=1, i.e. in the separate
+// libddmi_b200_prof.so the dev tools load (`make prof`); the shipping library carries no clock reads or counters.
+// Counters of CTA 0:
 // [0] E thread 0: cycles parked waiting for MMA groups   [1] cycles in epilogue stages (excl. gathers)
 // [2] cycles in gathers   [3] MMA thread: cycles waiting for operands   [4] cycles waiting for weights
 // [5] MMA thread total   [6] tiles   [7] spare
+// Trace: (event id << 48 | clock) records of CTA 0 during tile iteration kTraceIter (E thread 0 and the MMA lane).
+#ifndef DDMI_PROFILE
+#define DDMI_PROFILE 0
+#endif
 __device__ unsigned long long g_prof[8];
+constexpr int kTraceCap = 2048, kTraceIter = 5;
+__device__ unsigned long long g_trace[kTraceCap];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ long long prof_clock() { return DDMI_PROFILE ? clock64() : 0ll; }
+__device__ __forceinline__ void prof_add(int i, long long v) {
+  if (DDMI_PROFILE) atomicAdd(&g_prof[i], (unsigned long long)v);
+}
+// one record; `on` = this thread is a designated tracer and the CTA is in its traced tile iteration
+__device__ __forceinline__ void trace(bool on, uint32_t id) {
+  if (DDMI_PROFILE && on) {
+    const unsigned int k = atomicAdd(&g_trace_n, 1u);
+    if (k < (unsigned)kTraceCap) g_trace[k] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+  }
+}
 
 // ---------------------------------------------------------------------------
 // engine: producer + MMA issuer (program interpreters)
@@ -130,7 +150,7 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
 // tight per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.  The whole warp runs the loop
 // (warp-uniform), one elected lane issues.
 // SCHEME 1 (f16f8, pairs only): same 16-wide steps, slots and A-operand stepping, but a step is TWO MMAs: the fp16 main
-// term (a16 x w16, K = 16) and one K = 32 e4m3 correction MMA -- r8 x w8 on even steps, a8 x s8 on odd steps of a
+// term (a16 x w16, K = 16) and one K = 32 FP8 (e5m2 x e4m3) correction MMA -- r8 x w8 on even steps, a8 x s8 on odd steps of a
 // 32-wide pair (the A region keeps [r8 r8 a8 a8] K groups per pair, the slot [w16: 2 K groups | w8 or s8: 2 K groups]).
 // Steps are issued a PAIR per iteration (4 MMAs = 512 tensor cycles, 2 barrier probes, 1 commit): the issue loop's fixed
 // cost per iteration (probe round trips, descriptor moves to uniform registers, commit) is ~300-400 cycles.
@@ -142,13 +162,14 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
   constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
   uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
   long long q_a = 0, q_w = 0;
-  const long long q_start = clock64();
+  const long long q_start = prof_clock();
   // descriptors: hi word is constant (SBO = 128 B, version 1); lo word = addr >> 4 | LBO >> 4 << 16
   constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) | (1ull << 14)) << 32;
   const uint32_t a_lo32 = (a_base >> 4) | ((KG_BYTES >> 4) << 16);
   const uint32_t ring_lo32 = ring >> 4;
   for (long long t = 0; t < ntiles; ++t) {
     uint32_t op = __ldg(program);
+    const bool tr = DDMI_PROFILE && blockIdx.x == 0 && t == kTraceIter && (threadIdx.x & 31) == 0;
     for (int pc = 0;; ++pc) {
       const uint32_t nxt = __ldg(program + pc + 1);   // the table is padded with END ops
       const uint32_t kind = op & 3;
@@ -156,7 +177,7 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         const uint32_t n = op_n(op);
         const uint32_t nloc = PAIR ? n / 2 : n;                                   // B rows held by one CTA
         const uint32_t idesc = (SCHEME ? idesc_f16_f32(256, 0) : PAIR ? idesc2_bf16_f32(0) : idesc_bf16_f32(0)) | (n << 14);   // N >> 3 at bit 17
-        const uint32_t idesc8 = idesc_e4m3_f32(256, 0) | (n << 14);
+        const uint32_t idesc8 = idesc_f8_f32(256, 0) | (n << 14);
         const uint32_t acc = tmem + ((op >> 5) & 7) * 64;
         // A operand: K groups of the shared-memory A region, or (bit 29, CTA pairs only) of tensor memory, where one
         // K group = 4 columns counted from the TMEM base (so K group 64 sits right behind a 256-column accumulator)
@@ -172,12 +193,13 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
             return mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && r;
           };
           bool ready = probe();
+          trace(tr, 0x100 + pc);                                      // UNIT starts issuing
           for (int j = 0; j < cnt; j += 2) {
             if (!ready) {
-              const long long w0 = clock64();
+              const long long w0 = prof_clock();
               mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
               mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
-              q_w += clock64() - w0;
+              q_w += prof_clock() - w0;
             }
             tc_fence_after();
             const uint32_t w0lo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
@@ -215,10 +237,10 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         if (PAIR) ready = mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && ready;
         for (int j = 0; j < cnt; ++j) {
           if (!ready) {
-            const long long w0 = clock64();
+            const long long w0 = prof_clock();
             mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
             if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
-            q_w += clock64() - w0;
+            q_w += prof_clock() - w0;
           }
           tc_fence_after();
           const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
@@ -253,13 +275,16 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         }
       } else if (kind == OP_WAIT) {
         const uint32_t i = (op >> 2) & 7;
-        const long long w0 = clock64();
+        const long long w0 = prof_clock();
+        trace(tr, 0x200 + pc);                                        // WAIT begins
         mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
         ph_a ^= 1u << i;
         tc_fence_after();
-        q_a += clock64() - w0;
+        trace(tr, 0x300 + pc);                                        // WAIT satisfied
+        q_a += prof_clock() - w0;
       } else if (kind == OP_COMMIT) {
         const uint32_t db = bar + BAR_MMADONE + 8 * ((op >> 2) & 3);
+        trace(tr, 0x400 + pc);                                        // COMMIT issued
         if (elect_one()) {
           if (PAIR) mma2_commit_mc(db, 3);
           else      mma_commit(db);
@@ -270,11 +295,11 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
       op = nxt;
     }
   }
-  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
-    atomicAdd(&g_prof[3], (unsigned long long)q_a);
-    atomicAdd(&g_prof[4], (unsigned long long)q_w);
-    atomicAdd(&g_prof[5], (unsigned long long)(clock64() - q_start));
-    atomicAdd(&g_prof[6], (unsigned long long)ntiles);
+  if (DDMI_PROFILE && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    prof_add(3, q_a);
+    prof_add(4, q_w);
+    prof_add(5, prof_clock() - q_start);
+    prof_add(6, ntiles);
   }
 }
 

@@ -47,6 +47,47 @@ def _as_plane(t, name):
     return t.detach().to(torch.float32).contiguous()
 
 
+def _check_plane_set(planes, channels, names):
+    """Every plane of a decode shares ONE batch / channel count / device: the C ABI takes a single (batch, channels) pair for
+    all of them, so a smaller plane would be indexed past its end.  (The reference fails in grid_sample / cat on the same
+    inputs.)"""
+    b, dev = planes[0].shape[0], planes[0].device
+    for t, name in zip(planes, names):
+        if t.shape[0] != b:
+            raise RuntimeError(f"{name} has batch {t.shape[0]}, expected {b} (all planes of a decode share the batch)")
+        if t.shape[1] != channels:
+            raise RuntimeError(f"{name} has {t.shape[1]} channels, expected latent_dim = {channels}")
+        if t.device != dev:
+            raise RuntimeError(f"{name} is on {t.device}, expected {dev} (all planes of a decode live on one GPU)")
+        if t.shape[2] < 1 or t.shape[3] < 1:
+            raise RuntimeError(f"{name} has an empty extent {tuple(t.shape)}")
+
+
+class _ChannelsLastCache:
+    """Channels-last copies of the planes of the most recent decode, keyed by the identity of the source tensors
+    (data_ptr, version counter, shape).  The reference's callers query the SAME planes in a loop -- 100k-point chunks of one
+    latent in Generator3D.eval_points (convocc/src/conv_onet/generation.py:130-144), one render per pose in
+    tools/ldm/nerf.py:270 -- so the transposition runs once per latent instead of once per call.  As with the packed
+    weights, writes through `.data` that keep the version counter are not seen: re-create the tensor or call clear()."""
+
+    def __init__(self):
+        self.key, self.value, self.sources = None, None, None
+
+    def get(self, planes, sources, stream):
+        vers = [packing.tensor_version(t) for t in sources]
+        if any(v is None for v in vers):        # inference-mode tensors carry no version counter: never cached
+            return _lib.planes_channels_last(planes, stream)
+        key = tuple((t.data_ptr(), v, tuple(t.shape), str(t.device)) for t, v in zip(sources, vers))
+        if key != self.key:
+            self.value = _lib.planes_channels_last(planes, stream)
+            self.key = key
+            self.sources = list(sources)        # keep the sources alive: a freed tensor's address can be re-used
+        return self.value
+
+    def clear(self):
+        self.key, self.value, self.sources = None, None, None
+
+
 class _FusedDecoder(nn.Module):
     """Common plumbing: grad guard + packed-weight cache."""
 
@@ -56,6 +97,12 @@ class _FusedDecoder(nn.Module):
     def _init_fused(self, precision=None):
         self.precision = precision
         self._pack_cache = {}
+        self._nhwc_cache = _ChannelsLastCache()
+
+    def invalidate_packed(self):
+        """Drop every cached packed-weight blob and channels-last plane copy (they are rebuilt on the next call)."""
+        self._pack_cache = {}
+        self._nhwc_cache.clear()
 
     def _guard_grad(self, *tensors):
         if torch.is_grad_enabled() and (
@@ -67,7 +114,7 @@ class _FusedDecoder(nn.Module):
 
     def _packed(self, key, builder):
         fp = packing.param_fingerprint(self)
-        if self._pack_cache.get('fingerprint') != fp:      # parameters changed: drop every packed blob
+        if not packing.same_fingerprint(self._pack_cache.get('fingerprint'), fp):   # parameters changed: drop every packed blob
             self._pack_cache = {'fingerprint': fp, 'entries': {}}
         entries = self._pack_cache['entries']
         if key not in entries:
@@ -127,6 +174,7 @@ class MLP(_FusedDecoder):
         self._guard_grad(*hdbf)
         planes = [_as_plane(t, f'hdbf[{i}]') for i, t in enumerate(hdbf)]
         self._check_device(planes[0])
+        _check_plane_set(planes, self.latent_dim, [f'hdbf[{i}]' for i in range(3)])
         if coords.dim() != 4 or coords.shape[0] != 1 or coords.shape[1] != 2:
             raise RuntimeError(f"coords must be (1,2,h,w), got {tuple(coords.shape)}")
         _, _, h, w = coords.shape
@@ -179,8 +227,11 @@ class MLP3D(_FusedDecoder):
         for axis in hdbf:
             assert len(axis) == 3
         self._guard_grad(coords, *[t for axis in hdbf for t in axis])
-        planes = [_as_plane(hdbf[a][s], f'hdbf[{a}][{s}]') for a in range(3) for s in range(3)]
+        sources = [hdbf[a][s] for a in range(3) for s in range(3)]
+        names = [f'hdbf[{a}][{s}]' for a in range(3) for s in range(3)]
+        planes = [_as_plane(t, nm) for t, nm in zip(sources, names)]
         self._check_device(planes[0])
+        _check_plane_set(planes, self.latent_dim, names)
         b = planes[0].shape[0]
         if coords.dim() != 3 or coords.shape[-1] != 3 or coords.shape[0] not in (1, b):
             raise RuntimeError(f"coords must be ({b},N,3), got {tuple(coords.shape)}")
@@ -204,7 +255,7 @@ class MLP3D(_FusedDecoder):
         with torch.cuda.device(base.device):
             st = _stream_ptr(base.device)
             if prec != _lib.PREC_FP32:       # scattered queries: channels-last planes, float4 gathers
-                keep, arr = _lib.planes_channels_last(planes, st)
+                keep, arr = self._nhwc_cache.get(planes, sources, st)
                 layout = 1
             else:
                 keep, arr, layout = planes, _lib.planes_array(planes), 0
@@ -251,8 +302,10 @@ class MLPVideo(_FusedDecoder):
         xy_hdbf, yt_hdbf, xt_hdbf = hdbf
         assert len(xy_hdbf) == 3 and len(yt_hdbf) == 3 and len(xt_hdbf) == 3
         self._guard_grad(*xy_hdbf, *yt_hdbf, *xt_hdbf)
-        planes = [_as_plane(hdbf[a][s], f'hdbf[{a}][{s}]') for a in range(3) for s in range(3)]
+        names = [f'hdbf[{a}][{s}]' for a in range(3) for s in range(3)]
+        planes = [_as_plane(hdbf[a][s], names[3 * a + s]) for a in range(3) for s in range(3)]
         self._check_device(planes[0])
+        _check_plane_set(planes, self.latent_dim, names)
         dev = planes[0].device
         b, _, h, w = xy_hdbf[-1].shape
         t = yt_hdbf[-1].shape[2]
@@ -327,7 +380,7 @@ class MLPNeRF(_FusedDecoder):
         out = torch.empty((n, 1 if sigma_only else 4), device=xx.device, dtype=torch.float32)
         if n == 0:
             return out
-        packed = self.packed_weights()
+        packed = self.packed_weights('fp32')     # rows in, rows out: the fp32 kernel (the tcgen05 kernel is the fused render)
         with torch.cuda.device(xx.device):
             _lib.check(_lib.lib().ddmi_nerf_mlp(
                 xx.data_ptr(), n, xx.shape[1], 1 if sigma_only else 0, self.negative_slope,

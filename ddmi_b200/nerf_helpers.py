@@ -168,12 +168,18 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
         warnings.warn("ddmi_b200: a weight exceeds the f16f8 operand range (|w| >= 16); using precision='bf16x3'")
         precision = 'bf16x3'
         packed = module.packed_weights(precision)
-    planes = []
+    planes, sources = [], []
     for k in ('xy', 'yz', 'xz'):
         t = fea[k]
         if not t.is_cuda:
             raise RuntimeError("fea planes must be CUDA tensors (ddmi_b200 has no CPU path)")
+        if t.dim() != 4:
+            raise RuntimeError(f"fea['{k}'] must be (B,32,R,R), got {tuple(t.shape)}")
+        sources.append(t)
         planes.append(t.detach().to(torch.float32).contiguous())
+    from .mlp import _check_plane_set
+    _check_plane_set(planes, 32, [f"fea['{k}']" for k in ('xy', 'yz', 'xz')])
+    module._check_device(planes[0])
     dev = planes[0].device
     b = planes[0].shape[0]
     rays = rays.detach().to(device=dev, dtype=torch.float32).contiguous()
@@ -189,8 +195,8 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
     raw = torch.empty((b, n, N_samples, 4), device=dev, dtype=torch.float32) if need_raw else None
     with torch.cuda.device(dev):
         st = _stream_ptr(dev)
-        if umma:
-            keep, arr = _lib.planes_channels_last(planes, st)
+        if umma:       # one transposition per latent, not per pose (tools/ldm/nerf.py:270 renders a loop of poses)
+            keep, arr = module._nhwc_cache.get(planes, sources, st)
         else:
             keep, arr = planes, _lib.planes_array(planes)
         entry = _lib.lib().ddmi_nerf_render_z if per_ray else _lib.lib().ddmi_nerf_render

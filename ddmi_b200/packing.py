@@ -102,8 +102,9 @@ class UmmaProgram:
         self.ops.append(2 | (which << 2))
 
     def finish(self, device):
+        """-> (weight stream on `device`, program on `device`, program on the host)."""
         ops = torch.tensor(self.ops + [3, 3, 3, 3], dtype=torch.int64).to(torch.int32)
-        return torch.cat(self.segs).contiguous(), ops.to(device), ops.contiguous()
+        return torch.cat(self.segs).contiguous().to(device), ops.to(device), ops.contiguous()
 
 
 F8_SCALE = 4096.0
@@ -180,11 +181,51 @@ def umma_kstep_blocks(W32, lo, hi, n_pad=None):
 
 
 def _params64(module):
-    return {k: v.detach().to(torch.float64) for k, v in module.state_dict().items()}
+    """The module's state dict as float64 HOST tensors.  Folding and packing run on the CPU (a few ms of tiny matrix
+    algebra) and the packed blobs are shipped with three H2D copies: done on the device, the same algebra is ~700 tiny
+    kernel launches per pack.  One device-side cat + one D2H copy fetches all parameters."""
+    sd = module.state_dict()
+    keys = list(sd)
+    if not keys:
+        return {}
+    flat = torch.cat([sd[k].detach().reshape(-1).to(torch.float32) for k in keys]).cpu().to(torch.float64)
+    out, o = {}, 0
+    for k in keys:
+        n = sd[k].numel()
+        out[k] = flat[o:o + n].reshape(sd[k].shape)
+        o += n
+    return out
+
+
+def module_device(module):
+    return next(module.parameters()).device
+
+
+def tensor_version(t):
+    """The autograd version counter of `t`, or None for inference-mode tensors (they do not track one)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
 
 
 def param_fingerprint(module):
-    return tuple((p.data_ptr(), p._version, tuple(p.shape)) for p in module.parameters())
+    """Cache key of the packed weights: identity (data_ptr, shape, version counter) of every parameter PLUS a content
+    digest (L1 and L2 norm of every parameter, two fused multi-tensor kernels).  The digest catches writes that bypass the
+    version counter -- `p.data.copy_(...)`, the idiom of the reference's EMA swap (models/ema.py LitEma.copy_to / restore) --
+    which identity alone would miss.  Returns (identity tuple, digest tensor on the parameters' device)."""
+    params = [p.detach() for p in module.parameters()]
+    ident = tuple((p.data_ptr(), tensor_version(p), tuple(p.shape)) for p in params)
+    if not params:
+        return ident, torch.zeros(0)
+    digest = torch.stack(torch._foreach_norm(params, 1) + torch._foreach_norm(params, 2))
+    return ident, digest
+
+
+def same_fingerprint(a, b):
+    if a is None or b is None or a[0] != b[0]:
+        return False
+    return a[1].shape == b[1].shape and bool(torch.equal(a[1], b[1]))
 
 
 # ---------------------------------------------------------------------------
@@ -195,8 +236,7 @@ def image_style(p, si, ch=256):
     exact-erf GELU -> Linear.  Identical for every batch item (mlp.py:46-47)."""
     dim = ch // 4
     half = dim // 2
-    dev = p['time_mlp.1.weight'].device
-    freqs = torch.exp(torch.arange(half, device=dev, dtype=torch.float64) * -(math.log(10000) / (half - 1)))
+    freqs = torch.exp(torch.arange(half, dtype=torch.float64) * -(math.log(10000) / (half - 1)))
     e = float(si) * freqs
     emb = torch.cat((e.sin(), e.cos()))
     h = p['time_mlp.1.weight'] @ emb + p['time_mlp.1.bias']
@@ -269,6 +309,7 @@ def _image_vec(f, gain=1.0):
 
 def pack_image(module, si, precision, pair=True):
     f = fold_image(module, si)
+    dev = module_device(module)
     segs = []
     if precision == PREC_FP32:
         for i, d in enumerate(f['blocks']):
@@ -339,11 +380,11 @@ def pack_image(module, si, precision, pair=True):
             end_group()
         dense256(f['Wrgb'], 0, n_pad=16)   # ToRGB: N = 16 block (3 real rows)
         end_group()
-        gemm, prog_dev, prog_host = P.finish(f['Wrgb'].device)
-        return Packed(precision, gemm, _image_vec(f, gain), prog_dev, prog_host, pair)
+        gemm, prog_dev, prog_host = P.finish(dev)
+        return Packed(precision, gemm, _image_vec(f, gain).to(dev), prog_dev, prog_host, pair)
     else:
         raise ValueError(f"unknown precision {precision}")
-    return Packed(precision, gemm, _image_vec(f))
+    return Packed(precision, gemm.to(dev), _image_vec(f).to(dev))
 
 
 # ---------------------------------------------------------------------------
@@ -368,7 +409,7 @@ def _pack_resnet_chain(p, kx, precision):
     return segs, vec
 
 
-def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3):
+def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     """Program + stream + vec of csrc/decode_umma_occ.cuh.  A-region K groups: H hi 0..31, H lo 32..63,
     Xa (raw PE) hi 64..71 / lo 80..87, Xb (relu PE) hi 72..79 / lo 88..95; acc1 = TMEM cols 0.., acc2 = 256..
     Each ResnetBlockFC with a shortcut is three GEMM groups: shortcut on RAW h -> acc2, fc_0 on relu(h) -> acc1,
@@ -412,23 +453,24 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3):
                      p['net_res2.fc_0.bias'], p['net_res2.fc_1.bias'], p['net_res3.fc_0.bias'], p['net_res3.fc_1.bias'],
                      p['net_res4.fc_0.bias'], p['net_res3.fc_1.bias'] + p['net_res4.fc_1.bias'],
                      p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]).to(torch.float32).contiguous()
-    gemm, prog_dev, prog_host = P.finish(vec.device)
-    return Packed(precision, gemm, vec, prog_dev, prog_host, pair)
+    gemm, prog_dev, prog_host = P.finish(dev)
+    return Packed(precision, gemm, vec.to(dev), prog_dev, prog_host, pair)
 
 
 def pack_occupancy(module, precision=PREC_FP32, pair=True):
     p = _params64(module)
+    dev = module_device(module)
     if precision in (PREC_BF16X3, PREC_F16F8):
-        return _pack_occupancy_umma(p, pair, precision)
+        return _pack_occupancy_umma(p, pair, precision, dev)
     segs, vec = _pack_resnet_chain(p, 64, precision)
     vec[1] = vec[1] + p['net_p.bias']                       # net_p bias rides on R1.fc_1's
     vec += [p['net_p.weight'].t().contiguous().reshape(-1),  # [3][256]
             p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]
-    return Packed(precision, torch.cat(segs).to(torch.float32).contiguous(),
-                  torch.cat(vec).to(torch.float32).contiguous())
+    return Packed(precision, torch.cat(segs).to(torch.float32).contiguous().to(dev),
+                  torch.cat(vec).to(torch.float32).contiguous().to(dev))
 
 
-def _pack_video_umma(p, pair, precision=PREC_BF16X3):
+def _pack_video_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     """Program + stream + vec of csrc/decode_umma_video.cuh (the protocol is spelled out there).  A-region K groups
     as for occupancy: H hi 0..31 / lo 32..63, Xa (raw piece) hi 64..71 / lo 80..87, Xb (relu piece) hi 72..79 / lo 88..95.
     Operand barriers: 0..3 raw-h quarters / R1 pieces / later pieces, 4..7 relu-h and net quarters.
@@ -492,24 +534,25 @@ def _pack_video_umma(p, pair, precision=PREC_BF16X3):
                      p['net_res3.fc_0.bias'], p['net_res3.fc_1.bias'], p['net_res4.fc_0.bias'],
                      p['net_res3.fc_1.bias'] + p['net_res4.fc_1.bias'], p['net_out.weight'].reshape(-1),
                      p['net_out.bias'].reshape(-1)]).to(torch.float32).contiguous()
-    gemm, prog_dev, prog_host = P.finish(vec.device)
-    return Packed(precision, gemm, vec, prog_dev, prog_host, pair)
+    gemm, prog_dev, prog_host = P.finish(dev)
+    return Packed(precision, gemm, vec.to(dev), prog_dev, prog_host, pair)
 
 
 def pack_video(module, precision=PREC_FP32, pair=True):
     p = _params64(module)
+    dev = module_device(module)
     if precision in (PREC_BF16X3, PREC_F16F8):
-        return _pack_video_umma(p, pair, precision)
+        return _pack_video_umma(p, pair, precision, dev)
     segs, vec = _pack_resnet_chain(p, 192, precision)
     vec += [p['net_out.weight'].reshape(-1), p['net_out.bias'].reshape(-1)]
-    return Packed(precision, torch.cat(segs).to(torch.float32).contiguous(),
-                  torch.cat(vec).to(torch.float32).contiguous())
+    return Packed(precision, torch.cat(segs).to(torch.float32).contiguous().to(dev),
+                  torch.cat(vec).to(torch.float32).contiguous().to(dev))
 
 
 # ---------------------------------------------------------------------------
 # NeRF MLP (mlp.py:199-281), D=6, W=256, skips=[2,4], xyz 159, dir 27
 # ---------------------------------------------------------------------------
-def _pack_nerf_umma(p, precision=PREC_BF16X3):
+def _pack_nerf_umma(p, precision=PREC_BF16X3, dev='cpu'):
     """Program + stream + vec of csrc/decode_umma_nerf.cuh (CTA pairs).  A-region K groups: H hi 0..31, H lo 32..63,
     X ([latent 96 | gamma(pts) 63 | 0]) hi 64..83, lo 84..103; the 27-wide direction embedding reuses X's first 4
     K groups for the last layer.  One accumulator (TMEM columns 0..255)."""
@@ -548,13 +591,13 @@ def _pack_nerf_umma(p, precision=PREC_BF16X3):
     over_h(Wd[:, :256], True)
     P.block(pad_k(Wd[:, 256:283], 32), XH, XL, 0, False, a_in_tmem=True)
     P.commit()
-    z3 = torch.zeros(3, dtype=torch.float64, device=Wd.device)
+    z3 = torch.zeros(3, dtype=torch.float64)
     vec = torch.cat([p[f'xyz_encoding_{i + 1}.0.bias'] for i in range(6)]
                     + [p['xyz_encoding_final.bias'], p['dir_encoding.0.bias'], p['sigma.weight'].reshape(-1),
                        p['sigma.bias'].reshape(-1), z3, p['rgb.0.weight'].reshape(-1), p['rgb.0.bias'].reshape(-1)]
                     ).to(torch.float32).contiguous()
-    gemm, prog_dev, prog_host = P.finish(vec.device)
-    return Packed(precision, gemm, vec, prog_dev, prog_host, True)
+    gemm, prog_dev, prog_host = P.finish(dev)
+    return Packed(precision, gemm, vec.to(dev), prog_dev, prog_host, True)
 
 
 def pack_nerf(module, precision=PREC_FP32):
@@ -563,8 +606,9 @@ def pack_nerf(module, precision=PREC_FP32):
             "the fused NeRF kernel is specialised for D=6, W=256, in_channels_xyz=159, "
             "in_channels_dir=27, skips=[2,4] (configs/d2c-vae/srn_cars.yaml:45-49)")
     p = _params64(module)
+    dev = module_device(module)
     if precision in (PREC_BF16X3, PREC_F16F8):
-        return _pack_nerf_umma(p, precision)
+        return _pack_nerf_umma(p, precision, dev)
     segs, vec = [], []
     for i in range(6):
         W = p[f'xyz_encoding_{i + 1}.0.weight']
@@ -581,5 +625,5 @@ def pack_nerf(module, precision=PREC_FP32):
     vec += [p['xyz_encoding_final.bias'], p['dir_encoding.0.bias'],
             p['sigma.weight'].reshape(-1), p['sigma.bias'].reshape(-1),
             p['rgb.0.weight'].reshape(-1), p['rgb.0.bias'].reshape(-1)]
-    return Packed(precision, torch.cat(segs).to(torch.float32).contiguous(),
-                  torch.cat(vec).to(torch.float32).contiguous())
+    return Packed(precision, torch.cat(segs).to(torch.float32).contiguous().to(dev),
+                  torch.cat(vec).to(torch.float32).contiguous().to(dev))

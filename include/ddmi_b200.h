@@ -33,10 +33,15 @@
  *   DDMI_PREC_FP32    fp32 CUDA-core kernels (exact-arithmetic path)
  *   DDMI_PREC_BF16X3  tcgen05 tensor-core kernels, bf16 hi/lo split operands,
  *                     3 MMAs per product, fp32 accumulation in TMEM
- *   DDMI_PREC_F16F8   tcgen05 kernels, fp16 main term + two FP8 (e4m3) correction terms at twice
- *                     the MMA rate: 2/3 of the tensor-pipe time of BF16X3 at ~1e-4 max-abs error
- *                     (all four decoders; CTA-pair kernels only, weights must be pair-packed;
- *                     |weight| < 16, activations saturate at 65504)
+ *   DDMI_PREC_F16F8   tcgen05 kernels, fp16 main term + two FP8 correction terms (e5m2 activation side x
+ *                     e4m3 weight side) at twice the MMA rate: 2/3 of the tensor-pipe time of BF16X3 at
+ *                     ~2e-4 max-abs (6e-5 of |out|max) error (all four decoders; CTA-pair kernels only,
+ *                     weights must be pair-packed).  OPERAND RANGE: |weight| < 16 (checked by the packer);
+ *                     the relative accuracy holds for |plane value|, |hidden activation| <= 2.8e4 (the e5m2
+ *                     residual operand 4096 (a - fp16(a)) <= 2 |a| saturates at 57344); beyond that the
+ *                     correction terms clamp (accuracy degrades towards single-pass fp16, ~1e-3 relative)
+ *                     and at 65504 the fp16 main term clamps.  Nothing is detected at run time: callers with
+ *                     such signals use DDMI_PREC_BF16X3 (bf16 range).
  */
 #ifndef DDMI_B200_H
 #define DDMI_B200_H
@@ -54,7 +59,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 6
+#define DDMI_ABI_VERSION 7
 
 enum {
   DDMI_OK = 0,
@@ -219,18 +224,28 @@ DDMI_API int ddmi_selftest_umma2(const float* a, const float* b, float* d, int32
 
 /*
  * Same shapes as ddmi_selftest_umma through the DDMI_PREC_F16F8 operand scheme (one fp16 kind::f16 term + two
- * kind::f8f6f4 e4m3 correction terms into one accumulator); K a multiple of 32.
+ * kind::f8f6f4 correction terms, e5m2 x e4m3, into one accumulator); K a multiple of 32.
  */
 DDMI_API int ddmi_selftest_f16f8(const float* a, const float* b, float* d, int32_t N, int32_t K,
                                  void* stream);
 
 /*
- * Diagnostics: cycle counters accumulated by CTA 0 of the tcgen05 image kernel since the last
+ * Diagnostics.  The shipping library is built WITHOUT in-kernel instrumentation: these return zeros / an empty trace
+ * unless the library was built with -DDDMI_PROFILE=1 (`make -C ddmi_b200/csrc prof` -> libddmi_b200_prof.so, loaded by
+ * the dev tools through DDMI_B200_LIB).
+ * ddmi_debug_profile: cycle counters accumulated by CTA 0 of the tcgen05 image kernel since the last
  * reset (synchronises the device).  out[0] epilogue thread: cycles parked waiting for MMA groups,
  * [1] cycles in epilogue stages, [2] cycles in plane gathers, [3] MMA thread: cycles waiting for
  * operands, [4] cycles waiting for weight chunks, [5] MMA thread total, [6] tiles, [7] spare.
+ * ddmi_debug_trace: (event id << 48 | SM clock) records of one tile iteration of CTA 0 (epilogue thread 0 and the MMA
+ * lane); *count = records copied to `out` (host memory, `capacity` entries).
+ * ddmi_debug_microbench: epilogue building blocks in isolation (csrc/microbench.cu); out_dev[0] = cycles warp 0 spent,
+ * out_dev[1] = span over the 8 warps, for `iters` repetitions of one stage-sized unit.  All buffers are device memory.
  */
 DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset);
+DDMI_API int ddmi_debug_trace(uint64_t* out, int32_t capacity, int32_t* count, int32_t reset);
+DDMI_API int ddmi_debug_microbench(int32_t mode, int32_t iters, const float* seed, uint64_t* out_dev, float* sink_dev,
+                                   void* stream);
 
 #ifdef __cplusplus
 }

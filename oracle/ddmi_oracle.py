@@ -154,11 +154,14 @@ def occupancy_logits(sd, coords, hdbf):
     return F.linear(x, sd['net_out.weight'], sd['net_out.bias']).squeeze(-1)
 
 
-def video_decode(sd, coords, hdbf):
-    """MLPVideo.forward (mlp.py:128-157) -> (b,3,t,h,w)."""
+def video_decode(sd, coords, hdbf, thw=None):
+    """MLPVideo.forward (mlp.py:128-157) -> (b,3,t,h,w).  The reference takes (t,h,w) of the output from the finest planes
+    (:135-136); `thw` overrides them so tests can decode a row band of the query volume."""
     xy, yt, xt = hdbf
     b, _, h, w = xy[-1].shape
     t = yt[-1].shape[2]
+    if thw is not None:
+        t, h, w = thw
     dt = xy[-1].dtype
     cg = {k: coords[k].to(dt).repeat(b, 1, 1, 1).permute(0, 2, 3, 1).contiguous() for k in ('xy', 'yt', 'xt')}
     f = [triplane_concat(xy[s], yt[s], xt[s], cg['xy'], cg['yt'], cg['xt']) for s in range(3)]

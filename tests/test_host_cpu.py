@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ddmi_abi_version() == 6
+    assert L.ddmi_abi_version() == _lib.ABI_VERSION
     assert L.ddmi_status_string(1).decode() == 'bad argument'
 
 
@@ -168,3 +168,33 @@ def test_f16f8_default_falls_back_to_bf16x3_on_out_of_range_weights():
     m.precision = 'f16f8'
     with pytest.raises(packing.F16F8RangeError):
         m._packed_auto(_lib.PREC_F16F8, key_of, build_of)
+
+
+def test_packed_cache_sees_data_writes_that_keep_the_version_counter():
+    """`p.data.copy_(...)` -- the idiom of the reference's EMA swap (models/ema.py LitEma.copy_to / restore) -- changes a
+    parameter without bumping its version counter; the cache key carries a content digest, so the packed weights are rebuilt."""
+    from ddmi_b200 import _lib, packing
+    m = cases.build_module('occupancy')
+    built = []
+    build = lambda: built.append(1) or packing.pack_occupancy(m, _lib.PREC_FP32)
+    a = m._packed(('occ', 0), build)
+    assert m._packed(('occ', 0), build) is a and len(built) == 1
+    v0 = m.net_out.bias._version
+    m.net_out.bias.data.copy_(m.net_out.bias.data + 1.0)
+    assert m.net_out.bias._version == v0                      # the write is invisible to the version counter ...
+    b = m._packed(('occ', 0), build)
+    assert b is not a and len(built) == 2                     # ... but not to the digest
+    assert float(b.vec[-1] - a.vec[-1]) == 1.0
+    m.invalidate_packed()
+    assert m._packed(('occ', 0), build) is not b and len(built) == 3
+
+
+def test_mismatched_planes_are_rejected_before_any_launch():
+    """The C ABI takes ONE (batch, channels) pair for all planes of a decode; a smaller plane must raise, not be over-read."""
+    from ddmi_b200.mlp import _check_plane_set
+    ok = [torch.zeros(2, 64, 4, 4), torch.zeros(2, 64, 8, 8)]
+    _check_plane_set(ok, 64, ['a', 'b'])
+    with pytest.raises(RuntimeError, match="batch"):
+        _check_plane_set([ok[0], torch.zeros(1, 64, 8, 8)], 64, ['a', 'b'])
+    with pytest.raises(RuntimeError, match="channels"):
+        _check_plane_set([ok[0], torch.zeros(2, 32, 8, 8)], 64, ['a', 'b'])

@@ -136,16 +136,18 @@ def test_occupancy_shared_points_and_single_point(precision):
     assert float((out - ref).abs().max()) < tol
 
 
-def test_occupancy_dense_grid_chunks_like_eval_points():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_occupancy_dense_grid_chunks_like_eval_points(precision):
     """Generator3D.eval_points call shape: 1.1*make_3d_grid, split into chunks, mlp(pi[None], c).logits."""
     m = cases.build_module('occupancy').to(DEV)
+    m.precision = precision
     sd = cases.state_dict32(m)
     _, hdbf = cases.occupancy_inputs(batch=1, n=1)
     p = 1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (20,) * 3)
     c = _cuda(hdbf)
     got = torch.cat([m(pi[None].to(DEV), c).logits.squeeze(0).cpu() for pi in torch.split(p, 3000)])
     ref = orc.occupancy_logits(sd, p[None], hdbf)[0]
-    assert float((got - ref).abs().max()) < TOL          # default precision = bf16x3 (tcgen05)
+    assert float((got - ref).abs().max()) < TOL
     assert _sign_agreement(got, ref) >= 0.9999
 
 
@@ -237,23 +239,24 @@ def test_nerf_render_batch_and_ray_subset(precision):
         assert float((rgb[b].cpu() - ref).abs().max()) < tol
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
 @pytest.mark.parametrize("n_obj,n_rays", [(1, 37), (3, 64)])
-def test_nerf_render_fused_compositing_128_samples(n_obj, n_rays):
+def test_nerf_render_fused_compositing_128_samples(n_obj, n_rays, precision):
     """N_samples == 128: one tile == one ray, compositing runs inside the tcgen05 kernel (no raw round trip)."""
     m = cases.build_module('nerf').to(DEV)
     sd = cases.state_dict32(m)
     g = torch.Generator().manual_seed(13)
     fea = {k: torch.randn(n_obj, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
     rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][300:300 + n_rays]
-    rgb = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, precision='bf16x3')
-    rgb2, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, return_raw=True, precision='bf16x3')
+    rgb = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, precision=precision)
+    rgb2, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True, return_raw=True, precision=precision)
     assert float((rgb - rgb2).abs().max()) == 0.0
     for b in range(n_obj):
         fb = {k: v[b:b + 1] for k, v in fea.items()}
         ref, ref_raw = orc.nerf_render_rays(sd, rays, fb, 128, True, return_raw=True)
         assert float((raw[b].cpu() - ref_raw).abs().max()) < TOL
         assert float((rgb[b].cpu() - ref).abs().max()) < TOL
-    black = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, False, precision='bf16x3')
+    black = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, False, precision=precision)
     assert float((rgb - black).min()) >= -1e-6      # the white background only adds (1 - acc) >= 0
 
 
@@ -356,8 +359,8 @@ def test_umma2_selftest(N, K):
 
 @pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 64), (16, 256), (128, 32)])
 def test_f16f8_selftest(N, K):
-    """fp16 main term + two e4m3 correction terms (kind::f8f6f4) into one accumulator: checked against the exact
-    product and, tightly, against a torch emulation of the same operand rounding."""
+    """fp16 main term + two FP8 correction terms (kind::f8f6f4, e5m2 activations x e4m3 weights) into one accumulator:
+    checked against the exact product and, tightly, against a torch emulation of the same operand rounding."""
     from ddmi_b200 import _lib
     g = torch.Generator().manual_seed(N * 1000 + K + 13)
     a = torch.randn(128, K, generator=g)
@@ -368,11 +371,12 @@ def test_f16f8_selftest(N, K):
                                               torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     S = 4096.0
-    q8 = lambda x: x.clamp(-448, 448).to(torch.float8_e4m3fn).double()
+    q8 = lambda x: x.clamp(-448, 448).to(torch.float8_e4m3fn).double()           # weight side
+    q5 = lambda x: x.clamp(-57344, 57344).to(torch.float8_e5m2).double()         # activation side
     a16 = a.to(torch.float16)
     w16 = (b * S).to(torch.float16)
-    emu = (a16.double() @ w16.double().t() + q8((a - a16.float()) * S) @ q8(b).t()
-           + q8(a) @ q8(b * S - w16.float()).t()) / S
+    emu = (a16.double() @ w16.double().t() + q5((a - a16.float()) * S) @ q8(b).t()
+           + q5(a) @ q8(b * S - w16.float()).t()) / S
     ref = a.double() @ b.double().t()
     got = d.double().cpu()
     assert float((got - emu).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
@@ -406,7 +410,8 @@ def test_image_full_size_cross_check_and_crop_independence(scheme):
         assert torch.equal(one[0], full[1])
 
 
-def test_occupancy_full_grid_sign_agreement():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_occupancy_full_grid_sign_agreement(precision):
     """One item on the full 128^3 grid + 100k random points (config C4 per item): tcgen05 vs fp32 kernel."""
     m = cases.build_module('occupancy').to(DEV)
     _, hdbf = cases.occupancy_inputs(batch=1, n=1)
@@ -414,7 +419,7 @@ def test_occupancy_full_grid_sign_agreement():
     p = torch.cat([1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3),
                    (torch.rand(100000, 3, generator=g) - 0.5) * 1.1]).to(DEV)
     c = _cuda(hdbf)
-    m.precision = 'bf16x3'
+    m.precision = precision
     a = m(p[None], c).logits
     m.precision = 'fp32'
     b = m(p[None], c).logits
@@ -422,7 +427,8 @@ def test_occupancy_full_grid_sign_agreement():
     assert _sign_agreement(a, b) >= 0.9999
 
 
-def test_video_batch_independence_and_cross_check():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_video_batch_independence_and_cross_check(precision):
     m = cases.build_module('video').to(DEV)
     g = torch.Generator().manual_seed(23)
     T, R = 8, 64
@@ -431,7 +437,7 @@ def test_video_batch_independence_and_cross_check():
     xt = _cuda([torch.randn(3, 64, T, s, generator=g) for s in (16, 32, 64)])
     e, et = (R - 1) / R, (T - 1) / T
     coords = _cuda(ddmi_b200.convert_to_coord_format_3d(1, R, R, T, hstart=-e, hend=e, wstart=-e, wend=e, tstart=-et, tend=et))
-    m.precision = 'bf16x3'
+    m.precision = precision
     full = m(coords, (xy, yt, xt))
     one = m(coords, ([p[2:3] for p in xy], [p[2:3] for p in yt], [p[2:3] for p in xt]))
     assert torch.equal(one[0], full[2])
@@ -440,17 +446,193 @@ def test_video_batch_independence_and_cross_check():
     assert float((full - exact).abs().max()) < TOL
 
 
-def test_nerf_full_view_cross_check():
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+def test_nerf_full_view_cross_check(precision):
     """A full 64x64-ray view at 128 samples (fused compositing) vs the fp32 kernels (separate compositing kernel)."""
     m = cases.build_module('nerf').to(DEV)
     res, K, fea, c2w = cases.nerf_inputs(res=64, theta=110.0)
     ro, rd = nh.get_rays(res, res, K, c2w, 'cpu')
     vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
     rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(res * res, 1), 6. * torch.ones(res * res, 1), vd], -1).to(DEV)
-    a = nh.render_rays_fused(rays, _cuda(fea), m, 128, True, precision='bf16x3')
+    a = nh.render_rays_fused(rays, _cuda(fea), m, 128, True, precision=precision)
     b = nh.render_rays_fused(rays, _cuda(fea), m, 128, True, precision='fp32')
     assert float((a - b).abs().max()) < TOL
     assert float(a.max() - a.min()) > 0.2
+
+
+# ---------------------------------------------------------------- the BASELINE configs themselves against the oracle
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+@pytest.mark.parametrize("R,rows", [(1024, [(0, 8), (500, 532), (1016, 1024)]), (2048, [(0, 4), (1337, 1353), (2044, 2048)])])
+def test_image_bench_config_vs_oracle(R, rows, precision):
+    """configs[1] (the bench line): AFHQ-shape planes 64^2/128^2/256^2, the 1024^2 (si = 0.25) and 2048^2 (si = 0.125)
+    query grids.  The oracle decodes row bands of the full grid (top border, interior, bottom border); the kernel
+    decodes the FULL grid in one launch (so rows fall into tiles / CTA pairs as in the bench) and must match on the bands."""
+    m = cases.build_module('image').to(DEV)
+    m.precision = precision
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(41)
+    planes = [torch.randn(1, 64, s, s, generator=g) for s in (64, 128, 256)]
+    e = (R - 1) / R
+    coords = ddmi_b200.convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e)
+    si = ddmi_b200.get_scale_injection(R)
+    assert si == 256 / R
+    full = m(coords.to(DEV), hdbf=_cuda(planes), si=si).cpu()
+    for r0, r1 in rows:
+        ref = orc.image_decode(sd, coords[:, :, r0:r1], planes, si)
+        err = float((full[:, :, r0:r1] - ref).abs().max())
+        print(f"image {R}x{R} rows {r0}:{r1} {precision}: max abs vs oracle {err:.3e}")
+        assert err < TOL
+
+
+def test_video_config_shape_vs_oracle():
+    """configs[2], one item: 256x256x16 volume on 64/128/256 planes, default precision, oracle chunked over rows."""
+    m = cases.build_module('video').to(DEV)
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(42)
+    xy = [torch.randn(1, 64, s, s, generator=g) for s in (64, 128, 256)]
+    yt = [torch.randn(1, 64, 16, s, generator=g) for s in (64, 128, 256)]
+    xt = [torch.randn(1, 64, 16, s, generator=g) for s in (64, 128, 256)]
+    coords = ddmi_b200.convert_to_coord_format_3d(1, 256, 256, 16, hstart=-255 / 256, hend=255 / 256, wstart=-255 / 256,
+                                                  wend=255 / 256, tstart=-15 / 16, tend=15 / 16)
+    out = m(_cuda(coords), _cuda((xy, yt, xt))).cpu()
+    assert out.shape == (1, 3, 16, 256, 256)
+    worst = 0.0
+    for h0 in range(0, 256, 64):
+        sub = {'xy': coords['xy'][:, :, h0:h0 + 64], 'yt': coords['yt'][:, :, :, h0:h0 + 64], 'xt': coords['xt']}
+        ref = orc.video_decode(sd, sub, (xy, yt, xt), thw=(16, 64, 256))
+        worst = max(worst, float((out[:, :, :, h0:h0 + 64] - ref).abs().max()))
+    print(f"video 256x256x16 vs oracle: max abs {worst:.3e}")
+    assert worst < TOL
+
+
+def test_occupancy_config_shape_vs_oracle():
+    """configs[3], one item: every 4th z-slab of the 128^3 grid + 100k random points against the oracle."""
+    m = cases.build_module('occupancy').to(DEV)
+    sd = cases.state_dict32(m)
+    _, hdbf = cases.occupancy_inputs(batch=1, n=1)
+    g = torch.Generator().manual_seed(43)
+    grid = 1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3)
+    p = torch.cat([grid.reshape(128, 128 * 128, 3)[::4].reshape(-1, 3), (torch.rand(100000, 3, generator=g) - 0.5) * 1.1])
+    out = m(p[None].to(DEV), _cuda(hdbf)).logits.cpu()[0]
+    ref = torch.cat([orc.occupancy_logits(sd, pi[None], hdbf)[0] for pi in torch.split(p, 100000)])
+    err = float((out - ref).abs().max())
+    print(f"occupancy 128^3 slabs + 100k random vs oracle: max abs {err:.3e}, sign agreement {_sign_agreement(out, ref):.6f}")
+    assert err < TOL and _sign_agreement(out, ref) >= 0.9999
+
+
+def test_nerf_config_shape_vs_oracle():
+    """configs[4], one object: a 128x128-ray view x 128 samples, compositing fused, against the oracle (chunked over rays)."""
+    m = cases.build_module('nerf').to(DEV)
+    sd = cases.state_dict32(m)
+    res, K, fea, c2w = cases.nerf_inputs(res=128, theta=75.0)
+    ro, rd = nh.get_rays(res, res, K, c2w, 'cpu')
+    vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
+    rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(res * res, 1), 6. * torch.ones(res * res, 1), vd], -1)
+    rgb = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, 128, True)[0].cpu()
+    ref = torch.cat([orc.nerf_render_rays(sd, r, fea, 128, True) for r in torch.split(rays, 2048)])
+    err = float((rgb - ref).abs().max())
+    print(f"nerf 128x128x128 vs oracle: max abs {err:.3e}")
+    assert err < TOL and float(ref.max() - ref.min()) > 0.2
+
+
+# ---------------------------------------------------------------- operand range of the f16f8 scheme
+@pytest.mark.parametrize("scale", [10.0, 50.0, 300.0])
+def test_f16f8_holds_its_accuracy_on_large_signals(scale):
+    """Planes far from N(0,1) (x10, x50, x300: hidden activations up to ~2000 / ~1e4): the f16f8 scheme's correction operands
+    must not saturate (the activation side is e5m2, range 57344; include/ddmi_b200.h states the limit), so the error stays at
+    the same fraction of |out|max as on unit-scale planes."""
+    m = cases.build_module('image').to(DEV)
+    m.precision = 'f16f8'
+    coords, planes, si = cases.image_inputs(batch=2, sizes=(16, 32, 64), res=96)
+    planes = [p * scale for p in planes]
+    ref = orc.image_decode(cases.state_dict32(m), coords, planes, si)
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=si).cpu()
+    rel = float((out - ref).abs().max()) / float(ref.abs().max())
+    print(f"image planes x{scale:g}: |out|max {float(ref.abs().max()):.1f}, max err / |out|max {rel:.3e}")
+    assert rel < 3e-4
+
+    mo = cases.build_module('occupancy').to(DEV)
+    mo.precision = 'f16f8'
+    pts, hdbf = cases.occupancy_inputs(batch=1, n=20000)
+    hdbf = tuple([p * scale for p in axis] for axis in hdbf)
+    ref = orc.occupancy_logits(cases.state_dict32(mo), pts, hdbf)
+    out = mo(pts.to(DEV), _cuda(hdbf)).logits.cpu()
+    rel = float((out - ref).abs().max()) / float(ref.abs().max())
+    print(f"occupancy planes x{scale:g}: |logit|max {float(ref.abs().max()):.1f}, max err / |logit|max {rel:.3e}")
+    assert rel < 3e-4
+
+    mv = cases.build_module('video').to(DEV)
+    mv.precision = 'f16f8'
+    cv, hv = cases.video_inputs()
+    hv = tuple([p * scale for p in axis] for axis in hv)
+    ref = orc.video_decode(cases.state_dict32(mv), cv, hv)
+    out = mv(_cuda(cv), _cuda(hv)).cpu()
+    rel = float((out - ref).abs().max()) / float(ref.abs().max())
+    print(f"video planes x{scale:g}: |out|max {float(ref.abs().max()):.1f}, max err / |out|max {rel:.3e}")
+    assert rel < 3e-4
+
+
+# ---------------------------------------------------------------- host-side caches and input validation (ADVICE round 1)
+def test_data_writes_and_ema_style_swaps_reach_the_kernel():
+    m = cases.build_module('image').to(DEV)
+    coords, planes, si = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=16)
+    a = m(coords.to(DEV), hdbf=_cuda(planes), si=si)
+    m.torgb.bias.data.copy_(m.torgb.bias.data + 1.0)              # LitEma.copy_to idiom: no version bump
+    b = m(coords.to(DEV), hdbf=_cuda(planes), si=si)
+    assert float((b - a - 1.0).abs().max()) < 1e-5
+
+
+def test_mismatched_planes_raise():
+    m = cases.build_module('image').to(DEV)
+    coords, planes, si = cases.image_inputs(batch=2, sizes=(8, 16, 32), res=16)
+    bad = _cuda(planes)
+    bad[1] = bad[1][:1]
+    with pytest.raises(RuntimeError, match="batch"):
+        m(coords.to(DEV), hdbf=bad, si=si)
+    mo = cases.build_module('occupancy').to(DEV)
+    pts, hdbf = cases.occupancy_inputs(batch=2, n=64)
+    hb = _cuda(hdbf)
+    hb[2][1] = hb[2][1][:, :32]
+    with pytest.raises(RuntimeError, match="channels"):
+        mo(pts.to(DEV), hb)
+    mn = cases.build_module('nerf').to(DEV)
+    res, K, fea, c2w = cases.nerf_inputs(res=8)
+    fb = _cuda(fea)
+    fb['yz'] = fb['yz'].repeat(2, 1, 1, 1)
+    rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][:16]
+    with pytest.raises(RuntimeError, match="batch"):
+        nh.render_rays_fused(rays.to(DEV), fb, mn, 128, True)
+
+
+def test_nerf_mlp_forward_ignores_the_tensor_core_precision_override(monkeypatch):
+    """DDMI_B200_PRECISION selects the default of the fused decoders; MLPNeRF.forward (rows in, rows out) has an fp32 kernel only."""
+    monkeypatch.setenv('DDMI_B200_PRECISION', 'f16f8')
+    m = cases.build_module('nerf').to(DEV)
+    x = cases.nerf_mlp_inputs(n=200)
+    ref = orc.nerf_mlp(cases.state_dict32(m), x)
+    assert float((m(x.to(DEV)).cpu() - ref).abs().max()) < 2e-5
+
+
+def test_channels_last_plane_cache_tracks_the_planes():
+    """eval_points-style chunk loop: the channels-last copies are made once per latent; an in-place update of a plane (version
+    bump) or a new tensor invalidates them."""
+    m = cases.build_module('occupancy').to(DEV)
+    sd = cases.state_dict32(m)
+    pts, hdbf = cases.occupancy_inputs(batch=1, n=3000)
+    c = _cuda(hdbf)
+    a = m(pts.to(DEV), c).logits.cpu()
+    key = m._nhwc_cache.key
+    b = torch.cat([m(pi.to(DEV), c).logits.cpu() for pi in torch.split(pts, 1000, dim=1)], dim=1)
+    assert m._nhwc_cache.key == key and torch.equal(a, b)
+    c[0][2].mul_(0.5)                                              # in place: same storage, new version
+    hdbf[0][2].mul_(0.5)
+    d = m(pts.to(DEV), c).logits.cpu()
+    assert m._nhwc_cache.key != key
+    assert float((d - orc.occupancy_logits(sd, pts, hdbf)).abs().max()) < TOL
+    with torch.inference_mode():                                   # inference tensors have no version counter: never cached
+        ci = _cuda(hdbf)
+        e = m(pts.to(DEV), ci).logits.cpu()
+    assert float((e - d).abs().max()) == 0.0
 
 
 # ---------------------------------------------------------------- ragged / degenerate shapes
@@ -480,14 +662,15 @@ def test_video_ragged_volume():
     assert float((out - ref).abs().max()) < TOL
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
 @pytest.mark.parametrize("n_samples", [1, 100, 192])
-def test_nerf_sample_counts_that_straddle_tiles(n_samples):
+def test_nerf_sample_counts_that_straddle_tiles(n_samples, precision):
     m = cases.build_module('nerf').to(DEV)
     sd = cases.state_dict32(m)
     g = torch.Generator().manual_seed(33)
     fea = {k: torch.randn(1, 32, 64, 64, generator=g) for k in ('xy', 'yz', 'xz')}
     rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'][500:511]
-    rgb, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, n_samples, False, return_raw=True, precision='bf16x3')
+    rgb, raw = nh.render_rays_fused(rays.to(DEV), _cuda(fea), m, n_samples, False, return_raw=True, precision=precision)
     ref, ref_raw = orc.nerf_render_rays(sd, rays, fea, n_samples, False, return_raw=True)
     assert float((raw[0].cpu() - ref_raw).abs().max()) < TOL
     assert float((rgb[0].cpu() - ref).abs().max()) < TOL

@@ -1,0 +1,44 @@
+"""Dev tool (GPU box): timeline of ONE tile iteration of CTA 0 of the tcgen05 image kernel.
+Needs the profiling build:  make -C ddmi_b200/csrc prof && DDMI_B200_LIB=ddmi_b200/libddmi_b200_prof.so python tools/profile_timeline.py
+Event ids (csrc/umma_engine.cuh, decode_umma.cu): E thread 0: 0x01 parks on the MMA barrier, 0x02 woke, 0x03 accumulator drained,
+0x10+q quarter q published, 0x20 / 0x21 gather begin / end; MMA lane: 0x100+pc UNIT starts issuing, 0x200+pc WAIT begins,
+0x300+pc WAIT satisfied, 0x400+pc COMMIT issued."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from ddmi_b200 import _lib, convert_to_coord_format_2d, get_scale_injection
+torch.set_grad_enabled(False)
+B, R = 16, 1024
+dev = 'cuda:0'
+m = bench.build_mlp().to(dev)
+m.precision = os.environ.get('PREC', 'f16f8')
+g = torch.Generator().manual_seed(1)
+planes = [torch.randn(B, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
+e = (R - 1) / R
+c = convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
+L = _lib.lib()
+m(c, hdbf=planes, si=get_scale_injection(R))
+torch.cuda.synchronize()
+buf = (ctypes.c_uint64 * 4096)()
+n = ctypes.c_int32()
+_lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
+m(c, hdbf=planes, si=get_scale_injection(R))
+torch.cuda.synchronize()
+_lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
+ev = sorted(((buf[i] & ((1 << 48) - 1)), buf[i] >> 48) for i in range(n.value))
+if not ev:
+    print("no trace records: load the profiling build (DDMI_B200_LIB=ddmi_b200/libddmi_b200_prof.so)")
+    sys.exit(1)
+t0 = ev[0][0]
+names = {0x01: 'E park', 0x02: 'E woke', 0x03: 'E drained', 0x20: 'E gather begin', 0x21: 'E gather end'}
+prev = t0
+for t, i in ev:
+    if i >= 0x400: nm = f'M COMMIT pc{i - 0x400}'
+    elif i >= 0x300: nm = f'M WAIT ok pc{i - 0x300}'
+    elif i >= 0x200: nm = f'M WAIT .. pc{i - 0x200}'
+    elif i >= 0x100: nm = f'M UNIT pc{i - 0x100}'
+    elif 0x10 <= i < 0x14: nm = f'E publish q{i - 0x10}'
+    else: nm = names.get(i, hex(i))
+    print(f"{t - t0:8d} (+{t - prev:6d})  {nm}")
+    prev = t
