@@ -13,16 +13,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DDMI_B200_LIB") or os.path.join(_HERE, "libddmi_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 PREC_FP32 = 0
 PREC_BF16X3 = 1
 PREC_F16F8 = 2
 STORE_F32, STORE_F32_CLAMP, STORE_U8_CHANNELS_LAST = 0, 1, 2
 STORE_MODES = {None: 0, 'f32': 0, 'clamp': 1, 'u8': 2}
+NOISE_NONE, NOISE_TENSORS, NOISE_PHILOX = 0, 1, 2
 
 EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
-    "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
+    "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_decode_image_noise", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
     "ddmi_decode_video", "ddmi_decode_video_store",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
     "ddmi_debug_trace", "ddmi_debug_microbench",
@@ -74,6 +75,8 @@ def lib():
                                         ctypes.POINTER(Weights), vp, vp]
         L.ddmi_decode_image_store.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, i64,
                                               ctypes.POINTER(Weights), i32, vp, vp]
+        L.ddmi_decode_image_noise.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, i64, ctypes.POINTER(Weights), i32,
+                                              i32, ctypes.POINTER(vp), ctypes.c_uint64, vp, vp]
         L.ddmi_planes_to_channels_last.argtypes = [vp, vp, i32, i32, i32, i32, vp]
         L.ddmi_decode_occupancy.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i64, f32,
                                             ctypes.POINTER(Weights), vp, vp]

@@ -21,13 +21,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 // fp32 CUDA-core path (decode_fp32.cu)
-int launch_image_fp32(const PlaneSet&, int, int, const float*, const float*, long long, const float*, const float*, void*, int, cudaStream_t);
+int launch_image_fp32(const PlaneSet&, int, int, const float*, const float*, long long, const float*, const float*, void*, int, const NoiseArgs&, cudaStream_t);
 int launch_occupancy_fp32(const PlaneSet&, int, int, const float*, long long, long long, float, float, const float*, const float*, float*, cudaStream_t);
 int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const float*, const float*, void*, int, cudaStream_t);
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
 int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
-int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, cudaStream_t);
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, const NoiseArgs&, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
@@ -105,7 +105,26 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
 DDMI_API int ddmi_decode_image_store(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
                                      const float* coord_x, const float* coord_y, int64_t n_coords,
                                      const ddmi_weights_t* weights, int32_t store, void* out, void* stream) {
+  return ddmi_decode_image_noise(planes, batch, channels, coord_x, coord_y, n_coords, weights, store, DDMI_NOISE_NONE, nullptr,
+                                 0, out, stream);
+}
+
+DDMI_API int ddmi_decode_image_noise(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                                     const float* coord_x, const float* coord_y, int64_t n_coords,
+                                     const ddmi_weights_t* weights, int32_t store, int32_t noise_mode,
+                                     const float* const* noise, uint64_t seed, void* out, void* stream) {
   DDMI_REQUIRE(store >= DDMI_STORE_F32 && store <= DDMI_STORE_U8_CHANNELS_LAST, "unknown store mode %d", store);
+  DDMI_REQUIRE(noise_mode >= DDMI_NOISE_NONE && noise_mode <= DDMI_NOISE_PHILOX, "unknown noise mode %d", noise_mode);
+  NoiseArgs na = {};
+  na.mode = noise_mode;
+  na.seed = seed;
+  if (noise_mode == DDMI_NOISE_TENSORS) {
+    DDMI_REQUIRE(noise != nullptr, "noise_mode = DDMI_NOISE_TENSORS needs 12 noise pointers");
+    for (int l = 0; l < 12; ++l) {
+      DDMI_REQUIRE(noise[l] != nullptr, "noise[%d] is NULL", l);
+      na.p[l] = noise[l];
+    }
+  }
   PlaneSet ps = {};
   int rc = check_planes(planes, 3, &ps);
   if (rc) return rc;
@@ -121,10 +140,10 @@ DDMI_API int ddmi_decode_image_store(const ddmi_plane_t planes[3], int32_t batch
   if (weights->precision == DDMI_PREC_FP32) {
     // res1: c1[64] c2 c3 skip[64]; res2/3: c1[320] c2 c3 skip[320]; res4: c1 c2 c3
     const uint64_t kfl = (64 + 256 + 256 + 64) + 2 * (320 + 256 + 256 + 320) + 3 * 256;
-    rc = check_weights(weights, kfl * 256 * sizeof(float), 4096 + 768 + 3);
+    rc = check_weights(weights, kfl * 256 * sizeof(float), 4096 + 768 + 3 + 12);
     if (rc) return rc;
     return launch_image_fp32(ps, batch, channels, coord_x, coord_y, n_coords, (const float*)weights->gemm,
-                             weights->vec, out, store, st);
+                             weights->vec, out, store, na, st);
   } else if (weights->precision == DDMI_PREC_BF16X3 || weights->precision == DDMI_PREC_F16F8) {
     DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
     DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
@@ -132,7 +151,7 @@ DDMI_API int ddmi_decode_image_store(const ddmi_plane_t planes[3], int32_t batch
     DDMI_REQUIRE(!f16f8 || (weights->reserved & 1), "DDMI_PREC_F16F8 weights must be packed for CTA pairs");
     return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm, weights->gemm_bytes,
                              weights->program_host, weights->program_words, weights->program, weights->vec,
-                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, st);
+                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, na, st);
   }
   set_error("unknown precision %d", weights->precision);
   return DDMI_ERR_UNSUPPORTED;
@@ -358,7 +377,7 @@ DDMI_API int ddmi_debug_trace(uint64_t* out, int32_t capacity, int32_t* count, i
 }
 
 DDMI_API int ddmi_debug_microbench(int32_t mode, int32_t iters, const float* seed, uint64_t* out_dev, float* sink_dev, void* stream) {
-  DDMI_REQUIRE(mode >= 0 && mode <= 6 && iters >= 1, "mode must be 0..6 and iters >= 1");
+  DDMI_REQUIRE(mode >= 0 && mode <= 8 && iters >= 1, "mode must be 0..8 and iters >= 1");
   DDMI_REQUIRE(seed && out_dev && sink_dev, "seed (1024 floats) / out_dev (2 x u64) / sink_dev (256 floats) is NULL");
   return launch_microbench(mode, iters, seed, (unsigned long long*)out_dev, sink_dev, (cudaStream_t)stream);
 }

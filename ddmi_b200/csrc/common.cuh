@@ -155,6 +155,53 @@ __device__ __forceinline__ void store_rgb(void* out, int store, size_t b, long l
     reinterpret_cast<float*>(out)[((size_t)b * 3 + c) * n + gi] = v;
 }
 
+// ---------------------------------------------------------------------------
+// Noise injection of the image decoder's 12 StyledConv layers (models/d2c_vae/blocks.py:286-297, 349-356):
+// out = conv(x) + noise.weight * noise[b, 0, y, x] before the bias / leaky ReLU.  The reference draws N(0,1) inside forward
+// (not reproducible); here the noise is either 12 EXPLICIT tensors (mode 1: layer l reads p[l], (batch, n) fp32) or a
+// DOCUMENTED counter-based stream (mode 2), identical for every kernel, precision and tiling:
+//   x = Philox4x32-10(key = (seed lo, seed hi), counter = (g lo, g hi, b, blk)),  g = coordinate index, b = item, blk = l / 3
+//   u_i = ((x_i >> 9) + 0.5) * 2^-23;  z0, z1 = sqrt(-2 ln u0) * (cos, sin)(2 pi u1);  z2 = sqrt(-2 ln u2) * cos(2 pi u3)
+//   noise of conv1, conv2, conv3 of block blk = z0, z1, z2   (oracle/ddmi_oracle.py::philox_noise is the same in numpy)
+// ---------------------------------------------------------------------------
+struct NoiseArgs {
+  const float* p[12];
+  unsigned long long seed;
+  int mode;                 // DDMI_NOISE_NONE / _TENSORS / _PHILOX
+};
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c[0]), l0 = 0xD2511F53u * c[0];
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c[2]), l1 = 0xCD9E8D57u * c[2];
+    c[0] = h1 ^ c[1] ^ k0; c[1] = l1; c[2] = h0 ^ c[3] ^ k1; c[3] = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ void philox_normal3(unsigned long long seed, unsigned long long g, uint32_t b, uint32_t blk, float (&z)[3]) {
+  uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), b, blk};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  float u[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) u[i] = __fmul_rn(__fadd_rn((float)(c[i] >> 9), 0.5f), 1.1920928955078125e-7f);   // 2^-23
+  const float r0 = sqrtf(__fmul_rn(-2.f, logf(u[0]))), r1 = sqrtf(__fmul_rn(-2.f, logf(u[2])));
+  float s0, c0;
+  sincosf(__fmul_rn(6.2831853071795864769f, u[1]), &s0, &c0);
+  z[0] = __fmul_rn(r0, c0);
+  z[1] = __fmul_rn(r0, s0);
+  z[2] = __fmul_rn(r1, cosf(__fmul_rn(6.2831853071795864769f, u[3])));
+}
+// noise of the three StyledConv layers of block `blk` at (item b, coordinate gi)
+__device__ __forceinline__ void noise_block3(const NoiseArgs& na, int blk, size_t b, long long n, long long gi, float (&z)[3]) {
+  if (na.mode == DDMI_NOISE_TENSORS) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) z[j] = __ldg(na.p[3 * blk + j] + b * (size_t)n + gi);
+  } else {
+    philox_normal3(na.seed, (unsigned long long)gi, (uint32_t)b, (uint32_t)blk, z);
+  }
+}
+
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // torch.nn.functional.softplus (beta = 1, threshold = 20)

@@ -130,8 +130,9 @@ constexpr size_t IMG_SMEM = (size_t)(2 * TM * HS + TM * IMG_XS + 2 * WBUF) * siz
 __global__ void __launch_bounds__(NT, 1)
 image_kernel(PlaneSet ps, int C, const float* __restrict__ cx, const float* __restrict__ cy,
              long long n, int tiles_per_item, const float* __restrict__ Wg,
-             const float* __restrict__ vec, void* __restrict__ out, int store) {
+             const float* __restrict__ vec, void* __restrict__ out, int store, NoiseArgs na) {
   extern __shared__ float4 smem4[];
+  __shared__ float NZ[3 * TM];        // noise.weight * noise of the block's three StyledConvs, per tile row
   float* H = reinterpret_cast<float*>(smem4);
   float* Hn = H + TM * HS;
   float* X = Hn + TM * HS;
@@ -159,25 +160,32 @@ image_kernel(PlaneSet ps, int C, const float* __restrict__ cx, const float* __re
   for (int blk = 0; blk < 4; ++blk) {
     const bool hasH = blk > 0, hasX = blk < 3;
     const float* bv = vec + blk * 1024;
-    if (hasX) {
-      gather(blk);
-      __syncthreads();
+    if (na.mode != 0 && tid < TM) {
+      long long g = n0 + tid;
+      if (g > n - 1) g = n - 1;
+      float z[3];
+      noise_block3(na, blk, (size_t)b, n, g, z);
+      for (int j = 0; j < 3; ++j) NZ[j * TM + tid] = z[j] * __ldg(vec + 4096 + 768 + 3 + 3 * blk + j);
+    } else if (tid < TM) {
+      for (int j = 0; j < 3; ++j) NZ[j * TM + tid] = 0.f;
     }
+    if (hasX) gather(blk);
+    __syncthreads();
     // conv1
     zero_acc<4>(acc);
     if (hasH) { gemm_seg<4>(acc, H, HS, 256, false, wp, wbuf); wp += 256 * 256; }
     if (hasX) { gemm_seg<4>(acc, X, IMG_XS, C, false, wp, wbuf); wp += C * 256; }
-    store_acc<4>(acc, Hn, HS, [&](int, int col, float v) { return kSqrt2 * lrelu(v + __ldg(bv + col), 0.2f); });
+    store_acc<4>(acc, Hn, HS, [&](int row, int col, float v) { return kSqrt2 * lrelu(v + NZ[row] + __ldg(bv + col), 0.2f); });
     __syncthreads();
     // conv2
     zero_acc<4>(acc);
     gemm_seg<4>(acc, Hn, HS, 256, false, wp, wbuf); wp += 256 * 256;
-    store_acc<4>(acc, Hn, HS, [&](int, int col, float v) { return kSqrt2 * lrelu(v + __ldg(bv + 256 + col), 0.2f); });
+    store_acc<4>(acc, Hn, HS, [&](int row, int col, float v) { return kSqrt2 * lrelu(v + NZ[TM + row] + __ldg(bv + 256 + col), 0.2f); });
     __syncthreads();
     // conv3 (its sqrt2 cancels the block's 1/sqrt2)
     zero_acc<4>(acc);
     gemm_seg<4>(acc, Hn, HS, 256, false, wp, wbuf); wp += 256 * 256;
-    store_acc<4>(acc, Hn, HS, [&](int, int col, float v) { return lrelu(v + __ldg(bv + 512 + col), 0.2f); });
+    store_acc<4>(acc, Hn, HS, [&](int row, int col, float v) { return lrelu(v + NZ[2 * TM + row] + __ldg(bv + 512 + col), 0.2f); });
     // skip (weights pre-scaled by 1/sqrt2 on the host); own-element reads of Hn only
     if (blk < 3) {
       zero_acc<4>(acc);
@@ -606,13 +614,14 @@ static int check_grid(long long tiles) {
 }
 
 int launch_image_fp32(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy,
-                      long long n, const float* Wg, const float* vec, void* out, int store, cudaStream_t st) {
+                      long long n, const float* Wg, const float* vec, void* out, int store, const NoiseArgs& na,
+                      cudaStream_t st) {
   long long tpi = (n + fp32::TM - 1) / fp32::TM;
   int rc = check_grid(tpi * batch);
   if (rc) return rc;
   rc = set_smem(fp32::image_kernel, fp32::IMG_SMEM);
   if (rc) return rc;
-  fp32::image_kernel<<<(unsigned)(tpi * batch), fp32::NT, fp32::IMG_SMEM, st>>>(ps, C, cx, cy, n, (int)tpi, Wg, vec, out, store);
+  fp32::image_kernel<<<(unsigned)(tpi * batch), fp32::NT, fp32::IMG_SMEM, st>>>(ps, C, cx, cy, n, (int)tpi, Wg, vec, out, store, na);
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

@@ -71,16 +71,22 @@ __device__ __forceinline__ float2 image_act(float2 t, float2 b) {
   }
   return bias_lrelu_pair(t, b, 0.2f);
 }
-template <int MODE, int SCHEME, class Signal>
+// NOISE: nz = noise.weight (x activation gain) * noise[b, row] of this StyledConv, added to every column before the bias.
+template <int MODE, int SCHEME, int NOISE, class Signal>
 __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, uint32_t h_lo, int row, int sub,
                                             const float* __restrict__ bias, const float* __restrict__ cs,
-                                            StagePrefetch& pf, Signal signal, bool tr = false) {
+                                            StagePrefetch& pf, Signal signal, float nz, bool tr, uint32_t& trn) {
   constexpr bool WITH_CS = (MODE == 1 || MODE == 2);
+  const float2 nz2 = make_float2(nz, nz);
+  if (NOISE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pf.b[i] = __fadd2_rn(pf.b[i], nz2);
+  }
   float2 v[4][16];
 #pragma unroll
   for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
   tmem_ld_wait();
-  trace(tr, 0x03);                                      // accumulator drained
+  trace(tr, 0x03, trn, 0);                              // accumulator drained
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int col0 = q * 64 + sub * 32;
@@ -117,7 +123,7 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
     if (q < 3) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        pf.b[i] = bn[i];
+        pf.b[i] = NOISE ? __fadd2_rn(bn[i], nz2) : bn[i];
         if (WITH_CS) pf.c[i] = cn[i];
       }
     }
@@ -129,11 +135,12 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
 // ---------------------------------------------------------------------------
 using ImgL = Layout<8>;
 
-template <int PAIR, int SCHEME>
+template <int PAIR, int SCHEME, int NOISE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
-                  const uint32_t* __restrict__ program, const float* __restrict__ vec, void* __restrict__ out, int store) {
+                  const uint32_t* __restrict__ program, const float* __restrict__ vec, void* __restrict__ out, int store,
+                  NoiseArgs na) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase + ImgL::KG_HHI * KG_BYTES, h_lo = sbase + ImgL::KG_HLO * KG_BYTES;
@@ -162,6 +169,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     uint32_t ph_mma = 0;
     const bool prof = DDMI_PROFILE && (blockIdx.x == 0 && tid == 0);
     bool tr = false;                                    // this thread traces the current tile iteration (profiling build)
+    uint32_t trn = 0;
     long long p_wait = 0, p_epi = 0, p_gather = 0, p_t = prof_clock();
 
     // `part` 0 / 1 = first / second 16 of this thread's 32 channels (-1: both): the two halves are issued in two different
@@ -169,7 +177,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     // tensor core), so the L2-latency-bound gather delays neither epilogue by much
     auto gather = [&](long long tile, int s, int part) {
       const long long g0 = prof_clock();
-      trace(tr, 0x20);
+      trace(tr, 0x20, trn, 0);
       if (tile > total_tiles - 1) tile = total_tiles - 1;   // odd tail of a pair: decode a duplicate, store nothing
       const int b = (int)(tile / tiles_per_item);
       long long gi = (tile % tiles_per_item) * TILE + row;
@@ -209,7 +217,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         }
       }
       p_gather += prof_clock() - g0;
-      trace(tr, 0x21);
+      trace(tr, 0x21, trn, 0);
     };
     // make this warp's smem / TMEM writes visible to the MMA warp (of the leader CTA), then signal one quarter
     auto signal = [&](int q) {
@@ -217,7 +225,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
-      trace(tr, 0x10 + q);
+      trace(tr, 0x10 + q, trn, 0);
       if (q == 3) p_epi += prof_clock() - p_t;
     };
     auto signal_all = [&]() {
@@ -226,11 +234,11 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     };
     auto wait_mma = [&]() {
       const long long w0 = prof_clock();
-      trace(tr, 0x01);
+      trace(tr, 0x01, trn, 0);
       mbar_wait(bar + BAR_MMADONE, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
-      trace(tr, 0x02);
+      trace(tr, 0x02, trn, 0);
       p_t = prof_clock();
       p_wait += p_t - w0;
     };
@@ -243,27 +251,37 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       tr = prof && it == kTraceIter;
 #pragma unroll 1
       for (int blk = 0; blk < 4; ++blk, bv += 1024) {
+        // noise of this block's three StyledConvs at this thread's row, scaled by noise.weight (x the folded gain)
+        float nz[3] = {0.f, 0.f, 0.f};
+        if (NOISE) {
+          const long long tt = tile < total_tiles ? tile : total_tiles - 1;
+          long long gi = (tt % tiles_per_item) * TILE + row;
+          if (gi > n - 1) gi = n - 1;
+          noise_block3(na, blk, (size_t)(tt / tiles_per_item), n, gi, nz);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) nz[j] *= __ldg(vec + 4096 + 768 + 3 + 3 * blk + j);
+        }
         // ---- conv1 (+ skip into acc2 for blk < 3)
         StagePrefetch pf;
         stage_prefetch<false>(pf, bv, nullptr, sub);
         wait_mma();
-        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal, tr);
+        image_stage<0, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal, nz[0], tr, trn);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale), first half of the channels
         if (blk < 2) gather(tile, blk + 1, 0);
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
         // ---- conv2
         stage_prefetch<false>(pf, bv + 256, nullptr, sub);
         wait_mma();
-        image_stage<0, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal, tr);
+        image_stage<0, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal, nz[1], tr, trn);
         if (blk < 2) gather(tile, blk + 1, 1);                                   // second half, under conv3's GEMM
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 1);
         // ---- conv3 + skip
         if (blk < 3) stage_prefetch<true>(pf, bv + 512, bv + 768, sub);
         else stage_prefetch<false>(pf, bv + 512, nullptr, sub);
         wait_mma();
-        if (blk < 2) image_stage<1, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, tr);
-        else if (blk == 2) image_stage<2, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, tr);
-        else image_stage<3, SCHEME>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal, tr);
+        if (blk < 2) image_stage<1, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, nz[2], tr, trn);
+        else if (blk == 2) image_stage<2, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, nz[2], tr, trn);
+        else image_stage<3, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal, nz[2], tr, trn);
       }
       // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
@@ -383,7 +401,7 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
                       const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                       const uint32_t* program_dev, const float* vec, size_t vec_floats, void* out, int store, int pair,
-                      int f16f8, cudaStream_t st) {
+                      int f16f8, const NoiseArgs& na, cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
     set_error("tcgen05 image kernel is built for 64-channel planes");
@@ -394,7 +412,7 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
                need, gemm_bytes);
   DDMI_REQUIRE(!f16f8 || pair, "the f16f8 image kernel runs as CTA pairs only");
-  DDMI_REQUIRE(vec_floats == 4096 + 768 + 3, "packed vec blob is %zu floats, expected 4867", vec_floats);
+  DDMI_REQUIRE(vec_floats == 4096 + 768 + 3 + 12, "packed vec blob is %zu floats, expected 4879", vec_floats);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));
   DDMI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -407,18 +425,19 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   // CTA pairs: a 2-CTA cluster per pair of tiles (weights for the pair are packed [half 0 | half 1] per K step)
   const uint8_t* ws = (const uint8_t*)gemm;
   const int tpi_i = (int)tpi;
-  if (pair) {
-    const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
-    if (f16f8)
-      DDMI_CUDA(launch_engine(image_umma_kernel<1, 1>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
-                              total, ws, program_dev, vec, out, store));
-    else
-      DDMI_CUDA(launch_engine(image_umma_kernel<1, 0>, 1, (unsigned)(2 * npairs), ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i,
-                              total, ws, program_dev, vec, out, store));
-  } else {
-    DDMI_CUDA(launch_engine(image_umma_kernel<0, 0>, 0, (unsigned)(total < sms ? total : sms), ImgL::SMEM_BYTES, st, ps, cx, cy,
-                            n, tpi_i, total, ws, program_dev, vec, out, store));
-  }
+  const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
+  const unsigned ctas = pair ? (unsigned)(2 * npairs) : (unsigned)(total < sms ? total : sms);
+#define DDMI_IMG_LAUNCH(P, S, Z)                                                                                          \
+  DDMI_CUDA(launch_engine(image_umma_kernel<P, S, Z>, P, ctas, ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i, total, ws, \
+                          program_dev, vec, out, store, na))
+  const int nz = na.mode != 0;
+  if (pair && f16f8 && nz) { DDMI_IMG_LAUNCH(1, 1, 1); }
+  else if (pair && f16f8) { DDMI_IMG_LAUNCH(1, 1, 0); }
+  else if (pair && nz) { DDMI_IMG_LAUNCH(1, 0, 1); }
+  else if (pair) { DDMI_IMG_LAUNCH(1, 0, 0); }
+  else if (nz) { DDMI_IMG_LAUNCH(0, 0, 1); }
+  else { DDMI_IMG_LAUNCH(0, 0, 0); }
+#undef DDMI_IMG_LAUNCH
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }
@@ -450,15 +469,13 @@ int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* c
 }
 
 int debug_trace(unsigned long long* out, int cap, int* n, int reset) {
-  unsigned int cnt = 0;
-  DDMI_CUDA(cudaMemcpyFromSymbol(&cnt, ummak::g_trace_n, sizeof(cnt)));
-  if (cnt > (unsigned)ummak::kTraceCap) cnt = ummak::kTraceCap;
-  if ((int)cnt > cap) cnt = cap;
-  if (cnt) DDMI_CUDA(cudaMemcpyFromSymbol(out, ummak::g_trace, sizeof(unsigned long long) * cnt));
-  *n = (int)cnt;
+  // the whole buffer (unwritten slots are 0: the caller drops them)
+  int cnt = ummak::kTraceCap < cap ? ummak::kTraceCap : cap;
+  DDMI_CUDA(cudaMemcpyFromSymbol(out, ummak::g_trace, sizeof(unsigned long long) * cnt));
+  *n = cnt;
   if (reset) {
-    const unsigned int z = 0;
-    DDMI_CUDA(cudaMemcpyToSymbol(ummak::g_trace_n, &z, sizeof(z)));
+    static unsigned long long zeros[ummak::kTraceCap] = {};
+    DDMI_CUDA(cudaMemcpyToSymbol(ummak::g_trace, zeros, sizeof(zeros)));
   }
   return DDMI_OK;
 }

@@ -10,6 +10,8 @@
 //   mode 4: stage      drain + bias/lrelu + split + publish (one full image epilogue stage without the hand-shakes)
 //   mode 5: tmem store 4 x tcgen05.st.32x32b.x16 x 2 (128 values) + wait::st
 //   mode 6: convert    bf16 hi/lo split of 128 values per thread
+//   mode 7: publish    as mode 3 without the fence.proxy.async after each quarter
+//   mode 8: drain      one tcgen05.ld.32x32b.x32 + wait::ld at a time (4 dependent round trips)
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -74,7 +76,7 @@ microbench_kernel(int mode, int iters, const float* __restrict__ seed, unsigned 
 #pragma unroll
           for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
           tmem_ld_wait();
-          acc += v[it & 3][it & 15].x;
+          acc += v[0][0].x;
         } else if (mode == 2 || mode == 6) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -92,7 +94,14 @@ microbench_kernel(int mode, int iters, const float* __restrict__ seed, unsigned 
               }
             }
           }
-        } else if (mode == 3) {
+        } else if (mode == 8) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
+            tmem_ld_wait();
+          }
+          acc += v[0][0].x;
+        } else if (mode == 3 || mode == 7) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int col0 = q * 64 + sub * 32;
@@ -102,7 +111,7 @@ microbench_kernel(int mode, int iters, const float* __restrict__ seed, unsigned 
               st_shared_v4(a + g * KG_BYTES, make_uint4(it, g, q, tid));
               st_shared_v4(b + g * KG_BYTES, make_uint4(tid, q, g, it));
             }
-            fence_proxy_async();
+            if (mode == 3) fence_proxy_async();
           }
         } else if (mode == 4) {
 #pragma unroll
@@ -122,7 +131,7 @@ microbench_kernel(int mode, int iters, const float* __restrict__ seed, unsigned 
             store_step_f16f8(h_hi + (col0 / 8) * KG_BYTES + row * 16, h_lo + (col0 / 8) * KG_BYTES + row * 16, KG_BYTES, v[q]);
             fence_proxy_async();
           }
-          acc += v[it & 3][it & 15].y;
+          acc += v[1][3].y;
         } else if (mode == 5) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

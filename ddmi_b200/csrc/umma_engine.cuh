@@ -62,11 +62,13 @@ __device__ __forceinline__ long long prof_clock() { return DDMI_PROFILE ? clock6
 __device__ __forceinline__ void prof_add(int i, long long v) {
   if (DDMI_PROFILE) atomicAdd(&g_prof[i], (unsigned long long)v);
 }
-// one record; `on` = this thread is a designated tracer and the CTA is in its traced tile iteration
-__device__ __forceinline__ void trace(bool on, uint32_t id) {
+// one record; `on` = this thread is a designated tracer and the CTA is in its traced tile iteration.  Fire-and-forget stores
+// (no atomics: a returning atomic costs the tracer an L2 round trip per record): E thread 0 fills the lower half of the
+// buffer, the MMA lane the upper half, each with its own running index `n`; unwritten slots stay 0.
+__device__ __forceinline__ void trace(bool on, uint32_t id, uint32_t& n, uint32_t base) {
   if (DDMI_PROFILE && on) {
-    const unsigned int k = atomicAdd(&g_trace_n, 1u);
-    if (k < (unsigned)kTraceCap) g_trace[k] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    if (n < (uint32_t)kTraceCap / 2) g_trace[base + n] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    ++n;
   }
 }
 
@@ -170,6 +172,7 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
   for (long long t = 0; t < ntiles; ++t) {
     uint32_t op = __ldg(program);
     const bool tr = DDMI_PROFILE && blockIdx.x == 0 && t == kTraceIter && (threadIdx.x & 31) == 0;
+    uint32_t trn = 0;
     for (int pc = 0;; ++pc) {
       const uint32_t nxt = __ldg(program + pc + 1);   // the table is padded with END ops
       const uint32_t kind = op & 3;
@@ -193,7 +196,7 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
             return mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && r;
           };
           bool ready = probe();
-          trace(tr, 0x100 + pc);                                      // UNIT starts issuing
+          trace(tr, 0x100 + pc, trn, kTraceCap / 2);                                      // UNIT starts issuing
           for (int j = 0; j < cnt; j += 2) {
             if (!ready) {
               const long long w0 = prof_clock();
@@ -276,15 +279,15 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
       } else if (kind == OP_WAIT) {
         const uint32_t i = (op >> 2) & 7;
         const long long w0 = prof_clock();
-        trace(tr, 0x200 + pc);                                        // WAIT begins
+        trace(tr, 0x200 + pc, trn, kTraceCap / 2);                                        // WAIT begins
         mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
         ph_a ^= 1u << i;
         tc_fence_after();
-        trace(tr, 0x300 + pc);                                        // WAIT satisfied
+        trace(tr, 0x300 + pc, trn, kTraceCap / 2);                                        // WAIT satisfied
         q_a += prof_clock() - w0;
       } else if (kind == OP_COMMIT) {
         const uint32_t db = bar + BAR_MMADONE + 8 * ((op >> 2) & 3);
-        trace(tr, 0x400 + pc);                                        // COMMIT issued
+        trace(tr, 0x400 + pc, trn, kTraceCap / 2);                                        // COMMIT issued
         if (elect_one()) {
           if (PAIR) mma2_commit_mc(db, 3);
           else      mma_commit(db);

@@ -164,9 +164,32 @@ class MLP(_FusedDecoder):
         self.torgb = ToRGB(ch, out_ch, ch)
         self._init_fused(precision)
 
-    def forward(self, coords, hdbf, si=1, store=None):
+    def _noise_source(self, noise, b, h, w, dev):
+        """-> (mode, ctypes pointer array or None, seed, tensors to keep alive) for a decode whose NoiseInjection weights are
+        non-zero.  noise = None: a fresh seed from torch's default CPU generator per call (like the reference, which draws new
+        noise every forward; reproducible under torch.manual_seed) for the library's Philox stream; an int: that seed; 12
+        tensors (b,1,h,w) or one (12,b,1,h,w): explicit noise, order net_res1.conv1, conv2, conv3, net_res2.conv1, ..."""
+        import ctypes
+        if noise is None:
+            return _lib.NOISE_PHILOX, None, int(torch.randint(0, 2 ** 62, (1,)).item()), None
+        if isinstance(noise, int):
+            return _lib.NOISE_PHILOX, None, noise & (2 ** 64 - 1), None
+        ts = list(noise.unbind(0)) if torch.is_tensor(noise) else list(noise)
+        if len(ts) != 12:
+            raise RuntimeError(f"noise must hold 12 tensors (one per StyledConv), got {len(ts)}")
+        keep = []
+        for i, t in enumerate(ts):
+            if t.numel() != b * h * w or t.shape[0] != b:
+                raise RuntimeError(f"noise[{i}] must be ({b},1,{h},{w}), got {tuple(t.shape)}")
+            keep.append(t.detach().to(device=dev, dtype=torch.float32).contiguous())
+        arr = (ctypes.c_void_p * 12)(*[t.data_ptr() for t in keep])
+        return _lib.NOISE_TENSORS, arr, 0, keep
+
+    def forward(self, coords, hdbf, si=1, store=None, noise=None):
         """coords (1,2,h,w) in [-1,1]; hdbf = 3 planes (b,64,S,S) coarse->fine;
         returns (b,3,h,w).  mlp.py:34-66.
+        noise (extension; only read when some NoiseInjection.weight is non-zero, i.e. for trained checkpoints): None, an int
+        seed, or the 12 explicit (b,1,h,w) tensors -- see _noise_source.
         store (extension, the epilogue the reference's callers apply -- fused into the kernel's output stage):
         None / 'f32' -> the reference's value; 'clamp' -> .clamp(-1, 1) (evals/eval.py:162,226);
         'u8' -> ((x.clamp(-1,1) + 1) * 127.5).type(torch.uint8) channels-last, (b,h,w,3) (evals/eval.py:289,336-337)."""
@@ -193,11 +216,15 @@ class MLP(_FusedDecoder):
             out = torch.empty((b, 3, h, w), device=c.device, dtype=torch.float32)
         n = h * w
         cx, cy = c[0, 0], c[0, 1]
+        nmode, narr, seed, keep = (_lib.NOISE_NONE, None, 0, None)
+        if packed.noise_active:
+            nmode, narr, seed, keep = self._noise_source(noise, b, h, w, c.device)
         with torch.cuda.device(c.device):
             wst = _lib.weights_struct(packed)
-            _lib.check(_lib.lib().ddmi_decode_image_store(
+            _lib.check(_lib.lib().ddmi_decode_image_noise(
                 _lib.planes_array(planes), b, planes[0].shape[1], cx.data_ptr(), cy.data_ptr(), n,
-                wst, mode, out.data_ptr(), _stream_ptr(c.device)))
+                wst, mode, nmode, narr, seed, out.data_ptr(), _stream_ptr(c.device)))
+        del keep
         return out
 
 

@@ -34,6 +34,7 @@ class Packed:
     program: torch.Tensor = None        # bf16x3: int32 MMA program (device)
     program_host: torch.Tensor = None   # same, host copy (validated by the launcher)
     pair: bool = False                  # bf16x3: stream packed for CTA pairs ([half 0 | half 1] per K step)
+    noise_active: bool = False          # image: some NoiseInjection.weight is non-zero (the decode needs a noise source)
 
 
 class UmmaProgram:
@@ -265,11 +266,6 @@ def fold_image(module, si):
       activation gain cancels against it inside the kernel.
     """
     p = _params64(module)
-    for k, v in p.items():
-        if k.endswith('noise.weight') and float(v.abs().max()) != 0.0:
-            raise NotImplementedError(
-                f"{k} != 0: the reference draws fresh N(0,1) noise inside forward "
-                "(blocks.py:293-297), so its output is not reproducible; noise injection is unsupported")
     style = image_style(p, si)
     inv_sqrt2 = 1.0 / math.sqrt(2.0)
     blocks = []
@@ -286,6 +282,8 @@ def fold_image(module, si):
         d['b2'] = p[f'{pre}.conv2.activate.bias']
         d['W3'] = _modulated(p, f'{pre}.conv3.conv', style, True)
         d['b3'] = p[f'{pre}.conv3.activate.bias']
+        # NoiseInjection.weight of the three StyledConvs (blocks.py:286-297): out = conv + weight * noise, before the bias
+        d['nw'] = torch.cat([p[f'{pre}.conv{j}.noise.weight'].reshape(1) for j in (1, 2, 3)])
         if i < 4:
             Ws = p[f'{pre}.skip.0.weight'][:, :, 0, 0] * (1.0 / math.sqrt(kin)) * inv_sqrt2
             d['Ws'] = Ws[:, :nreal]
@@ -299,12 +297,20 @@ def fold_image(module, si):
 
 
 def _image_vec(f, gain=1.0):
-    """gain: sqrt(2) when the activation gain of conv1 / conv2 is folded into weights + biases."""
+    """gain: sqrt(2) when the activation gain of conv1 / conv2 is folded into weights + biases (the noise term sits inside
+    the activation, so its weight takes the same gain).  Layout: 4 x [b1 b2 b3 cs] (256 each) | Wrgb (3 x 256) | brgb (3) |
+    noise weights (12: conv1, conv2, conv3 of each block)."""
     v = []
     for d in f['blocks']:
         v += [d['b1'] * gain, d['b2'] * gain, d['b3'], d['cs']]
     v += [f['Wrgb'].reshape(-1), f['brgb']]
+    for d in f['blocks']:
+        v += [d['nw'] * torch.tensor([gain, gain, 1.0], dtype=d['nw'].dtype)]
     return torch.cat(v).to(torch.float32).contiguous()
+
+
+def _noise_active(f):
+    return any(float(d['nw'].abs().max()) != 0.0 for d in f['blocks'])
 
 
 def pack_image(module, si, precision, pair=True):
@@ -381,10 +387,10 @@ def pack_image(module, si, precision, pair=True):
         dense256(f['Wrgb'], 0, n_pad=16)   # ToRGB: N = 16 block (3 real rows)
         end_group()
         gemm, prog_dev, prog_host = P.finish(dev)
-        return Packed(precision, gemm, _image_vec(f, gain).to(dev), prog_dev, prog_host, pair)
+        return Packed(precision, gemm, _image_vec(f, gain).to(dev), prog_dev, prog_host, pair, _noise_active(f))
     else:
         raise ValueError(f"unknown precision {precision}")
-    return Packed(precision, gemm.to(dev), _image_vec(f).to(dev))
+    return Packed(precision, gemm.to(dev), _image_vec(f).to(dev), noise_active=_noise_active(f))
 
 
 # ---------------------------------------------------------------------------

@@ -59,7 +59,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 7
+#define DDMI_ABI_VERSION 8
 
 enum {
   DDMI_OK = 0,
@@ -123,6 +123,24 @@ DDMI_API int ddmi_decode_image(const ddmi_plane_t planes[3], int32_t batch, int3
 DDMI_API int ddmi_decode_image_store(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
                             const float* coord_x, const float* coord_y, int64_t n_coords,
                             const ddmi_weights_t* weights, int32_t store, void* out, void* stream);
+
+/*
+ * Image decode of a checkpoint whose NoiseInjection weights are non-zero (models/d2c_vae/blocks.py:286-297: every one of
+ * the 12 StyledConv layers adds noise.weight * N(0,1)[b,1,h,w] before its bias / leaky ReLU; the reference draws the noise
+ * inside forward).  noise_mode:
+ *   DDMI_NOISE_NONE     no noise term (what ddmi_decode_image[_store] do; right when every noise.weight is 0)
+ *   DDMI_NOISE_TENSORS  noise[l], l = 0..11 (net_res1.conv1, conv2, conv3, net_res2.conv1, ...): device pointers to
+ *                       (batch, n_coords) fp32 -- the explicit `noise=` tensors of NoiseInjection.forward
+ *   DDMI_NOISE_PHILOX   a counter-based N(0,1) stream keyed by `seed` (Philox4x32-10 + Box-Muller, defined in
+ *                       csrc/common.cuh and restated in oracle/ddmi_oracle.py::philox_noise): the same values for every
+ *                       precision, tiling and GPU count
+ * The per-layer weights (noise.weight times the folded activation gain) are the last 12 floats of the packed vec blob.
+ */
+enum { DDMI_NOISE_NONE = 0, DDMI_NOISE_TENSORS = 1, DDMI_NOISE_PHILOX = 2 };
+DDMI_API int ddmi_decode_image_noise(const ddmi_plane_t planes[3], int32_t batch, int32_t channels,
+                            const float* coord_x, const float* coord_y, int64_t n_coords,
+                            const ddmi_weights_t* weights, int32_t store, int32_t noise_mode,
+                            const float* const* noise, uint64_t seed, void* out, void* stream);
 
 /*
  * (batch, C, H, W) -> (batch, H, W, C).  Scattered queries (3-D points, ray samples) gather all

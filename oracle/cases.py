@@ -41,7 +41,7 @@ def _perturb_common(m, g):
 def build_module(kind, seed=SEED):
     torch.manual_seed(seed)
     g = _gen(seed + 1)
-    if kind == 'image':
+    if kind in ('image', 'image_noise'):
         m = ddmi_b200.MLP(in_ch=2, latent_dim=64, out_ch=3, ch=256)
     elif kind == 'occupancy':
         m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256)
@@ -55,6 +55,10 @@ def build_module(kind, seed=SEED):
     else:
         raise KeyError(kind)
     _perturb_common(m, g)
+    if kind == 'image_noise':          # a "trained" checkpoint: every NoiseInjection.weight non-zero (blocks.py:286-297)
+        for name, p in m.named_parameters():
+            if name.endswith('noise.weight'):
+                p.data = 0.05 + 0.15 * torch.rand(1, generator=g)
     return m.eval()
 
 
@@ -69,6 +73,12 @@ def image_inputs(batch=2, sizes=(16, 32, 64), res=96, seed=SEED):
     coords = ddmi_b200.convert_to_coord_format_2d(1, res, res, hstart=-e, hend=e, wstart=-e, wend=e)
     si = ddmi_b200.get_scale_injection(res, anchor_res=sizes[-1])
     return coords, planes, si
+
+
+def image_noise_tensors(batch, res, seed=SEED):
+    """12 explicit (batch,1,res,res) N(0,1) tensors, one per NoiseInjection (net_res1.conv1 .. net_res4.conv3)."""
+    g = _gen(seed + 11)
+    return [_randn(g, batch, 1, res, res) for _ in range(12)]
 
 
 def occupancy_inputs(batch=2, sizes=(16, 32, 64), n=20000, spread=0.65, seed=SEED):

@@ -91,18 +91,23 @@ def _modconv(sd, pre, x, style, demodulate):
     return out
 
 
-def _styled_conv(sd, pre, x, style):
+def _styled_conv(sd, pre, x, style, noise=None):
+    """StyledConv.forward (blocks.py:349-356): modulated conv -> NoiseInjection (blocks.py:292-297: image + weight * noise)
+    -> FusedLeakyReLU.  The reference draws the noise inside forward; parity is defined for noise.weight == 0 or for an
+    EXPLICIT noise tensor (b,1,h,w), the `noise=` argument NoiseInjection.forward already has."""
     out = _modconv(sd, pre + '.conv', x, style, True)
     nw = sd[pre + '.noise.weight']
     if float(nw.abs().max()) != 0.0:
-        raise ValueError("oracle parity is defined for noise.weight == 0 only (SURVEY.md F4)")
+        if noise is None:
+            raise ValueError("noise.weight != 0 needs an explicit noise tensor (the reference's own draw is not reproducible)")
+        out = out + nw * noise.to(out.dtype)
     return F.leaky_relu(out + sd[pre + '.activate.bias'].view(1, -1, 1, 1), 0.2) * math.sqrt(2)
 
 
-def _styled_res_block(sd, pre, x, style):
-    out = _styled_conv(sd, pre + '.conv1', x, style)
-    out = _styled_conv(sd, pre + '.conv2', out, style)
-    out = _styled_conv(sd, pre + '.conv3', out, style)
+def _styled_res_block(sd, pre, x, style, noise=(None, None, None)):
+    out = _styled_conv(sd, pre + '.conv1', x, style, noise[0])
+    out = _styled_conv(sd, pre + '.conv2', out, style, noise[1])
+    out = _styled_conv(sd, pre + '.conv3', out, style, noise[2])
     key = pre + '.skip.0.weight'
     if key in sd:
         w = sd[key]
@@ -112,8 +117,48 @@ def _styled_res_block(sd, pre, x, style):
     return (out + skip) / math.sqrt(2)
 
 
-def image_decode(sd, coords, hdbf, si=1.0):
-    """MLP.forward (mlp.py:34-66).  coords (1,2,h,w); hdbf 3 planes (b,64,S,S)."""
+# ---- the documented noise stream of the drop-in (ddmi_b200/csrc/common.cuh::philox_normal4) -------------------------
+def philox4x32_10(c, k):
+    """Philox-4x32-10 (Salmon et al., SC'11).  c: (..., 4) uint32 counters, k: (2,) uint32 key -> (..., 4) uint32."""
+    import numpy as np
+    c = [c[..., i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    M0, M1, W0, W1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0x9E3779B9), np.uint64(0xBB67AE85), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & mask, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & mask]
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return np.stack(c, -1).astype(np.uint32)
+
+
+def philox_noise(seed, batch, n):
+    """The noise tensors MLP.forward(..., noise=<int seed>) uses, as 12 tensors (batch,1,n): layer l (0..11, order
+    net_res1.conv1, conv2, conv3, net_res2.conv1, ...), item b, coordinate g:
+      x = Philox4x32-10(key = (seed & 0xffffffff, seed >> 32), counter = (g & 0xffffffff, g >> 32, b, l // 3)),
+      u_i = ((x_i >> 9) + 0.5) * 2^-23,  r = sqrt(-2 ln u_0),  noise = r cos(2 pi u_1), r sin(2 pi u_1), sqrt(-2 ln u_2) cos(2 pi u_3)
+      for conv1, conv2, conv3 of block l // 3 (fp32 arithmetic)."""
+    import numpy as np
+    g = np.arange(n, dtype=np.uint64)
+    out = []
+    for blk in range(4):
+        c = np.zeros((batch, n, 4), dtype=np.uint32)
+        c[..., 0] = (g & np.uint64(0xFFFFFFFF)).astype(np.uint32)[None]
+        c[..., 1] = (g >> np.uint64(32)).astype(np.uint32)[None]
+        c[..., 2] = np.arange(batch, dtype=np.uint32)[:, None]
+        c[..., 3] = blk
+        x = philox4x32_10(c, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+        u = ((x >> 9).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+        r0 = np.sqrt(np.float32(-2.0) * np.log(u[..., 0]))
+        r1 = np.sqrt(np.float32(-2.0) * np.log(u[..., 2]))
+        a0, a1 = np.float32(2 * math.pi) * u[..., 1], np.float32(2 * math.pi) * u[..., 3]
+        for v in (r0 * np.cos(a0), r0 * np.sin(a0), r1 * np.cos(a1)):
+            out.append(torch.from_numpy(v.astype(np.float32)).reshape(batch, 1, n))
+    return out
+
+
+def image_decode(sd, coords, hdbf, si=1.0, noise=None):
+    """MLP.forward (mlp.py:34-66).  coords (1,2,h,w); hdbf 3 planes (b,64,S,S).  noise: None, or the 12 explicit
+    (b,1,h,w) tensors the 12 NoiseInjection modules add (order net_res1.conv1 .. net_res4.conv3)."""
     b = hdbf[0].shape[0]
     dt = hdbf[0].dtype
     coords = coords.to(dt).repeat(b, 1, 1, 1)
@@ -123,10 +168,12 @@ def image_decode(sd, coords, hdbf, si=1.0):
     style = F.linear(style, sd['time_mlp.1.weight'], sd['time_mlp.1.bias'])
     style = F.linear(F.gelu(style), sd['time_mlp.3.weight'], sd['time_mlp.3.bias'])
     feats = [torch.cat((_gs(p, grid, False), sip), dim=1) for p in hdbf]
-    x = _styled_res_block(sd, 'net_res1', feats[0], style)
-    x = _styled_res_block(sd, 'net_res2', torch.cat((x, feats[1]), dim=1), style)
-    x = _styled_res_block(sd, 'net_res3', torch.cat((x, feats[2]), dim=1), style)
-    x = _styled_res_block(sd, 'net_res4', x, style)
+    h, w = coords.shape[2:]
+    nz = [None] * 12 if noise is None else [t.reshape(b, 1, h, w) for t in noise]
+    x = _styled_res_block(sd, 'net_res1', feats[0], style, nz[0:3])
+    x = _styled_res_block(sd, 'net_res2', torch.cat((x, feats[1]), dim=1), style, nz[3:6])
+    x = _styled_res_block(sd, 'net_res3', torch.cat((x, feats[2]), dim=1), style, nz[6:9])
+    x = _styled_res_block(sd, 'net_res4', x, style, nz[9:12])
     return _modconv(sd, 'torgb.conv', x, style, False) + sd['torgb.bias']
 
 

@@ -70,6 +70,36 @@ for tag, kw in (('image_96', dict(batch=2, sizes=(16, 32, 64), res=96)),
     print(f'  oracle-vs-reference {tag}: {float((out - o2).abs().max()):.3e}')
     save(tag, out, planes + list(sd.values()), {'si': si})
 
+# ---- image with noise injection: a checkpoint whose NoiseInjection weights are non-zero, EXPLICIT noise tensors ------------
+# StyledResBlock.forward does not forward a `noise=` argument (blocks.py:624-627), so the explicit tensors are handed to
+# NoiseInjection.forward (blocks.py:292-297, its own `noise` parameter) through a FIFO, in call order.
+_noise_fifo = []
+_orig_noise_forward = rblocks.NoiseInjection.forward
+
+
+def _noise_forward(self, image, noise=None):
+    if noise is None and _noise_fifo:
+        noise = _noise_fifo.pop(0)
+    return _orig_noise_forward(self, image, noise=noise)
+
+
+rblocks.NoiseInjection.forward = _noise_forward
+m = cases.build_module('image_noise')
+sd = cases.state_dict32(m)
+ref = rmlp.MLP(in_ch=2, latent_dim=64, out_ch=3, ch=256)
+ref.load_state_dict(sd, strict=True)
+coords, planes, si = cases.image_inputs(batch=2, sizes=(16, 32, 64), res=96)
+noise = cases.image_noise_tensors(2, 96)
+_noise_fifo.extend(noise)
+out = ref(coords, hdbf=planes, si=si)
+assert not _noise_fifo
+o2 = orc.image_decode(sd, coords, planes, si, noise=noise)
+o0 = orc.image_decode(cases.state_dict32(cases.build_module('image')), coords, planes, si)
+print(f'  oracle-vs-reference image_noise: {float((out - o2).abs().max()):.3e}; effect of the noise on the output '
+      f'{float((out - o0).abs().max()):.3f}')
+save('image_noise', out, planes + noise + list(sd.values()), {'si': si})
+rblocks.NoiseInjection.forward = _orig_noise_forward
+
 # ---- occupancy -------------------------------------------------------------
 m = cases.build_module('occupancy')
 sd = cases.state_dict32(m)

@@ -95,7 +95,7 @@ def test_packed_sizes_match_abi_constants():
         p = fn(cases.build_module(kind))
         assert p.gemm.numel() == gfl and p.vec.numel() == vfl, kind
     p = packing.pack_image(cases.build_module('image'), 1.0, _lib.PREC_FP32)
-    assert p.gemm.numel() == (640 + 2 * 1152 + 768) * 256 and p.vec.numel() == 4867
+    assert p.gemm.numel() == (640 + 2 * 1152 + 768) * 256 and p.vec.numel() == 4879
 
 
 def test_split_bf16_is_accurate():
@@ -116,11 +116,34 @@ def test_umma_kstep_layout():
     assert float(hi[k // 16, (k % 16) // 8, n, k % 8]) == float(W[n, k].to(torch.bfloat16))
 
 
-def test_noise_weight_is_rejected():
+def test_noise_weights_are_packed_with_the_folded_gain():
+    """NoiseInjection.weight != 0 (trained checkpoints): the 12 weights ride at the end of the vec blob, conv1 / conv2 with the
+    sqrt(2) activation gain the tcgen05 packing folds into weights and biases."""
+    from ddmi_b200 import _lib
     m = cases.build_module('image')
+    assert not packing.pack_image(m, 1.0, _lib.PREC_FP32).noise_active
     m.net_res2.conv1.noise.weight.data.fill_(0.1)
-    with pytest.raises(NotImplementedError):
-        packing.fold_image(m, 1.0)
+    m.net_res2.conv3.noise.weight.data.fill_(0.3)
+    p = packing.pack_image(m, 1.0, _lib.PREC_FP32)
+    assert p.noise_active and p.vec[-12:].tolist() == pytest.approx([0, 0, 0, 0.1, 0, 0.3, 0, 0, 0, 0, 0, 0])
+    q = packing.pack_image(m, 1.0, _lib.PREC_F16F8)
+    assert q.vec[-12:].tolist() == pytest.approx([0, 0, 0, 0.1 * 2 ** 0.5, 0, 0.3, 0, 0, 0, 0, 0, 0])
+
+
+def test_philox_noise_stream_is_standard_normal_and_keyed():
+    """The documented noise stream (oracle restatement of csrc/common.cuh::philox_normal3): known-answer for Philox4x32-10,
+    N(0,1) moments, distinct per layer / item / seed."""
+    import numpy as np
+    from oracle import ddmi_oracle as orc
+    # Random123 known-answer test: counter = key = 0 -> 6627e8d5 e169c58d bc57ac4c 9b00dbd8
+    out = orc.philox4x32_10(np.zeros((1, 4), dtype=np.uint32), (0, 0))[0]
+    assert [hex(int(v)) for v in out] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    z = orc.philox_noise(1234, 2, 50000)
+    assert len(z) == 12 and z[0].shape == (2, 1, 50000)
+    allz = torch.stack(z)
+    assert abs(float(allz.mean())) < 5e-3 and abs(float(allz.std()) - 1.0) < 5e-3
+    assert float((z[0] - z[1]).abs().max()) > 1 and float((z[0][0] - z[0][1]).abs().max()) > 1
+    assert float((orc.philox_noise(1235, 2, 64)[0] - z[0][:, :, :64]).abs().max()) > 0.5
 
 
 def test_cpu_tensors_fail_loudly():

@@ -38,6 +38,19 @@ def test_image(golden_dir, tag, kw):
     assert float((out - g['out']).abs().max()) < 2e-5
 
 
+def test_image_with_noise_injection(golden_dir):
+    """Reference run with explicit noise tensors handed to its 12 NoiseInjection modules (non-zero weights)."""
+    g = _load(golden_dir, 'image_noise')
+    sd = cases.state_dict32(cases.build_module('image_noise'))
+    coords, planes, si = cases.image_inputs(batch=2, sizes=(16, 32, 64), res=96)
+    noise = cases.image_noise_tensors(2, 96)
+    _check_inputs(g, planes + noise + list(sd.values()))
+    out = orc.image_decode(sd, coords, planes, si, noise=noise)
+    assert float((out - g['out']).abs().max()) < 2e-5
+    with pytest.raises(ValueError):
+        orc.image_decode(sd, coords, planes, si)
+
+
 def test_occupancy(golden_dir):
     g = _load(golden_dir, 'occupancy')
     sd = cases.state_dict32(cases.build_module('occupancy'))

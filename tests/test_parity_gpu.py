@@ -33,6 +33,16 @@ def _sign_agreement(a, b):
     return float(((a > 0) == (b > 0)).float().mean())
 
 
+def _signs_ok(out, ref):
+    """North star: same occupancy sign on >= 99.99 % of the query points.  A flip needs |logit| below the decode error
+    (~3e-5 of N(0,0.5)-like logits: about 5 points in 1e5), so on a set of fewer than 1e4 points the RATE is quantised above
+    the bar; there one flip is allowed.  In every case a flipped point must sit inside the max-abs tolerance of zero."""
+    flips = (out > 0) != (ref > 0)
+    n = out.numel()
+    allowed = max(1, int(1e-4 * n))
+    return int(flips.sum()) <= allowed and (not bool(flips.any()) or float(ref[flips].abs().max()) < TOL)
+
+
 def test_device_is_blackwell():
     from ddmi_b200 import _lib
     import ctypes
@@ -54,6 +64,50 @@ def test_image_golden(golden_dir, tag, kw, precision):
     assert out.shape == g['out'].shape
     err = float((out - g['out']).abs().max())
     assert err < (2e-5 if precision == 'fp32' else TOL), err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
+def test_image_noise_injection_golden(golden_dir, precision):
+    """A checkpoint with non-zero NoiseInjection weights (any trained one): explicit noise tensors, against the REFERENCE
+    run with the same tensors handed to NoiseInjection.forward (oracle/make_golden.py)."""
+    g = _golden(golden_dir, 'image_noise')
+    m = cases.build_module('image_noise').to(DEV)
+    m.precision = precision
+    coords, planes, si = cases.image_inputs(batch=2, sizes=(16, 32, 64), res=96)
+    noise = cases.image_noise_tensors(2, 96)
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=si, noise=_cuda(noise)).cpu()
+    err = float((out - g['out']).abs().max())
+    assert err < (3e-5 if precision == 'fp32' else TOL), err
+    stacked = m(coords.to(DEV), hdbf=_cuda(planes), si=si, noise=torch.stack(noise).to(DEV)).cpu()
+    assert torch.equal(stacked, out)
+    plain = cases.build_module('image').to(DEV)
+    plain.precision = precision
+    assert float((plain(coords.to(DEV), hdbf=_cuda(planes), si=si).cpu() - out).abs().max()) > 0.05   # the noise matters
+    with pytest.raises(RuntimeError, match="12 tensors"):
+        m(coords.to(DEV), hdbf=_cuda(planes), si=si, noise=_cuda(noise[:5]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16f8"])
+def test_image_noise_injection_seeded_stream(precision):
+    """noise=<seed>: the in-kernel Philox stream equals its numpy restatement fed as explicit tensors; ragged tile tail,
+    batch > 1; noise=None draws a fresh seed per call (reproducible under torch.manual_seed)."""
+    m = cases.build_module('image_noise').to(DEV)
+    m.precision = precision
+    sd = cases.state_dict32(m)
+    g = torch.Generator().manual_seed(7)
+    planes = [torch.randn(3, 64, s, s, generator=g) for s in (8, 16, 24)]
+    coords = torch.rand(1, 2, 9, 31, generator=g) * 2 - 1
+    seed = 0x1234567855AA
+    z = orc.philox_noise(seed, 3, 9 * 31)
+    ref = orc.image_decode(sd, coords, planes, 0.6, noise=z)
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=0.6, noise=seed).cpu()
+    assert float((out - ref).abs().max()) < (5e-5 if precision == 'fp32' else TOL)
+    torch.manual_seed(99)
+    a = m(coords.to(DEV), hdbf=_cuda(planes), si=0.6)
+    b = m(coords.to(DEV), hdbf=_cuda(planes), si=0.6)
+    torch.manual_seed(99)
+    c = m(coords.to(DEV), hdbf=_cuda(planes), si=0.6)
+    assert float((a - b).abs().max()) > 0.01 and torch.equal(a, c)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
@@ -148,7 +202,7 @@ def test_occupancy_dense_grid_chunks_like_eval_points(precision):
     got = torch.cat([m(pi[None].to(DEV), c).logits.squeeze(0).cpu() for pi in torch.split(p, 3000)])
     ref = orc.occupancy_logits(sd, p[None], hdbf)[0]
     assert float((got - ref).abs().max()) < TOL
-    assert _sign_agreement(got, ref) >= 0.9999
+    assert _signs_ok(got, ref)
 
 
 # ---------------------------------------------------------------- video

@@ -9,7 +9,8 @@ out = torch.zeros(2, dtype=torch.int64, device=dev)
 sink = torch.zeros(256, device=dev)
 L = _lib.lib()
 names = ['drain 4x ld.x32, 8 warps', 'drain 4x ld.x32, 4 warps', 'f16f8 split of 128 values', 'publish 32x st.shared.v4',
-         'full stage (drain+act+split+publish)', 'tmem store 128 values', 'bf16 hi/lo split of 128 values']
+         'full stage (drain+act+split+publish)', 'tmem store 128 values', 'bf16 hi/lo split of 128 values',
+         'publish 32x st.shared.v4, no fences', 'drain, one ld.x32 + wait at a time']
 iters = 2000
 for mode, nm in enumerate(names):
     for _ in range(2):

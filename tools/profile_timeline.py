@@ -26,7 +26,7 @@ _lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
 m(c, hdbf=planes, si=get_scale_injection(R))
 torch.cuda.synchronize()
 _lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
-ev = sorted(((buf[i] & ((1 << 48) - 1)), buf[i] >> 48) for i in range(n.value))
+ev = sorted(((buf[i] & ((1 << 48) - 1)), buf[i] >> 48) for i in range(n.value) if buf[i])
 if not ev:
     print("no trace records: load the profiling build (DDMI_B200_LIB=ddmi_b200/libddmi_b200_prof.so)")
     sys.exit(1)
