@@ -26,7 +26,7 @@ EXPORTS = (
     "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_decode_image_noise", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
     "ddmi_decode_video", "ddmi_decode_video_store",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
-    "ddmi_debug_trace", "ddmi_debug_microbench",
+    "ddmi_debug_trace", "ddmi_debug_set", "ddmi_debug_gatherbench", "ddmi_debug_ringbench", "ddmi_debug_microbench",
 )
 
 
@@ -93,6 +93,9 @@ def lib():
         L.ddmi_selftest_f16f8.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_debug_profile.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32]
         L.ddmi_debug_trace.argtypes = [ctypes.POINTER(ctypes.c_uint64), i32, ctypes.POINTER(i32), i32]
+        L.ddmi_debug_set.argtypes = [i32]
+        L.ddmi_debug_gatherbench.argtypes = [i32, i32, vp, ctypes.c_uint32, i32, i32, i32, vp, vp, vp]
+        L.ddmi_debug_ringbench.argtypes = [vp, ctypes.c_uint64, i32, i32, i32, i32, vp, vp]
         L.ddmi_debug_microbench.argtypes = [i32, i32, vp, vp, vp, vp]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError here = header / library out of sync

@@ -36,6 +36,9 @@ int launch_nerf_composite(const float*, const float*, int, const float*, int, in
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
 int debug_trace(unsigned long long*, int, int*, int);
+int debug_set(int);
+int launch_gatherbench(int, int, const float*, unsigned, int, int, int, unsigned long long*, float*, cudaStream_t);
+int launch_ringbench(const void*, unsigned long long, int, int, int, int, unsigned long long*, cudaStream_t);
 int launch_microbench(int, int, const float*, unsigned long long*, float*, cudaStream_t);
 int launch_selftest_umma2(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_selftest_f16f8(const float*, const float*, float*, int, int, cudaStream_t);
@@ -374,6 +377,26 @@ DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset) {
 DDMI_API int ddmi_debug_trace(uint64_t* out, int32_t capacity, int32_t* count, int32_t reset) {
   DDMI_REQUIRE(out != nullptr && count != nullptr && capacity >= 1, "out / count is NULL or capacity < 1");
   return debug_trace((unsigned long long*)out, capacity, count, reset);
+}
+
+DDMI_API int ddmi_debug_set(int32_t flags) { return debug_set(flags); }
+
+DDMI_API int ddmi_debug_gatherbench(int32_t variant, int32_t unroll, const float* table, uint32_t ntexel, int32_t iters,
+                                    int32_t smem_kb, int32_t ctas, uint64_t* out_dev, float* sink_dev, void* stream) {
+  DDMI_REQUIRE(table && out_dev && sink_dev && ntexel >= 1 && iters >= 1 && ctas >= 1, "bad gatherbench arguments");
+  DDMI_REQUIRE(smem_kb >= 1 && smem_kb <= 227, "smem_kb must be 1..227");
+  return launch_gatherbench(variant, unroll, table, ntexel, iters, smem_kb, ctas, (unsigned long long*)out_dev, sink_dev,
+                            (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_debug_ringbench(const void* src, uint64_t span_bytes, int32_t slot_bytes, int32_t nslots, int32_t iters,
+                                  int32_t ctas, uint64_t* out_dev, void* stream) {
+  DDMI_REQUIRE(src && out_dev && ((uintptr_t)src & 127) == 0, "src / out_dev is NULL or src not 128-byte aligned");
+  DDMI_REQUIRE(slot_bytes >= 1024 && slot_bytes % 1024 == 0 && nslots >= 1 && nslots <= 64 &&
+                   (long long)slot_bytes * nslots <= 196 * 1024,
+               "ring of %d x %d bytes does not fit", nslots, slot_bytes);
+  DDMI_REQUIRE(span_bytes >= (uint64_t)slot_bytes && iters >= 1 && ctas >= 1, "empty span / iters / ctas");
+  return launch_ringbench(src, span_bytes, slot_bytes, nslots, iters, ctas, (unsigned long long*)out_dev, (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_debug_microbench(int32_t mode, int32_t iters, const float* seed, uint64_t* out_dev, float* sink_dev, void* stream) {

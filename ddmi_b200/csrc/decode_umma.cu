@@ -77,6 +77,11 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
                                             const float* __restrict__ bias, const float* __restrict__ cs,
                                             StagePrefetch& pf, Signal signal, float nz, bool tr, uint32_t& trn) {
   constexpr bool WITH_CS = (MODE == 1 || MODE == 2);
+  if (dbg(1)) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) signal(q);
+    return;
+  }
   const float2 nz2 = make_float2(nz, nz);
   if (NOISE) {
 #pragma unroll
@@ -133,13 +138,18 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
 // ---------------------------------------------------------------------------
 // the fused image kernel
 // ---------------------------------------------------------------------------
+#ifdef DDMI_EXP_BIGRING
+// experiment (timing only, results are garbage): the PE-feature region becomes ring space -> 12 slots = 96 KB of weights in flight
+using ImgL = Layout<0, 98304>;
+#else
 using ImgL = Layout<8>;
+#endif
 
 template <int PAIR, int SCHEME, int NOISE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
-                  const uint32_t* __restrict__ program, const float* __restrict__ vec, void* __restrict__ out, int store,
+                  const __grid_constant__ ProgramParam prog, const float* __restrict__ vec, void* __restrict__ out, int store,
                   NoiseArgs na) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -177,6 +187,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     // tensor core), so the L2-latency-bound gather delays neither epilogue by much
     auto gather = [&](long long tile, int s, int part) {
       const long long g0 = prof_clock();
+      if (dbg(4)) return;
       trace(tr, 0x20, trn, 0);
       if (tile > total_tiles - 1) tile = total_tiles - 1;   // odd tail of a pair: decode a duplicate, store nothing
       const int b = (int)(tile / tiles_per_item);
@@ -307,7 +318,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       prof_add(2, p_gather);
     }
   } else {
-    engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME, 0>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME, 0>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -411,6 +422,9 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   const long long need = ummak::program_stream_bytes(program_host, program_words);
   DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
                need, gemm_bytes);
+  ProgramParam pp;
+  DDMI_REQUIRE(make_program_param(program_host, program_words, &pp), "MMA program has %zu words, at most %d fit the kernel parameter",
+               program_words, PROG_MAX);
   DDMI_REQUIRE(!f16f8 || pair, "the f16f8 image kernel runs as CTA pairs only");
   DDMI_REQUIRE(vec_floats == 4096 + 768 + 3 + 12, "packed vec blob is %zu floats, expected 4879", vec_floats);
   int dev = 0, sms = 0;
@@ -429,7 +443,7 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   const unsigned ctas = pair ? (unsigned)(2 * npairs) : (unsigned)(total < sms ? total : sms);
 #define DDMI_IMG_LAUNCH(P, S, Z)                                                                                          \
   DDMI_CUDA(launch_engine(image_umma_kernel<P, S, Z>, P, ctas, ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i, total, ws, \
-                          program_dev, vec, out, store, na))
+                          pp, vec, out, store, na))
   const int nz = na.mode != 0;
   if (pair && f16f8 && nz) { DDMI_IMG_LAUNCH(1, 1, 1); }
   else if (pair && f16f8) { DDMI_IMG_LAUNCH(1, 1, 0); }
@@ -477,6 +491,11 @@ int debug_trace(unsigned long long* out, int cap, int* n, int reset) {
     static unsigned long long zeros[ummak::kTraceCap] = {};
     DDMI_CUDA(cudaMemcpyToSymbol(ummak::g_trace, zeros, sizeof(zeros)));
   }
+  return DDMI_OK;
+}
+
+int debug_set(int flags) {
+  DDMI_CUDA(cudaMemcpyToSymbol(ummak::g_dbg, &flags, sizeof(flags)));
   return DDMI_OK;
 }
 

@@ -85,7 +85,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
                  int z_stride, int n_samples, float plane_extent, long long n /* rows per object */, int tiles_per_item,
                  long long total_tiles, float slope, int white_bkgd, int fuse,
-                 const uint8_t* __restrict__ wstream, const uint32_t* __restrict__ program,
+                 const uint8_t* __restrict__ wstream, const __grid_constant__ ProgramParam prog,
                  const float* __restrict__ vec, float* __restrict__ rgb_map, float* __restrict__ raw) {
   constexpr int PAIR = 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -353,7 +353,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       }
     }
   } else {
-    engine_service_warps<PAIR, NrfL::RING_BYTES, SCHEME>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, NrfL::RING_BYTES, SCHEME>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -370,6 +370,9 @@ inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* r
   const long long need = program_stream_bytes(program_host, program_words);
   DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
                need, gemm_bytes);
+  ProgramParam pp;
+  DDMI_REQUIRE(make_program_param(program_host, program_words, &pp), "MMA program has %zu words, at most %d fit the kernel parameter",
+               program_words, PROG_MAX);
   DDMI_REQUIRE(vec_floats == (size_t)NV_TOTAL, "packed vec blob is %zu floats, expected %d", vec_floats, NV_TOTAL);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));
@@ -386,12 +389,12 @@ inline int launch_nerf_umma(const PlaneSet& ps, int batch, int C, const float* r
     DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
     nerf_umma_kernel<1><<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
         ps, C, rays, ray_stride, t_vals, z_stride, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
-        (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
+        (const uint8_t*)gemm, pp, vec, rgb_map, raw);
   } else {
     DDMI_CUDA(cudaFuncSetAttribute(nerf_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, NRF_SMEM));
     nerf_umma_kernel<0><<<(unsigned)(2 * npairs), NTHREADS, NRF_SMEM, st>>>(
         ps, C, rays, ray_stride, t_vals, z_stride, n_samples, plane_extent, n, (int)tpi, total, slope, white_bkgd, fuse,
-        (const uint8_t*)gemm, program_dev, vec, rgb_map, raw);
+        (const uint8_t*)gemm, pp, vec, rgb_map, raw);
   }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;

@@ -23,7 +23,7 @@
 namespace ddmi {
 namespace ummak {
 
-using VidL = OccL;   // same carve-up: H | [Xa hi, Xb hi] | [Xa lo, Xb lo] | 4 x 8 KB ring | barriers
+using VidL = VidXL;  // H | [Xa hi, Xb hi] | [Xa lo, Xb lo] | 4 x 8 KB ring | barriers
 constexpr int VID_SMEM = VidL::OFF_BAR + BAR_BYTES;
 // [3][2][128] fp32 partial outputs live at the start of H: at the output stage the last GEMM that reads H has
 // committed and nothing writes H again before the named barrier that ends the stage.
@@ -34,7 +34,7 @@ template <int PAIR, int SCHEME>
 __global__ void __launch_bounds__(NTHREADS, 1)
 video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __restrict__ cyt,
                   const float* __restrict__ cxt, int T, int Hh, int Ww, int tiles_per_item, long long total_tiles,
-                  const uint8_t* __restrict__ wstream, const uint32_t* __restrict__ program,
+                  const uint8_t* __restrict__ wstream, const __grid_constant__ ProgramParam prog,
                   const float* __restrict__ vec, void* __restrict__ out, int store) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -186,7 +186,7 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       }
     }
   } else {
-    engine_service_warps<PAIR, VidL::RING_BYTES, SCHEME, 0>(program, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    engine_service_warps<PAIR, VidL::RING_BYTES, SCHEME, 0>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);
   }
   engine_end<PAIR>(tmem);
 }
@@ -207,6 +207,9 @@ inline int launch_video_umma(const PlaneSet& ps, int batch, int C, const float* 
   const long long need = program_stream_bytes(program_host, program_words);
   DDMI_REQUIRE(need > 0 && (size_t)need == gemm_bytes, "MMA program consumes %lld weight bytes but the stream has %zu",
                need, gemm_bytes);
+  ProgramParam pp;
+  DDMI_REQUIRE(make_program_param(program_host, program_words, &pp), "MMA program has %zu words, at most %d fit the kernel parameter",
+               program_words, PROG_MAX);
   DDMI_REQUIRE(vec_floats == (size_t)VV_TOTAL, "packed vec blob is %zu floats, expected %d", vec_floats, VV_TOTAL);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));
@@ -223,13 +226,13 @@ inline int launch_video_umma(const PlaneSet& ps, int batch, int C, const float* 
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
   if (f16f8) {
     DDMI_CUDA(launch_engine(video_umma_kernel<1, 1>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
-                            total, ws, program_dev, vec, out, store));
+                            total, ws, pp, vec, out, store));
   } else if (pair) {
     DDMI_CUDA(launch_engine(video_umma_kernel<1, 0>, 1, (unsigned)(2 * npairs), VID_SMEM, st, ps, cxy, cyt, cxt, T, H, W, tpi_i,
-                            total, ws, program_dev, vec, out, store));
+                            total, ws, pp, vec, out, store));
   } else {
     DDMI_CUDA(launch_engine(video_umma_kernel<0, 0>, 0, (unsigned)(total < sms ? total : sms), VID_SMEM, st, ps, cxy, cyt, cxt, T,
-                            H, W, tpi_i, total, ws, program_dev, vec, out, store));
+                            H, W, tpi_i, total, ws, pp, vec, out, store));
   }
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;

@@ -166,7 +166,117 @@ microbench_kernel(int mode, int iters, const float* __restrict__ seed, unsigned 
   if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+// Weight-stream micro-benchmark: every CTA (one per SM) streams `iters` slots of `slot_bytes` from a `span_bytes` window of
+// global memory (L2-resident when small) through a ring of `nslots` shared-memory slots with 1-D bulk copies, re-issuing a
+// slot as soon as it has landed (no consumer): bytes in flight per SM = nslots * slot_bytes, so the sustained rate shows the
+// L2 -> SM bulk-copy latency (Little's law) and where the chip-wide L2 bandwidth caps it.  out[0] = cycles of CTA 0.
+__global__ void __launch_bounds__(32, 1)
+ringbench_kernel(const uint8_t* __restrict__ src, unsigned long long span_bytes, int slot_bytes, int nslots, int iters,
+                 unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + (uint32_t)nslots * (uint32_t)slot_bytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nslots; ++s) mbar_init(bar + 8 * s, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const unsigned long long nchunk = span_bytes / (unsigned long long)slot_bytes;
+  unsigned long long c = (blockIdx.x * 37ull) % nchunk;
+  const long long t0 = clock64();
+  for (int i = 0; i < nslots && i < iters; ++i) {
+    if (elect_one()) {
+      mbar_expect_tx(bar + 8 * i, slot_bytes);
+      bulk_g2s(sbase + i * slot_bytes, src + c * slot_bytes, slot_bytes, bar + 8 * i);
+    }
+    c = c + 1 == nchunk ? 0 : c + 1;
+  }
+  uint32_t slot = 0, ph = 0;
+  for (int i = 0; i < iters; ++i) {
+    mbar_wait(bar + 8 * slot, ph);
+    if (i + nslots < iters && elect_one()) {
+      mbar_expect_tx(bar + 8 * slot, slot_bytes);
+      bulk_g2s(sbase + slot * slot_bytes, src + c * slot_bytes, slot_bytes, bar + 8 * slot);
+    }
+    c = c + 1 == nchunk ? 0 : c + 1;
+    if (++slot == (uint32_t)nslots) { slot = 0; ph ^= 1; }
+  }
+  const long long t1 = clock64();
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = (unsigned long long)(t1 - t0);
+}
+
+// Scattered-gather micro-benchmark: one CTA per SM with `smem_kb` of dynamic shared memory (the decode kernels leave ~4 KB of
+// L1), 256 threads; 8 threads fetch one 256-byte channels-last texel (2 x float4 each) at pseudo-random positions of a
+// `ntexel`-texel table, `U` texels in flight per thread, through one of several load forms:
+//   0 ld.global.nc (__ldg)   1 ld.global.cg   2 ld.global.nc.L1::no_allocate   3 ld.global.cv   4 ld.global.L1::evict_first
+// out[0] = cycles of CTA 0 for `iters` rounds of U texel-loads per 8-thread group.
+template <int VAR>
+__device__ __forceinline__ float4 ld_var(const float4* p) {
+  float4 v;
+  if (VAR == 0) asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (VAR == 1) asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (VAR == 2) asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (VAR == 3) asm volatile("ld.global.cv.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  if (VAR == 4) asm volatile("ld.global.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+template <int VAR, int U>
+__global__ void __launch_bounds__(256, 1)
+gatherbench_kernel(const float* __restrict__ table, unsigned ntexel, int iters, unsigned long long* __restrict__ out, float* __restrict__ sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, sub = tid & 7;
+  unsigned state = (blockIdx.x * 256u + (tid >> 3)) * 2654435761u + 12345u;
+  float acc = 0.f;
+  if (tid == 0) smem[0] = 1;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    float4 v[U][2];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      state = state * 1664525u + 1013904223u;
+      const unsigned tx = (state >> 8) % ntexel;
+      const float4* p = reinterpret_cast<const float4*>(table + (size_t)tx * 64) + sub * 2;
+      v[u][0] = ld_var<VAR>(p);
+      v[u][1] = ld_var<VAR>(p + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc += v[u][0].x + v[u][0].w + v[u][1].y + v[u][1].z;
+  }
+  const long long t1 = clock64();
+  sink[blockIdx.x * 256 + tid] = acc + smem[0];
+  if (blockIdx.x == 0 && tid == 0) out[0] = (unsigned long long)(t1 - t0);
+}
+
 }  // namespace mbench
+
+template <int VAR, int U>
+static int launch_gb(const float* table, unsigned ntexel, int iters, int smem_kb, int ctas, unsigned long long* out, float* sink,
+                     cudaStream_t st) {
+  using namespace mbench;
+  DDMI_CUDA(cudaFuncSetAttribute(gatherbench_kernel<VAR, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kb * 1024));
+  gatherbench_kernel<VAR, U><<<ctas, 256, smem_kb * 1024, st>>>(table, ntexel, iters, out, sink);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
+int launch_gatherbench(int var, int u, const float* table, unsigned ntexel, int iters, int smem_kb, int ctas,
+                       unsigned long long* out, float* sink, cudaStream_t st) {
+#define GB(V, UU) if (var == V && u == UU) return launch_gb<V, UU>(table, ntexel, iters, smem_kb, ctas, out, sink, st);
+  GB(0, 4) GB(0, 12) GB(1, 4) GB(1, 12) GB(2, 4) GB(2, 12) GB(3, 4) GB(3, 12) GB(4, 4) GB(4, 12)
+#undef GB
+  set_error("gatherbench: variant %d / unroll %d not built", var, u);
+  return DDMI_ERR_UNSUPPORTED;
+}
+
+int launch_ringbench(const void* src, unsigned long long span_bytes, int slot_bytes, int nslots, int iters, int ctas,
+                     unsigned long long* out, cudaStream_t st) {
+  using namespace mbench;
+  const int smem = 200 * 1024;     // one CTA per SM
+  DDMI_CUDA(cudaFuncSetAttribute(ringbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  ringbench_kernel<<<ctas, 32, smem, st>>>((const uint8_t*)src, span_bytes, slot_bytes, nslots, iters, out);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
 
 int launch_microbench(int mode, int iters, const float* seed, unsigned long long* out, float* sink, cudaStream_t st) {
   using namespace mbench;

@@ -21,12 +21,21 @@ constexpr int H_KG = 32;               // 256-wide running activation
 
 // program op encoding (ddmi_b200/packing.py::UmmaProgram)
 constexpr uint32_t OP_UNIT = 0, OP_WAIT = 1, OP_COMMIT = 2, OP_END = 3;
+// The op table travels as a KERNEL PARAMETER (constant bank): the interpreters' op fetches are then uniform constant loads
+// (ULDC) straight into uniform registers, so the whole decode -> descriptor -> tcgen05.mma chain of the issuer stays on the
+// uniform datapath.  Fetched with __ldg from global memory the ops landed in vector registers and every descriptor paid an
+// R2UR move: ~350 cycles per 4-MMA iteration, i.e. the issuer -- not the tensor pipe -- paced the kernel.
+constexpr int PROG_MAX = 192;
+struct ProgramParam {
+  uint32_t op[PROG_MAX];
+};
 
 // barriers, 8 B each, relative to the barrier block
-constexpr int BAR_WFULL = 0, BAR_WEMPTY = 64, BAR_PFULL = 128 /* leader: the peer's half of slot s landed */,
-              BAR_MMADONE = 192 /* D0..D3: COMMIT targets */, BAR_A0 = 224 /* A0..A7: operand barriers (WAIT ops) */,
-              TMEM_SLOT = 288;
-constexpr int BAR_BYTES = 320;
+constexpr int MAX_SLOTS = 16;        // ring slots a kernel may use (barrier block capacity)
+constexpr int BAR_WFULL = 0, BAR_WEMPTY = 8 * MAX_SLOTS, BAR_PFULL = 16 * MAX_SLOTS /* leader: the peer's half of slot s landed */,
+              BAR_MMADONE = 24 * MAX_SLOTS /* D0..D3: COMMIT targets */, BAR_A0 = BAR_MMADONE + 32 /* A0..A7: operand barriers (WAIT ops) */,
+              TMEM_SLOT = BAR_A0 + 64;
+constexpr int BAR_BYTES = TMEM_SLOT + 32;
 // Protocol rule for every mbarrier here: it must never complete two phases before its waiter has consumed the
 // first (a parity wait cannot tell 0 from 2 completed phases).  E threads therefore re-signal operand barrier i
 // only after waiting a COMMIT that follows the previous WAIT i in program order, and the program re-commits
@@ -55,6 +64,11 @@ constexpr float kInvSqrt2 = 0.70710678118654752440f;
 #define DDMI_PROFILE 0
 #endif
 __device__ unsigned long long g_prof[8];
+// what-if switches of the profiling build (ddmi_debug_set; results are garbage, timings are the point):
+// bit 0: epilogue stages only signal (no drain / convert / publish)   bit 1: the issuer skips the tcgen05.mma instructions
+// (hand-shakes and commits stay)   bit 2: no plane gathers
+__device__ int g_dbg;
+__device__ __forceinline__ bool dbg(int bit) { return DDMI_PROFILE && ((*(volatile int*)&g_dbg) & bit); }
 constexpr int kTraceCap = 2048, kTraceIter = 5;
 __device__ unsigned long long g_trace[kTraceCap];
 __device__ unsigned int g_trace_n;
@@ -91,7 +105,7 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
   for (long long t = 0; t < ntiles; ++t) {
     const uint8_t* src = wstream;
     for (int pc = 0;; ++pc) {
-      const uint32_t op = __ldg(program + pc);
+      const uint32_t op = program[pc];
       const uint32_t kind = op & 3;
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
@@ -133,7 +147,7 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
   const uint32_t leader_pfull = mapa_rank(bar + BAR_PFULL, 0);
   for (long long t = 0; t < ntiles; ++t) {
     for (int pc = 0;; ++pc) {
-      const uint32_t op = __ldg(program + pc);
+      const uint32_t op = program[pc];
       const uint32_t kind = op & 3;
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
@@ -148,20 +162,27 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
   }
 }
 
-// UNIT op = a run of `cnt` consecutive K steps of one (128 x PAIR?2:1) x N block; decoded once, then a
-// tight per-K-step loop: wait for the ring slot, 3 MMAs, release the slot.  The whole warp runs the loop
+// UNIT op = a run of `cnt` consecutive K steps of one (128 x PAIR?2:1) x N block.  The whole warp runs the loop
 // (warp-uniform), one elected lane issues.
+// SCHEME 0 (bf16x3): a step = one ring slot = 3 MMAs (Ahi*Bhi + Alo*Bhi + Ahi*Blo).
 // SCHEME 1 (f16f8, pairs only): same 16-wide steps, slots and A-operand stepping, but a step is TWO MMAs: the fp16 main
 // term (a16 x w16, K = 16) and one K = 32 FP8 (e5m2 x e4m3) correction MMA -- r8 x w8 on even steps, a8 x s8 on odd steps of a
-// 32-wide pair (the A region keeps [r8 r8 a8 a8] K groups per pair, the slot [w16: 2 K groups | w8 or s8: 2 K groups]).
-// Steps are issued a PAIR per iteration (4 MMAs = 512 tensor cycles, 2 barrier probes, 1 commit): the issue loop's fixed
-// cost per iteration (probe round trips, descriptor moves to uniform registers, commit) is ~300-400 cycles.
+// 32-wide pair (the A region keeps [r8 r8 a8 a8] K groups per pair, the slot [w16: 2 K groups | w8 or s8: 2 K groups]); the
+// ring hand-shake unit is the slot PAIR.
+// Steps are issued in CHUNKS of up to 4 slots (= one 64-wide K quarter: 8 f16f8 / 12 bf16x3 MMAs, 1024 / 1536 tensor cycles):
+// all of the chunk's ring barriers are probed back to back (their ~90-cycle latencies overlap), then every MMA and one
+// tcgen05.commit per hand-shake unit are issued in one elected region.  Per-iteration fixed costs (probe round trips, elect,
+// descriptor set-up) are paid once per chunk, so the issuer runs ahead of the tensor pipe instead of pacing it.
 // TS: the kernel uses A-from-TMEM units (op bit 29); compiled out otherwise to keep the loop small.
 template <int PAIR, int RING_BYTES, int SCHEME = 0, int TS = 1>
 __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, uint32_t a_base, uint32_t ring,
                                          uint32_t bar, uint32_t tmem, long long ntiles) {
   static_assert(SCHEME == 0 || PAIR == 1, "the f16f8 scheme is built for CTA pairs");
   constexpr uint32_t SLOT_BYTES = PAIR ? 8192 : 16384, NSLOT = RING_BYTES / SLOT_BYTES;
+  constexpr uint32_t USLOTS = SCHEME ? 2 : 1;          // ring slots per hand-shake unit
+  // hand-shake units per issue chunk: a 64-wide K quarter, but never more than half of the ring (the other half refills)
+  constexpr int CH = (4 / USLOTS) < (NSLOT / USLOTS / 2) ? (4 / USLOTS) : (NSLOT / USLOTS / 2);
+  static_assert(NSLOT % USLOTS == 0 && CH >= 1, "ring too small for chunked issue");
   uint32_t slot = 0, ph = 0, ph_a = 0;   // ph_a: bit i = parity of operand barrier i
   long long q_a = 0, q_w = 0;
   const long long q_start = prof_clock();
@@ -170,11 +191,10 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
   const uint32_t a_lo32 = (a_base >> 4) | ((KG_BYTES >> 4) << 16);
   const uint32_t ring_lo32 = ring >> 4;
   for (long long t = 0; t < ntiles; ++t) {
-    uint32_t op = __ldg(program);
     const bool tr = DDMI_PROFILE && blockIdx.x == 0 && t == kTraceIter && (threadIdx.x & 31) == 0;
     uint32_t trn = 0;
     for (int pc = 0;; ++pc) {
-      const uint32_t nxt = __ldg(program + pc + 1);   // the table is padded with END ops
+      const uint32_t op = program[pc];
       const uint32_t kind = op & 3;
       if (kind == OP_UNIT) {
         const uint32_t n = op_n(op);
@@ -189,105 +209,110 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         uint32_t ahi32 = a_in_tmem ? tmem + ((op >> 8) & 0xFF) * 4 : a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
         uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
-        const int cnt = (int)((op >> 24) & 31) + 1;
-        if (SCHEME) {
-          auto probe = [&]() {      // the pair's full barriers live at its even slot
-            const bool r = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
-            return mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && r;
-          };
-          bool ready = probe();
-          trace(tr, 0x100 + pc, trn, kTraceCap / 2);                                      // UNIT starts issuing
-          for (int j = 0; j < cnt; j += 2) {
-            if (!ready) {
-              const long long w0 = prof_clock();
-              mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
-              mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
-              q_w += prof_clock() - w0;
-            }
-            tc_fence_after();
-            const uint32_t w0lo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
-            const uint32_t w1lo = w0lo + (SLOT_BYTES >> 4);
-            // slot: [w16: 2 K groups | FP8: 2 K groups] x nloc rows x 16 B
-            const uint64_t b16_0 = kDescHi | w0lo, b8_0 = kDescHi | (w0lo + nloc * 2);
-            const uint64_t b16_1 = kDescHi | w1lo, b8_1 = kDescHi | (w1lo + nloc * 2);
-            if (elect_one()) {
-              if (a_in_tmem) {
-                mma2_bf16_ts(acc, ahi32, b16_0, idesc, accum);          // kind::f16 with fp16 formats (idesc)
-                mma2_bf16_ts(acc, ahi32 + a_step, b16_1, idesc, 1u);
-                mma2_f8_ts(acc, alo32, b8_0, idesc8, 1u);               // r8 x w8
-                mma2_f8_ts(acc, alo32 + a_step, b8_1, idesc8, 1u);      // a8 x s8
-              } else {
-                mma2_bf16(acc, kDescHi | ahi32, b16_0, idesc, accum);
-                mma2_bf16(acc, kDescHi | (ahi32 + a_step), b16_1, idesc, 1u);
-                mma2_f8(acc, kDescHi | alo32, b8_0, idesc8, 1u);
-                mma2_f8(acc, kDescHi | (alo32 + a_step), b8_1, idesc8, 1u);
+        const int units = ((int)((op >> 24) & 31) + 1) / (int)USLOTS;             // hand-shake units in this run
+        trace(tr, 0x100 + pc, trn, kTraceCap / 2);                                // UNIT starts
+        for (int j = 0; j < units; j += CH) {
+          const int nu = units - j < CH ? units - j : CH;
+          // ---- probe every ring barrier of the chunk back to back
+          bool ready = true;
+          {
+            uint32_t s = slot, p = ph;
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+              if (u < nu) {
+                const bool r = mbar_try_wait(bar + BAR_WFULL + 8 * s, p);
+                const bool r2 = PAIR ? mbar_try_wait(bar + BAR_PFULL + 8 * s, p) : true;
+                ready = ready && r && r2;
+                s += USLOTS;
+                if (s == NSLOT) { s = 0; p ^= 1; }
               }
-              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot + 8, 3);       // releases the slot pair
             }
-            accum = 1u;
-            ahi32 += 2 * a_step;
-            alo32 += 2 * a_step;
-            slot += 2;
-            if (slot == NSLOT) { slot = 0; ph ^= 1; }
-            if (j + 2 < cnt) ready = probe();
           }
-          op = nxt;
-          continue;
-        }
-        // The barrier probes of K step j+1 are issued right after the MMAs of step j (both probes back to back),
-        // so their ~90-cycle latencies overlap the issue work instead of heading every iteration.
-        bool ready = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
-        if (PAIR) ready = mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && ready;
-        for (int j = 0; j < cnt; ++j) {
           if (!ready) {
             const long long w0 = prof_clock();
-            mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
-            if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * slot, ph);
+            uint32_t s = slot, p = ph;
+            for (int u = 0; u < nu; ++u) {
+              mbar_wait(bar + BAR_WFULL + 8 * s, p);
+              if (PAIR) mbar_wait(bar + BAR_PFULL + 8 * s, p);
+              s += USLOTS;
+              if (s == NSLOT) { s = 0; p ^= 1; }
+            }
             q_w += prof_clock() - w0;
           }
           tc_fence_after();
-          const uint32_t wlo = (ring_lo32 + slot * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
-          const uint64_t bhi = kDescHi | wlo, blo = kDescHi | (wlo + nloc * 2);          // lo block at + nloc * 32 bytes
-          const uint64_t ahi = kDescHi | ahi32, alo = kDescHi | alo32;
+          // ---- issue the chunk
+          const bool skip_mma = dbg(2);
           if (elect_one()) {
-            if (PAIR && a_in_tmem) {
-              mma2_bf16_ts(acc, ahi32, bhi, idesc, accum);
-              mma2_bf16_ts(acc, alo32, bhi, idesc, 1u);
-              mma2_bf16_ts(acc, ahi32, blo, idesc, 1u);
-              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
-            } else if (PAIR) {
-              mma2_bf16(acc, ahi, bhi, idesc, accum);
-              mma2_bf16(acc, alo, bhi, idesc, 1u);
-              mma2_bf16(acc, ahi, blo, idesc, 1u);
-              mma2_commit_mc(bar + BAR_WEMPTY + 8 * slot, 3);
-            } else {
-              mma_bf16(acc, ahi, bhi, idesc, accum);
-              mma_bf16(acc, alo, bhi, idesc, 1u);
-              mma_bf16(acc, ahi, blo, idesc, 1u);
-              mma_commit(bar + BAR_WEMPTY + 8 * slot);
+            uint32_t s = slot, ah = ahi32, al = alo32, ac = accum;
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+              if (u < nu) {
+                const uint32_t w0lo = (ring_lo32 + s * (SLOT_BYTES >> 4)) | (nloc << 16);   // LBO = nloc * 16 bytes
+                if (SCHEME) {
+                  const uint32_t w1lo = w0lo + (SLOT_BYTES >> 4);
+                  // slot: [w16: 2 K groups | FP8: 2 K groups] x nloc rows x 16 B
+                  const uint64_t b16_0 = kDescHi | w0lo, b8_0 = kDescHi | (w0lo + nloc * 2);
+                  const uint64_t b16_1 = kDescHi | w1lo, b8_1 = kDescHi | (w1lo + nloc * 2);
+                  if (a_in_tmem) {
+                    mma2_bf16_ts(acc, ah, b16_0, idesc, ac);          // kind::f16 with fp16 formats (idesc)
+                    mma2_bf16_ts(acc, ah + a_step, b16_1, idesc, 1u);
+                    mma2_f8_ts(acc, al, b8_0, idesc8, 1u);               // r8 x w8
+                    mma2_f8_ts(acc, al + a_step, b8_1, idesc8, 1u);      // a8 x s8
+                  } else if (!skip_mma) {
+                    mma2_bf16(acc, kDescHi | ah, b16_0, idesc, ac);
+                    mma2_bf16(acc, kDescHi | (ah + a_step), b16_1, idesc, 1u);
+                    mma2_f8(acc, kDescHi | al, b8_0, idesc8, 1u);
+                    mma2_f8(acc, kDescHi | (al + a_step), b8_1, idesc8, 1u);
+                  }
+                  mma2_commit_mc(bar + BAR_WEMPTY + 8 * s + 8, 3);          // releases the slot pair
+                } else {
+                  const uint64_t bhi = kDescHi | w0lo, blo = kDescHi | (w0lo + nloc * 2);   // lo block at + nloc * 32 bytes
+                  if (PAIR && a_in_tmem) {
+                    mma2_bf16_ts(acc, ah, bhi, idesc, ac);
+                    mma2_bf16_ts(acc, al, bhi, idesc, 1u);
+                    mma2_bf16_ts(acc, ah, blo, idesc, 1u);
+                    mma2_commit_mc(bar + BAR_WEMPTY + 8 * s, 3);
+                  } else if (PAIR) {
+                    mma2_bf16(acc, kDescHi | ah, bhi, idesc, ac);
+                    mma2_bf16(acc, kDescHi | al, bhi, idesc, 1u);
+                    mma2_bf16(acc, kDescHi | ah, blo, idesc, 1u);
+                    mma2_commit_mc(bar + BAR_WEMPTY + 8 * s, 3);
+                  } else {
+                    mma_bf16(acc, kDescHi | ah, bhi, idesc, ac);
+                    mma_bf16(acc, kDescHi | al, bhi, idesc, 1u);
+                    mma_bf16(acc, kDescHi | ah, blo, idesc, 1u);
+                    mma_commit(bar + BAR_WEMPTY + 8 * s);
+                  }
+                }
+                ac = 1u;
+                ah += USLOTS * a_step;
+                al += USLOTS * a_step;
+                s += USLOTS;
+                if (s == NSLOT) s = 0;
+              }
             }
           }
+          // every lane advances the (warp-uniform) run state
           accum = 1u;
-          ahi32 += a_step;
-          alo32 += a_step;
-          if (++slot == NSLOT) { slot = 0; ph ^= 1; }
-          if (j + 1 < cnt) {
-            ready = mbar_try_wait(bar + BAR_WFULL + 8 * slot, ph);
-            if (PAIR) ready = mbar_try_wait(bar + BAR_PFULL + 8 * slot, ph) && ready;
+          ahi32 += (uint32_t)nu * USLOTS * a_step;
+          alo32 += (uint32_t)nu * USLOTS * a_step;
+          for (int u = 0; u < nu; ++u) {
+            slot += USLOTS;
+            if (slot == NSLOT) { slot = 0; ph ^= 1; }
           }
         }
       } else if (kind == OP_WAIT) {
         const uint32_t i = (op >> 2) & 7;
         const long long w0 = prof_clock();
-        trace(tr, 0x200 + pc, trn, kTraceCap / 2);                                        // WAIT begins
+        trace(tr, 0x200 + pc, trn, kTraceCap / 2);                    // WAIT begins
         mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
         ph_a ^= 1u << i;
         tc_fence_after();
-        trace(tr, 0x300 + pc, trn, kTraceCap / 2);                                        // WAIT satisfied
+        trace(tr, 0x300 + pc, trn, kTraceCap / 2);                    // WAIT satisfied
         q_a += prof_clock() - w0;
       } else if (kind == OP_COMMIT) {
         const uint32_t db = bar + BAR_MMADONE + 8 * ((op >> 2) & 3);
-        trace(tr, 0x400 + pc, trn, kTraceCap / 2);                                        // COMMIT issued
+        trace(tr, 0x400 + pc, trn, kTraceCap / 2);                    // COMMIT issued
         if (elect_one()) {
           if (PAIR) mma2_commit_mc(db, 3);
           else      mma_commit(db);
@@ -295,7 +320,6 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
       } else {
         break;
       }
-      op = nxt;
     }
   }
   if (DDMI_PROFILE && blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
@@ -383,7 +407,7 @@ __device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar) {
   const uint32_t bar = smem_u32(smem) + off_bar;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < MAX_SLOTS; ++s) {
       mbar_init(bar + BAR_WFULL + 8 * s, 1);
       mbar_init(bar + BAR_WEMPTY + 8 * s, 1);
       mbar_init(bar + BAR_PFULL + 8 * s, 1);
@@ -449,6 +473,13 @@ static inline cudaError_t launch_engine(Kernel kernel, int pair, unsigned ctas, 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// Host: the op table as a kernel parameter (END-padded); false if it does not fit.
+static inline bool make_program_param(const uint32_t* prog, size_t words, ProgramParam* out) {
+  if (words > (size_t)PROG_MAX) return false;
+  for (int i = 0; i < PROG_MAX; ++i) out->op[i] = (size_t)i < words ? prog[i] : OP_END;
+  return true;
 }
 
 // Walk a program on the host: number of weight bytes it consumes; -1 if malformed.

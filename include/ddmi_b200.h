@@ -262,6 +262,19 @@ DDMI_API int ddmi_selftest_f16f8(const float* a, const float* b, float* d, int32
  */
 DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset);
 DDMI_API int ddmi_debug_trace(uint64_t* out, int32_t capacity, int32_t* count, int32_t reset);
+/* profiling build only: what-if switches of the image kernel (bit 0: epilogue stages only signal, bit 1: the issuer skips
+ * the MMA instructions, bit 2: no plane gathers) -- outputs are garbage, the timings bound each side of the pipeline */
+DDMI_API int ddmi_debug_set(int32_t flags);
+/* L2 -> shared-memory bulk-copy stream in isolation (csrc/microbench.cu::ringbench_kernel): `ctas` CTAs (one per SM) each
+ * stream `iters` slots of `slot_bytes` from a `span_bytes` window at `src` through a ring of `nslots` slots with no consumer;
+ * out_dev[0] = cycles CTA 0 took. */
+/* scattered 256-byte texel gathers in isolation (csrc/microbench.cu::gatherbench_kernel): load form `variant` (0 ld.global.nc,
+ * 1 .cg, 2 .nc.L1::no_allocate, 3 .cv, 4 L1::evict_first), `unroll` (4 or 12) texels in flight per thread, `smem_kb` of
+ * dynamic shared memory held by each of `ctas` CTAs (what is left of the 228 KB is L1); sink_dev: ctas * 256 floats. */
+DDMI_API int ddmi_debug_gatherbench(int32_t variant, int32_t unroll, const float* table, uint32_t ntexel, int32_t iters,
+                                    int32_t smem_kb, int32_t ctas, uint64_t* out_dev, float* sink_dev, void* stream);
+DDMI_API int ddmi_debug_ringbench(const void* src, uint64_t span_bytes, int32_t slot_bytes, int32_t nslots, int32_t iters,
+                                  int32_t ctas, uint64_t* out_dev, void* stream);
 DDMI_API int ddmi_debug_microbench(int32_t mode, int32_t iters, const float* seed, uint64_t* out_dev, float* sink_dev,
                                    void* stream);
 

@@ -14,12 +14,14 @@ e = (R - 1) / R
 c = convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
 for _ in range(2): m(c, hdbf=planes, si=get_scale_injection(R))
 torch.cuda.synchronize()
+flags = int(os.environ.get('DBG', '0'))
+_lib.check(_lib.lib().ddmi_debug_set(flags))
 buf = (ctypes.c_uint64 * 8)()
 _lib.check(_lib.lib().ddmi_debug_profile(buf, 1))
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record(); m(c, hdbf=planes, si=get_scale_injection(R)); t1.record(); torch.cuda.synchronize()
 _lib.check(_lib.lib().ddmi_debug_profile(buf, 1))
 v = list(buf); tiles = max(v[6], 1)
-print(f"ms {t0.elapsed_time(t1):.2f}  coords/s {B*R*R/t0.elapsed_time(t1)*1e3:.3e}  tiles(cta0) {v[6]}")
+print(f"dbg {flags} ms {t0.elapsed_time(t1):.2f}  coords/s {B*R*R/t0.elapsed_time(t1)*1e3:.3e}  tiles(cta0) {v[6]}")
 print(f"per tile cycles: E-wait(MMA busy) {v[0]/tiles:.0f}  E-epilogue {v[1]/tiles:.0f}  E-gather {v[2]/tiles:.0f} | "
       f"MMA wait-operands {v[3]/tiles:.0f}  MMA wait-weights {v[4]/tiles:.0f}  MMA total {v[5]/tiles:.0f}")

@@ -11,20 +11,34 @@ from ddmi_b200 import _lib, convert_to_coord_format_2d, get_scale_injection
 torch.set_grad_enabled(False)
 B, R = 16, 1024
 dev = 'cuda:0'
-m = bench.build_mlp().to(dev)
-m.precision = os.environ.get('PREC', 'f16f8')
+kind = os.environ.get('KIND', 'image')
 g = torch.Generator().manual_seed(1)
-planes = [torch.randn(B, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
-e = (R - 1) / R
-c = convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
+if kind == 'image':
+    m = bench.build_mlp().to(dev)
+    planes = [torch.randn(B, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
+    e = (R - 1) / R
+    c = convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
+    run = lambda: m(c, hdbf=planes, si=get_scale_injection(R))
+else:
+    import ddmi_b200
+    m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
+    hdbf = tuple([torch.randn(4, 64, s, s, generator=g).to(dev) for s in (16, 32, 64)] for _ in range(3))
+    if os.environ.get('PTS', 'grid') == 'grid':
+        pts = (1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3)).to(dev)
+    else:
+        pts = ((torch.rand(2000000, 3, generator=g) - 0.5) * 1.1).to(dev)
+    run = lambda: m(pts[None].expand(4, -1, -1), hdbf).logits
+m.precision = os.environ.get('PREC', 'f16f8')
 L = _lib.lib()
-m(c, hdbf=planes, si=get_scale_injection(R))
+run()
 torch.cuda.synchronize()
 buf = (ctypes.c_uint64 * 4096)()
 n = ctypes.c_int32()
 _lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
-m(c, hdbf=planes, si=get_scale_injection(R))
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0.record(); run(); t1.record()
 torch.cuda.synchronize()
+print(f"{kind}: {t0.elapsed_time(t1):.2f} ms")
 _lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
 ev = sorted(((buf[i] & ((1 << 48) - 1)), buf[i] >> 48) for i in range(n.value) if buf[i])
 if not ev:
