@@ -11,6 +11,13 @@ resident in HBM; `e2e` = same through the public module API with pinned HOST buf
 (planes H2D + RGB D2H inside the timed region).  `--impl reference` times the CPU
 restatement of the reference decoder (oracle/, the reference itself is Python and
 cannot travel to the GPU box) on a bounded sample, all host threads.
+
+`--workload c1 | video | occupancy | nerf` prints the same line (value, e2e, clocks, roofline,
+cpu_baseline, gpu_eager_baseline) for the other BASELINE configs (configs[0], [2], [3], [4]);
+`gpu_eager_baseline` = the same oracle restatement as eager PyTorch fp32 (TF32 off) on the SAME
+B200 in the same run: the like-for-like GPU comparator.  With N > 1 GPUs the
+image line also carries `strong_scaling`: configs[1] with the batch of 64 split over the ranks by
+ddmi_b200.sharding, timed without and with the output all-gather.
 """
 import argparse
 import json
@@ -124,6 +131,94 @@ PREC_INFO = {
 }
 
 
+def eager_sync_time(fn, repeats=2):
+    """best-of wall time of fn() on the current CUDA device (synchronised)."""
+    best = float('inf')
+    for _ in range(repeats + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def gpu_eager_image(dev, res=1024, batch=2):
+    """The oracle restatement of MLP.forward as eager PyTorch on the GPU (fp32, TF32 off): the like-for-like GPU baseline."""
+    from oracle import ddmi_oracle as orc   # the checker, timed here as a baseline only
+    from ddmi_b200 import convert_to_coord_format_2d, get_scale_injection
+    tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.to(dev) for k, v in state_dict32(build_mlp()).items()}
+        g = torch.Generator().manual_seed(777)
+        planes = [torch.randn(1, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
+        e = (res - 1) / res
+        coords = convert_to_coord_format_2d(1, res, res, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
+        si = get_scale_injection(res)
+
+        def run():
+            for _ in range(batch):                      # one item at a time: (1, 322, res, res) fp32 activations = 1.35 GB
+                orc.image_decode(sd, coords, planes, si)
+        dt = eager_sync_time(run)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+    return {"value": batch * res * res / dt, "unit": UNIT, "kind": "oracle restatement of the reference decoder, eager PyTorch fp32 "
+            "(TF32 off) on this GPU", "sample": f"{batch} items @ {res}x{res}, one item per call, best of 3"}
+
+
+def pack_timing(mlp, grids, dev):
+    """Host cost of a NEW scale injection value (arbitrary-resolution decode changes si per resolution): fold + pack on the CPU
+    + three H2D copies; cached per (precision, si) afterwards."""
+    out = {}
+    for c, si, R in grids:
+        mlp.invalidate_packed()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mlp(c[:, :, :1, :128], hdbf=[torch.zeros(1, 64, 4, 4, device=dev)] * 3, si=si)
+        torch.cuda.synchronize()
+        out[str(R)] = (time.perf_counter() - t0) * 1e3
+    return out
+
+
+def strong_scaling(args, mlp, dev, world, rank, grids):
+    """configs[1] with its batch of 64 SPLIT over the ranks (ddmi_b200.sharding): time to decode, and to decode + assemble the
+    full signal on every rank with one all_gather_into_tensor of the owned slabs (NCCL)."""
+    import torch.distributed as dist
+    from ddmi_b200 import sharding
+    B = 64
+    g = torch.Generator().manual_seed(777)
+    planes = [torch.randn(B, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
+    res = {}
+    for c, si, R in grids:
+        if R > 1024 and world < 4:
+            continue                                           # the assembled 2048^2 signal is 3.2 GB per rank: keep it to N >= 4
+        row = {}
+        for gather in (False, True):
+            fn = lambda: sharding.decode_image_sharded(mlp, c, planes, si=si, gather=gather)
+            fn()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            out = fn()
+            t1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            row['decode_and_gather_ms' if gather else 'decode_ms'] = float(t[0])
+            del out
+        row['gather_ms'] = row['decode_and_gather_ms'] - row['decode_ms']
+        row['coords_per_s'] = B * R * R / (row['decode_ms'] * 1e-3)
+        row['coords_per_s_with_gather'] = B * R * R / (row['decode_and_gather_ms'] * 1e-3)
+        row['gathered_bytes_per_rank'] = B * 3 * R * R * 4 * (world - 1) // world
+        res[str(R)] = row
+    return {"scaling": "strong", "batch_total": B, "n_gpus": world, "per_grid": res,
+            "note": "time = max over ranks, CUDA events; gather = one all_gather_into_tensor of each rank's own items"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', 0))
@@ -140,6 +235,7 @@ def run_ours(args):
     host_planes, grids = image_workload(B, dev, pinned=True)
     planes = [p.to(dev) for p in host_planes]
     coords_per_step = sum(B * R * R for _, _, R in grids)
+    planes_gb = sum(p.numel() * 4 for p in planes) / 1e9
 
     def step():
         outs = []
@@ -227,6 +323,11 @@ def run_ours(args):
         t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms = float(t[0]), float(t[1])
+    strong = None
+    if world > 1 and not args.no_strong:
+        del planes
+        torch.cuda.empty_cache()
+        strong = strong_scaling(args, mlp, dev, world, rank, grids)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -254,7 +355,7 @@ def run_ours(args):
                    "coords_per_step_per_gpu": coords_per_step, "precision": args.precision,
                    "store": args.store + {"f32": " (the reference's output: (B,3,h,w) fp32)", "clamp": " (clamp(-1,1) fused)",
                                            "u8": " (uint8 (B,h,w,3) = trunc((clamp(x,-1,1)+1)*127.5) fused: the callers' epilogue)"}[args.store],
-                   "l2": "inputs larger than L2 (planes %.2f GB per GPU; no flush)" % (sum(p.numel() * 4 for p in planes) / 1e9),
+                   "l2": "inputs larger than L2 (planes %.2f GB per GPU; no flush)" % planes_gb,
                    "sharding": "batch items per rank, no collective"},
         "e2e": {"value": coords_per_step * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -299,67 +400,137 @@ def run_ours(args):
         mlp.precision = args.precision
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_res, args.cpu_batch)
+        line["gpu_eager_baseline"] = gpu_eager_image(dev)
+        line["gpu_eager_baseline"]["speedup_of_value"] = value / line["gpu_eager_baseline"]["value"]
+        line["pack_ms_per_new_si"] = pack_timing(mlp, grids, dev)
+    if world > 1:
+        line["strong_scaling"] = strong
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class OtherWorkload:
+    """One of the non-headline BASELINE configs: module, pinned host planes, fixed device-side query set, a decode over a
+    range of items, and the oracle on a bounded sample (CPU and eager-GPU baselines)."""
+
+    def __init__(self, kind, args, dev):
+        import numpy as np
+        import ddmi_b200
+        from ddmi_b200 import nerf_helpers as nh
+        self.kind, self.dev, self.precision = kind, dev, args.precision
+        g = torch.Generator().manual_seed(777)
+        torch.manual_seed(777)
+        pin = lambda t: t.pin_memory()
+        if kind == 'c1':
+            self.flop_kind, self.kernel = 'image', 'image_umma_kernel'
+            B = self.B = args.batch if args.batch != 64 else 4
+            self.m = build_mlp().to(dev)
+            self.host = [pin(torch.randn(B, 64, s, s, generator=g)) for s in (64, 128, 256)]
+            R, e = 256, 255 / 256
+            self.coords = ddmi_b200.convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
+            self.n_per_item = R * R
+            self.out_item = ((3, R, R), torch.float32)
+            self.decode = lambda planes: self.m(self.coords, hdbf=planes, si=1.0)
+            self.desc = f"AFHQ-shape image D2C-VAE decode (BASELINE configs[0]): planes 64^2/128^2/256^2 x64ch, 256x256 grid, si=1, batch {B}"
+        elif kind == 'occupancy':
+            self.flop_kind, self.kernel = 'occupancy', 'occupancy_umma_kernel'
+            B = self.B = args.batch if args.batch != 64 else 32
+            self.m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
+            for blk in (self.m.net_res1, self.m.net_res2, self.m.net_res3, self.m.net_res4):
+                torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
+            self.host = [[pin(torch.randn(B, 64, s, s, generator=g)) for s in (16, 32, 64)] for _ in range(3)]
+            self.pts = torch.cat([1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3),
+                                  (torch.rand(100000, 3, generator=g) - 0.5) * 1.1]).to(dev)
+            self.n_per_item = self.pts.shape[0]
+            self.out_item = ((self.n_per_item,), torch.float32)
+            self.decode = lambda planes: self.m(self.pts[None].expand(planes[0][0].shape[0], -1, -1), planes).logits
+            self.desc = (f"ShapeNet-shape occupancy decode (BASELINE configs[3]): triplanes 16^2/32^2/64^2 x64ch, 128^3 grid + "
+                         f"100k random points, batch {B}")
+        elif kind == 'video':
+            self.flop_kind, self.kernel = 'video', 'video_umma_kernel'
+            B = self.B = args.batch if args.batch != 64 else 16
+            self.m = ddmi_b200.MLPVideo(in_ch=2, latent_dim=64, out_ch=3, ch=256).to(dev)
+            for blk in (self.m.net_res1, self.m.net_res2, self.m.net_res3, self.m.net_res4):
+                torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
+            self.host = [[pin(torch.randn(B, 64, s, s, generator=g)) for s in (64, 128, 256)],
+                         [pin(torch.randn(B, 64, 16, s, generator=g)) for s in (64, 128, 256)],
+                         [pin(torch.randn(B, 64, 16, s, generator=g)) for s in (64, 128, 256)]]
+            c = ddmi_b200.convert_to_coord_format_3d(1, 256, 256, 16, hstart=-255 / 256, hend=255 / 256, wstart=-255 / 256,
+                                                     wend=255 / 256, tstart=-15 / 16, tend=15 / 16)
+            self.coords = {k: v.to(dev) for k, v in c.items()}
+            self.n_per_item = 256 * 256 * 16
+            self.out_item = ((3, 16, 256, 256), torch.float32)
+            self.decode = lambda planes: self.m(self.coords, planes)
+            self.desc = f"SkyTimelapse-shape video decode (BASELINE configs[2]): xy/yt/xt planes, 256x256x16 volume, batch {B}"
+        else:
+            self.flop_kind, self.kernel = 'nerf', 'nerf_umma_kernel'
+            B = self.B = args.batch if args.batch != 64 else 16
+            self.m = ddmi_b200.MLPNeRF(D=6, W=256, in_channels_xyz=159, skips=[2, 4], in_channels_dir=27).to(dev)
+            self.host = [pin(torch.randn(B, 32, 64, 64, generator=g)) for _ in range(3)]
+            H = W = 128
+            focal = .5 * W / np.tan(.5 * 0.6911112070083618)
+            K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+            ro, rd = nh.get_rays(H, W, K, nh.pose_spherical(40.0, -20, 5)[:3, :4], dev)
+            vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
+            self.rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(H * W, 1, device=dev),
+                                   6. * torch.ones(H * W, 1, device=dev), vd], -1)
+            self.n_per_item = H * W * 128
+            self.out_item = ((H * W, 3), torch.float32)
+            self.decode = lambda planes: nh.render_rays_fused(self.rays, dict(zip(('xy', 'yz', 'xz'), planes)), self.m, 128, True,
+                                                              precision=args.precision)
+            self.desc = (f"srn-cars-shape NeRF decode (BASELINE configs[4]): triplane 64^2 x32ch, 128x128 rays x 128 samples, "
+                         f"composited, batch {B} objects (coordinates = ray samples)")
+        self.m.precision = args.precision
+
+    def slice(self, host, a, b, dev=None):
+        f = (lambda t: t[a:b].to(dev, non_blocking=True)) if dev is not None else (lambda t: t[a:b])
+        return [([f(t) for t in x] if isinstance(x, list) else f(x)) for x in host]
+
+    def h2d_bytes(self):
+        return sum(t.numel() * 4 for x in self.host for t in (x if isinstance(x, list) else [x]))
+
+    def oracle_sample(self, dev, n_target):
+        """The oracle restatement on `dev` over a bounded sample of this workload -> (coords decoded, callable)."""
+        from oracle import ddmi_oracle as orc   # the checker, timed here as a baseline only
+        sd = {k: v.detach().float().to(dev) for k, v in self.m.state_dict().items()}
+        one = self.slice(self.host, 0, 1)
+        mv = lambda x: [mv(t) for t in x] if isinstance(x, list) else x.to(dev)
+        planes = mv(one)
+        if self.kind == 'c1':
+            c = self.coords.to(dev)
+            return self.n_per_item, lambda: orc.image_decode(sd, c, planes, 1.0), "1 item @ 256x256"
+        if self.kind == 'occupancy':
+            n = min(n_target, 100000)
+            p = self.pts[-n:][None].to(dev)                    # the reference's own chunk size (generation.py:130-144)
+            return n, lambda: orc.occupancy_logits(sd, p, planes), f"1 item, {n} random points (one eval_points chunk)"
+        if self.kind == 'video':
+            rows = max(1, min(256, n_target // (16 * 256)))
+            c = {k: v.to(dev) for k, v in self.coords.items()}
+            sub = {'xy': c['xy'][:, :, :rows], 'yt': c['yt'][:, :, :, :rows], 'xt': c['xt']}
+            return 16 * rows * 256, (lambda: orc.video_decode(sd, sub, planes, thw=(16, rows, 256))), \
+                f"1 item, 16 frames x {rows} rows x 256"
+        nr = max(1, min(self.rays.shape[0], n_target // 128))
+        r = self.rays[:nr].to(dev)
+        fea = dict(zip(('xy', 'yz', 'xz'), planes))
+        return nr * 128, lambda: orc.nerf_render_rays(sd, r, fea, 128, True), f"1 object, {nr} rays x 128 samples"
+
+
 def run_other(args):
-    """The other BASELINE configs (parity-test cases, not the headline): device-resident throughput only.
-    occupancy = configs[3] (B=32, 128^3 grid + 100k random points), video = configs[2] (B=16, 256x256x16),
-    nerf = configs[4] (B=16 objects, 128x128 rays x 128 samples, composited)."""
-    import numpy as np
-    import ddmi_b200
-    from ddmi_b200 import nerf_helpers as nh
+    """configs[0], [2], [3], [4]: the same line as the headline (value, e2e, clocks, roofline, cpu / eager-GPU baselines), 1 GPU."""
     torch.set_grad_enabled(False)
     dev = torch.device('cuda', 0)
-    torch.manual_seed(777)
-    g = torch.Generator().manual_seed(777)
-    kind = args.workload
-    if kind == 'occupancy':
-        B = args.batch if args.batch != 64 else 32
-        m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
-        torch.nn.init.kaiming_uniform_(m.net_res1.fc_1.weight, a=5 ** 0.5)
-        for blk in (m.net_res2, m.net_res3, m.net_res4):
-            torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
-        hdbf = tuple([torch.randn(B, 64, s, s, generator=g).to(dev) for s in (16, 32, 64)] for _ in range(3))
-        pts = torch.cat([1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3),
-                         (torch.rand(100000, 3, generator=g) - 0.5) * 1.1]).to(dev)
-        coords = B * pts.shape[0]
-        fn = lambda: m(pts[None].expand(B, -1, -1), hdbf).logits
-        desc = f"ShapeNet-shape occupancy decode: triplanes 16^2/32^2/64^2 x64ch, 128^3 grid + 100k random points, batch {B}"
-    elif kind == 'video':
-        B = args.batch if args.batch != 64 else 16
-        m = ddmi_b200.MLPVideo(in_ch=2, latent_dim=64, out_ch=3, ch=256).to(dev)
-        for blk in (m.net_res1, m.net_res2, m.net_res3, m.net_res4):
-            torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
-        xy = [torch.randn(B, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)]
-        yt = [torch.randn(B, 64, 16, s, generator=g).to(dev) for s in (64, 128, 256)]
-        xt = [torch.randn(B, 64, 16, s, generator=g).to(dev) for s in (64, 128, 256)]
-        c = ddmi_b200.convert_to_coord_format_3d(1, 256, 256, 16, hstart=-255 / 256, hend=255 / 256, wstart=-255 / 256,
-                                                 wend=255 / 256, tstart=-15 / 16, tend=15 / 16)
-        c = {k: v.to(dev) for k, v in c.items()}
-        coords = B * 256 * 256 * 16
-        fn = lambda: m(c, (xy, yt, xt))
-        desc = f"SkyTimelapse-shape video decode: xy/yt/xt planes, 256x256x16 volume, batch {B}"
-    else:
-        B = args.batch if args.batch != 64 else 16
-        m = ddmi_b200.MLPNeRF(D=6, W=256, in_channels_xyz=159, skips=[2, 4], in_channels_dir=27).to(dev)
-        fea = {k: torch.randn(B, 32, 64, 64, generator=g).to(dev) for k in ('xy', 'yz', 'xz')}
-        H = W = 128
-        focal = .5 * W / np.tan(.5 * 0.6911112070083618)
-        K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
-        ro, rd = nh.get_rays(H, W, K, nh.pose_spherical(40.0, -20, 5)[:3, :4], dev)
-        vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
-        rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(H * W, 1, device=dev),
-                          6. * torch.ones(H * W, 1, device=dev), vd], -1)
-        coords = B * H * W * 128
-        fn = lambda: nh.render_rays_fused(rays, fea, m, 128, True, precision=args.precision)
-        desc = f"srn-cars-shape NeRF decode: triplane 64^2 x32ch, 128x128 rays x 128 samples, composited, batch {B} objects"
-    m.precision = args.precision
+    torch.cuda.set_device(0)
+    W = OtherWorkload(args.workload, args, dev)
+    B = W.B
+    coords = B * W.n_per_item
+    planes = W.slice(W.host, 0, B, dev)
+    torch.cuda.synchronize()
+    fn = lambda: W.decode(planes)
     for _ in range(args.warmup):
         fn()
     torch.cuda.synchronize()
+    sampler = ClockSampler(0)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
@@ -367,14 +538,84 @@ def run_other(args):
     t1.record()
     torch.cuda.synchronize()
     ms = t0.elapsed_time(t1)
+    clocks = sampler.stop()
+
+    # ---- end to end: pinned host planes -> HBM, decode through the public call, result -> pinned host; items walked in chunks
+    CH = max(1, min(args.e2e_chunk, B))
+    shape, dt = W.out_item
+    out_host = torch.empty((B,) + shape, dtype=dt).pin_memory()
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def e2e_step():
+        main = torch.cuda.current_stream()
+        chunks = [(k, min(k + CH, B)) for k in range(0, B, CH)]
+        ups = []
+        with torch.cuda.stream(up):
+            for a, b in chunks:
+                dp = W.slice(W.host, a, b, dev)
+                ev = torch.cuda.Event()
+                ev.record(up)
+                ups.append((dp, ev))
+        for (a, b), (dp, ev) in zip(chunks, ups):
+            main.wait_event(ev)
+            o = W.decode(dp)
+            down.wait_stream(main)
+            with torch.cuda.stream(down):
+                out_host[a:b].copy_(o.reshape((b - a,) + shape), non_blocking=True)
+            o.record_stream(down)
+        main.wait_stream(down)
+        main.synchronize()
+
+    e2e_step()
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, 3))
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    a1.record()
+    torch.cuda.synchronize()
+    e2e_ms = a0.elapsed_time(a1)
+
     tf_peak, _, which = peaks()
-    achieved = coords * args.steps * FLOP_PER_COORD[kind] / (ms * 1e-3) / 1e12
-    print(json.dumps({"metric": METRIC, "value": coords * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1,
-                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": PREC_INFO[args.precision]['dtype'], "data": "synthetic",
-                      "config": {"workload": desc, "precision": args.precision},
-                      "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                                   "frac": achieved / tf_peak, "traffic": None, "peak_source": which}}))
+    value = coords * args.steps / (ms * 1e-3)
+    achieved = value * FLOP_PER_COORD[W.flop_kind] / 1e12
+    pi = PREC_INFO[args.precision]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": pi['dtype'], "data": "synthetic",
+            "config": {"workload": W.desc, "coords_per_step_per_gpu": coords, "precision": args.precision,
+                       "l2": "planes %.2f GB per step; every step re-reads them (larger than L2 for batch >= 8)" % (W.h2d_bytes() / 1e9)},
+            "e2e": {"value": coords * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W.h2d_bytes(),
+                    "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "steps": e2e_steps,
+                    "pipeline": f"items walked in chunks of {CH}; uploads / read-backs on side streams"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                         "traffic": None, "peak_source": which + " (bf16 sustained)", "kernel": W.kernel,
+                         "note": f"achieved = ALGORITHMIC flops ({FLOP_PER_COORD[W.flop_kind]} / coord, as-written layers); " + pi['note'],
+                         "executed_tflops": achieved * pi['executed'], "avg_launch_ms": ms / args.steps}}
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n, run, what = W.oracle_sample('cpu', args.cpu_coords)
+        best = float('inf')
+        for _ in range(2):
+            t = time.perf_counter()
+            run()
+            best = min(best, time.perf_counter() - t)
+        line["cpu_baseline"] = {"value": n / best, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle port of the reference decoder, fp32, {what}, best of 2, {cores} torch threads"}
+        tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        n, run, what = W.oracle_sample(dev, args.cpu_coords * 4)
+        dtg = eager_sync_time(run)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+        line["gpu_eager_baseline"] = {"value": n / dtg, "unit": UNIT, "kind": "oracle restatement of the reference decoder, eager "
+                                      "PyTorch fp32 (TF32 off) on this GPU", "sample": what + ", best of 3",
+                                      "speedup_of_value": value / (n / dtg)}
+    print(json.dumps(line))
 
 
 def cpu_baseline(res, batch, repeats=1):
@@ -451,8 +692,10 @@ if __name__ == '__main__':
     ap.add_argument('--cpu-res', type=int, default=512)
     ap.add_argument('--cpu-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--workload', default='image', choices=['image', 'occupancy', 'video', 'nerf'],
-                    help='image = the headline (BASELINE configs[1]); the others are the parity-case configs, 1 GPU')
+    ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling (sharded batch 64 + all-gather) leg')
+    ap.add_argument('--workload', default='image', choices=['image', 'c1', 'occupancy', 'video', 'nerf'],
+                    help='image = the headline (BASELINE configs[1]); c1 / video / occupancy / nerf = configs[0], [2], [3], [4], 1 GPU')
+    ap.add_argument('--cpu-coords', type=int, default=131072, help='coordinates in the CPU-baseline sample of the non-headline workloads')
     ARGS = ap.parse_args()
     if ARGS.impl == 'reference':
         run_reference(ARGS)

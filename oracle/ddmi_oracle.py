@@ -2,7 +2,7 @@
 
 A restatement of the reference's algorithm in plain torch CPU ops, taking a
 state dict with the reference's parameter names.  Only tests/,
-__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+__graft_entry__.smoke() and bench.py's baseline legs (cpu_baseline, --impl reference, gpu_eager_baseline) may
 import this module; the product package (ddmi_b200/) never does.
 
 Parity pin: the reference ships no tests or golden vectors for this path
@@ -69,7 +69,7 @@ def triplane_concat(p1, p2, p3, c1, c2, c3):
 # ---------------------------------------------------------------------------
 def _sinusoidal(x, dim):
     half = dim // 2
-    e = torch.exp(torch.arange(half, dtype=x.dtype) * -(math.log(10000) / (half - 1)))
+    e = torch.exp(torch.arange(half, dtype=x.dtype, device=x.device) * -(math.log(10000) / (half - 1)))
     e = x[:, None] * e[None, :]
     return torch.cat((e.sin(), e.cos()), dim=-1)
 
@@ -164,7 +164,7 @@ def image_decode(sd, coords, hdbf, si=1.0, noise=None):
     coords = coords.to(dt).repeat(b, 1, 1, 1)
     sip = torch.ones_like(coords) * si
     grid = coords.permute(0, 2, 3, 1).contiguous()
-    style = _sinusoidal(torch.ones(b, dtype=dt) * si, 64)
+    style = _sinusoidal(torch.ones(b, dtype=dt, device=hdbf[0].device) * si, 64)
     style = F.linear(style, sd['time_mlp.1.weight'], sd['time_mlp.1.bias'])
     style = F.linear(F.gelu(style), sd['time_mlp.3.weight'], sd['time_mlp.3.bias'])
     feats = [torch.cat((_gs(p, grid, False), sip), dim=1) for p in hdbf]
@@ -253,14 +253,14 @@ def nerf_sample_depths(rays, n_samples, perturb=0., lindisp=False):
     stratified with one torch.rand draw per interval."""
     dt = rays.dtype
     near, far = rays[:, 6:7], rays[:, 7:8]
-    t = torch.linspace(0., 1., steps=n_samples).to(dt)
+    t = torch.linspace(0., 1., steps=n_samples).to(device=rays.device, dtype=dt)
     z = near * (1. - t) + far * t if not lindisp else 1. / (1. / near * (1. - t) + 1. / far * t)
     z = z.expand(rays.shape[0], n_samples)
     if perturb > 0.:
         mids = .5 * (z[:, 1:] + z[:, :-1])
         upper = torch.cat([mids, z[:, -1:]], -1)
         lower = torch.cat([z[:, :1], mids], -1)
-        z = lower + (upper - lower) * torch.rand(z.shape).to(dt)
+        z = lower + (upper - lower) * torch.rand(z.shape).to(device=rays.device, dtype=dt)
     return z
 
 

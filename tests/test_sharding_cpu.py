@@ -25,6 +25,11 @@ def test_plan_units_covers_everything_once():
         sizes = [sum(r1 - r0 for _, r0, r1 in u) for u in plan]
         if batch * rows >= world:
             assert min(sizes) > 0
+        if rows >= world:                      # enough rows to cut: every rank owns the same number of units, rows within 1 slab
+            assert len({len(u) for u in plan}) == 1, (batch, rows, world)
+            assert max(sizes) - min(sizes) <= len(plan[0]), (batch, rows, world, sizes)
+    assert [len(u) for u in sharding.plan_units(3, 64, 4)] == [3, 3, 3, 3]      # was 2:1 imbalanced with round-robin slabs
+    assert sharding.plan_units(64, 1024, 8)[3] == [(i, 0, 1024) for i in range(24, 32)]   # whole items when the batch divides
 
 
 def _free_port():
@@ -51,7 +56,39 @@ def _worker(rank, world, port, q):
     full = sharding.decode_image_sharded(CpuStub(), coords, planes, si=si, gather=True)
     ref = orc.image_decode(sd, coords, planes, si)
     mine = sharding.decode_image_sharded(CpuStub(), coords, planes, si=si, gather=False)
-    q.put((rank, float((full - ref).abs().max()), [u for u, _ in mine]))
+    err = float((full - ref).abs().max())
+    at_root = sharding.decode_image_sharded(CpuStub(), coords, planes, si=si, gather='root')
+    assert (at_root is None) == (rank != 0)
+    if rank == 0:
+        err = max(err, float((at_root - ref).abs().max()))
+    # round-1 API: partial full-size tensors in, assembled tensor out (only the owned slabs travel)
+    partial = torch.zeros_like(ref)
+    for (item, r0, r1), t in mine:
+        partial[item, :, r0:r1] = t
+    err = max(err, float((sharding.all_gather_outputs(partial, sharding.plan_units(3, 12, world)) - ref).abs().max()))
+
+    # occupancy: items then point ranges
+    sdo = cases.state_dict32(cases.build_module('occupancy'))
+    pts, hdbf = cases.occupancy_inputs(batch=3, sizes=(4, 8, 16), n=50)
+
+    class OccStub:
+        def decode_logits(self, p, c):
+            return orc.occupancy_logits(sdo, p, c)
+
+    lo = sharding.decode_occupancy_sharded(OccStub(), pts, hdbf, gather=True)
+    err = max(err, float((lo - orc.occupancy_logits(sdo, pts, hdbf)).abs().max()))
+
+    # video: batch items
+    sdv = cases.state_dict32(cases.build_module('video'))
+    cv, hv = cases.video_inputs(batch=3, T=2, sizes=(4, 4, 8))
+
+    class VidStub:
+        def __call__(self, c, h):
+            return orc.video_decode(sdv, c, h)
+
+    vo = sharding.decode_video_sharded(VidStub(), cv, hv, gather=True)
+    err = max(err, float((vo - orc.video_decode(sdv, cv, hv)).abs().max()))
+    q.put((rank, err, [u for u, _ in mine]))
     dist.destroy_process_group()
 
 
@@ -71,4 +108,4 @@ def test_sharded_decode_gloo_world2():
     for rank, err, mine in res:
         assert err < 1e-5, (rank, err)
         units += mine
-    assert sorted(units) == [(0, 0, 12), (1, 0, 12), (2, 0, 12)]
+    assert sorted(units) == [(0, 0, 6), (0, 6, 12), (1, 0, 6), (1, 6, 12), (2, 0, 6), (2, 6, 12)]
