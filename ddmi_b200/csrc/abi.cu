@@ -37,6 +37,7 @@ int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, i
 int debug_profile(unsigned long long*, int);
 int debug_trace(unsigned long long*, int, int*, int);
 int debug_set(int);
+int launch_sample_pdf(const float*, const float*, const float*, long long, int, int, float*, cudaStream_t);
 int launch_gatherbench(int, int, const float*, unsigned, int, int, int, unsigned long long*, float*, cudaStream_t);
 int launch_ringbench(const void*, unsigned long long, int, int, int, int, unsigned long long*, cudaStream_t);
 int launch_microbench(int, int, const float*, unsigned long long*, float*, cudaStream_t);
@@ -346,6 +347,15 @@ static int nerf_render_impl(const ddmi_plane_t planes[3], int32_t batch, int32_t
   return launch_nerf_render_fp32(ps, batch, channels, rays, n_rays, ray_stride, t_vals, z_stride, n_samples, plane_extent,
                                  negative_slope, white_bkgd, (const float*)weights->gemm, weights->vec, rgb_map,
                                  raw, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays, int32_t n_bins,
+                             int32_t n_samples, float* out, void* stream) {
+  DDMI_REQUIRE(bins && weights && u && out, "bins / weights / u / out is NULL");
+  DDMI_REQUIRE(n_rays >= 1 && n_samples >= 1, "empty ray set (%lld rays x %d samples)", (long long)n_rays, n_samples);
+  DDMI_REQUIRE(n_bins >= 2 && n_bins <= 1024, "n_bins must be in [2, 1024] (got %d)", n_bins);
+  DDMI_REQUIRE(n_rays <= 4LL * 2147483647LL, "too many rays for one launch");
+  return launch_sample_pdf(bins, weights, u, n_rays, n_bins, n_samples, out, (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_t N, int32_t K, void* stream) {

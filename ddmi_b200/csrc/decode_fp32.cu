@@ -613,6 +613,59 @@ static int check_grid(long long tiles) {
   return DDMI_OK;
 }
 
+// Hierarchical sampling, utils/nerf_helpers.py:166-209 (sample_pdf): per ray, pdf = (w + 1e-5) / sum, cdf = [0, cumsum(pdf)],
+// then for every u: inds = searchsorted(cdf, u, right=True), below = max(inds - 1, 0), above = min(inds, n_bins - 1),
+// t = (u - cdf[below]) / (denom < 1e-5 ? 1 : denom), sample = bins[below] + t * (bins[above] - bins[below]).
+// One warp per ray; the cdf is accumulated sequentially (the order of torch.cumsum) in shared memory.
+namespace fp32 {
+constexpr int PDF_MAX_BINS = 1024;
+__global__ void __launch_bounds__(128)
+sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ u,
+                  long long n_rays, int n_bins, int n_samples, float* __restrict__ out) {
+  __shared__ float cdf_s[4][PDF_MAX_BINS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ray = (long long)blockIdx.x * 4 + warp;
+  if (ray >= n_rays) return;
+  float* cdf = cdf_s[warp];
+  const float* w = weights + ray * (n_bins - 1);
+  const float* b = bins + ray * n_bins;
+  float part = 0.f;
+  for (int i = lane; i < n_bins - 1; i += 32) part += __fadd_rn(__ldg(w + i), 1e-5f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) {
+    float c = 0.f;
+    cdf[0] = 0.f;
+    for (int i = 0; i < n_bins - 1; ++i) {
+      c = __fadd_rn(c, __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), part));
+      cdf[i + 1] = c;
+    }
+  }
+  __syncwarp();
+  for (int j = lane; j < n_samples; j += 32) {
+    const float uj = __ldg(u + ray * n_samples + j);
+    int lo = 0, hi = n_bins;                       // first index with cdf[idx] > uj  (searchsorted right=True)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= uj) lo = mid + 1; else hi = mid;
+    }
+    const int below = max(lo - 1, 0), above = min(lo, n_bins - 1);
+    float denom = __fsub_rn(cdf[above], cdf[below]);
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = __fdiv_rn(__fsub_rn(uj, cdf[below]), denom);
+    const float b0 = __ldg(b + below), b1 = __ldg(b + above);
+    out[ray * n_samples + j] = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+  }
+}
+}  // namespace fp32
+
+int launch_sample_pdf(const float* bins, const float* weights, const float* u, long long n_rays, int n_bins, int n_samples,
+                      float* out, cudaStream_t st) {
+  fp32::sample_pdf_kernel<<<(unsigned)((n_rays + 3) / 4), 128, 0, st>>>(bins, weights, u, n_rays, n_bins, n_samples, out);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
+}
+
 int launch_image_fp32(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy,
                       long long n, const float* Wg, const float* vec, void* out, int store, const NoiseArgs& na,
                       cudaStream_t st) {

@@ -149,6 +149,38 @@ def sample_depths(rays, N_samples, perturb=0., lindisp=False):
     return z_vals.contiguous()
 
 
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    """Hierarchical sampling (utils/nerf_helpers.py:166-209), same signature: bins (N_rays, N_bins) CUDA tensor, weights
+    (N_rays, N_bins - 1).  The uniform numbers are drawn exactly as the reference draws them (torch.linspace for `det`,
+    torch.rand on the CPU generator otherwise, numpy's seeded generator for `pytest`), the inverse-CDF lookup runs in the
+    library's kernel (ddmi_sample_pdf).  The reference's own N_importance > 0 branch of render_rays cannot run
+    (it reuses the coarse pass's plane coordinates), so this is exposed as the standalone function."""
+    import numpy as np
+    if not bins.is_cuda:
+        raise RuntimeError("sample_pdf: bins must be a CUDA tensor (ddmi_b200 has no CPU path)")
+    lead = list(weights.shape[:-1])
+    if det:
+        u = torch.linspace(0., 1., steps=N_samples).expand(lead + [N_samples])
+    else:
+        u = torch.rand(lead + [N_samples])
+    if pytest:
+        np.random.seed(0)
+        u = torch.Tensor(np.broadcast_to(np.linspace(0., 1., N_samples), lead + [N_samples]).copy() if det
+                         else np.random.rand(*(lead + [N_samples])))
+    dev = bins.device
+    b = bins.detach().to(torch.float32).reshape(-1, bins.shape[-1]).contiguous()
+    w = weights.detach().to(device=dev, dtype=torch.float32).reshape(-1, weights.shape[-1]).contiguous()
+    if w.shape[-1] != b.shape[-1] - 1 or w.shape[0] != b.shape[0]:
+        raise RuntimeError(f"sample_pdf: weights {tuple(weights.shape)} must be bins {tuple(bins.shape)} minus one along the last axis")
+    uu = u.to(device=dev, dtype=torch.float32).reshape(-1, N_samples).contiguous()
+    out = torch.empty_like(uu)
+    if out.numel():
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().ddmi_sample_pdf(b.data_ptr(), w.data_ptr(), uu.data_ptr(), b.shape[0], b.shape[1], N_samples,
+                                                  out.data_ptr(), _stream_ptr(dev)))
+    return out.reshape(lead + [N_samples])
+
+
 def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False, precision=None, perturb=0.,
                       lindisp=False):
     """rays (N,11) [o d near far viewdir]; fea = dict of (B,32,R,R) planes.

@@ -24,6 +24,7 @@
  *   ddmi_nerf_render       utils/nerf_helpers.py:296-452 render_rays
  *                          (+ :455-475 run_network, :82-112 Embedder.embed,
  *                             :487-530 raw2outputs)
+ *   ddmi_sample_pdf        utils/nerf_helpers.py:166-209 sample_pdf
  * The reference binds its native ops with pybind11 inside a JIT torch extension
  * (models/d2c_vae/op/fused_bias_act.cpp:18-20); INTEGRATION.md shows the ctypes
  * stub a maintainer adds instead.
@@ -223,6 +224,14 @@ DDMI_API int ddmi_nerf_render_z(const ddmi_plane_t planes[3], int32_t batch, int
                        const float* z_vals, int32_t n_samples, float plane_extent,
                        float negative_slope, int32_t white_bkgd, const ddmi_weights_t* weights,
                        float* rgb_map, float* raw, void* stream);
+
+/*
+ * Hierarchical (inverse-CDF) sampling of utils/nerf_helpers.py:166-209.  bins (n_rays, n_bins), weights (n_rays, n_bins - 1),
+ * u (n_rays, n_samples) uniform numbers in [0,1) drawn by the caller (torch.rand / linspace, as the reference does);
+ * out (n_rays, n_samples) fp32.  All device memory.
+ */
+DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays, int32_t n_bins,
+                             int32_t n_samples, float* out, void* stream);
 
 /*
  * Bring-up self test of the tcgen05 path: one 128 x N x K bf16 GEMM through the

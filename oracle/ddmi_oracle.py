@@ -264,6 +264,26 @@ def nerf_sample_depths(rays, n_samples, perturb=0., lindisp=False):
     return z
 
 
+def sample_pdf(bins, weights, u):
+    """sample_pdf (utils/nerf_helpers.py:166-209) for given uniform numbers u (N_rays, N_samples)."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
+    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
+    inds_g = torch.stack([below, above], -1)
+    shp = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
+    cdf_g = torch.gather(cdf.unsqueeze(1).expand(shp), 2, inds_g)
+    bins_g = torch.gather(bins.unsqueeze(1).expand(shp), 2, inds_g)
+    denom = cdf_g[..., 1] - cdf_g[..., 0]
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_g[..., 0]) / denom
+    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+
+
 def nerf_render_rays(sd, rays, fea, n_samples, white_bkgd=True, slope=1.0, return_raw=False, perturb=0., lindisp=False):
     """render_rays + run_network + raw2outputs (N_importance=0, raw_noise_std=0).
     rays (N,11) [o d near far viewdir]; fea planes (1,32,R,R)."""

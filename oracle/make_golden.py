@@ -147,6 +147,17 @@ o2 = orc.nerf_render_rays(sd, rays, fea, 64, True)
 print(f'  oracle-vs-reference nerf_render: {float((rgb - o2).abs().max()):.3e}; rgb range {float(rgb.min()):.3f}..{float(rgb.max()):.3f}')
 save('nerf_render', rgb, list(fea.values()) + list(sd.values()), {'rays': rays})
 
+# hierarchical sampling: the reference's sample_pdf on seeded bins / weights, deterministic u and its own pytest-mode u
+gpdf = torch.Generator().manual_seed(cases.SEED + 60)
+z = torch.sort(2. + 4. * torch.rand(300, 64, generator=gpdf), -1).values
+bins_pdf = .5 * (z[:, 1:] + z[:, :-1])                       # (300, 63), as render_rays builds z_vals_mid (:402-404)
+w_pdf = torch.rand(300, 62, generator=gpdf) ** 4             # peaky weights, some ~0
+w_pdf[7] = 0.                                                # an all-zero row (the 1e-5 floor makes it uniform)
+out_det = rnh.sample_pdf(bins_pdf, w_pdf, 128, det=True)
+out_rnd = rnh.sample_pdf(bins_pdf, w_pdf, 96, det=False, pytest=True)
+print(f'  oracle-vs-reference sample_pdf: {float((orc.sample_pdf(bins_pdf, w_pdf, torch.linspace(0., 1., 128).expand(300, 128)) - out_det).abs().max()):.3e}')
+save('sample_pdf', out_det, [bins_pdf, w_pdf], {'bins': bins_pdf, 'weights': w_pdf, 'out_pytest': out_rnd})
+
 # stratified sampling (perturb = 1: the training-time setting, one torch.rand draw on the CPU generator) and lindisp
 for tag, extra in (('nerf_render_perturb', dict(perturb=1.0)), ('nerf_render_lindisp', dict(lindisp=True)),
                    ('nerf_render_perturb_lindisp', dict(perturb=1.0, lindisp=True))):

@@ -118,3 +118,15 @@ def test_oracle_fp64_agrees():
     sd64 = {k: v.double() for k, v in sd.items()}
     o64 = orc.occupancy_logits(sd64, pts.double(), tuple([t.double() for t in a] for a in hdbf))
     assert float((o32.double() - o64).abs().max()) < 5e-5
+
+
+def test_sample_pdf(golden_dir):
+    """Hierarchical sampling (utils/nerf_helpers.py:166-209): deterministic u, and the reference's own pytest-mode u."""
+    import numpy as np
+    g = _load(golden_dir, 'sample_pdf')
+    _check_inputs(g, [g['bins'], g['weights']])
+    out = orc.sample_pdf(g['bins'], g['weights'], torch.linspace(0., 1., 128).expand(300, 128))
+    assert float((out - g['out']).abs().max()) < 1e-6
+    np.random.seed(0)
+    u = torch.Tensor(np.random.rand(300, 96))
+    assert float((orc.sample_pdf(g['bins'], g['weights'], u) - g['out_pytest']).abs().max()) < 1e-6

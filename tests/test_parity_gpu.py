@@ -380,6 +380,23 @@ def test_nerf_stratified_fused_compositing_128_samples():
     assert float((rgb[0].cpu() - ref).abs().max()) < TOL
 
 
+def test_sample_pdf_golden(golden_dir):
+    """nerf_helpers.sample_pdf (same signature as the reference's) against the reference's outputs: det=True and pytest=True."""
+    g = _golden(golden_dir, 'sample_pdf')
+    bins, w = g['bins'].to(DEV), g['weights'].to(DEV)
+    out = nh.sample_pdf(bins, w, 128, det=True).cpu()
+    assert out.shape == g['out'].shape and float((out - g['out']).abs().max()) < 2e-5
+    rnd = nh.sample_pdf(bins, w, 96, det=False, pytest=True).cpu()
+    assert float((rnd - g['out_pytest']).abs().max()) < 2e-5
+    # samples fall inside their ray's bin range and follow the weights: a ray with one dominant bin puts its samples there
+    assert bool((out >= g['bins'][:, :1] - 1e-6).all()) and bool((out <= g['bins'][:, -1:] + 1e-6).all())
+    w1 = torch.zeros(1, 62)
+    w1[0, 30] = 1.0
+    one = nh.sample_pdf(bins[:1], w1.to(DEV), 64, det=True).cpu()
+    inside = (one >= g['bins'][0, 30]) & (one <= g['bins'][0, 31])
+    assert float(inside.float().mean()) > 0.95
+
+
 # ---------------------------------------------------------------- tcgen05 bring-up
 @pytest.mark.parametrize("N,K", [(256, 256), (256, 64), (64, 64), (16, 256), (128, 32)])
 def test_umma_selftest(N, K):
