@@ -7,12 +7,15 @@
 // phases: the epilogue keeps h (fp32) in registers, publishes RAW h (shortcut GEMM -> acc2),
 // and after that GEMM committed rewrites the same buffer with relu(h) (fc_0 GEMM -> acc1);
 // fc_1 then accumulates ONTO the shortcut in acc2, so x_s + dx never leaves TMEM.
-// The 64-wide plane features X_s follow the same two phases in ONE buffer: X holds them raw for the shortcut GEMM and is
-// rewritten with relu(X_s) together with relu(h) (R1, whose input is X_0 alone, reads relu(X_0) from H's first 64 columns,
-// free at that point).  Between the two phases the gathering thread parks its 32 fp32 values in the acc1 columns of its own
-// TMEM lane (acc1 is idle from an fc_0 epilogue to the next fc_0 GEMM; tcgen05.st / ld, ~70 cycles) -- registers are full
-// (h stays there for its own two phases).  Keeping both forms resident cost 32 KB: the weight ring was 32 KB (1024 tensor
-// cycles of cover against a ~1800-cycle refill loop) and the tensor pipe starved; with one X buffer the ring is 64 KB.
+// The 64-wide plane features are kept in both forms (Xa raw, Xb relu).
+//
+// What bounds this kernel (round 2, profiles/r02_occupancy_timeline_grid.txt, r02_gatherbench_scattered_texels.txt): the
+// GATHERS.  A point needs 9 planes x 4 taps x 256 B of channels-last texels (9 KB); a B200 SM sustains ~32 B/clk on scattered
+// 256-byte texels through LDG whatever the load form, unroll depth or L1 size, so one scale costs the 256 epilogue threads
+// ~12-13 K cycles, three times per tile, against 39 K cycles of MMA work -- and the epilogue threads that gather are the
+// ones the next stage waits for.  Tried and measured slower: one X buffer + a 64 KB weight ring (the ring is not the limit
+// here), dedicated gather warps staging texels with cp.async (scattered LDGSTS tops out near 13 B/clk/SM; two warps cannot
+// hold enough LDG results in registers either).
 //
 // vec layout (floats): b0_1[64] b1_1'[256] Wp[3][256] b0_2[256] b1_2[256] b0_3[256] b1_3[256]
 //                      b0_4[256] (b1_3+b1_4)[256] w_out[256] b_out[1]          (b1_1' = b1_1 + net_p.bias)
@@ -22,10 +25,7 @@
 namespace ddmi {
 namespace ummak {
 
-using OccL = Layout<8, 65536>;    // X region: [X hi 8 | X lo 8] K groups (raw, then relu); 8 x 8 KB ring slots
-constexpr int OCC_KG_XH = 64, OCC_KG_XL = 72;
-// the video kernel keeps both forms of its (streamed) feature pieces: [Xa hi 8 | Xb hi 8] [Xa lo 8 | Xb lo 8], 4 ring slots
-using VidXL = Layout<16, 32768>;
+using OccL = Layout<16, 32768>;   // X region: [Xa hi 8 | Xb hi 8] [Xa lo 8 | Xb lo 8] K groups; 4 x 8 KB ring slots
 constexpr int OCC_KG_XAH = 64, OCC_KG_XBH = 72, OCC_KG_XAL = 80, OCC_KG_XBL = 88;
 constexpr int OCC_OFF_PART = OccL::OFF_BAR + BAR_BYTES;          // [2][128] fp32 partial logits
 constexpr int OCC_SMEM = OCC_OFF_PART + 1024;
@@ -136,7 +136,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase, h_lo = sbase + H_KG * KG_BYTES;
-  const uint32_t x_hi = sbase + OCC_KG_XH * KG_BYTES, x_lo = sbase + OCC_KG_XL * KG_BYTES;
+  const uint32_t xa_hi = sbase + OCC_KG_XAH * KG_BYTES, xa_lo = sbase + OCC_KG_XAL * KG_BYTES;
+  const uint32_t xb_hi = sbase + OCC_KG_XBH * KG_BYTES, xb_lo = sbase + OCC_KG_XBL * KG_BYTES;
   const uint32_t ring = sbase + OccL::OFF_RING, bar = sbase + OccL::OFF_BAR;
   float* part = reinterpret_cast<float*>(smem + OCC_OFF_PART);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -157,26 +158,21 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
     const int ghalf = tid >> 7;
     const uint32_t a_bar = PAIR ? mapa_rank(bar + BAR_A0, 0) : bar + BAR_A0;
     uint32_t ph_mma = 0;
-    bool tr = false;            // profiling build: this thread traces the current tile iteration
-    uint32_t trn = 0;
 
     auto signal = [&](int q) {
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
-      trace(tr, 0x10 + q, trn, 0);
     };
     auto signal_all = [&]() {
 #pragma unroll
       for (int q = 0; q < 4; ++q) signal(q);
     };
     auto wait_mma = [&]() {
-      trace(tr, 0x01, trn, 0);
       mbar_wait(bar + BAR_MMADONE, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
-      trace(tr, 0x02, trn, 0);
     };
     // this thread's query point of a tile (rows past the end replay the last point)
     auto point_of = [&](long long tile, float (&p)[3]) {
@@ -188,36 +184,11 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       p[0] = __ldg(pp); p[1] = __ldg(pp + 1); p[2] = __ldg(pp + 2);
       return b;
     };
-    // triplane 'add' gather of scale s: raw -> X, and into xr (this thread's 32 values) for the relu rewrite.
+    // triplane 'add' gather of scale s: raw -> Xa, relu -> Xb.
     // NHWC: 8 threads cooperate on one point -- thread (tid & 7) owns K group kg = 8 consecutive channels
     //   (two float4 per tap), so one warp instruction touches 4 points x 2 cache lines; 4 passes of 32 points.
     // NCHW: one thread per (point, 32-channel half), scalar loads (layout the VAE decoder emits).
-    auto stash_x = [&](const float (&xr)[4][8]) {          // this thread's 32 gathered values -> its lane of acc1
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        float2 t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = make_float2(xr[2 * h2 + i / 4][(2 * i) % 8], xr[2 * h2 + i / 4][(2 * i) % 8 + 1]);
-        tmem_st16(tmem_lane + sub * 32 + h2 * 16, t);
-      }
-      tmem_st_wait();
-    };
-    auto unstash_x = [&](float (&xr)[4][8]) {
-#pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        float2 t[8];
-        tmem_ld16(tmem_lane + sub * 32 + h2 * 16, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          xr[2 * h2 + i / 4][(2 * i) % 8] = t[i].x;
-          xr[2 * h2 + i / 4][(2 * i) % 8 + 1] = t[i].y;
-        }
-      }
-    };
     auto gather = [&](long long tile, int s) {
-      float xr[4][8];
-      trace(tr, 0x20, trn, 0);
       if (tile > total_tiles - 1) tile = total_tiles - 1;
       const int b = (int)(tile / tiles_per_item);
       const long long r0 = (tile % tiles_per_item) * TILE;
@@ -228,8 +199,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         const float* b0 = ps.data[s] + (size_t)b * hw0 * C;
         const float* b1 = ps.data[3 + s] + (size_t)b * hw1 * C;
         const float* b2 = ps.data[6 + s] + (size_t)b * hw2 * C;
-#pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {     // unrolled: xr is indexed at compile time (registers)
+#pragma unroll 1
+        for (int pass = 0; pass < 4; ++pass) {
           const int prow = pass * 32 + (tid >> 3);
           long long gi = r0 + prow;
           if (gi > n - 1) gi = n - 1;
@@ -239,15 +210,17 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
           const Tap txy = make_tap<true>(g0, g1, ps.h[s], ps.w[s]);
           const Tap tyz = make_tap<true>(g1, g2, ps.h[3 + s], ps.w[3 + s]);
           const Tap txz = make_tap<true>(g0, g2, ps.h[6 + s], ps.w[6 + s]);
-          float y[8], u[8], w[8];
+          float y[8], u[8], w[8], yr[8];
           tap_sample8_nhwc(b0, txy, C, kg * 8, y);
           tap_sample8_nhwc(b1, tyz, C, kg * 8, u);
           tap_sample8_nhwc(b2, txz, C, kg * 8, w);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = __fadd_rn(__fadd_rn(y[i], u[i]), w[i]);
-          store8<SCHEME>(x_hi, x_lo, prow, kg, y);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) xr[pass][i] = y[i];
+          for (int i = 0; i < 8; ++i) {
+            y[i] = __fadd_rn(__fadd_rn(y[i], u[i]), w[i]);
+            yr[i] = fmaxf(y[i], 0.f);
+          }
+          store8<SCHEME>(xa_hi, xa_lo, prow, kg, y);
+          store8<SCHEME>(xb_hi, xb_lo, prow, kg, yr);
         }
       } else {
         float p[3];
@@ -260,9 +233,9 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         const float* b0 = ps.data[s] + ((size_t)b * C + ghalf * 32) * hw0;
         const float* b1 = ps.data[3 + s] + ((size_t)b * C + ghalf * 32) * hw1;
         const float* b2 = ps.data[6 + s] + ((size_t)b * C + ghalf * 32) * hw2;
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          float y[8];
+          float y[8], yr[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c = g * 8 + i;
@@ -270,24 +243,11 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
             v = __fadd_rn(v, tap_sample(b1 + c * hw1, tyz));
             v = __fadd_rn(v, tap_sample(b2 + c * hw2, txz));
             y[i] = v;
-            xr[g][i] = v;
+            yr[i] = fmaxf(v, 0.f);
           }
-          store8<SCHEME>(x_hi, x_lo, row, ghalf * 4 + g, y);
+          store8<SCHEME>(xa_hi, xa_lo, row, ghalf * 4 + g, y);
+          store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g, yr);
         }
-      }
-      stash_x(xr);
-      trace(tr, 0x21, trn, 0);
-    };
-    // relu of the gathered features (parked in TMEM) -> the K groups at (dst_hi, dst_lo): X itself (R2 / R3) or H's first
-    // 64 columns (R1)
-    auto put_relu_x = [&](const float (&xr)[4][8], uint32_t dst_hi, uint32_t dst_lo) {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float yr[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) yr[i] = fmaxf(xr[p][i], 0.f);
-        if (NHWC) store8<SCHEME>(dst_hi, dst_lo, p * 32 + (tid >> 3), tid & 7, yr);
-        else store8<SCHEME>(dst_hi, dst_lo, row, ghalf * 4 + p, yr);
       }
     };
     // wait for the fc_0 GEMM, then relu(acc1 + b) -> H, quarter by quarter
@@ -296,18 +256,12 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       biased_stage<SCHEME>(tmem_lane, 0, sub, row, h_hi, h_lo, b0, 4, v, wait_mma, [](float2 t) { return relu_pair(t); }, signal, 0);
     };
 
-    if (ntiles > 0) gather(tile_of(0), 0);
+    if (ntiles > 0) {
+      gather(tile_of(0), 0);
+      signal_all();
+    }
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
-      tr = DDMI_PROFILE && blockIdx.x == 0 && tid == 0 && it == kTraceIter;
-      // every GEMM of the previous tile has committed: H is free.  R1's fc_0 operand relu(X_0) goes to H[:, 0:64]
-      // (X itself holds the raw X_0 for R1's shortcut)
-      {
-        float xr[4][8];
-        unstash_x(xr);
-        put_relu_x(xr, h_hi, h_lo);
-      }
-      signal_all();
       // ---- R1.fc_0 (N = 64): net = relu(acc1[:, 0:64] + b0) -> H[:, 0:64]
       {
         float2 v[16], b[16];
@@ -326,8 +280,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
         signal_all();
       }
-      // R1's fc_0 AND shortcut ran in that group, so X is free: gather the next scale now, overlapping R1.fc_1
-      // (every gather sits right after the group that last reads X)
+      // R1's fc_0 AND shortcut ran in that group, so both feature buffers are free: gather the next scale now,
+      // overlapping R1.fc_1 (every gather sits right after the group that last reads Xa / Xb)
       gather(tile, 1);
       // ---- R1 output h1 = acc2 + b1' + net_p(p); R2, R3: two operand phases (raw, then relu)
 #pragma unroll 1
@@ -350,20 +304,14 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
                                       }
                                     },
                                     signal, 0);
-        // phase 2: relu(h) and relu(X_s) (fc_0 operands) once the shortcut GEMM has consumed the raw copies; the X part of
-        // fc_0 is the group's last unit (after WAIT 3), so its rewrite rides in front of the last quarter's signal
+        // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
         wait_mma();
-        float xr[4][8];
-        unstash_x(xr);        // before signal(0): the fc_0 GEMM it releases overwrites acc1, where the values are parked
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]);
-          if (q == 3) put_relu_x(xr, x_hi, x_lo);
-          signal(q);
-        }
-        // fc_0 epilogue; X is free again: gather what comes next while fc_1 runs
+        for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
+        // fc_0 epilogue; Xa / Xb are free again: gather what comes next while fc_1 runs
         stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
         if (blk == 1) gather(tile, 2);
+        else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
       }
       // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
       {
@@ -373,9 +321,6 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       }
       // ---- R4.fc_0 epilogue
       stage_net(vec + OV_B04);
-      // X is free (last read by R3.fc_0) and so is acc1 from here to the next tile's R1 (the gather parks its values there):
-      // fetch the next tile's coarse scale while R4.fc_1 runs
-      if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
       // ---- logits = w_out . (acc2 + b1_3 + b1_4) + b_out   (vectors prefetched like in the other stages)
       {
         float2 v[4][16], b[16], w[16];
@@ -407,6 +352,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // part[] may be rewritten by the next tile
       }
+      if (it + 1 < ntiles) signal_all();
     }
   } else {
     engine_service_warps<PAIR, OccL::RING_BYTES, SCHEME, 0>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);

@@ -23,7 +23,7 @@
 namespace ddmi {
 namespace ummak {
 
-using VidL = VidXL;  // H | [Xa hi, Xb hi] | [Xa lo, Xb lo] | 4 x 8 KB ring | barriers
+using VidL = OccL;   // same carve-up: H | [Xa hi, Xb hi] | [Xa lo, Xb lo] | 4 x 8 KB ring | barriers
 constexpr int VID_SMEM = VidL::OFF_BAR + BAR_BYTES;
 // [3][2][128] fp32 partial outputs live at the start of H: at the output stage the last GEMM that reads H has
 // committed and nothing writes H again before the named barrier that ends the stage.

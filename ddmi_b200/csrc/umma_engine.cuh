@@ -69,7 +69,7 @@ __device__ unsigned long long g_prof[8];
 // (hand-shakes and commits stay)   bit 2: no plane gathers
 __device__ int g_dbg;
 __device__ __forceinline__ bool dbg(int bit) { return DDMI_PROFILE && ((*(volatile int*)&g_dbg) & bit); }
-constexpr int kTraceCap = 2048, kTraceIter = 5;
+constexpr int kTraceCap = 4096, kTraceIter = 5, kTraceRegion = 1024;   // regions: E thread 0, MMA lane, 2 x kernel-specific
 __device__ unsigned long long g_trace[kTraceCap];
 __device__ unsigned int g_trace_n;
 __device__ __forceinline__ long long prof_clock() { return DDMI_PROFILE ? clock64() : 0ll; }
@@ -81,7 +81,7 @@ __device__ __forceinline__ void prof_add(int i, long long v) {
 // buffer, the MMA lane the upper half, each with its own running index `n`; unwritten slots stay 0.
 __device__ __forceinline__ void trace(bool on, uint32_t id, uint32_t& n, uint32_t base) {
   if (DDMI_PROFILE && on) {
-    if (n < (uint32_t)kTraceCap / 2) g_trace[base + n] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    if (n < (uint32_t)kTraceRegion) g_trace[base + n] = ((unsigned long long)id << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
     ++n;
   }
 }
@@ -210,7 +210,7 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
         const int units = ((int)((op >> 24) & 31) + 1) / (int)USLOTS;             // hand-shake units in this run
-        trace(tr, 0x100 + pc, trn, kTraceCap / 2);                                // UNIT starts
+        trace(tr, 0x100 + pc, trn, kTraceRegion);                                // UNIT starts
         for (int j = 0; j < units; j += CH) {
           const int nu = units - j < CH ? units - j : CH;
           // ---- probe every ring barrier of the chunk back to back
@@ -304,15 +304,15 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
       } else if (kind == OP_WAIT) {
         const uint32_t i = (op >> 2) & 7;
         const long long w0 = prof_clock();
-        trace(tr, 0x200 + pc, trn, kTraceCap / 2);                    // WAIT begins
+        trace(tr, 0x200 + pc, trn, kTraceRegion);                    // WAIT begins
         mbar_wait(bar + BAR_A0 + 8 * i, (ph_a >> i) & 1);
         ph_a ^= 1u << i;
         tc_fence_after();
-        trace(tr, 0x300 + pc, trn, kTraceCap / 2);                    // WAIT satisfied
+        trace(tr, 0x300 + pc, trn, kTraceRegion);                    // WAIT satisfied
         q_a += prof_clock() - w0;
       } else if (kind == OP_COMMIT) {
         const uint32_t db = bar + BAR_MMADONE + 8 * ((op >> 2) & 3);
-        trace(tr, 0x400 + pc, trn, kTraceCap / 2);                    // COMMIT issued
+        trace(tr, 0x400 + pc, trn, kTraceRegion);                    // COMMIT issued
         if (elect_one()) {
           if (PAIR) mma2_commit_mc(db, 3);
           else      mma_commit(db);
@@ -402,8 +402,10 @@ __device__ __forceinline__ void store8(uint32_t h_hi, uint32_t h_lo, int row, in
 // kernel prologue / epilogue shared by every decoder
 // ---------------------------------------------------------------------------
 // Initialise the barrier block, allocate 512 TMEM columns (warp 9), sync; returns the TMEM base.
+// a_hi_count: arrivals that complete operand barriers A4..A7 (default: one per E warp of the CTA or CTA pair, like A0..A3;
+// kernels whose A4.. are signalled by other warps -- the occupancy kernel's gather warps -- pass their own count)
 template <int PAIR, int SCHEME = 0>
-__device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar) {
+__device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar, int a_hi_count = 8 * (1 + PAIR)) {
   const uint32_t bar = smem_u32(smem) + off_bar;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
@@ -413,7 +415,7 @@ __device__ __forceinline__ uint32_t engine_begin(uint8_t* smem, int off_bar) {
       mbar_init(bar + BAR_PFULL + 8 * s, 1);
     }
     for (int q = 0; q < 4; ++q) mbar_init(bar + BAR_MMADONE + 8 * q, 1);
-    for (int q = 0; q < 8; ++q) mbar_init(bar + BAR_A0 + 8 * q, 8 * (1 + PAIR));   // one arrival per E warp (of both CTAs)
+    for (int q = 0; q < 8; ++q) mbar_init(bar + BAR_A0 + 8 * q, q < 4 ? 8 * (1 + PAIR) : a_hi_count);   // A0..A3: one arrival per E warp (of both CTAs)
     fence_mbar_init();
   }
   if (warp == 9) {

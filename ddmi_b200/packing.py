@@ -417,11 +417,10 @@ def _pack_resnet_chain(p, kx, precision):
 
 def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     """Program + stream + vec of csrc/decode_umma_occ.cuh.  A-region K groups: H hi 0..31, H lo 32..63,
-    X (plane features: raw for the shortcut, rewritten with relu for fc_0) hi 64..71 / lo 72..79; acc1 = TMEM cols 0..,
-    acc2 = 256..  R1 (input X_0 alone) reads relu(X_0) from H's first 64 columns.
-    Each ResnetBlockFC with a shortcut is three GEMM groups: shortcut on RAW [h | X] -> acc2, fc_0 on relu([h | X]) -> acc1,
+    Xa (raw PE) hi 64..71 / lo 80..87, Xb (relu PE) hi 72..79 / lo 88..95; acc1 = TMEM cols 0.., acc2 = 256..
+    Each ResnetBlockFC with a shortcut is three GEMM groups: shortcut on RAW h -> acc2, fc_0 on relu(h) -> acc1,
     fc_1 on relu(net) accumulated ONTO acc2.  K runs over h follow the epilogue's quarter-by-quarter publication."""
-    HH, HL, XH, XL = 0, 32, 64, 72    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
+    HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
     P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
     def wait_all():
@@ -433,10 +432,10 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
             P.wait(q)
             P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, acc, first and q == 0)
 
-    # R1: x = PE(64).  fc_0 (relu copy, in H[:, 0:64]) and the shortcut (raw copy, in X) share one group
+    # R1: x = PE(64).  fc_0 and the shortcut share one group so both PE buffers are released together
     wait_all()
-    P.block(p['net_res1.fc_0.weight'], HH, HL, 0, True)                         # N = 64
-    P.block(p['net_res1.shortcut.weight'], XH, XL, 256, True)
+    P.block(p['net_res1.fc_0.weight'], XBH, XBL, 0, True)                       # N = 64
+    P.block(p['net_res1.shortcut.weight'], XAH, XAL, 256, True)
     P.commit()
     wait_all()
     P.block(p['net_res1.fc_1.weight'], HH, HL, 256, False)                      # K = 64 hidden, onto the shortcut
@@ -444,10 +443,10 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     for i in (2, 3):                                                            # x = [h(256) | PE(64)]
         Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
         over_h(Ws, 256, True)
-        P.block(Ws[:, 256:320], XH, XL, 256, False)                             # X holds the raw features ...
+        P.block(Ws[:, 256:320], XAH, XAL, 256, False)
         P.commit()
         over_h(W0, 0, True)
-        P.block(W0[:, 256:320], XH, XL, 0, False)                               # ... and relu(X) by now (after WAIT 3)
+        P.block(W0[:, 256:320], XBH, XBL, 0, False)
         P.commit()
         over_h(W1, 256, False)                                                  # x_s + dx accumulate in TMEM
         P.commit()

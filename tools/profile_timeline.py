@@ -32,14 +32,14 @@ m.precision = os.environ.get('PREC', 'f16f8')
 L = _lib.lib()
 run()
 torch.cuda.synchronize()
-buf = (ctypes.c_uint64 * 4096)()
+buf = (ctypes.c_uint64 * 8192)()
 n = ctypes.c_int32()
-_lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
+_lib.check(L.ddmi_debug_trace(buf, 8192, ctypes.byref(n), 1))
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record(); run(); t1.record()
 torch.cuda.synchronize()
 print(f"{kind}: {t0.elapsed_time(t1):.2f} ms")
-_lib.check(L.ddmi_debug_trace(buf, 4096, ctypes.byref(n), 1))
+_lib.check(L.ddmi_debug_trace(buf, 8192, ctypes.byref(n), 1))
 ev = sorted(((buf[i] & ((1 << 48) - 1)), buf[i] >> 48) for i in range(n.value) if buf[i])
 if not ev:
     print("no trace records: load the profiling build (DDMI_B200_LIB=ddmi_b200/libddmi_b200_prof.so)")
@@ -48,7 +48,10 @@ t0 = ev[0][0]
 names = {0x01: 'E park', 0x02: 'E woke', 0x03: 'E drained', 0x20: 'E gather begin', 0x21: 'E gather end'}
 prev = t0
 for t, i in ev:
-    if i >= 0x400: nm = f'M COMMIT pc{i - 0x400}'
+    if i >= 0x700: nm = {0x700: 'B wait X free', 0x710: 'B A4 (raw X ready)', 0x720: 'B D1 seen', 0x730: 'B A5 (relu X ready)'}.get(i & 0xFF0, hex(i)) + f' s{i & 15}'
+    elif i >= 0x600: nm = f'B blended s{(i - 0x600) // 64} c{(i - 0x600) % 64}'
+    elif i >= 0x500: nm = f'I issued s{(i - 0x500) // 64} c{(i - 0x500) % 64}'
+    elif i >= 0x400: nm = f'M COMMIT pc{i - 0x400}'
     elif i >= 0x300: nm = f'M WAIT ok pc{i - 0x300}'
     elif i >= 0x200: nm = f'M WAIT .. pc{i - 0x200}'
     elif i >= 0x100: nm = f'M UNIT pc{i - 0x100}'
