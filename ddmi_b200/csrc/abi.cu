@@ -27,7 +27,7 @@ int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, con
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
 int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
-int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, const NoiseArgs&, cudaStream_t);
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, const NoiseArgs&, int, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
@@ -37,6 +37,7 @@ int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, i
 int debug_profile(unsigned long long*, int);
 int debug_trace(unsigned long long*, int, int*, int);
 int debug_set(int);
+int launch_tma_selftest(const float*, int, int, int, int, int, int, int, int, void*, float*, cudaStream_t);
 int launch_sample_pdf(const float*, const float*, const float*, long long, int, int, float*, cudaStream_t);
 int launch_gatherbench(int, int, const float*, unsigned, int, int, int, unsigned long long*, float*, cudaStream_t);
 int launch_ringbench(const void*, unsigned long long, int, int, int, int, unsigned long long*, cudaStream_t);
@@ -155,7 +156,7 @@ DDMI_API int ddmi_decode_image_noise(const ddmi_plane_t planes[3], int32_t batch
     DDMI_REQUIRE(!f16f8 || (weights->reserved & 1), "DDMI_PREC_F16F8 weights must be packed for CTA pairs");
     return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm, weights->gemm_bytes,
                              weights->program_host, weights->program_words, weights->program, weights->vec,
-                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, na, st);
+                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, na, (weights->reserved >> 1) & 1, st);
   }
   set_error("unknown precision %d", weights->precision);
   return DDMI_ERR_UNSUPPORTED;
@@ -356,6 +357,12 @@ DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const floa
   DDMI_REQUIRE(n_bins >= 2 && n_bins <= 1024, "n_bins must be in [2, 1024] (got %d)", n_bins);
   DDMI_REQUIRE(n_rays <= 4LL * 2147483647LL, "too many rays for one launch");
   return launch_sample_pdf(bins, weights, u, n_rays, n_bins, n_samples, out, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_selftest_tma(const float* plane, int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t x,
+                               int32_t y, int32_t c, int32_t variant, void* map_dev, float* out, void* stream) {
+  DDMI_REQUIRE(plane && out && (variant == 0 || map_dev), "plane / out / map_dev is NULL");
+  return launch_tma_selftest(plane, batch, channels, height, width, x, y, c, variant, map_dev, out, (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_selftest_umma(const float* a, const float* b, float* d, int32_t N, int32_t K, void* stream) {

@@ -29,7 +29,9 @@
 // (align_corners=false, border) straight into the A-operand layout (bf16 hi/lo), 13 GEMM groups,
 // epilogues = the reference's fused_bias_act (op/fused_bias_act_kernel.cu:28-47) + residuals,
 // ToRGB as an N=16 block.
+#include <string.h>
 #include "umma_engine.cuh"
+#include "tma.cuh"
 #include "decode_umma_occ.cuh"
 #include "decode_umma_nerf.cuh"
 #include "decode_umma_video.cuh"
@@ -144,13 +146,25 @@ using ImgL = Layout<0, 98304>;
 #else
 using ImgL = Layout<8>;
 #endif
+// Plane patches for coherent query tiles (regular grids): when the bilinear taps of a tile's 128 coordinates fall inside a
+// PATCH_W x PATCH_H texel window of the plane, ONE 3-D TMA load (box PATCH_W x PATCH_H x 64 channels = 32 KB, straight from the
+// NCHW plane the VAE decoder emits) stages the window in the X region and every thread blends its row from shared memory --
+// instead of 4 x 32 scalar L2 loads per thread (1024^2 / 2048^2 grids on 64^2 .. 256^2 planes: windows of 9 .. 34 x 2 texels).
+// The coordinates are still taken literally from the caller's tensor: the window is the bounding box of the actual taps, and a
+// tile whose taps do not fit (scattered queries, tiles that straddle image rows, native-resolution grids) gathers as before.
+constexpr int PATCH_W = 64, PATCH_H = 2, PATCH_BYTES = PATCH_W * PATCH_H * 64 * 4;
+static_assert(PATCH_BYTES <= 2 * 8 * KG_BYTES * 2, "the patch is staged in the X region");
+constexpr int IMG_OFF_PBAR = TMEM_SLOT + 8;                        // inside the barrier block
+constexpr int IMG_OFF_SCRATCH = BAR_BYTES;                         // 8 warps x {xmin, xmax, ymin, ymax}
+constexpr int IMG_SMEM = ImgL::SMEM_BYTES + 128;
 
 template <int PAIR, int SCHEME, int NOISE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
                   const __grid_constant__ ProgramParam prog, const float* __restrict__ vec, void* __restrict__ out, int store,
-                  NoiseArgs na) {
+                  NoiseArgs na, const __grid_constant__ CUtensorMap pmap0, const __grid_constant__ CUtensorMap pmap1,
+                  const __grid_constant__ CUtensorMap pmap2, int patch_mask) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase + ImgL::KG_HHI * KG_BYTES, h_lo = sbase + ImgL::KG_HLO * KG_BYTES;
@@ -160,6 +174,9 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   constexpr int C = 64;
+  const uint32_t pbar = bar + IMG_OFF_PBAR;               // plane-patch (TMA) completion barrier
+  int* pscratch = reinterpret_cast<int*>(smem + ImgL::OFF_BAR + IMG_OFF_SCRATCH);
+  if (tid == 32) mbar_init(pbar, 1);                      // published by engine_begin's barrier init fence + sync
   const uint32_t tmem = engine_begin<PAIR, SCHEME>(smem, ImgL::OFF_BAR);
 
   // work split: CTA (or CTA pair) w of W takes iterations w, w + W, ...; a pair iteration = tiles 2u and 2u + 1
@@ -185,7 +202,97 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     // `part` 0 / 1 = first / second 16 of this thread's 32 channels (-1: both): the two halves are issued in two different
     // idle windows of the epilogue threads (after the conv1 and after the conv2 epilogue, while conv2 / conv3 run on the
     // tensor core), so the L2-latency-bound gather delays neither epilogue by much
-    auto gather = [&](long long tile, int s, int part) {
+    // ---- staged path state: decided in the first gather window, used in the second
+    bool pf_fits = false;
+    int pf_x = 0, pf_y = 0;
+    Tap pf_tap;
+    uint32_t ph_patch = 0;
+    // this thread's tap + the tile's tap window (bounding box over the 128 rows); true if a patch load covers it
+    auto patch_plan = [&](long long tile, int s) {
+      if (tile > total_tiles - 1) tile = total_tiles - 1;
+      long long gi = (tile % tiles_per_item) * TILE + row;
+      if (gi > n - 1) gi = n - 1;
+      const int W = ps.w[s];
+      pf_tap = make_tap<false>(__ldg(cx + gi), __ldg(cy + gi), ps.h[s], W);
+      const int x0 = pf_tap.o00 % W, y0 = pf_tap.o00 / W, x1 = pf_tap.o11 % W, y1 = pf_tap.o11 / W;
+      const int xmn = __reduce_min_sync(0xffffffffu, x0), xmx = __reduce_max_sync(0xffffffffu, x1);
+      const int ymn = __reduce_min_sync(0xffffffffu, y0), ymx = __reduce_max_sync(0xffffffffu, y1);
+      if (lane == 0) {
+        pscratch[warp * 4 + 0] = xmn; pscratch[warp * 4 + 1] = xmx; pscratch[warp * 4 + 2] = ymn; pscratch[warp * 4 + 3] = ymx;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int a = pscratch[0], bq = pscratch[1], c2 = pscratch[2], d = pscratch[3];
+#pragma unroll
+      for (int w8 = 1; w8 < 8; ++w8) {
+        a = min(a, pscratch[w8 * 4]); bq = max(bq, pscratch[w8 * 4 + 1]);
+        c2 = min(c2, pscratch[w8 * 4 + 2]); d = max(d, pscratch[w8 * 4 + 3]);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // the scratch may be rewritten
+      a &= ~3;                                            // TMA: the window's first texel must sit on a 16-byte boundary
+      pf_x = a; pf_y = c2;
+      pf_fits = ((patch_mask >> s) & 1) && (bq - a < PATCH_W) && (d - c2 < PATCH_H);
+    };
+    // X <- features of scale s blended from a TMA-staged plane window (all 32 channels of this thread)
+    // the window load is issued in the first gather window (X is free from there on), the blend runs in the second
+    auto patch_issue = [&](long long tile, int s) {
+      if (tile > total_tiles - 1) tile = total_tiles - 1;
+      const int b = (int)(tile / tiles_per_item);
+      if (tid == 0) {
+        mbar_expect_tx(pbar, PATCH_BYTES);
+        tma::load_3d(x_hi, s == 0 ? &pmap0 : (s == 1 ? &pmap1 : &pmap2), pf_x, pf_y, b * C, pbar);
+      }
+    };
+    auto gather_staged = [&](long long tile, int s) {
+      const long long g0 = prof_clock();
+      trace(tr, 0x20, trn, 0);
+      mbar_wait(pbar, ph_patch);
+      ph_patch ^= 1;
+      const int W = ps.w[s];
+      const int rx0 = pf_tap.o00 % W - pf_x, ry0 = pf_tap.o00 / W - pf_y, rx1 = pf_tap.o11 % W - pf_x, ry1 = pf_tap.o11 / W - pf_y;
+      const float* P = reinterpret_cast<const float*>(smem + ImgL::KG_XHI * KG_BYTES) + (size_t)(ghalf * 32) * (PATCH_H * PATCH_W);
+      const int i00 = ry0 * PATCH_W + rx0, i01 = ry0 * PATCH_W + rx1, i10 = ry1 * PATCH_W + rx0, i11 = ry1 * PATCH_W + rx1;
+      float y[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float* pc = P + c * (PATCH_H * PATCH_W);
+        float acc = pc[i00] * pf_tap.w00;                   // the order of tap_sample(): results are bit-identical to the direct path
+        acc = fmaf(pc[i01], pf_tap.w01, acc);
+        acc = fmaf(pc[i10], pf_tap.w10, acc);
+        acc = fmaf(pc[i11], pf_tap.w11, acc);
+        y[c] = acc;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // every thread has read the window: X may be overwritten
+      if (SCHEME) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float2 y2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y2[i] = make_float2(y[g * 16 + 2 * i], y[g * 16 + 2 * i + 1]);
+          uint4 a16[2], r8, a8;
+          split16_f16f8(y2, a16, r8, a8);
+          const uint32_t off = (uint32_t)(ghalf * 4 * KG_BYTES + row * 16);
+          st_shared_v4(x_hi + off + (2 * g) * KG_BYTES, a16[0]);
+          st_shared_v4(x_hi + off + (2 * g + 1) * KG_BYTES, a16[1]);
+          st_shared_v4(x_lo + off + g * KG_BYTES, r8);
+          st_shared_v4(x_lo + off + (2 + g) * KG_BYTES, a8);
+        }
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float y8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y8[i] = y[g * 8 + i];
+          uint4 hi, lo;
+          split8(y8, hi, lo);
+          const uint32_t off = (uint32_t)((ghalf * 4 + g) * KG_BYTES + row * 16);
+          st_shared_v4(x_hi + off, hi);
+          st_shared_v4(x_lo + off, lo);
+        }
+      }
+      p_gather += prof_clock() - g0;
+      trace(tr, 0x21, trn, 0);
+    };
+    auto gather_direct = [&](long long tile, int s, int part) {
       const long long g0 = prof_clock();
       if (dbg(4)) return;
       trace(tr, 0x20, trn, 0);
@@ -229,6 +336,21 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       }
       p_gather += prof_clock() - g0;
       trace(tr, 0x21, trn, 0);
+    };
+    // first window (part 0): decide; direct gathers take their first half now, staged ones wait for the second window
+    // (the X region is the staging buffer, and one TMA round trip + 32 channels from shared memory fit there easily)
+    auto gather = [&](long long tile, int s, int part) {
+      if (part != 1) {
+        const long long g0 = prof_clock();
+        patch_plan(tile, s);
+        if (pf_fits) patch_issue(tile, s);
+        p_gather += prof_clock() - g0;
+      }
+      if (pf_fits) {
+        if (part != 0) gather_staged(tile, s);
+      } else {
+        gather_direct(tile, s, part);
+      }
     };
     // make this warp's smem / TMEM writes visible to the MMA warp (of the leader CTA), then signal one quarter
     auto signal = [&](int q) {
@@ -412,7 +534,7 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
                       const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                       const uint32_t* program_dev, const float* vec, size_t vec_floats, void* out, int store, int pair,
-                      int f16f8, const NoiseArgs& na, cudaStream_t st) {
+                      int f16f8, const NoiseArgs& na, int no_patch, cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
     set_error("tcgen05 image kernel is built for 64-channel planes");
@@ -441,9 +563,17 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   const int tpi_i = (int)tpi;
   const long long work = (total + 1) / 2, npairs = work < sms / 2 ? work : sms / 2;
   const unsigned ctas = pair ? (unsigned)(2 * npairs) : (unsigned)(total < sms ? total : sms);
+  // plane windows through TMA where the plane layout allows a tensor map (16-byte aligned base, width a multiple of 4)
+  CUtensorMap pm[3];
+  int patch_mask = 0;
+  memset(pm, 0, sizeof(pm));
+  if (!no_patch) {
+    for (int s = 0; s < 3; ++s)
+      if (tma::make_plane_map(&pm[s], ps.data[s], batch, C, ps.h[s], ps.w[s], PATCH_W, PATCH_H, 64)) patch_mask |= 1 << s;
+  }
 #define DDMI_IMG_LAUNCH(P, S, Z)                                                                                          \
-  DDMI_CUDA(launch_engine(image_umma_kernel<P, S, Z>, P, ctas, ImgL::SMEM_BYTES, st, ps, cx, cy, n, tpi_i, total, ws, \
-                          pp, vec, out, store, na))
+  DDMI_CUDA(launch_engine(image_umma_kernel<P, S, Z>, P, ctas, IMG_SMEM, st, ps, cx, cy, n, tpi_i, total, ws, pp, vec, out, \
+                          store, na, pm[0], pm[1], pm[2], patch_mask))
   const int nz = na.mode != 0;
   if (pair && f16f8 && nz) { DDMI_IMG_LAUNCH(1, 1, 1); }
   else if (pair && f16f8) { DDMI_IMG_LAUNCH(1, 1, 0); }

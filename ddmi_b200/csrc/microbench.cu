@@ -12,8 +12,10 @@
 //   mode 6: convert    bf16 hi/lo split of 128 values per thread
 //   mode 7: publish    as mode 3 without the fence.proxy.async after each quarter
 //   mode 8: drain      one tcgen05.ld.32x32b.x32 + wait::ld at a time (4 dependent round trips)
+#include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
+#include "tma.cuh"
 
 namespace ddmi {
 namespace mbench {
@@ -266,6 +268,44 @@ int launch_gatherbench(int var, int u, const float* table, unsigned ntexel, int 
 #undef GB
   set_error("gatherbench: variant %d / unroll %d not built", var, u);
   return DDMI_ERR_UNSUPPORTED;
+}
+
+// Bring-up self test of the plane-window TMA path: one 64 x 2 x 64 box of an NCHW fp32 plane -> shared memory -> out.
+// variant 0: tensor map as a __grid_constant__ kernel parameter; 1: tensor map read from global memory.
+namespace mbench {
+__global__ void __launch_bounds__(128, 1)
+tma_selftest_kernel(const __grid_constant__ CUtensorMap pmap, const CUtensorMap* gmap, int x, int y, int c, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + 32768;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, 32768);
+    tma::load_3d(sbase, gmap ? gmap : &pmap, x, y, c, bar);
+  }
+  mbar_wait(bar, 0);
+  for (int i = threadIdx.x; i < 8192; i += 128) out[i] = reinterpret_cast<const float*>(smem)[i];
+}
+}  // namespace mbench
+
+int launch_tma_selftest(const float* plane, int batch, int C, int H, int W, int x, int y, int c, int variant, void* map_dev,
+                        float* out, cudaStream_t st) {
+  using namespace mbench;
+  CUtensorMap m;
+  memset(&m, 0, sizeof(m));
+  if (!tma::make_plane_map(&m, plane, batch, C, H, W, 64, 2, 64)) {
+    set_error("cuTensorMapEncodeTiled failed (or is unavailable) for a %dx%d plane", H, W);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  if (variant == 1) DDMI_CUDA(cudaMemcpyAsync(map_dev, &m, sizeof(m), cudaMemcpyHostToDevice, st));
+  DDMI_CUDA(cudaFuncSetAttribute(tma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 64));
+  tma_selftest_kernel<<<1, 128, 32768 + 64, st>>>(m, variant == 1 ? (const CUtensorMap*)map_dev : nullptr, x, y, c, out);
+  DDMI_CUDA(cudaGetLastError());
+  return DDMI_OK;
 }
 
 int launch_ringbench(const void* src, unsigned long long span_bytes, int slot_bytes, int nslots, int iters, int ctas,

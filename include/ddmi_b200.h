@@ -90,7 +90,8 @@ typedef struct {
 /* Host-folded, packed MLP weights (device memory). */
 typedef struct {
   int32_t precision;   /* DDMI_PREC_* */
-  int32_t reserved;    /* bit 0: tcgen05 stream is packed for CTA pairs ([half 0 | half 1] per K step) */
+  int32_t reserved;    /* bit 0: tcgen05 stream is packed for CTA pairs ([half 0 | half 1] per K step);
+                          bit 1: image decode: never stage plane windows with TMA (diagnostic: every tile gathers directly) */
   const void* gemm;    /* GEMM operands, layout per precision (device)            */
   uint64_t gemm_bytes;
   const float* vec;    /* fp32 vectors: biases, folded constants, small heads (device) */
@@ -232,6 +233,14 @@ DDMI_API int ddmi_nerf_render_z(const ddmi_plane_t planes[3], int32_t batch, int
  */
 DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays, int32_t n_bins,
                              int32_t n_samples, float* out, void* stream);
+
+/*
+ * Bring-up self test of the plane-window TMA path (cp.async.bulk.tensor.3d over an NCHW fp32 plane batch): the 64 (x) x 2 (y)
+ * x 64 (channel) box at element coordinates (x, y, c) -> out[64][2][64] fp32 (channel-major), out-of-range elements 0.
+ * variant 0 hands the tensor map to the kernel as a parameter, 1 through `map_dev` (128 B of device memory, 64-byte aligned).
+ */
+DDMI_API int ddmi_selftest_tma(const float* plane, int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t x,
+                               int32_t y, int32_t c, int32_t variant, void* map_dev, float* out, void* stream);
 
 /*
  * Bring-up self test of the tcgen05 path: one 128 x N x K bf16 GEMM through the

@@ -461,6 +461,47 @@ def test_f16f8_selftest(N, K):
     assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("x,y,c", [(0, 0, 0), (36, 5, 64), (100, 127, 64), (124, 126, 0)])
+def test_tma_plane_window_selftest(x, y, c, variant):
+    """cp.async.bulk.tensor.3d over an NCHW fp32 plane batch: a 64 x 2 x 64-channel box at (x, y, channel c); texels outside the
+    plane read as 0 (windows at the right / bottom edge)."""
+    from ddmi_b200 import _lib
+    B, C, H, W = 2, 64, 128, 128
+    plane = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(3)).to(DEV)
+    out = torch.full((64, 2, 64), float('nan'), device=DEV)
+    mapd = torch.zeros(64, dtype=torch.int32, device=DEV)
+    _lib.check(_lib.lib().ddmi_selftest_tma(plane.data_ptr(), B, C, H, W, x, y, c, variant, mapd.data_ptr(), out.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = torch.zeros(64, 2, 64, device=DEV)
+    xs, ys = min(64, W - x), min(2, H - y)
+    ref[:, :ys, :xs] = plane.reshape(B * C, H, W)[c:c + 64, y:y + ys, x:x + xs]
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("precision", ["f16f8", "bf16x3"])
+@pytest.mark.parametrize("R,sizes,span", [(512, (64, 128, 256), 1.0), (1024, (64, 128, 256), 1.0), (320, (32, 64, 128), 1.25),
+                                          (256, (18, 36, 72), 1.0), (200, (64, 128, 256), 1.0)])
+def test_image_tma_staged_windows_match_the_direct_gather(R, sizes, span, precision, monkeypatch):
+    """Regular grids take their plane windows through TMA (decode_umma.cu: patch_plan / gather_staged); the blend order is the
+    direct gather's, so both paths must agree BIT FOR BIT -- on grids that reach past [-1, 1] (border clamp), on plane widths
+    TMA cannot map (18: not a multiple of 4 -> direct), and on row lengths that make tiles straddle image rows (200)."""
+    g = torch.Generator().manual_seed(R)
+    m = cases.build_module('image').to(DEV)
+    m.precision = precision
+    planes = _cuda([torch.randn(2, 64, s, s, generator=g) for s in sizes])
+    e = span * (R - 1) / R
+    coords = ddmi_b200.convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(DEV)
+    monkeypatch.setenv("DDMI_B200_NO_TMA_PATCH", "0")
+    staged = m(coords, hdbf=planes, si=0.5)
+    monkeypatch.setenv("DDMI_B200_NO_TMA_PATCH", "1")
+    direct = m(coords, hdbf=planes, si=0.5)
+    assert torch.equal(staged, direct)
+    m.precision = 'fp32'
+    assert float((staged - m(coords, hdbf=planes, si=0.5)).abs().max()) < TOL
+
+
 # ---------------------------------------------------------------- size-independent properties at larger shapes
 @pytest.mark.parametrize("scheme", ["bf16x3", "f16f8"])
 def test_image_full_size_cross_check_and_crop_independence(scheme):
