@@ -147,7 +147,8 @@ def weights_struct(packed):
     """packed: packing.Packed (precision, gemm tensor, vec tensor)."""
     w = Weights()
     w.precision = packed.precision
-    w.reserved = (1 if getattr(packed, "pair", False) else 0) | (2 if os.environ.get("DDMI_B200_NO_TMA_PATCH") == "1" else 0)
+    w.reserved = ((1 if getattr(packed, "pair", False) else 0) | (2 if os.environ.get("DDMI_B200_NO_TMA_PATCH") == "1" else 0)
+                  | (4 if getattr(packed, "ts", False) else 0))
     w.gemm = packed.gemm.data_ptr()
     w.gemm_bytes = packed.gemm.numel() * packed.gemm.element_size()
     w.vec = packed.vec.data_ptr()

@@ -417,7 +417,8 @@ DDMI_API int ddmi_debug_ringbench(const void* src, uint64_t span_bytes, int32_t 
 }
 
 DDMI_API int ddmi_debug_microbench(int32_t mode, int32_t iters, const float* seed, uint64_t* out_dev, float* sink_dev, void* stream) {
-  DDMI_REQUIRE(mode >= 0 && mode <= 8 && iters >= 1, "mode must be 0..8 and iters >= 1");
+  DDMI_REQUIRE(((mode >= 0 && mode <= 8) || (mode >= 100 && mode < 132) || (mode >= 200 && mode < 232)) && iters >= 1,
+               "mode must be 0..8 (epilogue blocks) or 100.. / 200.. + variant (tcgen05.mma rate) and iters >= 1");
   DDMI_REQUIRE(seed && out_dev && sink_dev, "seed (1024 floats) / out_dev (2 x u64) / sink_dev (256 floats) is NULL");
   return launch_microbench(mode, iters, seed, (unsigned long long*)out_dev, sink_dev, (cudaStream_t)stream);
 }

@@ -74,12 +74,20 @@ __device__ __forceinline__ float2 image_act(float2 t, float2 b) {
   return bias_lrelu_pair(t, b, 0.2f);
 }
 // NOISE: nz = noise.weight (x activation gain) * noise[b, row] of this StyledConv, added to every column before the bias.
-template <int MODE, int SCHEME, int NOISE, class Signal>
+// N split: a layer's GEMM group may finish its output columns 0..127 (COMMIT 0) a K-half before columns 128..255
+// (COMMIT 1) -- see packing.pack_image.  The stage is entered after COMMIT 0: it drains and publishes the first half
+// (quarters 0, 1: the operand columns 0..127 they overwrite are dead by then, the program reads them in the first K-half
+// only), waits for COMMIT 1 after quarter 0 (`wait_b`), drains the second half, reports the accumulator free (`drained`:
+// operand barrier 4) and carries on with quarters 1..3.  With an unsplit program both commits arrive together.
+template <int MODE, int SCHEME, int NOISE, class Signal, class WaitB, class Drained>
 __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, uint32_t h_lo, int row, int sub,
                                             const float* __restrict__ bias, const float* __restrict__ cs,
-                                            StagePrefetch& pf, Signal signal, float nz, bool tr, uint32_t& trn) {
+                                            StagePrefetch& pf, Signal signal, WaitB wait_b, Drained drained, float nz, bool tr,
+                                            uint32_t& trn) {
   constexpr bool WITH_CS = (MODE == 1 || MODE == 2);
   if (dbg(1)) {
+    wait_b();
+    drained();
 #pragma unroll
     for (int q = 0; q < 4; ++q) signal(q);
     return;
@@ -91,12 +99,19 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
   }
   float2 v[4][16];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
+  for (int q = 0; q < 2; ++q) tmem_ld32(tmem_lane + q * 64 + sub * 32, v[q]);
   tmem_ld_wait();
-  trace(tr, 0x03, trn, 0);                              // accumulator drained
+  trace(tr, 0x03, trn, 0);                              // first accumulator half drained
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int col0 = q * 64 + sub * 32;
+    if (q == 1) {
+      wait_b();
+#pragma unroll
+      for (int q2 = 2; q2 < 4; ++q2) tmem_ld32(tmem_lane + q2 * 64 + sub * 32, v[q2]);
+      tmem_ld_wait();
+      drained();
+    }
     float2 bn[16], cn[16];
     if (q < 3) {                                        // next quarter's vectors: in flight during this conversion
       load_vec<16>(bias + col0 + 64, bn);
@@ -361,19 +376,36 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       trace(tr, 0x10 + q, trn, 0);
       if (q == 3) p_epi += prof_clock() - p_t;
     };
+    // the second accumulator half is in registers: operand barrier 4 (the program waits it before it writes columns 128..255)
+    auto drained = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_bar + 8 * 4);
+      trace(tr, 0x14, trn, 0);
+    };
     auto signal_all = [&]() {
+      drained();
 #pragma unroll
       for (int q = 0; q < 4; ++q) signal(q);
     };
-    auto wait_mma = [&]() {
+    auto wait_mma = [&]() {                               // COMMIT 0: output columns 0..127 (or the whole group) are complete
       const long long w0 = prof_clock();
       trace(tr, 0x01, trn, 0);
       mbar_wait(bar + BAR_MMADONE, ph_mma);
-      ph_mma ^= 1;
       tc_fence_after();
       trace(tr, 0x02, trn, 0);
       p_t = prof_clock();
       p_wait += p_t - w0;
+    };
+    auto wait_b = [&]() {                                 // COMMIT 1: columns 128..255 too
+      const long long w0 = prof_clock();
+      mbar_wait(bar + BAR_MMADONE + 8, ph_mma);
+      ph_mma ^= 1;
+      tc_fence_after();
+      trace(tr, 0x04, trn, 0);
+      const long long w1 = prof_clock();
+      p_wait += w1 - w0;
+      p_t += w1 - w0;
     };
 
     if (ntiles > 0) gather(tile_of(0), 0, -1);
@@ -398,26 +430,27 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
         StagePrefetch pf;
         stage_prefetch<false>(pf, bv, nullptr, sub);
         wait_mma();
-        image_stage<0, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal, nz[0], tr, trn);
+        image_stage<0, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv, nullptr, pf, signal, wait_b, drained, nz[0], tr, trn);
         // the PE buffer is free now: prefetch the next scale (or the next tile's coarse scale), first half of the channels
         if (blk < 2) gather(tile, blk + 1, 0);
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
         // ---- conv2
         stage_prefetch<false>(pf, bv + 256, nullptr, sub);
         wait_mma();
-        image_stage<0, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal, nz[1], tr, trn);
+        image_stage<0, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 256, nullptr, pf, signal, wait_b, drained, nz[1], tr, trn);
         if (blk < 2) gather(tile, blk + 1, 1);                                   // second half, under conv3's GEMM
         else if (blk == 2 && it + 1 < ntiles) gather(tile_of(it + 1), 0, 1);
         // ---- conv3 + skip
         if (blk < 3) stage_prefetch<true>(pf, bv + 512, bv + 768, sub);
         else stage_prefetch<false>(pf, bv + 512, nullptr, sub);
         wait_mma();
-        if (blk < 2) image_stage<1, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, nz[2], tr, trn);
-        else if (blk == 2) image_stage<2, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, nz[2], tr, trn);
-        else image_stage<3, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal, nz[2], tr, trn);
+        if (blk < 2) image_stage<1, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, wait_b, drained, nz[2], tr, trn);
+        else if (blk == 2) image_stage<2, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, bv + 768, pf, signal, wait_b, drained, nz[2], tr, trn);
+        else image_stage<3, SCHEME, NOISE>(tmem_lane, h_hi, h_lo, row, sub, bv + 512, nullptr, pf, signal, wait_b, drained, nz[2], tr, trn);
       }
       // ---- ToRGB: acc1[:, 0:16]
       wait_mma();
+      wait_b();
       if (sub == 0 && tile < total_tiles) {
         float2 v[8];
         tmem_ld16(tmem_lane, v);   // only columns 0..2 are meaningful

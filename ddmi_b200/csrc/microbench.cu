@@ -318,8 +318,99 @@ int launch_ringbench(const void* src, unsigned long long span_bytes, int slot_by
   return DDMI_OK;
 }
 
+
+// tcgen05.mma issue / execution rate in the decode kernels' configuration (CTA pair, M = 256, operands zero-filled):
+// one elected thread of the leader issues `iters` rounds of 8 MMAs and one commit per round, then waits for the last commit.
+//   variant bit 0: N = 128 instead of 256      bit 1: A operand in tensor memory (TS) instead of shared memory (SS)
+//   bit 2: FP8 (kind::f8f6f4, K = 32) instead of fp16 (kind::f16, K = 16)    bit 3: the f16f8 mix (f16 f16 f8 f8) x 2
+//   bit 4: 8 other warps store to shared memory (st.shared.v4, A-operand-like pattern) for the duration
+// out[0] = cycles from the first issue to the completion of the last commit, out[1] = MMAs issued.
+namespace mbench {
+constexpr int MM_A = 0, MM_B = 65536, MM_ST = 65536 + 16384, MM_BAR = MM_ST + 65536, MM_SMEM = MM_BAR + 64;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+mmabench_kernel(int variant, int iters, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar = sbase + MM_BAR;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = tid; i < MM_BAR / 16; i += 320) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  volatile int* flag = reinterpret_cast<volatile int*>(smem + MM_BAR + 32);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    *flag = 0;
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc2(bar + 16, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + MM_BAR + 16);
+  const int n = (variant & 1) ? 128 : 256, nloc = n / 2;
+  const bool ts = variant & 2, f8 = variant & 4, mix = variant & 8, stores = variant & 16;
+  if (warp == 9 && rank == 0) {
+    constexpr uint64_t kDescHi = ((uint64_t)(128 >> 4) | (1ull << 14)) << 32;
+    const uint32_t idesc16 = idesc_f16_f32(256, 0) | ((uint32_t)n << 14), idesc8 = idesc_f8_f32(256, 0) | ((uint32_t)n << 14);
+    const uint32_t a_lo = ((sbase + MM_A) >> 4) | ((2048 >> 4) << 16);
+    const uint32_t b_lo = ((sbase + MM_B) >> 4) | ((uint32_t)nloc << 16);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool use8 = mix ? ((j & 3) >= 2) : f8;
+          const uint64_t bd = kDescHi | (b_lo + (uint32_t)(j & 3) * (uint32_t)(nloc * 2));
+          const uint32_t acc = tmem + ((variant & 1) ? (uint32_t)(j & 1) * 128u : 0u);
+          if (ts) {
+            if (use8) mma2_f8_ts(acc, tmem + 256 + j * 8, bd, idesc8, 1u);
+            else mma2_bf16_ts(acc, tmem + 256 + j * 8, bd, idesc16, 1u);
+          } else {
+            const uint64_t ad = kDescHi | (a_lo + (uint32_t)j * (4096 >> 4));
+            if (use8) mma2_f8(acc, ad, bd, idesc8, 1u);
+            else mma2_bf16(acc, ad, bd, idesc16, 1u);
+          }
+        }
+        if (it == iters - 1) mma2_commit_mc(bar, 3);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    *flag = 1;
+    if ((tid & 31) == 0 && blockIdx.x == 0) {
+      out[0] = (unsigned long long)(t1 - t0);
+      out[1] = (unsigned long long)iters * 8ull;
+    }
+  } else if (warp == 9) {
+    mbar_wait(bar, 0);
+    *flag = 1;
+  } else if (warp < 8 && stores) {
+    const int row = tid & 127;
+    uint32_t k = 0;
+    while (*flag == 0) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) st_shared_v4(sbase + MM_ST + ((k + g) & 31) * 2048 + row * 16, make_uint4(k, g, row, tid));
+      k += 8;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 9) tmem_dealloc2(tmem, 512);
+}
+}  // namespace mbench
+
 int launch_microbench(int mode, int iters, const float* seed, unsigned long long* out, float* sink, cudaStream_t st) {
   using namespace mbench;
+  if (mode >= 100) {     // tcgen05.mma rate: 100 + variant on one CTA pair, 200 + variant on every SM
+    const int full = mode >= 200, variant = mode - (full ? 200 : 100);
+    DDMI_CUDA(cudaFuncSetAttribute(mmabench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MM_SMEM));
+    int sms = 0;
+    DDMI_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    mmabench_kernel<<<full ? (sms / 2) * 2 : 2, 320, MM_SMEM, st>>>(variant, iters, out);
+    DDMI_CUDA(cudaGetLastError());
+    return DDMI_OK;
+  }
   DDMI_CUDA(cudaFuncSetAttribute(microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MB_SMEM));
   microbench_kernel<<<1, 288, MB_SMEM, st>>>(mode, iters, seed, out, sink);
   DDMI_CUDA(cudaGetLastError());

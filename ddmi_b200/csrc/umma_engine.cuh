@@ -25,7 +25,7 @@ constexpr uint32_t OP_UNIT = 0, OP_WAIT = 1, OP_COMMIT = 2, OP_END = 3;
 // (ULDC) straight into uniform registers, so the whole decode -> descriptor -> tcgen05.mma chain of the issuer stays on the
 // uniform datapath.  Fetched with __ldg from global memory the ops landed in vector registers and every descriptor paid an
 // R2UR move: ~350 cycles per 4-MMA iteration, i.e. the issuer -- not the tensor pipe -- paced the kernel.
-constexpr int PROG_MAX = 192;
+constexpr int PROG_MAX = 256;
 struct ProgramParam {
   uint32_t op[PROG_MAX];
 };
@@ -109,10 +109,12 @@ __device__ __forceinline__ void producer_loop(const uint32_t* __restrict__ progr
       const uint32_t kind = op & 3;
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
-      const uint32_t bytes = op_n(op) * (PAIR ? 32 : 64);    // this CTA's share of one K step
+      // this CTA's share of one K step; half-width units (op bit 30, f16f8): of one 32-wide step PAIR of the 128-row block
+      const bool half = SCHEME && ((op >> 30) & 1);
+      const uint32_t bytes = half ? 8192u : op_n(op) * (PAIR ? 32 : 64);
       const int cnt = (int)((op >> 24) & 31) + 1;
       if (SCHEME) {
-        for (int j = 0; j < cnt; j += 2) {
+        for (int j = 0; j < cnt; j += half ? 4 : 2) {
           const uint32_t full = bar + BAR_WFULL + 8 * slot;
           mbar_wait(bar + BAR_WEMPTY + 8 * slot + 8, ph ^ 1);
           if (elect_one()) {
@@ -152,7 +154,8 @@ __device__ __forceinline__ void forward_loop(const uint32_t* __restrict__ progra
       if (kind == OP_END) break;
       if (kind != OP_UNIT) continue;
       const int cnt = (int)((op >> 24) & 31) + 1;
-      for (int j = 0; j < cnt; j += SCHEME ? 2 : 1) {
+      const int per_unit = SCHEME ? (((op >> 30) & 1) ? 4 : 2) : 1;
+      for (int j = 0; j < cnt; j += per_unit) {
         mbar_wait(bar + BAR_WFULL + 8 * slot, ph);
         if (elect_one()) mbar_arrive_remote(leader_pfull + 8 * slot);
         slot += SCHEME ? 2 : 1;
@@ -209,7 +212,12 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
         uint32_t ahi32 = a_in_tmem ? tmem + ((op >> 8) & 0xFF) * 4 : a_lo32 + ((op >> 8) & 0xFF) * (KG_BYTES >> 4);
         uint32_t alo32 = a_in_tmem ? tmem + ((op >> 16) & 0xFF) * 4 : a_lo32 + ((op >> 16) & 0xFF) * (KG_BYTES >> 4);
         uint32_t accum = (op >> 4) & 1;
-        const int units = ((int)((op >> 24) & 31) + 1) / (int)USLOTS;             // hand-shake units in this run
+        // half-width units (op bit 30; f16f8, N = 128): a hand-shake unit is still two 8 KB slots, but each slot holds one
+        // 32-wide step PAIR of the 128-row block ([w16 | FP8] of its two steps, 2 KB each per CTA), i.e. the unit covers 64
+        // K columns in 8 MMAs of half the length -- the N split that lets half of a layer's output columns finish early
+        const bool half = SCHEME && ((op >> 30) & 1);
+        const uint32_t ustep = half ? 2 * USLOTS : USLOTS;                          // 16-wide A steps per hand-shake unit
+        const int units = ((int)((op >> 24) & 31) + 1) / (int)ustep;              // hand-shake units in this run
         trace(tr, 0x100 + pc, trn, kTraceRegion);                                // UNIT starts
         for (int j = 0; j < units; j += CH) {
           const int nu = units - j < CH ? units - j : CH;
@@ -253,7 +261,28 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
                   // slot: [w16: 2 K groups | FP8: 2 K groups] x nloc rows x 16 B
                   const uint64_t b16_0 = kDescHi | w0lo, b8_0 = kDescHi | (w0lo + nloc * 2);
                   const uint64_t b16_1 = kDescHi | w1lo, b8_1 = kDescHi | (w1lo + nloc * 2);
-                  if (a_in_tmem) {
+                  if (half) {
+                    // slot s: steps 0, 1; slot s + 1: steps 2, 3 -- each [w16 step 0 | FP8 even | w16 step 1 | FP8 odd] x 64 rows
+                    if (!skip_mma) {
+#pragma unroll
+                      for (uint32_t p2 = 0; p2 < 2; ++p2) {
+                        const uint32_t base = w0lo + p2 * (SLOT_BYTES >> 4);
+                        const uint64_t c16_0 = kDescHi | base, c8_0 = kDescHi | (base + 128);
+                        const uint64_t c16_1 = kDescHi | (base + 256), c8_1 = kDescHi | (base + 384);
+                        if (a_in_tmem) {
+                          mma2_bf16_ts(acc, ah + (2 * p2) * a_step, c16_0, idesc, p2 ? 1u : ac);
+                          mma2_bf16_ts(acc, ah + (2 * p2 + 1) * a_step, c16_1, idesc, 1u);
+                          mma2_f8_ts(acc, al + (2 * p2) * a_step, c8_0, idesc8, 1u);       // r8 x w8
+                          mma2_f8_ts(acc, al + (2 * p2 + 1) * a_step, c8_1, idesc8, 1u);   // a8 x s8
+                        } else {
+                          mma2_bf16(acc, kDescHi | (ah + (2 * p2) * a_step), c16_0, idesc, p2 ? 1u : ac);
+                          mma2_bf16(acc, kDescHi | (ah + (2 * p2 + 1) * a_step), c16_1, idesc, 1u);
+                          mma2_f8(acc, kDescHi | (al + (2 * p2) * a_step), c8_0, idesc8, 1u);       // r8 x w8
+                          mma2_f8(acc, kDescHi | (al + (2 * p2 + 1) * a_step), c8_1, idesc8, 1u);   // a8 x s8
+                        }
+                      }
+                    }
+                  } else if (a_in_tmem) {
                     mma2_bf16_ts(acc, ah, b16_0, idesc, ac);          // kind::f16 with fp16 formats (idesc)
                     mma2_bf16_ts(acc, ah + a_step, b16_1, idesc, 1u);
                     mma2_f8_ts(acc, al, b8_0, idesc8, 1u);               // r8 x w8
@@ -285,8 +314,8 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
                   }
                 }
                 ac = 1u;
-                ah += USLOTS * a_step;
-                al += USLOTS * a_step;
+                ah += ustep * a_step;
+                al += ustep * a_step;
                 s += USLOTS;
                 if (s == NSLOT) s = 0;
               }
@@ -294,8 +323,8 @@ __device__ __forceinline__ void mma_loop(const uint32_t* __restrict__ program, u
           }
           // every lane advances the (warp-uniform) run state
           accum = 1u;
-          ahi32 += (uint32_t)nu * USLOTS * a_step;
-          alo32 += (uint32_t)nu * USLOTS * a_step;
+          ahi32 += (uint32_t)nu * ustep * a_step;
+          alo32 += (uint32_t)nu * ustep * a_step;
           for (int u = 0; u < nu; ++u) {
             slot += USLOTS;
             if (slot == NSLOT) { slot = 0; ph ^= 1; }

@@ -35,6 +35,7 @@ class Packed:
     program_host: torch.Tensor = None   # same, host copy (validated by the launcher)
     pair: bool = False                  # bf16x3: stream packed for CTA pairs ([half 0 | half 1] per K step)
     noise_active: bool = False          # image: some NoiseInjection.weight is non-zero (the decode needs a noise source)
+    ts: bool = False                    # image, f16f8: program of the TMEM-resident-activation kernel (image_ts_kernel)
 
 
 class UmmaProgram:
@@ -62,20 +63,27 @@ class UmmaProgram:
         self.scheme = scheme
         assert scheme in ('bf16x3', 'f16f8') and (scheme == 'bf16x3' or pair)
 
-    def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None, a_in_tmem=False):
+    def block(self, W, a_hi_kg, a_lo_kg, acc_col, first, n_pad=None, a_in_tmem=False, half=False):
         """acc[:, acc_col:acc_col+N] (+)= A[:, K] @ W.T ; W is (N, K), K zero-padded to 16.  a_in_tmem: the A operand
-        lives in tensor memory (K group g = TMEM columns 4g..4g+3), CTA-pair kernels only (op bit 29)."""
+        lives in tensor memory (K group g = TMEM columns 4g..4g+3), CTA-pair kernels only (op bit 29).
+        half (f16f8, N = 128, K a multiple of 64; op bit 30): a half-width unit of an N-split layer.  The stream then holds,
+        per 32-wide step pair, [CTA 0: step 0 | step 1][CTA 1: step 0 | step 1] (8 KB each), so one 8 KB ring slot = one
+        pair and the two-slot hand-shake unit covers 64 K columns (the engine copies whole 8 KB slots either way)."""
         n = W.shape[0] if n_pad is None else n_pad
         assert n in self.NCODE and acc_col % 64 == 0 and acc_col + n <= 512
         if self.scheme == 'f16f8':
             k32 = (W.shape[1] + 31) // 32
             assert 1 <= k32 <= 16 and a_hi_kg + 4 * k32 <= 256 and a_lo_kg + 4 * k32 <= 256
             assert not a_in_tmem or 4 * (a_lo_kg + 4 * k32) <= 512
+            assert not half or (n == 128 and W.shape[1] % 64 == 0)
             self.ops.append(0 | (self.NCODE[n] << 2) | ((0 if first else 1) << 4) | ((acc_col // 64) << 5)
-                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((2 * k32 - 1) << 24) | ((1 if a_in_tmem else 0) << 29))
+                            | (a_hi_kg << 8) | (a_lo_kg << 16) | ((2 * k32 - 1) << 24) | ((1 if a_in_tmem else 0) << 29)
+                            | ((1 if half else 0) << 30))
             Wp = W.new_zeros(n, 32 * k32)
             Wp[:W.shape[0], :W.shape[1]] = W
-            halves = [f16f8_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)]).reshape(2 * k32, -1) for h in (0, 1)]
+            # per CTA half: (steps, bytes per step); half-width: regrouped per step pair
+            halves = [f16f8_kstep_blocks(Wp[h * (n // 2):(h + 1) * (n // 2)]).reshape(k32 if half else 2 * k32, -1)
+                      for h in (0, 1)]
             self.segs.append(torch.cat(halves, dim=1).reshape(-1))
             return
         k16 = (W.shape[1] + 15) // 16
@@ -313,10 +321,93 @@ def _noise_active(f):
     return any(float(d['nw'].abs().max()) != 0.0 for d in f['blocks'])
 
 
+def _pack_image_ts(f, dev):
+    """Program + stream of csrc/decode_umma.cu::image_ts_kernel (f16f8, CTA pairs): the 256-wide running activation H lives
+    in TENSOR memory (A-from-TMEM MMAs run at the tensor pipe's full rate, 136 cycles per 256 x 256 x 16 step; with the A
+    operand in shared memory the same step takes 162-173) next to ONE accumulator:
+      TMEM columns [0, 256) acc | [256, 384) H fp16 (K group g = columns 256 + 4g) | [384, 512) H FP8, per 32 columns [r8 x8 | a8 x8]
+      shared-memory K groups 64..79: the PE features X (SS units);  K groups 0..63: the parked skip values (epilogue threads only).
+    Every GEMM group is N-split, [a: K 0..127][b: K 0..127][X part, full width][a: K 128..255] COMMIT 0 [b: K 128..255] COMMIT 1
+    (a / b = output columns 0..127 / 128..255 as half-width units), so the epilogue threads convert and publish a's columns
+    while the tensor core still works on b's -- in place: operand columns 0..127 are dead once a's second K-half has run.
+    The skip GEMM of a block is its own group in front of conv1 (both read the block's input); its result is parked in shared
+    memory by the thread that will add it in conv3's epilogue.  ToRGB is evaluated by the epilogue threads in fp32.
+    Operand barriers: 0..3 = H quarters published (groups that follow a publishing stage), 5 / 4 = accumulator columns
+    0..127 / 128..255 drained (every group)."""
+    gain = math.sqrt(2.0)
+    HT16, HT8, XH, XL = 64, 96, 64, 72
+    P = UmmaProgram(pair=True, scheme='f16f8')
+    nsplit = os.environ.get('DDMI_B200_NSPLIT', 'full')
+    assert nsplit in ('mixed', 'full')
+
+    def group(W, k_h, k_x, published):
+        """W: (256, k_h + k_x); k_h in (0, 256) columns from H (TMEM), k_x in (0, 64) from X (shared memory)."""
+        waited = set()
+
+        def wait(*which):
+            for w in which:
+                if w not in waited:
+                    P.wait(w)
+                    waited.add(w)
+
+        def over_h(h, quarters, first):
+            rows = slice(128 * h, 128 * h + 128) if h is not None else slice(0, 256)
+            # maximal runs of quarters that need no new WAIT in between become one unit
+            runs = []
+            for q in quarters:
+                if (published and q not in waited) or not runs:
+                    runs.append([q])
+                else:
+                    runs[-1].append(q)
+            for r in runs:
+                if published:
+                    wait(r[0])
+                P.block(W[rows, 64 * r[0]:64 * r[-1] + 64], HT16 + 8 * r[0], HT8 + 8 * r[0], 0 if h is None else 128 * h,
+                        first and r[0] == quarters[0], a_in_tmem=True, half=h is not None)
+
+        if k_h:
+            if nsplit == 'full':
+                wait(5)
+                over_h(0, (0, 1), True)
+                wait(4)
+                over_h(1, (0, 1), True)
+            else:
+                wait(5, 4)
+                over_h(None, (0, 1), True)
+            if k_x:
+                P.block(W[:, k_h:k_h + k_x], XH, XL, 0, False)
+            over_h(0, (2, 3), False)
+            P.commit(0)
+            over_h(1, (2, 3), False)
+            P.commit(1)
+        else:                                  # block 0: X only
+            if published:
+                wait(0, 1, 2, 3)
+            wait(5)
+            P.block(W[0:128, 0:k_x], XH, XL, 0, True, half=True)
+            P.commit(0)
+            wait(4)
+            P.block(W[128:256, 0:k_x], XH, XL, 128, True, half=True)
+            P.commit(1)
+        assert not published or waited >= {0, 1, 2, 3}
+
+    for i, d in enumerate(f['blocks']):
+        k_h, k_x = (256 if i > 0 else 0), (64 if i < 3 else 0)
+        if d['Ws'] is not None:
+            group(d['Ws'], k_h, k_x, True)                    # skip -> parked
+        group(d['W1'] * gain, k_h, k_x, d['Ws'] is None)      # conv1 (follows the skip group: nothing new was published)
+        group(d['W2'] * gain, 256, 0, True)
+        group(d['W3'], 256, 0, True)
+    gemm, prog_dev, prog_host = P.finish(dev)
+    return Packed(PREC_F16F8, gemm, _image_vec(f, gain).to(dev), prog_dev, prog_host, True, _noise_active(f), ts=True)
+
+
 def pack_image(module, si, precision, pair=True):
     f = fold_image(module, si)
     dev = module_device(module)
     segs = []
+    if precision == PREC_F16F8 and pair and os.environ.get('DDMI_B200_IMAGE_TS', '0') != '0':
+        return _pack_image_ts(f, dev)
     if precision == PREC_FP32:
         for i, d in enumerate(f['blocks']):
             hk = 256 if i > 0 else 0          # columns fed by the running activation
@@ -347,43 +438,88 @@ def pack_image(module, si, precision, pair=True):
         #   'serial'   : every run needs all four       (no overlap; reference schedule)
         sched = os.environ.get('DDMI_B200_SCHEDULE', 'quarters')
         need = {'quarters': (1, 2, 3, 4), 'halves': (2, 2, 4, 4), 'serial': (4, 4, 4, 4)}[sched]
-        state = {'waited': 0}
+        # N split (f16f8): the second K-half of a layer runs as two half-width (N = 128) passes, output columns 0..127 first
+        # (COMMIT 0), then 128..255 (COMMIT 1).  The epilogue threads convert and publish the first half of the layer's
+        # output while the tensor core still works on the second, so the next layer's first K-half can start as soon as that
+        # finishes: the exposed drain -> convert -> publish chain of every layer shrinks to the accumulator hand-over.
+        # Publishing in place is safe because operand columns 0..127 are only read by the first K-half ('full': every K-half
+        # is N-split, [a: K 0..127][b: K 0..127][a: K 128..255][b: K 128..255]; 'off': one COMMIT pair at the end).
+        # Operand barrier 4 = "accumulator columns 128..255 drained": waited before the first unit that overwrites them.
+        nsplit = os.environ.get('DDMI_B200_NSPLIT', 'off') if precision == PREC_F16F8 else 'off'
+        assert nsplit in ('mixed', 'full', 'off')
+        state = {'waited': set()}
 
-        def wait_upto(k):              # emit WAITs so that barriers 0..k-1 have been consumed in this group
-            while state['waited'] < k:
-                P.wait(state['waited'])
-                state['waited'] += 1
+        def wait(*which):              # consume operand barriers (each exactly once per GEMM group)
+            for w in which:
+                if w not in state['waited']:
+                    P.wait(w)
+                    state['waited'].add(w)
 
-        def end_group():
-            wait_upto(4)               # every group consumes each barrier exactly once
-            P.commit()
-            state['waited'] = 0
+        def wait_upto(k):
+            wait(*range(k))
 
-        def dense256(W, acc, n_pad=None, first=True):          # K = 256 from H
-            for q in range(4):
+        def end_group(split_done=False):
+            wait(0, 1, 2, 3, 4)        # every group consumes each barrier exactly once
+            if not split_done:
+                P.commit(0)
+            P.commit(1)
+            state['waited'] = set()
+
+        def dense256(W, acc, n_pad=None, first=True, quarters=(0, 1, 2, 3)):          # K = 256 from H, full width
+            for q in quarters:
                 wait_upto(need[q])
-                P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, acc, first and q == 0, n_pad=n_pad)
+                wait(4)
+                P.block(W[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, acc, first and q == quarters[0], n_pad=n_pad)
+
+        def half_pass(W, h, quarters, first):      # output columns 128h..128h+127 over the given K quarters
+            Wh = W[128 * h:128 * h + 128]
+            if h == 1:
+                wait(4)
+            for q in quarters:
+                wait_upto(need[q])
+                P.block(Wh[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 128 * h, first and q == quarters[0], half=True)
+
+        def layer256(W, first=True, mid=None):
+            """One 256 -> 256 layer into acc1 and its two commits; `mid()` emits extra units (the skip GEMM) that must read
+            the operand before either half of it is overwritten."""
+            if nsplit == 'off':
+                dense256(W, 0, first=first)
+                if mid: mid()
+                end_group()
+                return
+            if nsplit == 'mixed':
+                dense256(W, 0, first=first, quarters=(0, 1))
+            else:
+                half_pass(W, 0, (0, 1), first)
+                half_pass(W, 1, (0, 1), first)
+            if mid: mid()
+            half_pass(W, 0, (2, 3), False)
+            wait(0, 1, 2, 3, 4)
+            P.commit(0)
+            half_pass(W, 1, (2, 3), False)
+            end_group(split_done=True)
 
         for i, d in enumerate(f['blocks']):
             W1 = d['W1'] * gain
             if i == 0:                 # x = PE only (K = 64)
-                wait_upto(4)
+                wait(0, 1, 2, 3, 4)
                 P.block(d['Ws'][:, 0:64], XH, XL, 256, True)
                 P.block(W1[:, 0:64], XH, XL, 0, True)
+                end_group()
             elif i < 3:                # x = [h (256) | PE (64)], conv1 -> acc1, skip -> acc2
-                wait_upto(need[0])     # the accumulator is drained once barrier 0 has completed
+                wait_upto(need[0])     # the accumulator is drained once barriers 0 and 4 have completed
+                wait(4)
                 P.block(W1[:, 256:320], XH, XL, 0, True)
-                dense256(W1, 0, first=False)
-                wait_upto(4)           # acc2 is read by the previous conv3 epilogue until its last quarter
-                P.block(d['Ws'][:, 0:256], HH, HL, 256, True)
-                P.block(d['Ws'][:, 256:320], XH, XL, 256, False)
+
+                def skip(d=d):
+                    wait(0, 1, 2, 3)   # acc2 is read by the previous conv3 epilogue until its last quarter
+                    P.block(d['Ws'][:, 0:256], HH, HL, 256, True)
+                    P.block(d['Ws'][:, 256:320], XH, XL, 256, False)
+                layer256(W1, first=False, mid=skip)
             else:
-                dense256(W1, 0)
-            end_group()
-            dense256(d['W2'] * gain, 0)
-            end_group()
-            dense256(d['W3'], 0)
-            end_group()
+                layer256(W1)
+            layer256(d['W2'] * gain)
+            layer256(d['W3'])
         dense256(f['Wrgb'], 0, n_pad=16)   # ToRGB: N = 16 block (3 real rows)
         end_group()
         gemm, prog_dev, prog_host = P.finish(dev)

@@ -277,6 +277,9 @@ DDMI_API int ddmi_selftest_f16f8(const float* a, const float* b, float* d, int32
  * lane); *count = records copied to `out` (host memory, `capacity` entries).
  * ddmi_debug_microbench: epilogue building blocks in isolation (csrc/microbench.cu); out_dev[0] = cycles warp 0 spent,
  * out_dev[1] = span over the 8 warps, for `iters` repetitions of one stage-sized unit.  All buffers are device memory.
+ * Modes 100 + v (one CTA pair) / 200 + v (every SM): tcgen05.mma rate, `iters` rounds of 8 MMAs; v bit 0: N = 128 (else 256),
+ * bit 1: A operand in tensor memory, bit 2: FP8, bit 3: the f16f8 mix, bit 4: concurrent shared-memory stores; out_dev[0] =
+ * cycles, out_dev[1] = MMAs issued.
  */
 DDMI_API int ddmi_debug_profile(uint64_t out[8], int32_t reset);
 DDMI_API int ddmi_debug_trace(uint64_t* out, int32_t capacity, int32_t* count, int32_t reset);

@@ -93,8 +93,9 @@ class EngineModelF16F8(EngineModel):
     def q8(x):
         return x.clamp(-448, 448).to(torch.float8_e4m3fn).float()
 
-    def write(self, kg, x):                       # kg: fp16 K group of the first column (0 = H, 64 = X)
-        f8 = {0: 32, 64: 72}[kg]
+    def write(self, kg, x):                       # kg: fp16 K group of the first column (0.. = H, 64.. = X), a multiple of 4
+        assert kg % 4 == 0
+        f8 = 32 + kg if kg < 32 else 72 + (kg - 64)
         a16 = x.to(torch.float16).float()
         self.A16[:, kg * 8:kg * 8 + x.shape[1]] = a16
         r8, a8 = self.q8((x - a16) * self.S), self.q8(x)
@@ -121,11 +122,24 @@ class EngineModelF16F8(EngineModel):
                 accum, col = (op >> 4) & 1, ((op >> 5) & 7) * 64
                 kg16, kg8, cnt = (op >> 8) & 0xFF, (op >> 16) & 0xFF, ((op >> 24) & 31) + 1
                 assert cnt % 2 == 0                                     # steps come in 32-wide pairs
+                half = (op >> 30) & 1                                   # half-width unit: the stream is grouped per step PAIR
+                assert not half or (n == 128 and cnt % 4 == 0)
+                blocks = {}
+                if half:
+                    for pr in range(cnt // 2):
+                        for h in range(2):
+                            for st in range(2):
+                                blocks[(2 * pr + st, h)] = self.stream[self.pos:self.pos + nloc * 64]
+                                self.pos += nloc * 64
+                else:
+                    for j in range(cnt):
+                        for h in range(2):
+                            blocks[(j, h)] = self.stream[self.pos:self.pos + nloc * 64]
+                            self.pos += nloc * 64
                 for j in range(cnt):
                     W16, F8 = torch.zeros(n, 16), torch.zeros(n, 32)
                     for h in range(2):
-                        b = self.stream[self.pos:self.pos + nloc * 64]
-                        self.pos += nloc * 64
+                        b = blocks[(j, h)]
                         rows = slice(h * nloc, (h + 1) * nloc)
                         W16[rows] = b[:nloc * 32].view(torch.float16).float().reshape(2, nloc, 8).permute(1, 0, 2).reshape(nloc, 16)
                         F8[rows] = b[nloc * 32:].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
@@ -135,8 +149,13 @@ class EngineModelF16F8(EngineModel):
                     self.acc[:, col:col + n] = d + (self.acc[:, col:col + n] if (accum or j > 0) else 0)
 
 
-@pytest.mark.parametrize("pair,scheme", [(True, 'bf16x3'), (False, 'bf16x3'), (True, 'f16f8')])
-def test_image_program_and_stream_reproduce_the_oracle(pair, scheme):
+@pytest.mark.parametrize("pair,scheme,nsplit", [(True, 'bf16x3', 'off'), (False, 'bf16x3', 'off'), (True, 'f16f8', 'off'),
+                                                (True, 'f16f8', 'mixed'), (True, 'f16f8', 'full')])
+def test_image_program_and_stream_reproduce_the_oracle(pair, scheme, nsplit, monkeypatch):
+    """The epilogue sequence of image_umma_kernel, including the N split: after COMMIT 0 the model overwrites operand
+    columns 0..127 with the layer's first output half, runs the rest of the group, and only after COMMIT 1 writes columns
+    128..255 -- a program that still read the dead columns after COMMIT 0 would not reproduce the oracle."""
+    monkeypatch.setenv('DDMI_B200_NSPLIT', nsplit)
     m = cases.build_module('image')
     sd = cases.state_dict32(m)
     coords, planes, si = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=12)
@@ -150,24 +169,46 @@ def test_image_program_and_stream_reproduce_the_oracle(pair, scheme):
     E = EngineModel(packed, rows=144)
     lr = lambda v: torch.nn.functional.leaky_relu(v, 0.2)
     E.write(64, X[0])                                                    # X region: K groups 64.. (hi), 72.. (lo)
+
+    def stage(out_of_acc, after_first=None):
+        """One GEMM group + its epilogue stage; out_of_acc(lo, hi) -> the stage's output columns [lo, hi)."""
+        waits, done = E.run_group()
+        assert done == 0
+        E.write(0, out_of_acc(0, 128))
+        waits2, done = E.run_group()                                     # the second accumulator half
+        assert done == 1 and sorted(waits + waits2) == [0, 1, 2, 3, 4]
+        E.write(16, out_of_acc(128, 256))
+
     for blk in range(4):
         bv = vec[blk * 1024:(blk + 1) * 1024]
-        waits, done = E.run_group()                                      # conv1 (+ skip)
-        assert sorted(waits) == [0, 1, 2, 3] and done == 0
-        E.write(0, lr(E.acc[:, :256] + bv[:256]))
+        stage(lambda lo, hi: lr(E.acc[:, lo:hi] + bv[lo:hi]))           # conv1 (+ skip)
         if blk < 2:
             E.write(64, X[blk + 1])
-        E.run_group()                                                    # conv2
-        E.write(0, lr(E.acc[:, :256] + bv[256:512]))
-        E.run_group()                                                    # conv3
-        h = lr(E.acc[:, :256] + bv[512:768]) + E.acc[:, 256:512] + (bv[768:1024] if blk < 3 else 0)
-        if blk == 2:
-            E.acc[:, 256:512] = h / math.sqrt(2.0)                       # stash res4's identity skip
-        E.write(0, h)
-    E.run_group()                                                        # ToRGB
+        stage(lambda lo, hi: lr(E.acc[:, lo:hi] + bv[256 + lo:256 + hi]))   # conv2
+        stash = {}
+
+        def conv3(lo, hi, blk=blk, bv=bv, stash=stash):
+            h = lr(E.acc[:, lo:hi] + bv[512 + lo:512 + hi]) + E.acc[:, 256 + lo:256 + hi] + (bv[768 + lo:768 + hi] if blk < 3 else 0)
+            if blk == 2:
+                E.acc[:, 256 + lo:256 + hi] = h / math.sqrt(2.0)          # stash res4's identity skip
+            return h
+        stage(conv3)
+    waits, done = E.run_group()                                          # ToRGB
+    waits2, done2 = E.run_group()
+    assert (done, done2) == (0, 1) and sorted(waits + waits2) == [0, 1, 2, 3, 4]
     out = (E.acc[:, :3] + vec[4096 + 768:4096 + 771]).t().reshape(1, 3, 12, 12)
     assert E.ops[E.pc] & 3 == 3 and E.pos == E.stream.numel()            # program and stream end together
     assert float((out - ref).abs().max()) < 1e-3                         # (the model keeps acc / S; the kernel keeps acc)
+    if nsplit != 'off':                                                  # the split really is in the program
+        units_between = 0
+        ops = E.ops
+        for i, o in enumerate(ops):
+            if o & 3 == 2 and (o >> 2) & 3 == 0:
+                j = i + 1
+                while ops[j] & 3 != 2:
+                    units_between += ops[j] & 3 == 0
+                    j += 1
+        assert units_between >= 11
 
 
 def test_programs_consume_exactly_their_streams():
