@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DDMI_B200_LIB") or os.path.join(_HERE, "libddmi_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 PREC_FP32 = 0
 PREC_BF16X3 = 1
 PREC_F16F8 = 2
@@ -38,7 +38,8 @@ class Weights(ctypes.Structure):
     _fields_ = [("precision", ctypes.c_int32), ("reserved", ctypes.c_int32),
                 ("gemm", ctypes.c_void_p), ("gemm_bytes", ctypes.c_uint64),
                 ("vec", ctypes.c_void_p), ("vec_floats", ctypes.c_uint64),
-                ("program", ctypes.c_void_p), ("program_host", ctypes.c_void_p), ("program_words", ctypes.c_uint64)]
+                ("program", ctypes.c_void_p), ("program_host", ctypes.c_void_p), ("program_words", ctypes.c_uint64),
+                ("vec_host", ctypes.c_void_p)]
 
 
 def build_library(verbose=False):
@@ -157,4 +158,6 @@ def weights_struct(packed):
         w.program = packed.program.data_ptr()
         w.program_host = packed.program_host.data_ptr()
         w.program_words = packed.program_host.numel()
+    if getattr(packed, "vec_host", None) is not None:
+        w.vec_host = packed.vec_host.data_ptr()
     return w

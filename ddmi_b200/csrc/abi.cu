@@ -27,7 +27,7 @@ int launch_video_fp32(const PlaneSet&, int, int, const float*, const float*, con
 int launch_nerf_mlp_fp32(const float*, long long, int, int, float, const float*, const float*, float*, cudaStream_t);
 int launch_nerf_render_fp32(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const float*, const float*, float*, float*, cudaStream_t);
 // tcgen05 path (decode_umma.cu)
-int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, const NoiseArgs&, int, cudaStream_t);
+int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, long long, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, const NoiseArgs&, int, int, const float*, cudaStream_t);
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
@@ -156,7 +156,8 @@ DDMI_API int ddmi_decode_image_noise(const ddmi_plane_t planes[3], int32_t batch
     DDMI_REQUIRE(!f16f8 || (weights->reserved & 1), "DDMI_PREC_F16F8 weights must be packed for CTA pairs");
     return launch_image_umma(ps, batch, channels, coord_x, coord_y, n_coords, weights->gemm, weights->gemm_bytes,
                              weights->program_host, weights->program_words, weights->program, weights->vec,
-                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, na, (weights->reserved >> 1) & 1, st);
+                             weights->vec_floats, out, store, weights->reserved & 1, f16f8, na, (weights->reserved >> 1) & 1,
+                             (weights->reserved >> 2) & 1, weights->vec_host, st);
   }
   set_error("unknown precision %d", weights->precision);
   return DDMI_ERR_UNSUPPORTED;

@@ -32,6 +32,7 @@
 #include <string.h>
 #include "umma_engine.cuh"
 #include "tma.cuh"
+#include "image_ts_issuer.cuh"
 #include "decode_umma_occ.cuh"
 #include "decode_umma_nerf.cuh"
 #include "decode_umma_video.cuh"
@@ -153,6 +154,146 @@ __device__ __forceinline__ void image_stage(uint32_t tmem_lane, uint32_t h_hi, u
 }
 
 // ---------------------------------------------------------------------------
+// TS = 1 (f16f8, CTA pairs; packing._pack_image_ts): the 256-wide running activation H lives in TENSOR memory.
+//   TMEM columns [0, 256) the ONE accumulator | [256, 384) H fp16 (two per column) | [384, 512) H FP8, per 32 K columns
+//   [r8: 8 columns | a8: 8 columns].  tcgen05.mma with the A operand in tensor memory runs at the tensor pipe's own rate
+//   (136 cycles per 256 x 256 x 16 step against 162-173 with A in shared memory: profiles/r02_mmabench.txt), and an epilogue
+//   stage publishes with tcgen05.st (265 cycles per 128 values) instead of 32 st.shared.v4 (1556 cycles: the shared-memory
+//   store bandwidth bounded the epilogue, profiles/r02_microbench_epilogue.txt).
+//   With one accumulator the skip GEMM of a block is its own group in front of conv1 and its result is PARKED: the 128 KB of
+//   shared memory that held H (K groups 0..63) keep, per epilogue thread, 32 private 16-byte chunks (chunk c at c * 4096 +
+//   tid * 16: conflict-free) with the thread's 128 fp32 skip values until conv3's epilogue adds them.
+//   Every group is N-split (COMMIT 0: output columns 0..127, COMMIT 1: 128..255; see image_stage) and every stage reports
+//   "columns 0..127 / 128..255 of the accumulator are in registers" on operand barriers 5 / 4.
+//   ToRGB (256 -> 3) is evaluated by the epilogue threads in fp32 from res4's output (weights: kernel parameter).
+// MODE 0: H = lrelu(acc + b)                          (conv1 / conv2)
+// MODE 1: H = lrelu(acc + b) + parked + cs            (conv3 + skip; res1, res2)
+// MODE 2: as 1, and parked <- H / sqrt2               (res3: res4's identity skip)
+// MODE 3: y = lrelu(acc + b) + parked -> rgb += Wrgb y (res4 + ToRGB; nothing is published)
+// MODE 4: parked <- acc                               (skip GEMM)
+// ---------------------------------------------------------------------------
+struct RgbParam {
+  float w[3 * 256];
+};
+
+// this thread's 32 columns [col0, col0 + 32) of H -> tensor memory
+__device__ __forceinline__ void publish_ts(uint32_t tmem_lane, int col0, const float2* y) {
+  uint4 a16[4], r8[2], a8[2];
+  split32_f16f8(y, a16, r8, a8);
+  uint32_t w16[16], wr[8], wa[8];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    w16[4 * g] = a16[g].x; w16[4 * g + 1] = a16[g].y; w16[4 * g + 2] = a16[g].z; w16[4 * g + 3] = a16[g].w;
+  }
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    wr[4 * g] = r8[g].x; wr[4 * g + 1] = r8[g].y; wr[4 * g + 2] = r8[g].z; wr[4 * g + 3] = r8[g].w;
+    wa[4 * g] = a8[g].x; wa[4 * g + 1] = a8[g].y; wa[4 * g + 2] = a8[g].z; wa[4 * g + 3] = a8[g].w;
+  }
+  tmem_st16w(tmem_lane + 256 + col0 / 2, w16);
+  tmem_st8w(tmem_lane + 384 + (col0 / 32) * 16, wr);
+  tmem_st8w(tmem_lane + 384 + (col0 / 32) * 16 + 8, wa);
+}
+
+constexpr uint32_t PARK_STRIDE = NEPI * 16;   // chunk c of a thread: park + c * PARK_STRIDE
+
+// CODE SIZE is a first-order concern here: with every stage, quarter and call site unrolled the epilogue threads walked ~160 KB
+// of straight-line code per tile and 35 % of their stall samples were instruction-cache misses (profiles/r02_image_ts_ncu.md).
+// A stage is therefore a two-trip loop over accumulator halves (two quarters unrolled in the body), conv1 / conv2 share one
+// call site, and the three conv3 flavours are one body with run-time switches.
+// KIND 0: H = lrelu(acc + b)                                         (conv1 / conv2)
+// KIND 1: y = lrelu(acc + b) + parked;  blk 2: parked <- y / sqrt2 (res4's identity skip);
+//         blk < 3: H = y, else rgb += Wrgb y (ToRGB; nothing is published)
+// KIND 2: parked <- acc + cs                                         (skip GEMM; cs = the folded scale-injection columns)
+template <int KIND, int NOISE, class Sig, class WaitA, class WaitB>
+__device__ __forceinline__ void image_ts_stage(uint32_t tmem_lane, uint32_t park, int sub, const float* __restrict__ vecs,
+                                               Sig sig, WaitA wait_a, WaitB wait_b, float nz, int blk, bool more,
+                                               const RgbParam& rgbw, float (&rgb)[3]) {
+  // vecs: KIND 0 / 1 the bias, KIND 2 the skip constant (256 floats); this thread's 32 columns of quarter q start at q * 64 + sub * 32
+  const float* vp = vecs + sub * 32;
+  float2 pb[16];                                          // vector of the quarter about to be converted
+  load_vec<16>(vp, pb);                                   // in flight while the thread parks on the MMA barrier
+  const float2 nz2 = make_float2(nz, nz);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    if (h == 0) wait_a(); else wait_b();                  // COMMIT 0 / 1: output columns 0..127 / 128..255 are complete
+    float2 v[2][16];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) tmem_ld32(tmem_lane + (2 * h + j) * 64 + sub * 32, v[j]);
+    tmem_ld_wait();
+    sig(5 - h);                                           // this accumulator half is in registers
+    if (KIND == 1 && h == 1 && blk == 3 && more) {        // the next tile's first groups read X only: let them start
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) sig(q2);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int q = 2 * h + j, col0 = q * 64 + sub * 32;
+      float2 bn[16];
+      if (j == 0 || h == 0) load_vec<16>(vp + (q + 1) * 64, bn);   // next quarter's vector, in flight during this conversion
+      if (KIND == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 a = __ffma2_rn(pb[2 * i], make_float2(kF8Scale, kF8Scale), v[j][2 * i]);
+          const float2 c = __ffma2_rn(pb[2 * i + 1], make_float2(kF8Scale, kF8Scale), v[j][2 * i + 1]);
+          st_shared_v4(park + (q * 8 + i) * PARK_STRIDE,
+                       make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y)));
+        }
+      } else {
+        if (NOISE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pb[i] = __fadd2_rn(pb[i], nz2);
+        }
+        if (KIND == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[j][i] = image_act<1>(v[j][i], pb[i]);
+        } else {
+          float2 sp[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 u = ld_shared_v4(park + (q * 8 + i) * PARK_STRIDE);
+            sp[2 * i] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
+            sp[2 * i + 1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[j][i] = __ffma2_rn(sp[i], make_float2(kF8InvScale, kF8InvScale), image_act<1>(v[j][i], pb[i]));
+          if (blk == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 a = __fmul2_rn(v[j][2 * i], make_float2(kInvSqrt2 * kF8Scale, kInvSqrt2 * kF8Scale));
+              const float2 c = __fmul2_rn(v[j][2 * i + 1], make_float2(kInvSqrt2 * kF8Scale, kInvSqrt2 * kF8Scale));
+              st_shared_v4(park + (q * 8 + i) * PARK_STRIDE,
+                           make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y)));
+            }
+          }
+        }
+        if (KIND == 1 && blk == 3) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              a0 = fmaf(v[j][i].x, rgbw.w[c * 256 + col0 + 2 * i], a0);
+              a1 = fmaf(v[j][i].y, rgbw.w[c * 256 + col0 + 2 * i + 1], a1);
+            }
+            rgb[c] += a0 + a1;
+          }
+        } else {
+          publish_ts(tmem_lane, col0, v[j]);
+          tmem_st_wait();
+          sig(q);
+        }
+      }
+      if (j == 0 || h == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pb[i] = bn[i];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // the fused image kernel
 // ---------------------------------------------------------------------------
 #ifdef DDMI_EXP_BIGRING
@@ -171,15 +312,17 @@ constexpr int PATCH_W = 64, PATCH_H = 2, PATCH_BYTES = PATCH_W * PATCH_H * 64 * 
 static_assert(PATCH_BYTES <= 2 * 8 * KG_BYTES * 2, "the patch is staged in the X region");
 constexpr int IMG_OFF_PBAR = TMEM_SLOT + 8;                        // inside the barrier block
 constexpr int IMG_OFF_SCRATCH = BAR_BYTES;                         // 8 warps x {xmin, xmax, ymin, ymax}
-constexpr int IMG_SMEM = ImgL::SMEM_BYTES + 128;
+constexpr int IMG_OFF_RGBX = IMG_OFF_SCRATCH + 128;                  // TS: [3][128] partial ToRGB sums of the sub = 1 threads
+constexpr int IMG_SMEM = ImgL::SMEM_BYTES + 128 + 3 * 128 * 4;
 
-template <int PAIR, int SCHEME, int NOISE>
+template <int PAIR, int SCHEME, int NOISE, int TS = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __restrict__ cy, long long n,
                   int tiles_per_item, long long total_tiles, const uint8_t* __restrict__ wstream,
                   const __grid_constant__ ProgramParam prog, const float* __restrict__ vec, void* __restrict__ out, int store,
                   NoiseArgs na, const __grid_constant__ CUtensorMap pmap0, const __grid_constant__ CUtensorMap pmap1,
-                  const __grid_constant__ CUtensorMap pmap2, int patch_mask) {
+                  const __grid_constant__ CUtensorMap pmap2, int patch_mask, const __grid_constant__ RgbParam rgbw) {
+  static_assert(!TS || (PAIR && SCHEME), "the TMEM-resident-activation kernel is f16f8 on CTA pairs");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t h_hi = sbase + ImgL::KG_HHI * KG_BYTES, h_lo = sbase + ImgL::KG_HLO * KG_BYTES;
@@ -366,6 +509,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       } else {
         gather_direct(tile, s, part);
       }
+      if (TS) fence_proxy_async();                        // TS signals carry no proxy fence of their own (H is in TMEM)
     };
     // make this warp's smem / TMEM writes visible to the MMA warp (of the leader CTA), then signal one quarter
     auto signal = [&](int q) {
@@ -408,6 +552,69 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       p_t += w1 - w0;
     };
 
+    if constexpr (TS) {
+      // ---- TMEM-resident activation: 15 GEMM groups per tile (skip, conv1, conv2, conv3 per block; res4 has no skip)
+      const uint32_t park = sbase + (uint32_t)tid * 16;
+      float* rgbx = reinterpret_cast<float*>(smem + ImgL::OFF_BAR + IMG_OFF_RGBX);
+      auto sig = [&](int i) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(a_bar + 8 * i);
+        trace(tr, 0x10 + i, trn, 0);
+      };
+      if (ntiles > 0) {
+        gather(tile_of(0), 0, -1);
+        sig(5);
+        sig(4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sig(q);
+      }
+      for (long long it = 0; it < ntiles; ++it) {
+        const long long tile = tile_of(it);
+        const float* bv = vec;
+        const bool more = it + 1 < ntiles;
+        tr = prof && it == kTraceIter;
+        float rgb[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk, bv += 1024) {
+          float nz[3] = {0.f, 0.f, 0.f};
+          if (NOISE) {
+            const long long tt = tile < total_tiles ? tile : total_tiles - 1;
+            long long gi = (tt % tiles_per_item) * TILE + row;
+            if (gi > n - 1) gi = n - 1;
+            noise_block3(na, blk, (size_t)(tt / tiles_per_item), n, gi, nz);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) nz[j] *= __ldg(vec + 4096 + 768 + 3 + 3 * blk + j);
+          }
+          // ---- skip GEMM of the block -> parked (+ the block's skip constant)
+          if (blk < 3) image_ts_stage<2, NOISE>(tmem_lane, park, sub, bv + 768, sig, wait_mma, wait_b, 0.f, blk, more, rgbw, rgb);
+          // ---- conv1, conv2; after each, one half of the next PE scale (or of the next tile's coarse scale) is gathered:
+          // X is free once conv1's group is complete
+#pragma unroll 1
+          for (int cv = 0; cv < 2; ++cv) {
+            image_ts_stage<0, NOISE>(tmem_lane, park, sub, bv + 256 * cv, sig, wait_mma, wait_b, cv ? nz[1] : nz[0], blk, more, rgbw, rgb);
+            if (blk < 2 || (blk == 2 && more)) gather(blk < 2 ? tile : tile_of(it + 1), blk < 2 ? blk + 1 : 0, cv);
+          }
+          // ---- conv3 + parked skip (res4: + ToRGB)
+          image_ts_stage<1, NOISE>(tmem_lane, park, sub, bv + 512, sig, wait_mma, wait_b, nz[2], blk, more, rgbw, rgb);
+        }
+        // ---- ToRGB: the two threads of a row add their partial sums
+        if (sub == 1) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rgbx[c * 128 + row] = rgb[c];
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (sub == 0 && tile < total_tiles) {
+          const int b = (int)(tile / tiles_per_item);
+          const long long gi = (tile % tiles_per_item) * TILE + row;
+          if (gi < n) {
+            const float* brgb = vec + 4096 + 768;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) store_rgb(out, store, b, n, gi, c, rgb[c] + rgbx[c * 128 + row] + __ldg(brgb + c));
+          }
+        }
+      }
+    } else {
     if (ntiles > 0) gather(tile_of(0), 0, -1);
     if (ntiles > 0) signal_all();
     for (long long it = 0; it < ntiles; ++it) {
@@ -467,13 +674,22 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
       }
       if (it + 1 < ntiles) signal_all();
     }
+    }
     if (prof) {
       prof_add(0, p_wait);
       prof_add(1, p_epi);
       prof_add(2, p_gather);
     }
   } else {
-    engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME, 0>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    if constexpr (TS) {
+      // producer and forwarder interpret the op table (byte counts only); the issuer is image_ts_issuer.cuh's straight-line code
+      reg_dec<72>();
+      if (warp == 8) producer_loop<PAIR, ImgL::RING_BYTES, SCHEME>(prog.op, wstream, ring, bar, ntiles, rank);
+      else if (warp == 9 && rank == 0) image_ts_issue_loop(sbase, ring, bar, tmem, ImgL::KG_XHI, ImgL::KG_XLO, ntiles);
+      else if (warp == 9) forward_loop<ImgL::RING_BYTES, SCHEME>(prog.op, bar, ntiles);
+    } else {
+      engine_service_warps<PAIR, ImgL::RING_BYTES, SCHEME, 0>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);
+    }
   }
   engine_end<PAIR>(tmem);
 }
@@ -567,7 +783,7 @@ selftest_kernel(const float* __restrict__ a, const float* __restrict__ b, float*
 int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, const float* cy, long long n,
                       const void* gemm, size_t gemm_bytes, const uint32_t* program_host, size_t program_words,
                       const uint32_t* program_dev, const float* vec, size_t vec_floats, void* out, int store, int pair,
-                      int f16f8, const NoiseArgs& na, int no_patch, cudaStream_t st) {
+                      int f16f8, const NoiseArgs& na, int no_patch, int ts, const float* vec_host, cudaStream_t st) {
   using namespace ummak;
   if (C != 64) {
     set_error("tcgen05 image kernel is built for 64-channel planes");
@@ -581,6 +797,10 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   DDMI_REQUIRE(make_program_param(program_host, program_words, &pp), "MMA program has %zu words, at most %d fit the kernel parameter",
                program_words, PROG_MAX);
   DDMI_REQUIRE(!f16f8 || pair, "the f16f8 image kernel runs as CTA pairs only");
+  DDMI_REQUIRE(!ts || (f16f8 && vec_host), "a TMEM-resident-activation program needs DDMI_PREC_F16F8 and weights->vec_host");
+  static RgbParam rgbw;   // zero for the programs that do not use it; filled below (by value into the launch) otherwise
+  RgbParam rgbv = rgbw;
+  if (ts) memcpy(rgbv.w, vec_host + 4096, sizeof(rgbv.w));
   DDMI_REQUIRE(vec_floats == 4096 + 768 + 3 + 12, "packed vec blob is %zu floats, expected 4879", vec_floats);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));
@@ -606,15 +826,21 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
   }
 #define DDMI_IMG_LAUNCH(P, S, Z)                                                                                          \
   DDMI_CUDA(launch_engine(image_umma_kernel<P, S, Z>, P, ctas, IMG_SMEM, st, ps, cx, cy, n, tpi_i, total, ws, pp, vec, out, \
-                          store, na, pm[0], pm[1], pm[2], patch_mask))
+                          store, na, pm[0], pm[1], pm[2], patch_mask, rgbv))
+#define DDMI_IMG_LAUNCH_TS(Z)                                                                                              \
+  DDMI_CUDA(launch_engine(image_umma_kernel<1, 1, Z, 1>, 1, ctas, IMG_SMEM, st, ps, cx, cy, n, tpi_i, total, ws, pp, vec, out, \
+                          store, na, pm[0], pm[1], pm[2], patch_mask, rgbv))
   const int nz = na.mode != 0;
-  if (pair && f16f8 && nz) { DDMI_IMG_LAUNCH(1, 1, 1); }
+  if (ts && nz) { DDMI_IMG_LAUNCH_TS(1); }
+  else if (ts) { DDMI_IMG_LAUNCH_TS(0); }
+  else if (pair && f16f8 && nz) { DDMI_IMG_LAUNCH(1, 1, 1); }
   else if (pair && f16f8) { DDMI_IMG_LAUNCH(1, 1, 0); }
   else if (pair && nz) { DDMI_IMG_LAUNCH(1, 0, 1); }
   else if (pair) { DDMI_IMG_LAUNCH(1, 0, 0); }
   else if (nz) { DDMI_IMG_LAUNCH(0, 0, 1); }
   else { DDMI_IMG_LAUNCH(0, 0, 0); }
 #undef DDMI_IMG_LAUNCH
+#undef DDMI_IMG_LAUNCH_TS
   DDMI_CUDA(cudaGetLastError());
   return DDMI_OK;
 }

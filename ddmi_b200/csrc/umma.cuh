@@ -299,6 +299,19 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint2& v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v.x), "r"(v.y) : "memory");
 }
+// 32 lanes x 16 / 8 consecutive 32-bit columns of packed operand words (fp16 pairs / FP8 quads along K)
+__device__ __forceinline__ void tmem_st16w(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(r[0]),
+      "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8w(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr)
+               : "memory");
+}
 // arrive on the mbarrier at this offset in every CTA of `mask` once all prior MMAs of the pair completed
 __device__ __forceinline__ void mma2_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),

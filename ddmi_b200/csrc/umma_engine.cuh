@@ -67,8 +67,8 @@ __device__ unsigned long long g_prof[8];
 // what-if switches of the profiling build (ddmi_debug_set; results are garbage, timings are the point):
 // bit 0: epilogue stages only signal (no drain / convert / publish)   bit 1: the issuer skips the tcgen05.mma instructions
 // (hand-shakes and commits stay)   bit 2: no plane gathers
-__device__ int g_dbg;
-__device__ __forceinline__ bool dbg(int bit) { return DDMI_PROFILE && ((*(volatile int*)&g_dbg) & bit); }
+__constant__ int g_dbg;   // constant bank: a what-if test costs the issuer no global-memory round trip
+__device__ __forceinline__ bool dbg(int bit) { return DDMI_PROFILE && (g_dbg & bit); }
 constexpr int kTraceCap = 4096, kTraceIter = 5, kTraceRegion = 1024;   // regions: E thread 0, MMA lane, 2 x kernel-specific
 __device__ unsigned long long g_trace[kTraceCap];
 __device__ unsigned int g_trace_n;

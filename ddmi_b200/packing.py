@@ -35,7 +35,8 @@ class Packed:
     program_host: torch.Tensor = None   # same, host copy (validated by the launcher)
     pair: bool = False                  # bf16x3: stream packed for CTA pairs ([half 0 | half 1] per K step)
     noise_active: bool = False          # image: some NoiseInjection.weight is non-zero (the decode needs a noise source)
-    ts: bool = False                    # image, f16f8: program of the TMEM-resident-activation kernel (image_ts_kernel)
+    ts: bool = False                    # image, f16f8: program of the TMEM-resident-activation kernel (image_umma_kernel<.., TS>)
+    vec_host: torch.Tensor = None       # host copy of vec (ts: the ToRGB weights travel as a kernel parameter)
 
 
 class UmmaProgram:
@@ -337,8 +338,7 @@ def _pack_image_ts(f, dev):
     gain = math.sqrt(2.0)
     HT16, HT8, XH, XL = 64, 96, 64, 72
     P = UmmaProgram(pair=True, scheme='f16f8')
-    nsplit = os.environ.get('DDMI_B200_NSPLIT', 'full')
-    assert nsplit in ('mixed', 'full')
+    nsplit = 'full'            # csrc/image_ts_issuer.cuh writes this sequence out as straight-line code: keep them in step
 
     def group(W, k_h, k_x, published):
         """W: (256, k_h + k_x); k_h in (0, 256) columns from H (TMEM), k_x in (0, 64) from X (shared memory)."""
@@ -399,14 +399,15 @@ def _pack_image_ts(f, dev):
         group(d['W2'] * gain, 256, 0, True)
         group(d['W3'], 256, 0, True)
     gemm, prog_dev, prog_host = P.finish(dev)
-    return Packed(PREC_F16F8, gemm, _image_vec(f, gain).to(dev), prog_dev, prog_host, True, _noise_active(f), ts=True)
+    vec_host = _image_vec(f, gain)
+    return Packed(PREC_F16F8, gemm, vec_host.to(dev), prog_dev, prog_host, True, _noise_active(f), ts=True, vec_host=vec_host)
 
 
 def pack_image(module, si, precision, pair=True):
     f = fold_image(module, si)
     dev = module_device(module)
     segs = []
-    if precision == PREC_F16F8 and pair and os.environ.get('DDMI_B200_IMAGE_TS', '0') != '0':
+    if precision == PREC_F16F8 and pair and os.environ.get('DDMI_B200_IMAGE_TS', '1') != '0':
         return _pack_image_ts(f, dev)
     if precision == PREC_FP32:
         for i, d in enumerate(f['blocks']):

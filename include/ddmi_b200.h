@@ -60,7 +60,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 8
+#define DDMI_ABI_VERSION 9
 
 enum {
   DDMI_OK = 0,
@@ -91,7 +91,9 @@ typedef struct {
 typedef struct {
   int32_t precision;   /* DDMI_PREC_* */
   int32_t reserved;    /* bit 0: tcgen05 stream is packed for CTA pairs ([half 0 | half 1] per K step);
-                          bit 1: image decode: never stage plane windows with TMA (diagnostic: every tile gathers directly) */
+                          bit 1: image decode: never stage plane windows with TMA (diagnostic: every tile gathers directly)
+                          bit 2: image decode, DDMI_PREC_F16F8: `program` drives the TMEM-resident-activation kernel
+                                 (packing._pack_image_ts; needs vec_host) */
   const void* gemm;    /* GEMM operands, layout per precision (device)            */
   uint64_t gemm_bytes;
   const float* vec;    /* fp32 vectors: biases, folded constants, small heads (device) */
@@ -101,6 +103,9 @@ typedef struct {
   const uint32_t* program;
   const uint32_t* program_host;
   uint64_t program_words;
+  /* host copy of `vec` (may be NULL unless reserved bit 2 is set): small heads that a kernel takes as launch parameters
+     (constant bank) instead of reading them from device memory -- the image decoder's ToRGB weights */
+  const float* vec_host;
 } ddmi_weights_t;
 
 DDMI_API int ddmi_abi_version(void);

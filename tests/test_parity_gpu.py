@@ -66,6 +66,26 @@ def test_image_golden(golden_dir, tag, kw, precision):
     assert err < (2e-5 if precision == 'fp32' else TOL), err
 
 
+@pytest.mark.parametrize("nsplit", ["off", "full"])
+def test_image_golden_shared_memory_operand_kernel(golden_dir, nsplit, monkeypatch):
+    """f16f8 defaults to the TMEM-resident-activation kernel (image_umma_kernel<.., TS = 1>); the kernel that keeps the
+    activation in shared memory (DDMI_B200_IMAGE_TS=0, the interpreter-driven engine, with and without the N split) stays
+    built and must hold the same bar, noise included."""
+    monkeypatch.setenv('DDMI_B200_IMAGE_TS', '0')
+    monkeypatch.setenv('DDMI_B200_NSPLIT', nsplit)
+    g = _golden(golden_dir, 'image_96')
+    m = cases.build_module('image').to(DEV)
+    m.precision = 'f16f8'
+    coords, planes, si = cases.image_inputs(batch=2, sizes=(16, 32, 64), res=96)
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=si).cpu()
+    assert float((out - g['out']).abs().max()) < TOL
+    g = _golden(golden_dir, 'image_noise')
+    m = cases.build_module('image_noise').to(DEV)
+    m.precision = 'f16f8'
+    out = m(coords.to(DEV), hdbf=_cuda(planes), si=si, noise=_cuda(cases.image_noise_tensors(2, 96))).cpu()
+    assert float((out - g['out']).abs().max()) < TOL
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "f16f8"])
 def test_image_noise_injection_golden(golden_dir, precision):
     """A checkpoint with non-zero NoiseInjection weights (any trained one): explicit noise tensors, against the REFERENCE
@@ -386,11 +406,14 @@ def test_sample_pdf_golden(golden_dir):
     bins, w = g['bins'].to(DEV), g['weights'].to(DEV)
     # The reference's lookup is DIScontinuous at bins whose pdf is below its 1e-5 guard (t is then taken against a unit
     # denominator), so a last-bit difference in the normalising sum (tree vs vectorised order) may move a sample that sits on
-    # such an edge to the neighbouring bin: all but a handful agree to 2e-5, a moved sample stays within one bin width.
+    # such an edge to the neighbouring bin -- and with det=True the last sample of EVERY ray (u = 1.0) sits exactly on the end of
+    # the cdf, whose last bit decides the bin.  So: at most about one moved sample per ray (measured: 41 of 38400), everything
+    # else within 2e-5, and a moved sample stays within one bin width.
     def close(a, ref):
         d = (a - ref).abs()
         width = float((g['bins'][:, 1:] - g['bins'][:, :-1]).max())
-        return float((d < 2e-5).float().mean()) > 0.999 and float(d.max()) <= width
+        moved = int((d >= 2e-5).sum())
+        return moved <= a.shape[0] // 2 and float(d.max()) <= width
     out = nh.sample_pdf(bins, w, 128, det=True).cpu()
     assert out.shape == g['out'].shape and close(out, g['out'])
     rnd = nh.sample_pdf(bins, w, 96, det=False, pytest=True).cpu()

@@ -156,6 +156,7 @@ def test_image_program_and_stream_reproduce_the_oracle(pair, scheme, nsplit, mon
     columns 0..127 with the layer's first output half, runs the rest of the group, and only after COMMIT 1 writes columns
     128..255 -- a program that still read the dead columns after COMMIT 0 would not reproduce the oracle."""
     monkeypatch.setenv('DDMI_B200_NSPLIT', nsplit)
+    monkeypatch.setenv('DDMI_B200_IMAGE_TS', '0')                        # the shared-memory-operand kernel's program
     m = cases.build_module('image')
     sd = cases.state_dict32(m)
     coords, planes, si = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=12)
@@ -209,6 +210,118 @@ def test_image_program_and_stream_reproduce_the_oracle(pair, scheme, nsplit, mon
                     units_between += ops[j] & 3 == 0
                     j += 1
         assert units_between >= 11
+
+
+class EngineModelTS(EngineModelF16F8):
+    """A-from-TMEM units (op bit 29): K groups count 4 TMEM columns from the TMEM base; the image kernel keeps H there as
+    fp16 at columns 256.. (two values per column) and FP8 at 384.. (per 32 K columns [r8: 8 columns | a8: 8 columns])."""
+
+    def __init__(self, packed, rows):
+        super().__init__(packed, rows)
+        self.T16 = torch.zeros(rows, 256)
+        self.T8 = torch.zeros(rows, 2, 256)       # [:, 0] = r8, [:, 1] = a8
+
+    def write_h(self, k0, x):
+        a16 = x.to(torch.float16).float()
+        self.T16[:, k0:k0 + x.shape[1]] = a16
+        self.T8[:, 0, k0:k0 + x.shape[1]] = self.q8((x - a16) * self.S)
+        self.T8[:, 1, k0:k0 + x.shape[1]] = self.q8(x)
+
+    def operands(self, op, j):
+        kg16, kg8 = (op >> 8) & 0xFF, (op >> 16) & 0xFF
+        if not (op >> 29) & 1:
+            return (self.A16[:, (kg16 + 2 * j) * 8:(kg16 + 2 * j) * 8 + 16],
+                    self.A8[:, (kg8 + 2 * j) * 16:(kg8 + 2 * j) * 16 + 32])
+        c16, c8 = kg16 * 4 + 8 * j, kg8 * 4 + 8 * j                     # TMEM columns of this 16-wide step
+        assert 256 <= c16 and c16 + 8 <= 384 and 384 <= c8 and c8 + 8 <= 512
+        k16 = (c16 - 256) * 2
+        pair, which = divmod(c8 - 384, 16)
+        assert which in (0, 8) and which == 8 * (j & 1) and 32 * pair == k16 - 16 * (j & 1)
+        return self.T16[:, k16:k16 + 16], self.T8[:, which // 8, 32 * pair:32 * pair + 32]
+
+    def run_group(self):
+        waits = []
+        while True:
+            op = self.ops[self.pc]
+            self.pc += 1
+            kind = op & 3
+            if kind == 1:
+                waits.append((op >> 2) & 7)
+            elif kind == 2:
+                return waits, (op >> 2) & 3
+            elif kind == 3:
+                raise AssertionError("END inside a tile")
+            else:
+                n = NCODE[(op >> 2) & 3]
+                nloc = n // 2
+                accum, col, cnt = (op >> 4) & 1, ((op >> 5) & 7) * 64, ((op >> 24) & 31) + 1
+                half = (op >> 30) & 1
+                assert cnt % (4 if half else 2) == 0 and (not half or n == 128)
+                blocks = {}
+                for j0 in range(0, cnt, 2 if half else 1):               # stream order: per step (pair, if half-width), per CTA
+                    for h in range(2):
+                        for st in range(2 if half else 1):
+                            blocks[(j0 + st, h)] = self.stream[self.pos:self.pos + nloc * 64]
+                            self.pos += nloc * 64
+                for j in range(cnt):
+                    W16, F8 = torch.zeros(n, 16), torch.zeros(n, 32)
+                    for h in range(2):
+                        b = blocks[(j, h)]
+                        rows = slice(h * nloc, (h + 1) * nloc)
+                        W16[rows] = b[:nloc * 32].view(torch.float16).float().reshape(2, nloc, 8).permute(1, 0, 2).reshape(nloc, 16)
+                        F8[rows] = b[nloc * 32:].view(torch.float8_e4m3fn).float().reshape(2, nloc, 16).permute(1, 0, 2).reshape(nloc, 32)
+                    a16, a8 = self.operands(op, j)
+                    d = (a16 @ W16.t() + a8 @ F8.t()) / self.S
+                    self.acc[:, col:col + n] = d + (self.acc[:, col:col + n] if (accum or j > 0) else 0)
+
+
+def test_image_ts_program_and_stream_reproduce_the_oracle(monkeypatch):
+    """The epilogue sequence of image_umma_kernel<.., TS = 1> (H in tensor memory, one accumulator, parked skip, ToRGB in fp32):
+    after COMMIT 0 the model overwrites H columns 0..127 in place, after COMMIT 1 columns 128..255."""
+    monkeypatch.setenv('DDMI_B200_IMAGE_TS', '1')
+    m = cases.build_module('image')
+    sd = cases.state_dict32(m)
+    coords, planes, si = cases.image_inputs(batch=1, sizes=(8, 16, 32), res=12)
+    ref = orc.image_decode(sd, coords, planes, si)
+    packed = packing.pack_image(m, si, _lib.PREC_F16F8, pair=True)
+    assert packed.ts and packed.vec_host is not None and len(packed.program_host) <= 256
+    vec = packed.vec.cpu()
+    g = coords.permute(0, 2, 3, 1)
+    X = [torch.nn.functional.grid_sample(p, g, mode='bilinear', padding_mode='border', align_corners=False)[0]
+         .reshape(64, -1).t().contiguous() for p in planes]
+    E = EngineModelTS(packed, rows=144)
+    lr = lambda v: torch.nn.functional.leaky_relu(v, 0.2)
+    E.write(64, X[0])
+    parked = torch.zeros(144, 256)
+
+    def stage(out_of_acc, published, publishes=True):
+        waits, done = E.run_group()
+        assert done == 0
+        lo = out_of_acc(0, 128)
+        if publishes:
+            E.write_h(0, lo)
+        waits2, done = E.run_group()
+        assert done == 1 and sorted(waits + waits2) == ([0, 1, 2, 3, 4, 5] if published else [4, 5])
+        hi = out_of_acc(128, 256)
+        if publishes:
+            E.write_h(128, hi)
+        return torch.cat([lo, hi], dim=1)
+
+    for blk in range(4):
+        bv = vec[blk * 1024:(blk + 1) * 1024]
+        if blk < 3:
+            parked = stage(lambda lo, hi: E.acc[:, lo:hi].clone(), True, publishes=False)      # skip GEMM -> parked
+        stage(lambda lo, hi: lr(E.acc[:, lo:hi] + bv[lo:hi]), blk == 3)                         # conv1
+        if blk < 2:
+            E.write(64, X[blk + 1])
+        stage(lambda lo, hi: lr(E.acc[:, lo:hi] + bv[256 + lo:256 + hi]), True)                 # conv2
+        h = stage(lambda lo, hi: lr(E.acc[:, lo:hi] + bv[512 + lo:512 + hi]) + parked[:, lo:hi]
+                  + (bv[768 + lo:768 + hi] if blk < 3 else 0), True, publishes=blk < 3)         # conv3 + skip
+        if blk == 2:
+            parked = h / math.sqrt(2.0)
+    assert E.ops[E.pc] & 3 == 3 and E.pos == E.stream.numel()
+    out = (h @ vec[4096:4096 + 768].reshape(3, 256).t() + vec[4096 + 768:4096 + 771]).t().reshape(1, 3, 12, 12)
+    assert float((out - ref).abs().max()) < 1e-3
 
 
 def test_programs_consume_exactly_their_streams():

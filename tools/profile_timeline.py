@@ -45,11 +45,13 @@ if not ev:
     print("no trace records: load the profiling build (DDMI_B200_LIB=ddmi_b200/libddmi_b200_prof.so)")
     sys.exit(1)
 t0 = ev[0][0]
-names = {0x01: 'E park', 0x02: 'E woke', 0x03: 'E drained', 0x20: 'E gather begin', 0x21: 'E gather end'}
+names = {0x01: 'E park', 0x02: 'E woke (COMMIT 0)', 0x03: 'E drained', 0x04: 'E COMMIT 1 seen', 0x14: 'E acc cols 128.. drained', 0x15: 'E acc cols 0..127 drained',
+         0x20: 'E gather begin', 0x21: 'E gather end'}
 prev = t0
 for t, i in ev:
     if i >= 0x700: nm = {0x700: 'B wait X free', 0x710: 'B A4 (raw X ready)', 0x720: 'B D1 seen', 0x730: 'B A5 (relu X ready)'}.get(i & 0xFF0, hex(i)) + f' s{i & 15}'
     elif i >= 0x600: nm = f'B blended s{(i - 0x600) // 64} c{(i - 0x600) % 64}'
+    elif i in (0x500, 0x501, 0x502): nm = {0x500: 'M unit begins', 0x501: 'M  MMAs issued', 0x502: 'M  slots released'}[i]
     elif i >= 0x500: nm = f'I issued s{(i - 0x500) // 64} c{(i - 0x500) % 64}'
     elif i >= 0x400: nm = f'M COMMIT pc{i - 0x400}'
     elif i >= 0x300: nm = f'M WAIT ok pc{i - 0x300}'

@@ -1,0 +1,2 @@
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -4
