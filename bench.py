@@ -627,6 +627,104 @@ def run_other(args):
     print(json.dumps(line))
 
 
+def run_mesh(args):
+    """Occupancy post-step: one mesh = the reference's dense-grid generation of one decoded latent
+    (generation.py:84-98,123-186) -- 128^3 queries in eval_points chunks of 100k, then marching cubes -- everything on the
+    device.  metric = meshes / s; the marching-cubes kernels are HBM / latency-bound index work, so the roofline leg is their
+    algorithmic bytes over the measured copy bandwidth.  CPU baseline = the reference's own post-step: logits -> host ->
+    libmcubes (oracle/_ref), the decode excluded."""
+    import numpy as np
+    import ddmi_b200
+    from ddmi_b200 import generation as gen
+    torch.set_grad_enabled(False)
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator().manual_seed(777)
+    torch.manual_seed(777)
+    B = args.batch if args.batch != 64 else 8
+    m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
+    for blk in (m.net_res1, m.net_res2, m.net_res3, m.net_res4):
+        torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
+    m.precision = args.precision
+    host = [[(3.0 * torch.randn(B, 64, s, s, generator=g)).pin_memory() for s in (16, 32, 64)] for _ in range(3)]
+    planes = [[t.to(dev) for t in axis] for axis in host]
+    item = lambda P, i: tuple([t[i:i + 1] for t in axis] for axis in P)
+    nx = 128
+
+    def step(P=planes):
+        out = []
+        for i in range(B):
+            out.append(gen.generate_mesh(item(P, i), m, resolution0=nx))
+        return out
+    for _ in range(args.warmup):
+        res = step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        res = step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    clocks = sampler.stop()
+    # marching cubes alone on the resident grids
+    grids = [r[2] for r in res]
+    for gr in grids:
+        gen.extract_mesh(gr)
+    torch.cuda.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for gr in grids:
+        gen.extract_mesh(gr)
+    m1.record()
+    torch.cuda.synchronize()
+    mc_ms = m0.elapsed_time(m1) / B
+    nv = sum(r[0].shape[0] for r in res) / B
+    nt = sum(r[1].shape[0] for r in res) / B
+    # end to end: pinned host planes -> device, mesh -> pinned host
+    def e2e():
+        P = [[t.to(dev, non_blocking=True) for t in axis] for axis in host]
+        return [(v.cpu(), t.cpu()) for v, t, _ in step(P)]
+    e2e()
+    torch.cuda.synchronize()
+    a = time.perf_counter()
+    out = e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - a
+    _, hbm_peak, which = peaks()
+    cells = (nx + 1) ** 3
+    alg_bytes = 2 * 4 * nx ** 3 + cells * (4 + 8 + 8 + 4 + 8) + nv * 24 + nt * 24   # grid twice, info + counts + scan + re-reads, outputs
+    line = {"metric": "meshes extracted / s (128^3 occupancy grid: eval_points + marching cubes)", "value": B * args.steps / (ms * 1e-3),
+            "unit": "meshes/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 vertices / int64 indices (decode: " + args.precision + ")",
+            "data": "synthetic",
+            "config": {"workload": f"occupancy post-step: {B} latents (triplanes 16^2/32^2/64^2 x64ch), each 128^3 queries in 100k chunks "
+                                   f"+ marching cubes at logit(0.2), padded with -1e6", "mean_vertices": nv, "mean_triangles": nt,
+                       "l2": "logit grid 8.4 MB + 34 MB of per-cell bookkeeping per mesh: L2-resident"},
+            "e2e": {"value": B / e2e_s, "unit": "meshes/s", "h2d_bytes_per_step": sum(t.numel() * 4 for ax in host for t in ax),
+                    "d2h_bytes_per_step": int(sum(v.numel() * 8 + t.numel() * 8 for v, t in out)), "steps": 1},
+            "gpu_launches": args.steps * B * (21 + 5), "clocks": clocks,
+            "breakdown_ms_per_mesh": {"eval_points_plus_marching_cubes": ms / args.steps / B, "marching_cubes": mc_ms},
+            "roofline": {"bound": "hbm", "achieved": alg_bytes / (mc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / (mc_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": which,
+                         "kernel": "mcubes::classify / scan / emit (5 launches + one 16-byte read-back per mesh)",
+                         "note": "small, launch- and latency-bound: 2.1 M cells per mesh"}}
+    if not args.no_cpu_baseline:
+        from oracle import mcubes_oracle as mo      # the checker, timed as the baseline only
+        gr = grids[0]
+        t = time.perf_counter()
+        h = gr.cpu().numpy().astype(np.float64)
+        refm = mo.extract_mesh(h, 0.2, 0.1, mc=mo.ref_marching_cubes) if mo.ref_marching_cubes(np.zeros((2, 2, 2)), 0.5) is not None else None
+        dt = time.perf_counter() - t
+        if refm is not None:
+            same = bool(np.array_equal(refm[0], res[0][0].cpu().numpy()) and np.array_equal(refm[1], res[0][1].cpu().numpy()))
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "meshes/s (post-step only: D2H + libmcubes)", "cores": 1, "kind": "reference",
+                                    "sample": "one 128^3 grid: .cpu() + the reference's marching cubes (oracle/_ref) + vertex normalisation",
+                                    "identical_to_gpu_mesh": same, "gpu_post_step_speedup": dt / (mc_ms * 1e-3)}
+    print(json.dumps(line))
+
+
 def cpu_baseline(res, batch, repeats=1):
     """The oracle port of the reference decoder on the host cores (bounded sample of the same workload)."""
     from oracle import ddmi_oracle as orc   # the checker, timed here as the CPU baseline only
@@ -702,12 +800,14 @@ if __name__ == '__main__':
     ap.add_argument('--cpu-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling (sharded batch 64 + all-gather) leg')
-    ap.add_argument('--workload', default='image', choices=['image', 'c1', 'occupancy', 'video', 'nerf'],
+    ap.add_argument('--workload', default='image', choices=['image', 'c1', 'occupancy', 'video', 'nerf', 'mesh'],
                     help='image = the headline (BASELINE configs[1]); c1 / video / occupancy / nerf = configs[0], [2], [3], [4], 1 GPU')
     ap.add_argument('--cpu-coords', type=int, default=131072, help='coordinates in the CPU-baseline sample of the non-headline workloads')
     ARGS = ap.parse_args()
     if ARGS.impl == 'reference':
         run_reference(ARGS)
+    elif ARGS.workload == 'mesh':
+        run_mesh(ARGS)
     elif ARGS.workload != 'image':
         run_other(ARGS)
     else:

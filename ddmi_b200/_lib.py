@@ -25,7 +25,7 @@ EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
     "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_decode_image_noise", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
     "ddmi_decode_video", "ddmi_decode_video_store",
-    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_sample_pdf", "ddmi_selftest_tma", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
+    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_sample_pdf", "ddmi_mcubes_workspace_bytes", "ddmi_mcubes_count", "ddmi_mcubes_emit", "ddmi_selftest_tma", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
     "ddmi_debug_trace", "ddmi_debug_set", "ddmi_debug_gatherbench", "ddmi_debug_ringbench", "ddmi_debug_microbench",
 )
 
@@ -90,6 +90,9 @@ def lib():
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]
         L.ddmi_nerf_render_z.argtypes = L.ddmi_nerf_render.argtypes
         L.ddmi_sample_pdf.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+        L.ddmi_mcubes_workspace_bytes.argtypes = [i32, i32, i32, i32, vp]
+        L.ddmi_mcubes_count.argtypes = [vp, i32, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, ctypes.c_uint64, vp, vp]
+        L.ddmi_mcubes_emit.argtypes = [vp, i32, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]
         L.ddmi_selftest_tma.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp]
         L.ddmi_selftest_umma.argtypes = [vp, vp, vp, i32, i32, vp]
         L.ddmi_selftest_umma2.argtypes = [vp, vp, vp, i32, i32, vp]

@@ -70,6 +70,9 @@ static int check_weights(const ddmi_weights_t* w, uint64_t need_gemm_bytes, uint
   return DDMI_OK;
 }
 
+int mcubes_workspace_bytes(int, int, int, int, unsigned long long*);
+int launch_mcubes_count(const float*, int, int, int, int, double, double, void*, unsigned long long, unsigned long long*, cudaStream_t);
+int launch_mcubes_emit(const float*, int, int, int, int, double, double, const void*, const double*, double*, long long*, cudaStream_t);
 }  // namespace ddmi
 
 using namespace ddmi;
@@ -358,6 +361,29 @@ DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const floa
   DDMI_REQUIRE(n_bins >= 2 && n_bins <= 1024, "n_bins must be in [2, 1024] (got %d)", n_bins);
   DDMI_REQUIRE(n_rays <= 4LL * 2147483647LL, "too many rays for one launch");
   return launch_sample_pdf(bins, weights, u, n_rays, n_bins, n_samples, out, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_mcubes_workspace_bytes(int32_t nx, int32_t ny, int32_t nz, int32_t pad, uint64_t* bytes) {
+  DDMI_REQUIRE(bytes, "bytes is NULL");
+  unsigned long long b = 0;
+  const int rc = mcubes_workspace_bytes(nx, ny, nz, pad, &b);
+  *bytes = b;
+  return rc;
+}
+
+DDMI_API int ddmi_mcubes_count(const float* grid, int32_t nx, int32_t ny, int32_t nz, int32_t pad, double pad_value, double isovalue,
+                               void* workspace, uint64_t workspace_bytes, uint64_t* totals_dev, void* stream) {
+  DDMI_REQUIRE(grid && workspace && totals_dev, "grid / workspace / totals_dev is NULL");
+  return launch_mcubes_count(grid, nx, ny, nz, pad, pad_value, isovalue, workspace, workspace_bytes,
+                             (unsigned long long*)totals_dev, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_mcubes_emit(const float* grid, int32_t nx, int32_t ny, int32_t nz, int32_t pad, double pad_value, double isovalue,
+                              const void* workspace, const double* affine, double* vertices, int64_t* triangles, void* stream) {
+  DDMI_REQUIRE(grid && workspace, "grid / workspace is NULL");
+  DDMI_REQUIRE(vertices && triangles, "vertices / triangles is NULL (an empty mesh needs no emit call)");
+  return launch_mcubes_emit(grid, nx, ny, nz, pad, pad_value, isovalue, workspace, affine, vertices, (long long*)triangles,
+                            (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_selftest_tma(const float* plane, int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t x,

@@ -205,14 +205,81 @@ constexpr uint32_t PARK_STRIDE = NEPI * 16;   // chunk c of a thread: park + c *
 // KIND 1: y = lrelu(acc + b) + parked;  blk 2: parked <- y / sqrt2 (res4's identity skip);
 //         blk < 3: H = y, else rgb += Wrgb y (ToRGB; nothing is published)
 // KIND 2: parked <- acc + cs                                         (skip GEMM; cs = the folded scale-injection columns)
+// One quarter of a stage (this thread's 32 columns starting at col0 = q * 64 + sub * 32); pb = the quarter's bias / skip constant.
+template <int KIND, int NOISE, class Sig>
+__device__ __forceinline__ void image_ts_quarter(uint32_t tmem_lane, uint32_t park, int q, int col0, float2 (&v)[16],
+                                                 float2 (&pb)[16], Sig sig, float2 nz2, int blk, const RgbParam& rgbw,
+                                                 float (&rgb)[3]) {
+  if (KIND == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = __ffma2_rn(pb[2 * i], make_float2(kF8Scale, kF8Scale), v[2 * i]);
+      const float2 c = __ffma2_rn(pb[2 * i + 1], make_float2(kF8Scale, kF8Scale), v[2 * i + 1]);
+      st_shared_v4(park + (q * 8 + i) * PARK_STRIDE,
+                   make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y)));
+    }
+    return;
+  }
+  if (NOISE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pb[i] = __fadd2_rn(pb[i], nz2);
+  }
+  if (KIND == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = image_act<1>(v[i], pb[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = ld_shared_v4(park + (q * 8 + i) * PARK_STRIDE);
+      v[2 * i] = __ffma2_rn(make_float2(__uint_as_float(u.x), __uint_as_float(u.y)), make_float2(kF8InvScale, kF8InvScale),
+                            image_act<1>(v[2 * i], pb[2 * i]));
+      v[2 * i + 1] = __ffma2_rn(make_float2(__uint_as_float(u.z), __uint_as_float(u.w)), make_float2(kF8InvScale, kF8InvScale),
+                                image_act<1>(v[2 * i + 1], pb[2 * i + 1]));
+    }
+    if (blk == 2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 a = __fmul2_rn(v[2 * i], make_float2(kInvSqrt2 * kF8Scale, kInvSqrt2 * kF8Scale));
+        const float2 c = __fmul2_rn(v[2 * i + 1], make_float2(kInvSqrt2 * kF8Scale, kInvSqrt2 * kF8Scale));
+        st_shared_v4(park + (q * 8 + i) * PARK_STRIDE,
+                     make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y)));
+      }
+    }
+  }
+  if (KIND == 1 && blk == 3) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        a0 = fmaf(v[i].x, rgbw.w[c * 256 + col0 + 2 * i], a0);
+        a1 = fmaf(v[i].y, rgbw.w[c * 256 + col0 + 2 * i + 1], a1);
+      }
+      rgb[c] += a0 + a1;
+    }
+  } else {
+    publish_ts(tmem_lane, col0, v);
+    tmem_st_wait();
+    sig(q);
+  }
+}
+
+// CODE SIZE is a first-order concern here: with every stage, quarter and call site unrolled the epilogue threads walked ~160 KB
+// of straight-line code per tile and 35 % of their stall samples were instruction-cache misses
+// (profiles/r02_image_ts_ncu_before_code_diet.md).  A stage is therefore a two-trip loop over accumulator halves (two quarters
+// unrolled in the body), conv1 / conv2 share one call site, and the three conv3 flavours are one body with run-time switches.
+// KIND 0: H = lrelu(acc + b)                                         (conv1 / conv2)
+// KIND 1: y = lrelu(acc + b) + parked;  blk 2: parked <- y / sqrt2 (res4's identity skip);
+//         blk < 3: H = y, else rgb += Wrgb y (ToRGB; nothing is published)
+// KIND 2: parked <- acc + cs                                         (skip GEMM; cs = the folded scale-injection columns)
 template <int KIND, int NOISE, class Sig, class WaitA, class WaitB>
 __device__ __forceinline__ void image_ts_stage(uint32_t tmem_lane, uint32_t park, int sub, const float* __restrict__ vecs,
                                                Sig sig, WaitA wait_a, WaitB wait_b, float nz, int blk, bool more,
                                                const RgbParam& rgbw, float (&rgb)[3]) {
   // vecs: KIND 0 / 1 the bias, KIND 2 the skip constant (256 floats); this thread's 32 columns of quarter q start at q * 64 + sub * 32
   const float* vp = vecs + sub * 32;
-  float2 pb[16];                                          // vector of the quarter about to be converted
-  load_vec<16>(vp, pb);                                   // in flight while the thread parks on the MMA barrier
+  float2 pa[16], pb[16];                                  // vectors of the even / odd quarter: no copies between them
+  load_vec<16>(vp, pa);                                   // quarter 0's: in flight while the thread parks on the MMA barrier
   const float2 nz2 = make_float2(nz, nz);
 #pragma unroll 1
   for (int h = 0; h < 2; ++h) {
@@ -226,70 +293,10 @@ __device__ __forceinline__ void image_ts_stage(uint32_t tmem_lane, uint32_t park
 #pragma unroll
       for (int q2 = 0; q2 < 4; ++q2) sig(q2);
     }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int q = 2 * h + j, col0 = q * 64 + sub * 32;
-      float2 bn[16];
-      if (j == 0 || h == 0) load_vec<16>(vp + (q + 1) * 64, bn);   // next quarter's vector, in flight during this conversion
-      if (KIND == 2) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 a = __ffma2_rn(pb[2 * i], make_float2(kF8Scale, kF8Scale), v[j][2 * i]);
-          const float2 c = __ffma2_rn(pb[2 * i + 1], make_float2(kF8Scale, kF8Scale), v[j][2 * i + 1]);
-          st_shared_v4(park + (q * 8 + i) * PARK_STRIDE,
-                       make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y)));
-        }
-      } else {
-        if (NOISE) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pb[i] = __fadd2_rn(pb[i], nz2);
-        }
-        if (KIND == 0) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[j][i] = image_act<1>(v[j][i], pb[i]);
-        } else {
-          float2 sp[16];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint4 u = ld_shared_v4(park + (q * 8 + i) * PARK_STRIDE);
-            sp[2 * i] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y));
-            sp[2 * i + 1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            v[j][i] = __ffma2_rn(sp[i], make_float2(kF8InvScale, kF8InvScale), image_act<1>(v[j][i], pb[i]));
-          if (blk == 2) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float2 a = __fmul2_rn(v[j][2 * i], make_float2(kInvSqrt2 * kF8Scale, kInvSqrt2 * kF8Scale));
-              const float2 c = __fmul2_rn(v[j][2 * i + 1], make_float2(kInvSqrt2 * kF8Scale, kInvSqrt2 * kF8Scale));
-              st_shared_v4(park + (q * 8 + i) * PARK_STRIDE,
-                           make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(c.x), __float_as_uint(c.y)));
-            }
-          }
-        }
-        if (KIND == 1 && blk == 3) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              a0 = fmaf(v[j][i].x, rgbw.w[c * 256 + col0 + 2 * i], a0);
-              a1 = fmaf(v[j][i].y, rgbw.w[c * 256 + col0 + 2 * i + 1], a1);
-            }
-            rgb[c] += a0 + a1;
-          }
-        } else {
-          publish_ts(tmem_lane, col0, v[j]);
-          tmem_st_wait();
-          sig(q);
-        }
-      }
-      if (j == 0 || h == 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pb[i] = bn[i];
-      }
-    }
+    load_vec<16>(vp + (2 * h + 1) * 64, pb);              // in flight during the even quarter's conversion
+    image_ts_quarter<KIND, NOISE>(tmem_lane, park, 2 * h, (2 * h) * 64 + sub * 32, v[0], pa, sig, nz2, blk, rgbw, rgb);
+    if (h == 0) load_vec<16>(vp + 128, pa);               // quarter 2's, in flight during the odd quarter's conversion
+    image_ts_quarter<KIND, NOISE>(tmem_lane, park, 2 * h + 1, (2 * h + 1) * 64 + sub * 32, v[1], pb, sig, nz2, blk, rgbw, rgb);
   }
 }
 

@@ -25,6 +25,8 @@
  *                          (+ :455-475 run_network, :82-112 Embedder.embed,
  *                             :487-530 raw2outputs)
  *   ddmi_sample_pdf        utils/nerf_helpers.py:166-209 sample_pdf
+ *   ddmi_mcubes_*          convocc/src/utils/libmcubes/marchingcubes.h:23-193 mc::marching_cubes (libmcubes.marching_cubes,
+ *                          pywrapper.cpp:90-107) + the vertex post-processing of convocc/src/conv_onet/generation.py:152-186
  * The reference binds its native ops with pybind11 inside a JIT torch extension
  * (models/d2c_vae/op/fused_bias_act.cpp:18-20); INTEGRATION.md shows the ctypes
  * stub a maintainer adds instead.
@@ -238,6 +240,28 @@ DDMI_API int ddmi_nerf_render_z(const ddmi_plane_t planes[3], int32_t batch, int
  */
 DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays, int32_t n_bins,
                              int32_t n_samples, float* out, void* stream);
+
+/*
+ * Occupancy post-step: marching cubes on a decoded logit grid, on the GPU (the reference copies the grid to the host and runs
+ * libmcubes there: generation.py:130-144,166-168).  grid: (nx, ny, nz) fp32 device memory, z fastest -- the order of
+ * make_3d_grid / value_grid (generation.py:90-97).  pad = 1 surrounds it with one layer of pad_value (the reference pads with
+ * -1e6 so the mesh closes: generation.py:164-165), pad = 0 takes it as is.  The mesh is the reference's bit for bit: vertices
+ * (float64, + 0.5 grid units as libmcubes leaves them) and triangles in the order its sequential sweep appends them, the
+ * duplicated vertices on the low faces of the volume included.
+ *   1. ddmi_mcubes_workspace_bytes -> size of the scratch buffer (16 B per cell of the padded volume)
+ *   2. ddmi_mcubes_count: classify + prefix sums; totals_dev[0] = vertices, totals_dev[1] = triangle corners (3 per triangle),
+ *      two uint64 in device memory -- read them back to size the outputs
+ *   3. ddmi_mcubes_emit: vertices (totals[0] x 3 float64) and triangles (totals[1] int64 vertex indices), device memory.
+ *      affine = NULL, or 7 host doubles {sub0, sub1, div_x, div_y, div_z, sub2, mul}: every vertex component becomes
+ *      mul * ((((v - sub0) - sub1) / div_axis) - sub2), float64, in that order -- Generator3D.extract_mesh's
+ *      "vertices -= 0.5; vertices -= 1; vertices /= (n - 1); vertices = box_size * (vertices - 0.5)".
+ * At most 2^28 - 1 cells per call.
+ */
+DDMI_API int ddmi_mcubes_workspace_bytes(int32_t nx, int32_t ny, int32_t nz, int32_t pad, uint64_t* bytes);
+DDMI_API int ddmi_mcubes_count(const float* grid, int32_t nx, int32_t ny, int32_t nz, int32_t pad, double pad_value, double isovalue,
+                               void* workspace, uint64_t workspace_bytes, uint64_t* totals_dev, void* stream);
+DDMI_API int ddmi_mcubes_emit(const float* grid, int32_t nx, int32_t ny, int32_t nz, int32_t pad, double pad_value, double isovalue,
+                              const void* workspace, const double* affine, double* vertices, int64_t* triangles, void* stream);
 
 /*
  * Bring-up self test of the plane-window TMA path (cp.async.bulk.tensor.3d over an NCHW fp32 plane batch): the 64 (x) x 2 (y)

@@ -124,3 +124,16 @@ def nerf_mlp_inputs(n=1500, seed=SEED):
 
 def checksum(tensors):
     return float(sum(t.double().abs().sum() for t in tensors))
+
+
+# ---------------------------------------------------------------------------
+# occupancy post-step (marching cubes): seeded logit-like volumes
+# ---------------------------------------------------------------------------
+def mcubes_volume(shape, seed=0, noise=0.8, scale=1.0):
+    """float32 (nx, ny, nz): a noisy ball (positive inside) -- many surface cases, touches the volume faces for small shapes."""
+    g = torch.Generator().manual_seed(SEED + 70 + seed)
+    ax = [torch.arange(s, dtype=torch.float32) - (s - 1) / 2 for s in shape]
+    gx, gy, gz = torch.meshgrid(*ax, indexing='ij')
+    r = torch.sqrt(gx * gx + gy * gy + gz * gz)
+    vol = 0.4 * min(shape) - r + noise * torch.randn(shape, generator=g)
+    return (scale * vol).to(torch.float32).contiguous()

@@ -130,3 +130,28 @@ def test_sample_pdf(golden_dir):
     np.random.seed(0)
     u = torch.Tensor(np.random.rand(300, 96))
     assert float((orc.sample_pdf(g['bins'], g['weights'], u) - g['out_pytest']).abs().max()) < 1e-6
+
+
+def test_marching_cubes_oracle_is_the_reference(golden_dir):
+    """Occupancy post-step: the Python restatement of libmcubes against the REFERENCE's outputs (oracle/_ref, committed as
+    tests/golden/mcubes.pt) -- bit for bit, vertex and triangle order included; and against oracle/_ref itself when built."""
+    import numpy as np
+    from oracle import mcubes_oracle as mo
+    g = torch.load(os.path.join(golden_dir, 'mcubes.pt'))
+    for i, name in enumerate(('a', 'b', 'c')):
+        c = g[name]
+        vol = cases.mcubes_volume(c['shape'], seed=i)
+        assert float(vol.double().sum()) == c['vol_sum']
+        v, t = mo.marching_cubes(vol.numpy(), c['iso'])
+        assert np.array_equal(v, c['vertices'].numpy().reshape(-1, 3)) and np.array_equal(t, c['triangles'].numpy().reshape(-1, 3))
+        ref = mo.ref_marching_cubes(vol.numpy(), c['iso'])
+        if ref is not None:
+            assert np.array_equal(ref[0], v) and np.array_equal(ref[1], t)
+    c = g['mesh']
+    vol = cases.mcubes_volume(c['shape'], seed=9, noise=0.5, scale=1.5)
+    v, t = mo.extract_mesh(vol.numpy(), 0.2, 0.1)
+    assert np.array_equal(v, c['vertices'].numpy()) and np.array_equal(t, c['triangles'].numpy())
+    # a closed surface: the -1e6 padding makes every edge of the mesh shared by exactly two triangles
+    e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert (cnt == 2).all()

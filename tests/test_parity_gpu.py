@@ -476,12 +476,13 @@ def test_f16f8_selftest(N, K):
     q5 = lambda x: x.clamp(-57344, 57344).to(torch.float8_e5m2).double()         # activation side
     a16 = a.to(torch.float16)
     w16 = (b * S).to(torch.float16)
+    a8 = (a16.view(torch.int16) & -256).view(torch.float16).double()             # e5m2(a) = the high byte of fp16(a) (truncation)
     emu = (a16.double() @ w16.double().t() + q5((a - a16.float()) * S) @ q8(b).t()
-           + q5(a) @ q8(b * S - w16.float()).t()) / S
+           + a8 @ q8(b * S - w16.float()).t()) / S
     ref = a.double() @ b.double().t()
     got = d.double().cpu()
     assert float((got - emu).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
-    assert float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) < 2e-4 * max(1.0, float(ref.abs().max()))
 
 
 @pytest.mark.parametrize("variant", [0, 1])
@@ -854,3 +855,69 @@ def test_repeated_decodes_are_bit_identical(precision):
     rays = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'nerf_render.pt'))['rays'].to(DEV).repeat(3, 1)
     ro = [nh.render_rays_fused(rays, fea, mn, 128, True, precision=precision) for _ in range(3)]
     assert torch.equal(ro[0], ro[1]) and torch.equal(ro[0], ro[2])
+
+
+# ---------------------------------------------------------------- occupancy post-step
+def test_marching_cubes_golden(golden_dir):
+    """ddmi_mcubes_* against the reference's libmcubes outputs (tests/golden/mcubes.pt): bit-exact float64 vertices and int64
+    triangles in the reference's order -- open volumes (no padding), a degenerate one-layer volume, and extract_mesh."""
+    from ddmi_b200 import generation as gen
+    g = torch.load(os.path.join(golden_dir, 'mcubes.pt'))
+    for i, name in enumerate(('a', 'b', 'c')):
+        c = g[name]
+        vol = cases.mcubes_volume(c['shape'], seed=i)
+        v, t = gen.marching_cubes(vol.to(DEV), c['iso'])
+        assert v.dtype == torch.float64 and t.dtype == torch.int64
+        assert torch.equal(v.cpu(), c['vertices'].reshape(-1, 3)) and torch.equal(t.cpu(), c['triangles'].reshape(-1, 3))
+    c = g['mesh']
+    vol = cases.mcubes_volume(c['shape'], seed=9, noise=0.5, scale=1.5)
+    v, t = gen.extract_mesh(vol.to(DEV), 0.2, 0.1)
+    assert torch.equal(v.cpu(), c['vertices']) and torch.equal(t.cpu(), c['triangles'])
+    with pytest.raises(RuntimeError):
+        gen.marching_cubes(vol, 0.0)                         # CPU tensor
+    with pytest.raises(RuntimeError):
+        gen.marching_cubes(vol.to(DEV)[0], 0.0)              # not 3-D
+
+
+def test_marching_cubes_full_grid_vs_reference_and_oracle():
+    """128^3 (the reference's generation resolution): against the reference's own code (oracle/_ref) when it travelled with
+    the snapshot, and always through size-independent properties: closed surface (every edge in exactly two triangles),
+    every vertex on a grid edge between a sample above and one below the threshold, index range, empty volume."""
+    import numpy as np
+    from ddmi_b200 import generation as gen
+    from oracle import mcubes_oracle as mo
+    vol = cases.mcubes_volume((128, 128, 128), seed=5, noise=0.3)
+    v, t = gen.extract_mesh(vol.to(DEV), 0.2, 0.1)
+    assert v.shape[0] > 50000 and int(t.min()) == 0 and int(t.max()) == v.shape[0] - 1
+    ref = mo.ref_marching_cubes(np.pad(vol.numpy().astype(np.float64), 1, 'constant', constant_values=-1e6),
+                                np.log(0.2) - np.log(0.8))
+    if ref is not None:
+        rv = 1.1 * ((ref[0] - 0.5 - 1) / 127.0 - 0.5)
+        assert np.array_equal(rv, v.cpu().numpy()) and np.array_equal(ref[1], t.cpu().numpy())
+    tt = t.cpu().numpy()
+    e = np.sort(np.concatenate([tt[:, [0, 1]], tt[:, [1, 2]], tt[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e, axis=0, return_counts=True)
+    assert (cnt == 2).all()
+    # raw grid-unit vertices: exactly one coordinate is off the half-integer lattice (or the vertex sits on a sample)
+    rawv, _ = gen.marching_cubes(torch.nn.functional.pad(vol, (1,) * 6, value=-1e6).to(DEV), np.log(0.2) - np.log(0.8))
+    frac = (rawv - 0.5) - torch.floor(rawv - 0.5)
+    assert int(((frac != 0).sum(dim=1) <= 1).all())
+    ev, et = gen.extract_mesh(torch.full((16, 16, 16), -5.0, device=DEV), 0.2, 0.1)
+    assert ev.shape == (0, 3) and et.shape == (0, 3)
+
+
+def test_generate_mesh_pipeline_matches_oracle_on_decoded_logits():
+    """eval_points -> value grid -> extract_mesh, all on the device, against the oracle's mesh of the SAME decoded logits
+    (the decode itself is covered by the occupancy parity tests), and eval_points' chunking against one big query."""
+    import numpy as np
+    from ddmi_b200 import generation as gen
+    from oracle import mcubes_oracle as mo
+    m = cases.build_module('occupancy').to(DEV)
+    _, hdbf = cases.occupancy_inputs(n=10)
+    c = tuple([t[:1].to(DEV) * 3.0 for t in axis] for axis in hdbf)
+    v, t, grid = gen.generate_mesh(c, m, resolution0=24, points_batch_size=5000)
+    assert grid.shape == (24, 24, 24)
+    pts = (1.1 * ddmi_b200.make_3d_grid((-0.5,) * 3, (0.5,) * 3, (24,) * 3)).to(DEV)
+    assert torch.equal(grid.reshape(-1), m(pts[None], c).logits[0])
+    ov, ot = mo.extract_mesh(grid.cpu().numpy(), 0.2, 0.1)
+    assert np.array_equal(ov.reshape(-1, 3), v.cpu().numpy()) and np.array_equal(ot.reshape(-1, 3), t.cpu().numpy())
