@@ -394,7 +394,7 @@ def run_ours(args):
         line["parity"] = {"max_abs_vs_fp32_kernel": float((got - exact).abs().max()), "tolerance": 1e-3,
                           "sample": "4 items @ 256x256, same planes and weights"}
         other = {'f16f8': 'bf16x3', 'bf16x3': 'f16f8'}.get(args.precision)
-        if other:
+        if other and not args.no_cpu_baseline:        # context legs are skipped together (profiler runs, quick checks)
             mlp.precision = other
             step()
             torch.cuda.synchronize()
