@@ -200,7 +200,7 @@ def strong_scaling(args, mlp, dev, world, rank, grids):
         def timed(fn, reps):
             best = float('inf')
             out = None
-            for _ in range(reps):
+            for _ in range(reps + 1):                          # the first repetition warms up (allocations after empty_cache)
                 dist.barrier()
                 torch.cuda.synchronize()
                 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -211,6 +211,7 @@ def strong_scaling(args, mlp, dev, world, rank, grids):
                 t = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 best = min(best, float(t[0]))
+                row.setdefault('all_ms', []).append(round(float(t[0]), 2))
             return best, out
 
         row['decode_ms'], mine = timed(lambda: sharding.decode_image_sharded(mlp, c, planes, si=si, gather=False), 2)
