@@ -805,9 +805,19 @@ int launch_image_umma(const PlaneSet& ps, int batch, int C, const float* cx, con
                program_words, PROG_MAX);
   DDMI_REQUIRE(!f16f8 || pair, "the f16f8 image kernel runs as CTA pairs only");
   DDMI_REQUIRE(!ts || (f16f8 && vec_host), "a TMEM-resident-activation program needs DDMI_PREC_F16F8 and weights->vec_host");
-  static RgbParam rgbw;   // zero for the programs that do not use it; filled below (by value into the launch) otherwise
-  RgbParam rgbv = rgbw;
-  if (ts) memcpy(rgbv.w, vec_host + 4096, sizeof(rgbv.w));
+  RgbParam rgbv = {};     // ToRGB weights as a launch parameter (constant bank); unused (zero) by the other programs
+  if (ts) {
+    // the issuer of the TS kernel is the op table written out as code (image_ts_issuer.cuh): refuse any other table
+    uint32_t h = 0x811C9DC5u;
+    size_t nops = 0;
+    while (nops < program_words && (program_host[nops] & 3) != OP_END) ++nops;
+    for (size_t i = 0; i < nops; ++i)
+      for (int b = 0; b < 4; ++b) h = (h ^ ((program_host[i] >> (8 * b)) & 0xFF)) * 0x01000193u;
+    DDMI_REQUIRE(nops == kImageTsProgramOps && h == kImageTsProgramHash,
+                 "the MMA program (%zu ops, FNV-1a %08x) is not the one image_ts_issuer.cuh implements (%d ops, %08x): "
+                 "packing._pack_image_ts and the issuer must change together", nops, h, kImageTsProgramOps, kImageTsProgramHash);
+    memcpy(rgbv.w, vec_host + 4096, sizeof(rgbv.w));
+  }
   DDMI_REQUIRE(vec_floats == 4096 + 768 + 3 + 12, "packed vec blob is %zu floats, expected 4879", vec_floats);
   int dev = 0, sms = 0;
   DDMI_CUDA(cudaGetDevice(&dev));

@@ -18,6 +18,11 @@
 namespace ddmi {
 namespace ummak {
 
+// The op table this file writes out (packing._pack_image_ts): number of ops and FNV-1a over their bytes.  The launcher checks the
+// program it is handed against these, tests/test_umma_program_cpu.py pins them on the packing side.
+constexpr int kImageTsProgramOps = 190;
+constexpr uint32_t kImageTsProgramHash = 0x97232c81u;
+
 struct TsIssuer {
   uint32_t bar, tmem, ring_lo32, x16_lo32, x8_lo32;   // x*: descriptor low words of X's fp16 / FP8 K groups in shared memory
   uint32_t ph;                                        // ring phase of the slots about to be consumed

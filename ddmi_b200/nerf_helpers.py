@@ -275,3 +275,20 @@ def render(H, W, K, fea, pose, idx, device, chunk=1024 * 32, rays=None, c2w=None
     rgb = render_rays_fused(ray_batch, fea, module, N_samples, bool(kwargs.get('white_bkgd', False)),
                             perturb=float(kwargs.get('perturb', 0.) or 0.), lindisp=bool(kwargs.get('lindisp', False)))
     return rgb[0] if rgb.shape[0] == 1 else rgb
+
+
+def render_poses(H, W, K, fea, poses, device, near=0., far=1., **kwargs):
+    """Batching across views: the reference renders a Python loop of poses, one `render(...)` call each
+    (tools/ldm/nerf.py:266-272).  Rays are independent, so the rays of all V poses go down as ONE launch.
+    poses: sequence / tensor of V camera-to-world matrices (3x4 or 4x4).  -> (V, H*W, 3), or (B, V, H*W, 3) for B objects.
+    Identical to stacking `render(H, W, K, fea, None, 0, device, c2w=pose, near=near, far=far, use_viewdirs=True, **kwargs)`
+    over the poses when perturb == 0 (with perturb the reference draws its stratified offsets per call, i.e. in a different
+    order of the same CPU generator)."""
+    ro, rd = [], []
+    for c2w in poses:
+        o, d = get_rays(H, W, K, c2w[:3, :4], device)
+        ro.append(o.reshape(-1, 3))
+        rd.append(d.reshape(-1, 3))
+    V = len(ro)
+    rgb = render(H, W, K, fea, None, 0, device, rays=(torch.cat(ro), torch.cat(rd)), near=near, far=far, use_viewdirs=True, **kwargs)
+    return rgb.reshape(V, H * W, 3) if rgb.dim() == 2 else rgb.reshape(rgb.shape[0], V, H * W, 3)

@@ -921,3 +921,25 @@ def test_generate_mesh_pipeline_matches_oracle_on_decoded_logits():
     assert torch.equal(grid.reshape(-1), m(pts[None], c).logits[0])
     ov, ot = mo.extract_mesh(grid.cpu().numpy(), 0.2, 0.1)
     assert np.array_equal(ov.reshape(-1, 3), v.cpu().numpy()) and np.array_equal(ot.reshape(-1, 3), t.cpu().numpy())
+
+
+def test_nerf_render_poses_equals_the_loop_of_renders():
+    """SURVEY 8f row 4, batching across views: one launch over the rays of all poses == the reference's loop of render() calls."""
+    m = cases.build_module('nerf').to(DEV)
+    res, K, fea, _ = cases.nerf_inputs(res=12)
+    embed_fn, _ = nh.get_embedder(10, 0)
+    embeddirs_fn, _ = nh.get_embedder(4, 0)
+    cfg = {'model': {'TN': {'netchunk': 40000, 'peturb': 0, 'N_importance': 0, 'N_samples': 128, 'use_viewdirs': True,
+                            'white_bkgd': True, 'raw_noise_std': 0}}}
+    kw = nh.get_render_kwargs(cfg, m, embed_fn, embeddirs_fn)
+    near, far = kw.pop('near'), kw.pop('far')
+    kw.pop('use_viewdirs', None)
+    kw.pop('ndc', None)
+    poses = [nh.pose_spherical(th, -20, 5) for th in (0.0, 95.0, 250.0)]
+    feac = _cuda(fea)
+    batched = nh.render_poses(res, res, K, feac, poses, DEV, near=near, far=far, **kw)
+    assert batched.shape == (3, res * res, 3)
+    for v, pose in enumerate(poses):
+        one = nh.render(res, res, K, feac, None, 0, DEV, chunk=4096, c2w=pose[:3, :4], near=near, far=far, use_viewdirs=True,
+                        verbose=True, retraw=True, hw_idx=None, **kw)
+        assert torch.equal(one, batched[v])

@@ -6,6 +6,7 @@ without a GPU, that stream order, K-group addressing, accumulator columns, accum
 CTA-pair half split and the folded biases all line up (the GPU tests then only have to prove the
 CUDA side)."""
 import math
+import os
 
 import pytest
 import torch
@@ -285,6 +286,14 @@ def test_image_ts_program_and_stream_reproduce_the_oracle(monkeypatch):
     ref = orc.image_decode(sd, coords, planes, si)
     packed = packing.pack_image(m, si, _lib.PREC_F16F8, pair=True)
     assert packed.ts and packed.vec_host is not None and len(packed.program_host) <= 256
+    # csrc/image_ts_issuer.cuh is this op table written out as code: the launcher refuses any other (kImageTsProgramOps / Hash)
+    ops = [o & 0xFFFFFFFF for o in packed.program_host.tolist()][:-4]
+    h = 0x811C9DC5
+    for o in ops:
+        for b in range(4):
+            h = ((h ^ ((o >> (8 * b)) & 0xFF)) * 0x01000193) & 0xFFFFFFFF
+    src = open(os.path.join(os.path.dirname(__file__), '..', 'ddmi_b200', 'csrc', 'image_ts_issuer.cuh')).read()
+    assert f'kImageTsProgramOps = {len(ops)};' in src and f'kImageTsProgramHash = 0x{h:08x}u;' in src
     vec = packed.vec.cpu()
     g = coords.permute(0, 2, 3, 1)
     X = [torch.nn.functional.grid_sample(p, g, mode='bilinear', padding_mode='border', align_corners=False)[0]
