@@ -8,7 +8,9 @@ and marching cubes runs in the library's kernels (ddmi_mcubes_*), producing the 
 
 Not built: MISE refinement (upsampling_steps > 0, libmise), normals estimation, mesh simplification / refinement, trimesh and
 pytorch3d containers -- callers get tensors (vertices float64 (V,3), triangles int64 (T,3)) to wrap as they like."""
+import contextlib
 import ctypes
+import functools
 import math
 
 import torch
@@ -71,10 +73,22 @@ def extract_mesh(occ_hat, threshold=0.2, padding=0.1):
 
 def eval_points(p, c, mlp, points_batch_size=100000):
     """Generator3D.eval_points (generation.py:123-144): occupancy logits of points p (N,3) for ONE latent c = (xy, yz, xz)
-    plane lists, queried in chunks of points_batch_size like the reference -- but the chunks stay on the device.
-    (The fused decoder takes any N in one launch; the chunking is kept for call-pattern parity and bounded scratch.)"""
-    outs = [mlp(pi.unsqueeze(0), c).logits.squeeze(0).to(torch.float32) for pi in torch.split(p, points_batch_size)]
-    return torch.cat(outs, dim=0) if outs else torch.empty(0, device=p.device)
+    plane lists; the result stays on the device.  The reference queries chunks of points_batch_size to bound its memory
+    (every chunk materialises (N, 320) features); points are independent, so chunking does not change a single logit, and the
+    fused decoder streams 128-point tiles: points_batch_size is accepted and the query goes down in launches of up to 2^23
+    points (21 launches of 100k points cost 2.5x the time of one launch of 2.1 M: wave quantisation + per-call host work)."""
+    if p.shape[0] == 0:
+        return torch.empty(0, device=p.device)
+    with mlp.weights_unchanged() if hasattr(mlp, 'weights_unchanged') else contextlib.nullcontext():
+        outs = [mlp(pi.unsqueeze(0), c).logits.squeeze(0).to(torch.float32) for pi in torch.split(p, max(points_batch_size, 1 << 23))]
+    return torch.cat(outs, dim=0) if len(outs) > 1 else outs[0]
+
+
+@functools.lru_cache(maxsize=4)
+def _query_grid(nx, box_size, dev):
+    """box_size * make_3d_grid((-0.5,)*3, (0.5,)*3, (nx,)*3) on the device (25 MB at 128^3: built and uploaded once per
+    resolution, not once per mesh -- the reference rebuilds it for every latent)."""
+    return (box_size * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)).to(dev)
 
 
 def generate_mesh(c, mlp, resolution0=128, threshold=0.2, padding=0.1, points_batch_size=100000):
@@ -84,7 +98,7 @@ def generate_mesh(c, mlp, resolution0=128, threshold=0.2, padding=0.1, points_ba
     dev = c[0][0].device
     nx = resolution0
     box_size = 1 + padding
-    pointsf = (box_size * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)).to(dev)
+    pointsf = _query_grid(nx, box_size, str(dev))
     value_grid = eval_points(pointsf, c, mlp, points_batch_size).reshape(nx, nx, nx)
     vertices, triangles = extract_mesh(value_grid, threshold, padding)
     return vertices, triangles, value_grid

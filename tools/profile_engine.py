@@ -7,9 +7,10 @@ from ddmi_b200 import _lib
 kind = sys.argv[1]
 buf = (ctypes.c_uint64 * 8)()
 class A: pass
-a = A(); a.workload = kind; a.batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4; a.steps = 1; a.warmup = 1; a.precision = os.environ.get("DDMI_B200_PRECISION", "f16f8")
+a = A(); a.workload = kind; a.batch = int(sys.argv[2]) if len(sys.argv) > 2 else 4; a.steps = 1; a.warmup = 1; a.precision = os.environ.get("DDMI_B200_PRECISION", "f16f8"); a.no_cpu_baseline = True; a.e2e_chunk = 8; a.cpu_coords = 131072
 import io, contextlib
 bench.ARGS = a
+_lib.check(_lib.lib().ddmi_debug_set(int(os.environ.get('DBG', '0'))))   # what-if switches (1: no epilogue work, 2: no MMAs, 4: no gathers)
 with contextlib.redirect_stdout(io.StringIO()):
     bench.run_other(a)            # warm-up + 1 step
 torch.cuda.synchronize()
