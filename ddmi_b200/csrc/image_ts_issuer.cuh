@@ -38,7 +38,7 @@ constexpr uint32_t kTsSlot16 = 8192 >> 4;                                      /
 __device__ __forceinline__ void ts_spin(uint32_t bar, uint32_t parity) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity))
-    if (++n > (1u << 28)) __trap();   // watchdog by iteration count (seconds): a protocol bug traps instead of hanging the GPU
+    if (++n > (1u << 24)) __trap();   // watchdog by iteration count (0.3 s of spinning at least): a protocol bug traps instead of hanging the GPU
 }
 
 template <int I>
