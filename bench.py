@@ -13,7 +13,10 @@ restatement of the reference decoder (oracle/, the reference itself is Python an
 cannot travel to the GPU box) on a bounded sample, all host threads.
 
 `--workload c1 | video | occupancy | nerf` prints the same line (value, e2e, clocks, roofline,
-cpu_baseline, gpu_eager_baseline) for the other BASELINE configs (configs[0], [2], [3], [4]);
+cpu_baseline, gpu_eager_baseline) for the other BASELINE configs (configs[0], [2], [3], [4]) and
+`--workload mesh` the occupancy post-step (128^3 grid -> mesh); the default (headline) line also carries
+`other_configs`: the device-resident throughput + roofline fraction of those four configs, measured in the
+same command;
 `gpu_eager_baseline` = the same oracle restatement as eager PyTorch fp32 (TF32 off) on the SAME
 B200 in the same run: the like-for-like GPU comparator.  With N > 1 GPUs the
 image line also carries `strong_scaling`: configs[1] with the batch of 64 split over the ranks by
@@ -409,6 +412,10 @@ def run_ours(args):
                                        "unit": UNIT, "steps": 2}
         mlp.precision = args.precision
     if world == 1 and not args.no_cpu_baseline:
+        del planes
+        torch.cuda.empty_cache()
+        # the other BASELINE configs, device-resident, in this same command (their full lines: --workload c1 | video | ...)
+        line["other_configs"] = {k: quick_other(k, args, dev) for k in ('c1', 'video', 'occupancy', 'nerf')}
         line["cpu_baseline"] = cpu_baseline(args.cpu_res, args.cpu_batch)
         line["gpu_eager_baseline"] = gpu_eager_image(dev)
         line["gpu_eager_baseline"]["speedup_of_value"] = value / line["gpu_eager_baseline"]["value"]
@@ -524,6 +531,33 @@ class OtherWorkload:
         r = self.rays[:nr].to(dev)
         fea = dict(zip(('xy', 'yz', 'xz'), planes))
         return nr * 128, lambda: orc.nerf_render_rays(sd, r, fea, 128, True), f"1 object, {nr} rays x 128 samples"
+
+
+def quick_other(kind, args, dev):
+    """Device-resident throughput of one of the non-headline BASELINE configs (3 timed steps after 2 warm-ups), for the
+    `other_configs` key of the headline line: every config is then measured in the same driver-run command."""
+    a = argparse.Namespace(**vars(args))
+    a.batch = 64                                   # = "the config's own batch" in OtherWorkload
+    W = OtherWorkload(kind, a, dev)
+    planes = W.slice(W.host, 0, W.B, dev)
+    for _ in range(2):
+        W.decode(planes)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(3):
+        W.decode(planes)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 3
+    coords = W.B * W.n_per_item
+    tf_peak, _, _ = peaks()
+    value = coords / (ms * 1e-3)
+    out = {"workload": W.desc, "value": value, "unit": UNIT, "ms_per_step": ms, "kernel": W.kernel,
+           "roofline_frac": value * FLOP_PER_COORD[W.flop_kind] / 1e12 / tf_peak}
+    del planes, W
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_other(args):

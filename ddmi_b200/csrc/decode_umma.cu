@@ -373,12 +373,23 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
     Tap pf_tap;
     uint32_t ph_patch = 0;
     // this thread's tap + the tile's tap window (bounding box over the 128 rows); true if a patch load covers it
-    auto patch_plan = [&](long long tile, int s) {
+    // this row's query position of a tile: the three scales of a tile share it, so it is fetched once per tile (an exposed
+    // L2 round trip per scale otherwise), and `coord_prefetch` starts the next tile's fetch a stage before it is needed
+    long long c_tile = -1;
+    float c_x = 0.f, c_y = 0.f;
+    auto coord_fetch = [&](long long tile) {
       if (tile > total_tiles - 1) tile = total_tiles - 1;
+      if (tile == c_tile) return;
       long long gi = (tile % tiles_per_item) * TILE + row;
       if (gi > n - 1) gi = n - 1;
+      c_x = __ldg(cx + gi);
+      c_y = __ldg(cy + gi);
+      c_tile = tile;
+    };
+    auto patch_plan = [&](long long tile, int s) {
+      coord_fetch(tile);
       const int W = ps.w[s];
-      pf_tap = make_tap<false>(__ldg(cx + gi), __ldg(cy + gi), ps.h[s], W);
+      pf_tap = make_tap<false>(c_x, c_y, ps.h[s], W);
       const int x0 = pf_tap.o00 % W, y0 = pf_tap.o00 / W, x1 = pf_tap.o11 % W, y1 = pf_tap.o11 / W;
       const int xmn = __reduce_min_sync(0xffffffffu, x0), xmx = __reduce_max_sync(0xffffffffu, x1);
       const int ymn = __reduce_min_sync(0xffffffffu, y0), ymx = __reduce_max_sync(0xffffffffu, y1);
@@ -593,6 +604,7 @@ image_umma_kernel(PlaneSet ps, const float* __restrict__ cx, const float* __rest
 #pragma unroll
             for (int j = 0; j < 3; ++j) nz[j] *= __ldg(vec + 4096 + 768 + 3 + 3 * blk + j);
           }
+          if (blk == 2 && more) coord_fetch(tile_of(it + 1));     // in flight during the skip stage; used after conv1
           // ---- skip GEMM of the block -> parked (+ the block's skip constant)
           if (blk < 3) image_ts_stage<2, NOISE>(tmem_lane, park, sub, bv + 768, sig, wait_mma, wait_b, 0.f, blk, more, rgbw, rgb);
           // ---- conv1, conv2; after each, one half of the next PE scale (or of the next tile's coarse scale) is gathered:
