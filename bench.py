@@ -760,6 +760,74 @@ def run_mesh(args):
     print(json.dumps(line))
 
 
+def run_planes(args):
+    """Plane-producer tail at the AFHQ decoder's shapes (configs/d2c-vae/afhq.yaml:27-42: ch 128, ch_mult
+    [1,2,4], hdbf at 128 and 64, out_ch 64): heads 512 -> 64 @64^2 and 256 -> 64 @128^2, tail GroupNorm + swish + 3x3 conv
+    128 -> 64 @256^2.  metric = plane sets / s.  fp32 CUDA-core kernels: compared with eager PyTorch (cuDNN / cuBLAS fp32, TF32 off)
+    on the same GPU and with the oracle on the host cores."""
+    import ddmi_b200
+    torch.set_grad_enabled(False)
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(0)
+    g = torch.Generator().manual_seed(777)
+    B = args.batch if args.batch != 64 else 16
+    t = ddmi_b200.PlaneTail(128, 64, (None, 256, 512)).to(dev)
+    hs = [torch.randn(B, 512, 64, 64, generator=g).to(dev), torch.randn(B, 256, 128, 128, generator=g).to(dev),
+          torch.randn(B, 128, 256, 256, generator=g).to(dev)]
+
+    def step(channels_last=False):
+        return [t.head(2, hs[0], channels_last), t.head(1, hs[1], channels_last), t.tail(hs[2], channels_last)]
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10                                      # a step is ~7 ms: ten per "step" so that the clock sampler's start-up does not show
+    t0.record()
+    for _ in range(args.steps * reps):
+        out = step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / (args.steps * reps)
+    clocks = sampler.stop()
+    flops = 2 * B * (64 * 64 * 512 * 64 + 128 * 128 * 256 * 64 + 256 * 256 * 128 * 9 * 64)
+    bytes_ = 4 * sum(h.numel() for h in hs) + 4 * sum(o.numel() for o in out)
+    tf_peak, hbm_peak, which = peaks()
+    line = {"metric": "plane sets emitted / s (AFHQ decoder tail: 2 hdbf heads + norm_out/swish/conv_out)", "value": B / (ms * 1e-3),
+            "unit": "plane sets/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (CUDA cores)", "data": "synthetic",
+            "config": {"workload": f"plane-producer tail, batch {B}: heads 512->64 @64^2, 256->64 @128^2, tail 128->64 3x3 @256^2",
+                       "l2": "inputs %.2f GB per step, larger than L2" % (4 * sum(h.numel() for h in hs) / 1e9)},
+            "gpu_launches": 4 * args.steps * reps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": bytes_ / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": bytes_ / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": which,
+                         "kernel": "ptail::plane_conv_kernel<3, 64, true> (+ gn_stats_kernel, two 1x1 heads)",
+                         "note": "algorithmic bytes = feature maps once + planes once; the 3x3 tail is fp32-FMA-bound, not HBM-bound: "
+                                 "%.1f TFLOP/s of fp32 FMA on the CUDA cores (a tcgen05 implicit GEMM is the next step; the tail is "
+                                 "~2 %% of a generation step)" % (flops / (ms * 1e-3) / 1e12)}}
+    if not args.no_cpu_baseline:
+        from oracle import plane_tail_oracle as po      # the checker, timed as the baseline only
+        tf = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        sd = {k: v.detach() for k, v in t.state_dict().items()}
+        eager = lambda: [po.head(sd, 2, hs[0]), po.head(sd, 1, hs[1]), po.tail(sd, hs[2], 32, False)]
+        ref = eager()
+        dtg = eager_sync_time(eager)
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
+        line["gpu_eager_baseline"] = {"value": B / dtg, "unit": "plane sets/s", "kind": "the oracle (torch conv2d / group_norm, fp32, TF32 off) on this GPU",
+                                      "max_abs_vs_ours": max(float((a - b).abs().max()) for a, b in zip(ref, out))}
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sdc = {k: v.cpu() for k, v in sd.items()}
+        hc = [h[:1].cpu() for h in hs]
+        tt = time.perf_counter()
+        po.head(sdc, 2, hc[0]); po.head(sdc, 1, hc[1]); po.tail(sdc, hc[2], 32, False)
+        line["cpu_baseline"] = {"value": 1.0 / (time.perf_counter() - tt), "unit": "plane sets/s", "cores": cores, "kind": "port",
+                                "sample": "one item, the oracle's torch ops on the host cores"}
+    print(json.dumps(line))
+
+
 def cpu_baseline(res, batch, repeats=1):
     """The oracle port of the reference decoder on the host cores (bounded sample of the same workload)."""
     from oracle import ddmi_oracle as orc   # the checker, timed here as the CPU baseline only
@@ -835,7 +903,7 @@ if __name__ == '__main__':
     ap.add_argument('--cpu-batch', type=int, default=1)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling (sharded batch 64 + all-gather) leg')
-    ap.add_argument('--workload', default='image', choices=['image', 'c1', 'occupancy', 'video', 'nerf', 'mesh'],
+    ap.add_argument('--workload', default='image', choices=['image', 'c1', 'occupancy', 'video', 'nerf', 'mesh', 'planes'],
                     help='image = the headline (BASELINE configs[1]); c1 / video / occupancy / nerf = configs[0], [2], [3], [4], 1 GPU')
     ap.add_argument('--cpu-coords', type=int, default=131072, help='coordinates in the CPU-baseline sample of the non-headline workloads')
     ARGS = ap.parse_args()
@@ -843,6 +911,8 @@ if __name__ == '__main__':
         run_reference(ARGS)
     elif ARGS.workload == 'mesh':
         run_mesh(ARGS)
+    elif ARGS.workload == 'planes':
+        run_planes(ARGS)
     elif ARGS.workload != 'image':
         run_other(ARGS)
     else:

@@ -9,6 +9,7 @@ from .general_utils import (convert_to_coord_format_2d, convert_to_coord_format_
                             get_scale_injection, make_3d_grid)
 from . import nerf_helpers  # noqa: F401
 from . import generation  # noqa: F401
+from .plane_tail import PlaneTail  # noqa: F401
 
 __all__ = ['MLP', 'MLP3D', 'MLPVideo', 'MLPNeRF', 'convert_to_coord_format_2d',
-           'convert_to_coord_format_3d', 'get_scale_injection', 'make_3d_grid', 'nerf_helpers', 'generation']
+           'convert_to_coord_format_3d', 'get_scale_injection', 'make_3d_grid', 'nerf_helpers', 'generation', 'PlaneTail']

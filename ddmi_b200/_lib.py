@@ -25,7 +25,7 @@ EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
     "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_decode_image_noise", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
     "ddmi_decode_video", "ddmi_decode_video_store",
-    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_sample_pdf", "ddmi_mcubes_workspace_bytes", "ddmi_mcubes_count", "ddmi_mcubes_emit", "ddmi_selftest_tma", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
+    "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_sample_pdf", "ddmi_plane_head", "ddmi_plane_tail", "ddmi_mcubes_workspace_bytes", "ddmi_mcubes_count", "ddmi_mcubes_emit", "ddmi_selftest_tma", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
     "ddmi_debug_trace", "ddmi_debug_set", "ddmi_debug_gatherbench", "ddmi_debug_ringbench", "ddmi_debug_microbench",
 )
 
@@ -90,6 +90,8 @@ def lib():
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]
         L.ddmi_nerf_render_z.argtypes = L.ddmi_nerf_render.argtypes
         L.ddmi_sample_pdf.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp]
+        L.ddmi_plane_head.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, i32, vp, vp]
+        L.ddmi_plane_tail.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, ctypes.c_float, vp, vp, i32, i32, i32, vp, vp, vp]
         L.ddmi_mcubes_workspace_bytes.argtypes = [i32, i32, i32, i32, vp]
         L.ddmi_mcubes_count.argtypes = [vp, i32, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, ctypes.c_uint64, vp, vp]
         L.ddmi_mcubes_emit.argtypes = [vp, i32, i32, i32, i32, ctypes.c_double, ctypes.c_double, vp, vp, vp, vp, vp]
@@ -129,6 +131,13 @@ def planes_array(tensors):
     return arr
 
 
+def is_channels_last(t):
+    """(B,C,H,W) fp32 tensor whose memory is (B,H,W,C) dense -- torch.channels_last, e.g. the planes ddmi_b200.plane_tail emits."""
+    import torch
+    return (t.dtype == torch.float32 and t.dim() == 4 and t.shape[1] > 1 and t.stride(1) == 1
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
 def planes_channels_last(tensors, stream):
     """Channels-last copies (B,H,W,C) of contiguous fp32 CUDA planes (B,C,H,W), made by the library's own
     transpose kernel.  Returns (list of NHWC tensors, ctypes plane array)."""
@@ -136,6 +145,10 @@ def planes_channels_last(tensors, stream):
     outs = []
     for t in tensors:
         b, c, h, w = t.shape
+        if is_channels_last(t):          # emitted channels-last by the producer (plane_tail): consumed as is, no copy
+            outs.append(t.permute(0, 2, 3, 1))
+            continue
+        t = t.contiguous()
         o = torch.empty((b, h, w, c), device=t.device, dtype=torch.float32)
         check(lib().ddmi_planes_to_channels_last(t.data_ptr(), o.data_ptr(), b, c, h, w, stream))
         outs.append(o)

@@ -70,6 +70,7 @@ static int check_weights(const ddmi_weights_t* w, uint64_t need_gemm_bytes, uint
   return DDMI_OK;
 }
 
+int launch_plane_conv(const float*, int, int, int, int, int, const float*, const float*, int, float, const float*, const float*, int, int, int, float*, float*, cudaStream_t);
 int mcubes_workspace_bytes(int, int, int, int, unsigned long long*);
 int launch_mcubes_count(const float*, int, int, int, int, double, double, void*, unsigned long long, unsigned long long*, cudaStream_t);
 int launch_mcubes_emit(const float*, int, int, int, int, double, double, const void*, const double*, double*, long long*, cudaStream_t);
@@ -361,6 +362,30 @@ DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const floa
   DDMI_REQUIRE(n_bins >= 2 && n_bins <= 1024, "n_bins must be in [2, 1024] (got %d)", n_bins);
   DDMI_REQUIRE(n_rays <= 4LL * 2147483647LL, "too many rays for one launch");
   return launch_sample_pdf(bins, weights, u, n_rays, n_bins, n_samples, out, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_plane_head(const float* h, int32_t batch, int32_t in_channels, int32_t height, int32_t width, const float* weight,
+                             const float* bias, int32_t out_channels, int32_t out_layout, float* out, void* stream) {
+  DDMI_REQUIRE(h && weight && bias && out, "h / weight / bias / out is NULL");
+  DDMI_REQUIRE(batch >= 1 && in_channels >= 1 && height >= 1 && width >= 1, "empty feature map");
+  DDMI_REQUIRE(out_channels == 64 || out_channels == 32, "plane heads emit 64 (or 32: srn-cars) channels, got %d", out_channels);
+  DDMI_REQUIRE(out_layout == DDMI_LAYOUT_NCHW || out_layout == DDMI_LAYOUT_NHWC, "out_layout must be DDMI_LAYOUT_NCHW / _NHWC");
+  DDMI_REQUIRE(batch <= 65535, "batch %d too large for one launch", batch);
+  return launch_plane_conv(h, batch, in_channels, height, width, 1, nullptr, nullptr, 1, 0.f, weight, bias, out_channels, 0,
+                           out_layout == DDMI_LAYOUT_NHWC, nullptr, out, (cudaStream_t)stream);
+}
+
+DDMI_API int ddmi_plane_tail(const float* h, int32_t batch, int32_t in_channels, int32_t height, int32_t width, const float* gn_weight,
+                             const float* gn_bias, int32_t groups, float eps, const float* weight, const float* bias,
+                             int32_t out_channels, int32_t tanh_out, int32_t out_layout, float* stats, float* out, void* stream) {
+  DDMI_REQUIRE(h && gn_weight && gn_bias && weight && bias && stats && out, "a tensor pointer is NULL");
+  DDMI_REQUIRE(batch >= 1 && in_channels >= 1 && height >= 1 && width >= 1, "empty feature map");
+  DDMI_REQUIRE(groups >= 1 && in_channels % groups == 0, "in_channels %d is not a multiple of groups %d", in_channels, groups);
+  DDMI_REQUIRE(out_channels == 64 || out_channels == 32, "the tail emits 64 (or 32: srn-cars) channels, got %d", out_channels);
+  DDMI_REQUIRE(out_layout == DDMI_LAYOUT_NCHW || out_layout == DDMI_LAYOUT_NHWC, "out_layout must be DDMI_LAYOUT_NCHW / _NHWC");
+  DDMI_REQUIRE(batch <= 65535, "batch %d too large for one launch", batch);
+  return launch_plane_conv(h, batch, in_channels, height, width, 3, gn_weight, gn_bias, groups, eps, weight, bias, out_channels,
+                           tanh_out, out_layout == DDMI_LAYOUT_NHWC, stats, out, (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_mcubes_workspace_bytes(int32_t nx, int32_t ny, int32_t nz, int32_t pad, uint64_t* bytes) {

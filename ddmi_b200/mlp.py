@@ -40,12 +40,17 @@ def _stream_ptr(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _as_plane(t, name):
+def _as_plane(t, name, keep_channels_last=False):
+    """keep_channels_last: the caller gathers from channels-last planes anyway (occupancy / NeRF tensor-core kernels), so a
+    plane that already IS channels-last (torch.channels_last strides, as ddmi_b200.plane_tail emits them) is passed through."""
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (ddmi_b200 has no CPU path)")
     if t.dim() != 4:
         raise RuntimeError(f"{name} must be (B,C,H,W), got {tuple(t.shape)}")
-    return t.detach().to(torch.float32).contiguous()
+    t = t.detach()
+    if keep_channels_last and _lib.is_channels_last(t):
+        return t
+    return t.to(torch.float32).contiguous()
 
 
 def _check_plane_set(planes, channels, names):
@@ -272,7 +277,7 @@ class MLP3D(_FusedDecoder):
         self._guard_grad(coords, *[t for axis in hdbf for t in axis])
         sources = [hdbf[a][s] for a in range(3) for s in range(3)]
         names = [f'hdbf[{a}][{s}]' for a in range(3) for s in range(3)]
-        planes = [_as_plane(t, nm) for t, nm in zip(sources, names)]
+        planes = [_as_plane(t, nm, keep_channels_last=True) for t, nm in zip(sources, names)]
         self._check_device(planes[0])
         _check_plane_set(planes, self.latent_dim, names)
         b = planes[0].shape[0]
@@ -301,6 +306,7 @@ class MLP3D(_FusedDecoder):
                 keep, arr = self._nhwc_cache.get(planes, sources, st)
                 layout = 1
             else:
+                planes = [p.contiguous() for p in planes]
                 keep, arr, layout = planes, _lib.planes_array(planes), 0
             _lib.check(_lib.lib().ddmi_decode_occupancy(
                 arr, b, planes[0].shape[1], layout, base.data_ptr(), n, bstride, 0.1,

@@ -208,7 +208,7 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
         if t.dim() != 4:
             raise RuntimeError(f"fea['{k}'] must be (B,32,R,R), got {tuple(t.shape)}")
         sources.append(t)
-        planes.append(t.detach().to(torch.float32).contiguous())
+        planes.append(t.detach() if _lib.is_channels_last(t.detach()) else t.detach().to(torch.float32).contiguous())
     from .mlp import _check_plane_set
     _check_plane_set(planes, 32, [f"fea['{k}']" for k in ('xy', 'yz', 'xz')])
     module._check_device(planes[0])
@@ -230,6 +230,7 @@ def render_rays_fused(rays, fea, module, N_samples, white_bkgd, return_raw=False
         if umma:       # one transposition per latent, not per pose (tools/ldm/nerf.py:270 renders a loop of poses)
             keep, arr = module._nhwc_cache.get(planes, sources, st)
         else:
+            planes = [p.contiguous() for p in planes]
             keep, arr = planes, _lib.planes_array(planes)
         entry = _lib.lib().ddmi_nerf_render_z if per_ray else _lib.lib().ddmi_nerf_render
         _lib.check(entry(

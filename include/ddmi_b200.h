@@ -25,6 +25,8 @@
  *                          (+ :455-475 run_network, :82-112 Embedder.embed,
  *                             :487-530 raw2outputs)
  *   ddmi_sample_pdf        utils/nerf_helpers.py:166-209 sample_pdf
+ *   ddmi_plane_head / _tail models/d2c_vae/autoencoder_unet.py:770-771,812-814 (hdbf 1x1 convs) / :822-827 (norm_out -> swish ->
+ *                          conv_out [-> tanh]); same tail at :1111-1142, :1531-1562
  *   ddmi_mcubes_*          convocc/src/utils/libmcubes/marchingcubes.h:23-193 mc::marching_cubes (libmcubes.marching_cubes,
  *                          pywrapper.cpp:90-107) + the vertex post-processing of convocc/src/conv_onet/generation.py:152-186
  * The reference binds its native ops with pybind11 inside a JIT torch extension
@@ -240,6 +242,23 @@ DDMI_API int ddmi_nerf_render_z(const ddmi_plane_t planes[3], int32_t batch, int
  */
 DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const float* u, int64_t n_rays, int32_t n_bins,
                              int32_t n_samples, float* out, void* stream);
+
+/*
+ * Plane-producer tail: the layers of the D2C-VAE decoders that EMIT the PE planes, fused, writing each
+ * plane once in the layout its consumer gathers from (out_layout: DDMI_LAYOUT_NCHW (batch, C_out, H, W) for the image / video
+ * decoders, DDMI_LAYOUT_NHWC (batch, H, W, C_out) for the scattered-query decoders -- hand the latter to the occupancy / NeRF
+ * entry points with plane_layout = DDMI_LAYOUT_NHWC and no transposition runs).  fp32, all device memory.
+ *   ddmi_plane_head: out = conv1x1(h; weight (C_out, C_in), bias)                       -- `up[i].hdbf[0]`, nn.Conv2d(block_in, out_ch, 1)
+ *   ddmi_plane_tail: out = [tanh] conv3x3(swish(GroupNorm(h; groups, eps, gn_weight, gn_bias)); weight (C_out, C_in, 3, 3), bias), zero
+ *                    padding 1 -- `norm_out` (GroupNorm(32, eps 1e-6)), x * sigmoid(x), `conv_out`, `tanh_out`.
+ *                    stats: scratch of batch * groups * 2 floats (mean / rstd per item and group).
+ * C_out must be 64 or 32.
+ */
+DDMI_API int ddmi_plane_head(const float* h, int32_t batch, int32_t in_channels, int32_t height, int32_t width, const float* weight,
+                             const float* bias, int32_t out_channels, int32_t out_layout, float* out, void* stream);
+DDMI_API int ddmi_plane_tail(const float* h, int32_t batch, int32_t in_channels, int32_t height, int32_t width, const float* gn_weight,
+                             const float* gn_bias, int32_t groups, float eps, const float* weight, const float* bias,
+                             int32_t out_channels, int32_t tanh_out, int32_t out_layout, float* stats, float* out, void* stream);
 
 /*
  * Occupancy post-step: marching cubes on a decoded logit grid, on the GPU (the reference copies the grid to the host and runs

@@ -155,3 +155,14 @@ def test_marching_cubes_oracle_is_the_reference(golden_dir):
     e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
     _, cnt = np.unique(e, axis=0, return_counts=True)
     assert (cnt == 2).all()
+
+
+def test_plane_tail_oracle_is_the_reference(golden_dir):
+    """Plane-producer tail: the oracle's restatement against inputs / outputs captured inside the reference Decoder's forward."""
+    from oracle import plane_tail_oracle as po
+    g = torch.load(os.path.join(golden_dir, 'plane_tail.pt'))
+    for tag in ('plain', 'tanh'):
+        c = g[tag]
+        assert float((po.tail(c['sd'], c['tail_in'], 32, c['tanh_out']) - c['tail_out']).abs().max()) < 1e-6
+        for k, (hin, hout) in c['heads'].items():
+            assert float((po.head(c['sd'], int(k[4:]), hin) - hout).abs().max()) < 1e-6

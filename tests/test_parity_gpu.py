@@ -943,3 +943,60 @@ def test_nerf_render_poses_equals_the_loop_of_renders():
         one = nh.render(res, res, K, feac, None, 0, DEV, chunk=4096, c2w=pose[:3, :4], near=near, far=far, use_viewdirs=True,
                         verbose=True, retraw=True, hw_idx=None, **kw)
         assert torch.equal(one, batched[v])
+
+
+# ---------------------------------------------------------------- plane-producer tail
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_plane_tail_golden(golden_dir, channels_last):
+    """ddmi_plane_head / ddmi_plane_tail against the layers' inputs and outputs captured inside the reference Decoder's own
+    forward (tests/golden/plane_tail.pt), both output layouts; fp32 kernels: 2e-5 of |out|max."""
+    g = torch.load(os.path.join(golden_dir, 'plane_tail.pt'))
+    for tag in ('plain', 'tanh'):
+        c = g[tag]
+        sd = c['sd']
+        ins = [sd[f'up.{i}.hdbf.0.weight'].shape[1] if f'up.{i}.hdbf.0.weight' in sd else None for i in range(3)]
+        t = ddmi_b200.PlaneTail(sd['conv_out.weight'].shape[1], 64, ins, tanh_out=c['tanh_out']).to(DEV)
+        t.load_state_dict(sd, strict=True)
+        out = t.tail(c['tail_in'].to(DEV), channels_last=channels_last)
+        assert out.shape == c['tail_out'].shape
+        assert out.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        assert float((out.cpu() - c['tail_out']).abs().max()) < 2e-5 * max(1.0, float(c['tail_out'].abs().max()))
+        for k, (hin, hout) in c['heads'].items():
+            o = t.head(int(k[4:]), hin.to(DEV), channels_last=channels_last)
+            assert float((o.cpu() - hout).abs().max()) < 2e-5 * max(1.0, float(hout.abs().max()))
+    with pytest.raises(RuntimeError):
+        t.tail(c['tail_in'])                                 # CPU tensor
+    with pytest.raises(RuntimeError):
+        t.tail(torch.zeros(1, 7, 8, 8, device=DEV))          # wrong channel count
+
+
+def test_plane_tail_odd_shapes_and_srn_cars_width():
+    """Ragged tiles (H, W not multiples of the 8 x 32 output tile), C_in not a multiple of the 8-channel chunk, 32 output
+    channels (srn-cars planes), against the oracle."""
+    from oracle import plane_tail_oracle as po
+    g = torch.Generator().manual_seed(11)
+    t = ddmi_b200.PlaneTail(96, 32, (None, 44), tanh_out=False).to(DEV)
+    for p in t.parameters():
+        p.data = torch.randn(p.shape, generator=g).to(DEV) * 0.2
+    sd = {k: v.cpu() for k, v in t.state_dict().items()}
+    h = torch.randn(3, 96, 37, 45, generator=g) * 2 + 0.5
+    out = t.tail(h.to(DEV))
+    ref = po.tail(sd, h, 32, False)
+    assert float((out.cpu() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+    h1 = torch.randn(2, 44, 5, 70, generator=g)
+    o1 = t.head(1, h1.to(DEV), channels_last=True)
+    assert float((o1.cpu() - po.head(sd, 1, h1)).abs().max()) < 2e-5 * 10
+
+
+def test_channels_last_planes_from_the_tail_feed_the_occupancy_decoder_without_a_copy():
+    """A plane emitted channels-last by PlaneTail (torch.channels_last strides) goes into MLP3D as is: same logits as the NCHW
+    planes, and the library's transposition kernel does not run (the cache holds views of the caller's storage)."""
+    m = cases.build_module('occupancy').to(DEV)
+    pts, hdbf = cases.occupancy_inputs(batch=2, n=3000)
+    nchw = _cuda(hdbf)
+    cl = tuple([t.contiguous(memory_format=torch.channels_last) for t in axis] for axis in nchw)
+    a = m(pts.to(DEV), nchw).logits
+    b = m(pts.to(DEV), cl).logits
+    assert torch.equal(a, b)
+    held = m._nhwc_cache.value[0]
+    assert all(x.data_ptr() == t.data_ptr() for x, t in zip(held, [t for axis in cl for t in axis]))
