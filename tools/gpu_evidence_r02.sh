@@ -3,7 +3,7 @@
 set -x
 timeout 300 python __graft_entry__.py smoke > gpurun_out/r02u_smoke.log 2>&1; tail -3 gpurun_out/r02u_smoke.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_r02.json 2> gpurun_out/bench_r02.err; tail -2 gpurun_out/bench_r02.err
-for w in c1 video occupancy nerf mesh; do timeout 400 python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/bench_r02_$w.json 2> gpurun_out/bench_r02_$w.err; tail -2 gpurun_out/bench_r02_$w.err; done
+for w in c1 video occupancy nerf mesh planes; do timeout 400 python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/bench_r02_$w.json 2> gpurun_out/bench_r02_$w.err; tail -2 gpurun_out/bench_r02_$w.err; done
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r02_ref.json 2>/dev/null
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02_launches_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:image_umma -s 1 -c 1 -o /tmp/r02_image python bench.py --batch 8 --res 1024 --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
