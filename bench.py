@@ -60,6 +60,10 @@ class ClockSampler:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.FIELDS}',
                                        '--format=csv,noheader,nounits', '-lms', '200'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
+            # nvidia-smi's start-up stalls the device for ~0.2 s: let it print its first sample before anything is timed
+            t0 = time.time()
+            while time.time() - t0 < 2.0 and os.path.getsize(self.f.name) == 0:
+                time.sleep(0.05)
         except OSError:
             self.p = None
 
@@ -261,10 +265,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started BEFORE the warm-up: its start-up stalls the device briefly
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     # per-launch device times of the dominant kernel, on the launching (current) stream
     evs = []
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -571,10 +575,10 @@ def run_other(args):
     planes = W.slice(W.host, 0, B, dev)
     torch.cuda.synchronize()
     fn = lambda: W.decode(planes)
+    sampler = ClockSampler(0)                      # before the warm-up: nvidia-smi's start-up stalls the device briefly
     for _ in range(args.warmup):
         fn()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
@@ -691,10 +695,10 @@ def run_mesh(args):
         for i in range(B):
             out.append(gen.generate_mesh(item(P, i), m, resolution0=nx))
         return out
+    sampler = ClockSampler(0)
     for _ in range(args.warmup):
         res = step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
@@ -777,12 +781,12 @@ def run_planes(args):
 
     def step(channels_last=False):
         return [t.head(2, hs[0], channels_last), t.head(1, hs[1], channels_last), t.tail(hs[2], channels_last)]
+    sampler = ClockSampler(0)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(0)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 10                                      # a step is ~7 ms: ten per "step" so that the clock sampler's start-up does not show
+    reps = 30                                      # a step is ~6 ms: thirty per "step"
     t0.record()
     for _ in range(args.steps * reps):
         out = step()

@@ -57,7 +57,7 @@ constexpr int TY = 8, TX = 32;              // output tile
 constexpr int PX = 4, CG = 16;              // register tile of one thread: 4 consecutive pixels x 16 output channels
 
 template <int KS, int COUT, bool NORM>
-__global__ void __launch_bounds__(TY * TX)
+__global__ void __launch_bounds__(TY * TX, 2)
 plane_conv_kernel(const float* __restrict__ x, int C, int H, int W, const float* __restrict__ stats, int groups,
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ wt,
                   const float* __restrict__ bias, int tanh_out, int nhwc, float* __restrict__ out) {
@@ -85,26 +85,38 @@ plane_conv_kernel(const float* __restrict__ x, int C, int H, int W, const float*
   for (int c0 = 0; c0 < C; c0 += CK) {
     // ---- stage the chunk: input tile with halo (zero padded AFTER the activation, like conv2d's padding of its input);
     // column q of the tile = image column tx0 + q - R
-    for (int i = threadIdx.x; i < CK * IY * (TX + 2 * R); i += TY * TX) {
-      const int c = i / (IY * (TX + 2 * R)), r = (i / (TX + 2 * R)) % IY, q = i % (TX + 2 * R);
-      const int gy = ty0 + r - R, gx = tx0 + q - R, ch = c0 + c;
-      float v = 0.f;
-      if (ch < C && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-        v = __ldg(xb + (size_t)ch * hw + (size_t)gy * W + gx);
-        if (NORM) {
-          const int g = ch / cpg;
-          const float mean = __ldg(stats + 2 * (b * groups + g)), rstd = __ldg(stats + 2 * (b * groups + g) + 1);
-          v = fmaf((v - mean) * rstd, __ldg(gamma + ch), __ldg(beta + ch));     // GroupNorm affine
-          v = v / (1.f + __expf(-v));                                          // swish: x * sigmoid(x)
+    // (unrolled by 4: the loads of four of a thread's ~11 elements are in flight together; two blocks per SM cover the rest)
+    constexpr int NSTAGE = CK * IY * (TX + 2 * R);
+#pragma unroll 4
+    for (int k = 0; k < (NSTAGE + TY * TX - 1) / (TY * TX); ++k) {
+      const int i = threadIdx.x + k * TY * TX;
+      if (i < NSTAGE) {
+        const int c = i / (IY * (TX + 2 * R)), r = (i / (TX + 2 * R)) % IY, q = i % (TX + 2 * R);
+        const int gy = ty0 + r - R, gx = tx0 + q - R, ch = c0 + c;
+        float v = 0.f;
+        if (ch < C && gy >= 0 && gy < H && gx >= 0 && gx < W) {
+          v = __ldg(xb + (size_t)ch * hw + (size_t)gy * W + gx);
+          if (NORM) {
+            const int g = ch / cpg;
+            const float mean = __ldg(stats + 2 * (b * groups + g)), rstd = __ldg(stats + 2 * (b * groups + g) + 1);
+            v = fmaf((v - mean) * rstd, __ldg(gamma + ch), __ldg(beta + ch));     // GroupNorm affine
+            v = v / (1.f + __expf(-v));                                          // swish: x * sigmoid(x)
+          }
         }
+        s_in[c][r][q] = v;
       }
-      s_in[c][r][q] = v;
     }
-    // weights of the chunk: wt is (COUT, C, KS, KS) as nn.Conv2d stores it -> s_w[c][tap][co]
-    for (int i = threadIdx.x; i < CK * TAPS * COUT; i += TY * TX) {
-      const int co = i % COUT, tap = (i / COUT) % TAPS, c = i / (COUT * TAPS);
-      const int ch = c0 + c;
-      s_w[c][tap][co] = ch < C ? __ldg(wt + ((size_t)co * C + ch) * TAPS + tap) : 0.f;
+    // weights of the chunk: wt arrives as (C, KS * KS, COUT) (the host transposes nn.Conv2d's (COUT, C, KS, KS) once), so a
+    // chunk is one contiguous run of CK * TAPS * COUT floats
+    constexpr int NW4 = CK * TAPS * COUT / 4;
+#pragma unroll
+    for (int k = 0; k < (NW4 + TY * TX - 1) / (TY * TX); ++k) {
+      const int i = threadIdx.x + k * TY * TX;
+      if (i < NW4) {
+        const int ch = c0 + (4 * i) / (TAPS * COUT);
+        reinterpret_cast<float4*>(&s_w[0][0][0])[i] =
+            ch < C ? __ldg(reinterpret_cast<const float4*>(wt + (size_t)c0 * TAPS * COUT) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     __syncthreads();
 #pragma unroll 1

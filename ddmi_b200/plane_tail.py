@@ -71,7 +71,7 @@ class PlaneTail(nn.Module):
         if c != conv.in_channels:
             raise RuntimeError(f"h has {c} channels, the level-{i_level} head takes {conv.in_channels}")
         out = _out(b, self.out_ch, hh, ww, x.device, channels_last)
-        w = conv.weight.detach().to(torch.float32).reshape(self.out_ch, c).contiguous()
+        w = conv.weight.detach().to(torch.float32).reshape(self.out_ch, c).t().contiguous()       # (C_in, 1, C_out)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ddmi_plane_head(x.data_ptr(), b, c, hh, ww, w.data_ptr(), conv.bias.detach().float().data_ptr(),
                                                   self.out_ch, 1 if channels_last else 0, out.data_ptr(), _stream_ptr(x.device)))
@@ -87,7 +87,8 @@ class PlaneTail(nn.Module):
         g = self.norm_out.num_groups
         stats = torch.empty(b * g * 2, device=x.device, dtype=torch.float32)
         f = lambda p: p.detach().to(torch.float32).contiguous()
-        gw, gb, w, bias = f(self.norm_out.weight), f(self.norm_out.bias), f(self.conv_out.weight), f(self.conv_out.bias)
+        gw, gb, bias = f(self.norm_out.weight), f(self.norm_out.bias), f(self.conv_out.bias)
+        w = self.conv_out.weight.detach().to(torch.float32).permute(1, 2, 3, 0).contiguous()       # (C_in, 3 * 3, C_out)
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().ddmi_plane_tail(x.data_ptr(), b, c, hh, ww, gw.data_ptr(), gb.data_ptr(), g, float(self.norm_out.eps),
                                                   w.data_ptr(), bias.data_ptr(), self.out_ch, 1 if self.tanh_out else 0,

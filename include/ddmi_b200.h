@@ -248,10 +248,12 @@ DDMI_API int ddmi_sample_pdf(const float* bins, const float* weights, const floa
  * plane once in the layout its consumer gathers from (out_layout: DDMI_LAYOUT_NCHW (batch, C_out, H, W) for the image / video
  * decoders, DDMI_LAYOUT_NHWC (batch, H, W, C_out) for the scattered-query decoders -- hand the latter to the occupancy / NeRF
  * entry points with plane_layout = DDMI_LAYOUT_NHWC and no transposition runs).  fp32, all device memory.
- *   ddmi_plane_head: out = conv1x1(h; weight (C_out, C_in), bias)                       -- `up[i].hdbf[0]`, nn.Conv2d(block_in, out_ch, 1)
- *   ddmi_plane_tail: out = [tanh] conv3x3(swish(GroupNorm(h; groups, eps, gn_weight, gn_bias)); weight (C_out, C_in, 3, 3), bias), zero
+ *   ddmi_plane_head: out = conv1x1(h; weight, bias)                                     -- `up[i].hdbf[0]`, nn.Conv2d(block_in, out_ch, 1)
+ *   ddmi_plane_tail: out = [tanh] conv3x3(swish(GroupNorm(h; groups, eps, gn_weight, gn_bias)); weight, bias), zero
  *                    padding 1 -- `norm_out` (GroupNorm(32, eps 1e-6)), x * sigmoid(x), `conv_out`, `tanh_out`.
  *                    stats: scratch of batch * groups * 2 floats (mean / rstd per item and group).
+ * `weight` is nn.Conv2d's (C_out, C_in, k, k) tensor TRANSPOSED ONCE by the caller to (C_in, k * k, C_out), contiguous (the kernels
+ * stream input-channel chunks of it with vector loads).
  * C_out must be 64 or 32.
  */
 DDMI_API int ddmi_plane_head(const float* h, int32_t batch, int32_t in_channels, int32_t height, int32_t width, const float* weight,
