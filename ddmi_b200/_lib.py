@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DDMI_B200_LIB") or os.path.join(_HERE, "libddmi_b200.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 PREC_FP32 = 0
 PREC_BF16X3 = 1
 PREC_F16F8 = 2
@@ -24,7 +24,7 @@ NOISE_NONE, NOISE_TENSORS, NOISE_PHILOX = 0, 1, 2
 EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
     "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_decode_image_noise", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
-    "ddmi_decode_video", "ddmi_decode_video_store",
+    "ddmi_decode_video", "ddmi_decode_video_store", "ddmi_decode_video_ws", "ddmi_video_workspace_bytes",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_sample_pdf", "ddmi_plane_head", "ddmi_plane_tail", "ddmi_mcubes_workspace_bytes", "ddmi_mcubes_count", "ddmi_mcubes_emit", "ddmi_selftest_tma", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
     "ddmi_debug_trace", "ddmi_debug_set", "ddmi_debug_gatherbench", "ddmi_debug_ringbench", "ddmi_debug_microbench",
 )
@@ -85,6 +85,10 @@ def lib():
                                         ctypes.POINTER(Weights), vp, vp]
         L.ddmi_decode_video_store.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
                                               ctypes.POINTER(Weights), i32, vp, vp]
+        L.ddmi_decode_video_ws.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
+                                           ctypes.POINTER(Weights), i32, vp, vp, ctypes.c_uint64, vp]
+        L.ddmi_video_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+        L.ddmi_video_workspace_bytes.restype = ctypes.c_int64
         L.ddmi_nerf_mlp.argtypes = [vp, i64, i32, i32, f32, ctypes.POINTER(Weights), vp, vp]
         L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i32, vp, i32, f32, f32,
                                        i32, ctypes.POINTER(Weights), vp, vp, vp]

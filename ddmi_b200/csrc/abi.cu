@@ -31,7 +31,8 @@ int launch_image_umma(const PlaneSet&, int, int, const float*, const float*, lon
 int launch_selftest_umma(const float*, const float*, float*, int, int, cudaStream_t);
 int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long long, long long, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, cudaStream_t);
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
-int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, cudaStream_t);
+int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, void*, size_t, cudaStream_t);
+size_t video_workspace_bytes(int, int, int, int);
 int launch_nerf_composite(const float*, const float*, int, const float*, int, int, long long, int, int, float*, cudaStream_t);
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
@@ -231,6 +232,19 @@ DDMI_API int ddmi_decode_video_store(const ddmi_plane_t planes[9], int32_t batch
                                      const float* coords_xy, const float* coords_yt, const float* coords_xt,
                                      int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, int32_t store,
                                      void* out, void* stream) {
+  return ddmi_decode_video_ws(planes, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W, weights, store, out, nullptr, 0,
+                              stream);
+}
+
+DDMI_API int64_t ddmi_video_workspace_bytes(int32_t batch, int32_t T, int32_t H, int32_t W, int32_t precision) {
+  if (precision != DDMI_PREC_F16F8 || batch < 1 || T < 1 || H < 1 || W < 1) return 0;
+  return (int64_t)video_workspace_bytes(batch, T, H, W);
+}
+
+DDMI_API int ddmi_decode_video_ws(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                                  const float* coords_xy, const float* coords_yt, const float* coords_xt,
+                                  int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, int32_t store,
+                                  void* out, void* workspace, uint64_t workspace_bytes, void* stream) {
   DDMI_REQUIRE(store >= DDMI_STORE_F32 && store <= DDMI_STORE_U8_CHANNELS_LAST, "unknown store mode %d", store);
   PlaneSet ps = {};
   int rc = check_planes(planes, 9, &ps);
@@ -249,7 +263,8 @@ DDMI_API int ddmi_decode_video_store(const ddmi_plane_t planes[9], int32_t batch
     return launch_video_umma_entry(ps, batch, channels, coords_xy, coords_yt, coords_xt, T, H, W, weights->gemm,
                                    weights->gemm_bytes, weights->program_host, weights->program_words, weights->program,
                                    weights->vec, weights->vec_floats, out, store, weights->reserved & 1,
-                                   weights->precision == DDMI_PREC_F16F8, (cudaStream_t)stream);
+                                   weights->precision == DDMI_PREC_F16F8, workspace, (size_t)workspace_bytes,
+                                   (cudaStream_t)stream);
   }
   if (weights->precision != DDMI_PREC_FP32) {
     set_error("video decode: unknown precision %d", weights->precision);

@@ -895,10 +895,12 @@ int launch_nerf_umma_entry(const PlaneSet& ps, int batch, int C, const float* ra
 int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* cxy, const float* cyt, const float* cxt, int T,
                             int H, int W, const void* gemm, size_t gemm_bytes, const uint32_t* program_host,
                             size_t program_words, const uint32_t* program_dev, const float* vec, size_t vec_floats,
-                            void* out, int store, int pair, int f16f8, cudaStream_t st) {
+                            void* out, int store, int pair, int f16f8, void* workspace, size_t workspace_bytes,
+                            cudaStream_t st) {
   return launch_video_umma(ps, batch, C, cxy, cyt, cxt, T, H, W, gemm, gemm_bytes, program_host, program_words, program_dev,
-                           vec, vec_floats, out, store, pair, f16f8, st);
+                           vec, vec_floats, out, store, pair, f16f8, workspace, workspace_bytes, st);
 }
+size_t video_workspace_bytes(int batch, int T, int H, int W) { return video_table_bytes(batch, T, H, W); }
 
 int debug_trace(unsigned long long* out, int cap, int* n, int reset) {
   // the whole buffer (unwritten slots are 0: the caller drops them)

@@ -377,9 +377,16 @@ class MLPVideo(_FusedDecoder):
         out = torch.empty((b, T * H * W, self.out_ch) if u8 else (b, self.out_ch, T * H * W), device=dev,
                           dtype=torch.uint8 if u8 else torch.float32)
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().ddmi_decode_video_store(
+            # feature tables (include/ddmi_b200.h, ddmi_decode_video_ws): scratch for this call, sized by the library; very large
+            # volumes / batches decode with direct gathers instead (DDMI_B200_VIDEO_TABLE_MAX bytes, default 8 GB; 0 disables)
+            ws, ws_bytes = None, int(_lib.lib().ddmi_video_workspace_bytes(b, T, H, W, prec))
+            if 0 < ws_bytes <= int(os.environ.get('DDMI_B200_VIDEO_TABLE_MAX', 8 << 30)):
+                ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            _lib.check(_lib.lib().ddmi_decode_video_ws(
                 _lib.planes_array(planes), b, planes[0].shape[1], cxy.data_ptr(), cyt.data_ptr(),
-                cxt.data_ptr(), T, H, W, _lib.weights_struct(packed), mode, out.data_ptr(), _stream_ptr(dev)))
+                cxt.data_ptr(), T, H, W, _lib.weights_struct(packed), mode, out.data_ptr(),
+                ws.data_ptr() if ws is not None else None, ws_bytes if ws is not None else 0, _stream_ptr(dev)))
+            del ws       # stream-ordered caching allocator: the block is not handed out again before this stream's work is done
         return out.reshape(b, t, h, w, self.out_ch) if u8 else out.reshape(b, self.out_ch, t, h, w)
 
 

@@ -617,25 +617,27 @@ def _pack_video_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     """Program + stream + vec of csrc/decode_umma_video.cuh (the protocol is spelled out there).  A-region K groups
     as for occupancy: H hi 0..31 / lo 32..63, Xa (raw piece) hi 64..71 / lo 80..87, Xb (relu piece) hi 72..79 / lo 88..95.
     Operand barriers: 0..3 raw-h quarters / R1 pieces / later pieces, 4..7 relu-h and net quarters.
-    Completion barriers: D0 = "accumulators final for this phase", D1 = "piece consumed, Xa / Xb free"."""
+    Completion barriers: D0 = "accumulators final for this phase", D1 = "piece consumed, Xa / Xb free" (R2 / R3 only)."""
     HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
     P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
-    def piece(Ws, W0, col0, first, n0_split):
-        """one 64-wide piece: fc_0 (relu piece, acc1) and shortcut (raw piece, acc2)"""
-        if n0_split:                                   # R1: fc_0 has N = 192 -> a 128 and a 64 block
-            P.block(W0[0:128, col0:col0 + 64], XBH, XBL, 0, first)
-            P.block(W0[128:192, col0:col0 + 64], XBH, XBL, 128, first)
-        else:
-            P.block(W0[:, col0:col0 + 64], XBH, XBL, 0, first)
-        P.block(Ws[:, col0:col0 + 64], XAH, XAL, 256, first)
+    def piece(Ws, W0, col0, first, kg=None):
+        """one 64-wide piece: fc_0 (relu piece, acc1) and shortcut (raw piece, acc2); kg = (raw hi, raw lo, relu hi, relu lo)
+        K groups of the piece (default: the X region)"""
+        ah, al, bh, bl = kg or (XAH, XAL, XBH, XBL)
+        P.block(W0[:, col0:col0 + 64], bh, bl, 0, first)
+        P.block(Ws[:, col0:col0 + 64], ah, al, 256, first)
 
-    # ---- R1: x = [xy | yt | xt] of scale 0
+    # ---- R1: x = [xy | yt | xt] of scale 0.  The activation buffer H is idle until R1's hidden layer is published, so pieces
+    # 1 and 2 sit in H (piece j: raw K groups 16(j-1).., relu 16(j-1)+8..) next to piece 0 in the X region: the three pieces
+    # run back to back without a hand-shake per piece.  fc_0 (192 outputs) is zero-padded to one N = 256 block: one unit
+    # per piece instead of an N = 128 and an N = 64 one (the issuer's cost per unit, not the MMAs, is what counted).
     Ws, W0, W1 = p['net_res1.shortcut.weight'], p['net_res1.fc_0.weight'], p['net_res1.fc_1.weight']
+    W0 = torch.cat([W0, W0.new_zeros(64, W0.shape[1])])
     for j in range(3):
         P.wait(j)
-        piece(Ws, W0, 64 * j, j == 0, True)
-        P.commit(1 if j < 2 else 0)
+        piece(Ws, W0, 64 * j, j == 0, None if j == 0 else (HH + 16 * (j - 1), HL + 16 * (j - 1), HH + 16 * (j - 1) + 8, HL + 16 * (j - 1) + 8))
+    P.commit(0)
     for q in range(3):                                 # fc_1: K = 192 hidden, onto the shortcut
         P.wait(4 + q)
         P.block(W1[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 256, False)
@@ -649,16 +651,16 @@ def _pack_video_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
         P.commit(0)
         P.wait(4)                                      # relu(h) quarter 0 (+ piece 0, gathered meanwhile)
         P.block(W0[:, 0:64], HH, HL, 0, True)
-        piece(Ws, W0, 256, False, False)
+        piece(Ws, W0, 256, False)
         P.commit(1)
         for q in range(1, 4):
             P.wait(4 + q)
             P.block(W0[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 0, False)
         P.wait(0)
-        piece(Ws, W0, 320, False, False)
+        piece(Ws, W0, 320, False)
         P.commit(1)
         P.wait(1)
-        piece(Ws, W0, 384, False, False)
+        piece(Ws, W0, 384, False)
         P.commit(0)
         for q in range(4):                             # fc_1 onto the shortcut
             P.wait(4 + q)

@@ -64,7 +64,7 @@ extern "C" {
 #define DDMI_API
 #endif
 
-#define DDMI_ABI_VERSION 9
+#define DDMI_ABI_VERSION 10
 
 enum {
   DDMI_OK = 0,
@@ -193,6 +193,20 @@ DDMI_API int ddmi_decode_video_store(const ddmi_plane_t planes[9], int32_t batch
                             const float* coords_xy, const float* coords_yt, const float* coords_xt,
                             int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, int32_t store,
                             void* out, void* stream);
+
+/*
+ * ddmi_decode_video_store with a caller-provided device workspace (ABI 10).  The three query grids of a video are separable
+ * by construction (xy by (h,w), yt by (t,h), xt by (t,w): utils/general_utils.py:38-52), so only H W + T H + T W distinct
+ * feature vectors exist per scale; with a workspace of ddmi_video_workspace_bytes() bytes (16-byte aligned; 0 = this
+ * precision has no table path) the DDMI_PREC_F16F8 kernel samples each of them once into operand-format tables and the decode
+ * reads those instead of gathering 36 taps x 64 channels per voxel.  Results are bit-identical to workspace = NULL (direct gathers).
+ * The workspace is scratch: it may be reused or freed once the call's work on `stream` has completed.
+ */
+DDMI_API int64_t ddmi_video_workspace_bytes(int32_t batch, int32_t T, int32_t H, int32_t W, int32_t precision);
+DDMI_API int ddmi_decode_video_ws(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,
+                         const float* coords_xy, const float* coords_yt, const float* coords_xt,
+                         int32_t T, int32_t H, int32_t W, const ddmi_weights_t* weights, int32_t store,
+                         void* out, void* workspace, uint64_t workspace_bytes, void* stream);
 
 /*
  * NeRF MLP on pre-embedded rows.  x: (n, 186) = [latent 96 | embed(pts) 63 |

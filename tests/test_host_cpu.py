@@ -18,7 +18,7 @@ torch.set_grad_enabled(False)
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, 'include', 'ddmi_b200.h')).read()
-    declared = set(re.findall(r'DDMI_API\s+(?:const\s+char\*|int)\s+(ddmi_[a-z0-9_]+)\s*\(', hdr))
+    declared = set(re.findall(r'DDMI_API\s+(?:const\s+char\*|int64_t|int)\s+(ddmi_[a-z0-9_]+)\s*\(', hdr))
     assert declared == set(_lib.EXPORTS)
     L = _lib.lib()
     for name in declared:

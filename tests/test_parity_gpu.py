@@ -805,6 +805,32 @@ def test_video_ragged_volume():
     assert float((out - ref).abs().max()) < TOL
 
 
+@pytest.mark.parametrize("shape", [(3, 7, 19), (4, 16, 128), (2, 24, 320)])
+def test_video_feature_tables_match_the_direct_gather(shape, monkeypatch):
+    """f16f8: the operand-format feature tables (one record per distinct (h,w) / (t,h) / (t,w) grid entry, ddmi_decode_video_ws)
+    reproduce the per-voxel gather bit for bit -- ragged volumes, tiles that straddle rows, batch > 1, out-of-range coords,
+    negative-zero and tiny features (the relu copy is the raw record with negative channels masked)."""
+    m = cases.build_module('video').to(DEV)
+    m.precision = 'f16f8'
+    g = torch.Generator().manual_seed(57)
+    T, H, W = shape
+    mk = lambda *sz: torch.randn(*sz, generator=g)
+    xy = [mk(2, 64, max(H // 4, 2), max(W // 4, 2)), mk(2, 64, max(H // 2, 2), max(W // 2, 2)), mk(2, 64, H, W)]
+    yt = [mk(2, 64, max(T // 2, 1), max(H // 4, 2)), mk(2, 64, T, max(H // 2, 2)), mk(2, 64, T, H)]
+    xt = [mk(2, 64, max(T // 2, 1), max(W // 4, 2)), mk(2, 64, T, max(W // 2, 2)), mk(2, 64, T, W)]
+    xy[2][:, :8] = 0.0
+    xy[2][:, 8:16] = -0.0
+    xy[2][:, 16:24] *= 1e-9
+    coords = _cuda(ddmi_b200.convert_to_coord_format_3d(1, H, W, T, hstart=-1.2, hend=1.1, wstart=-.9, wend=1.3, tstart=-1, tend=1))
+    hdbf = _cuda((xy, yt, xt))
+    assert ddmi_b200._lib.lib().ddmi_video_workspace_bytes(2, T, H, W, ddmi_b200._lib.PREC_F16F8) == 2 * 3 * (H * W + T * H + T * W) * 256
+    tab = m(coords, hdbf)
+    monkeypatch.setenv('DDMI_B200_VIDEO_TABLE_MAX', '0')
+    direct = m(coords, hdbf)
+    assert torch.equal(tab, direct)
+    assert float(tab.abs().max()) > 0
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
 @pytest.mark.parametrize("n_samples", [1, 100, 192])
 def test_nerf_sample_counts_that_straddle_tiles(n_samples, precision):

@@ -19,6 +19,16 @@ if kind == 'image':
     e = (R - 1) / R
     c = convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
     run = lambda: m(c, hdbf=planes, si=get_scale_injection(R))
+elif kind == 'video':
+    import ddmi_b200
+    m = ddmi_b200.MLPVideo(in_ch=2, latent_dim=64, out_ch=3, ch=256).to(dev)
+    hd = [[torch.randn(4, 64, s, s, generator=g).to(dev) for s in (64, 128, 256)],
+          [torch.randn(4, 64, 16, s, generator=g).to(dev) for s in (64, 128, 256)],
+          [torch.randn(4, 64, 16, s, generator=g).to(dev) for s in (64, 128, 256)]]
+    cv = ddmi_b200.convert_to_coord_format_3d(1, 256, 256, 16, hstart=-255 / 256, hend=255 / 256, wstart=-255 / 256,
+                                              wend=255 / 256, tstart=-15 / 16, tend=15 / 16)
+    cv = {k: v.to(dev) for k, v in cv.items()}
+    run = lambda: m(cv, hd)
 else:
     import ddmi_b200
     m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
