@@ -10,13 +10,13 @@
 // beside piece 0 in Xa / Xb and the three pieces run back to back; they are stored -- and signalled -- inside the PREVIOUS
 // tile's output stage, right after the accumulator drain, so the tensor core works on R1 while the output head is evaluated.
 // Per ResnetBlockFC with input [h | X] (R2, R3):
-//   E: publish RAW h (A0..A3)            | MMA: shortcut over h            -> COMMIT D0
-//   E: gather piece 0 meanwhile
-//   E: wait D0, publish relu(h) (A4..A7) | MMA: fc_0 over h quarter 0, piece 0 (both accumulators) -> COMMIT D1
-//                                        |      fc_0 over h quarters 1..3
-//   E: wait D1, gather piece 1, A0       | MMA: piece 1 -> COMMIT D1
-//   E: wait D1, gather piece 2, A1       | MMA: piece 2 -> COMMIT D0
-//   E: wait D0, net = relu(acc1 + b0) (A4..A7) | MMA: fc_1 ONTO acc2 -> COMMIT D0
+//   E: store piece 0 (Xa / Xb are free), then publish RAW h (A0..A3) | MMA: shortcut over h -> COMMIT D0
+//   E: wait D0, publish relu(h) (A4..A7)        | MMA: piece 0 (fc_0 starts acc1 here, shortcut adds to acc2) -> COMMIT D1
+//                                               |      fc_0 over relu(h) quarters 0, 1
+//   E: wait D1, store piece 1, A0               | MMA: piece 1 -> COMMIT D1;  fc_0 over quarters 2, 3
+//   E: wait D1, store piece 2, A1               | MMA: piece 2 -> COMMIT D0
+//   E: wait D0, net = relu(acc1 + b0) (A4..A7)  | MMA: fc_1 ONTO acc2 -> COMMIT D0
+// (every hand-shake round trip of the epilogue threads has MMAs of another operand to hide behind)
 // The grids are taken literally (the 'yt' / 'xt' planes are read with transposed axes).
 //
 //
@@ -222,12 +222,14 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       }
     };
     // R1's pieces 1 and 2 of `tile` -> H (idle between R4.fc_1's commit and R1's hidden layer), published on A1 / A2
+    auto r1_dst = [&](int j) {
+      const uint32_t o = (uint32_t)(16 * (j - 1) * KG_BYTES);
+      return VidDst{h_hi + o, h_lo + o, h_hi + o + 8 * KG_BYTES, h_lo + o + 8 * KG_BYTES};
+    };
     auto r1_pieces = [&](long long tile) {
 #pragma unroll
       for (int j = 1; j < 3; ++j) {
-        const uint32_t o = (uint32_t)(16 * (j - 1) * KG_BYTES);
-        const VidDst d = {h_hi + o, h_lo + o, h_hi + o + 8 * KG_BYTES, h_lo + o + 8 * KG_BYTES};
-        piece(tile, 0, j, -1, d);
+        piece(tile, 0, j, -1, r1_dst(j));
         signal(j);
       }
     };
@@ -245,12 +247,12 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
         float2 v[4][16];
+        piece(tile, blk, 0, -1, dX);            // Xa / Xb are free (the previous stage_net waited the commit behind piece 2)
         output_stage<SCHEME, false>(tmem_lane, 256, sub, row, h_hi, h_lo, vec + (blk == 1 ? VV_B11 : VV_B12), v,
-                                    [&]() { wait_done(0); }, [](int, float2 (&)[16]) {}, signal, 0);               // raw h
-        piece(tile, blk, 0, -1, dX);                                                                         // overlaps the shortcut GEMM
+                                    [&]() { wait_done(0); }, [](int, float2 (&)[16]) {}, signal, 0);               // raw h (+ piece 0)
         wait_done(0);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(4 + q); }   // relu(h) (+ piece 0)
+        for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(4 + q); }   // relu(h)
         piece(tile, blk, 1, 1, dX); signal(0);
         piece(tile, blk, 2, 1, dX); signal(1);
         stage_net(vec + (blk == 1 ? VV_B02 : VV_B03), 4);
@@ -265,17 +267,24 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
       }
       stage_net(vec + VV_B04, 4);
       // ================= out = w_out . lrelu(acc2 + b1_3 + b1_4, 0.2) + b_out =================
-      wait_done(0);
+      const bool more = it + 1 < ntiles;
+      if (TAB && more) {
+        // the next tile's R1 pieces 1 and 2: records loaded while this thread would park anyway, stored as soon as H is free
+        // (R4.fc_1 committed) and published at once; piece 0 (already in Xa / Xb) is published after the drain below --
+        // R1's first MMAs overwrite acc2
+        VidRec x1, x2;
+        tab_load(tile_of(it + 1), 0, 1, x1);
+        tab_load(tile_of(it + 1), 0, 2, x2);
+        wait_done(0);
+        tab_store(x1, r1_dst(1)); signal(1);
+        tab_store(x2, r1_dst(2)); signal(2);
+      } else {
+        wait_done(0);
+      }
       {
         float2 v[4][16];
         drain128(tmem_lane, 256, sub, v);
-        // acc2 is in registers and H is free: hand the next tile's R1 to the tensor core before evaluating the head
-        // (table path: two 8-load records; the direct gather is too heavy to sit on 128 live values -- it goes last)
-        const bool more = it + 1 < ntiles;
-        if (more) {
-          signal(0);
-          if (TAB) r1_pieces(tile_of(it + 1));
-        }
+        if (more) signal(0);   // acc2 is in registers: the tensor core works on the next tile's R1 while the head is evaluated
         float2 a3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {

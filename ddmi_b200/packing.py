@@ -621,11 +621,11 @@ def _pack_video_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
     P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
-    def piece(Ws, W0, col0, first, kg=None):
+    def piece(Ws, W0, col0, first, kg=None, fc0_first=None):
         """one 64-wide piece: fc_0 (relu piece, acc1) and shortcut (raw piece, acc2); kg = (raw hi, raw lo, relu hi, relu lo)
-        K groups of the piece (default: the X region)"""
+        K groups of the piece (default: the X region); first / fc0_first: the shortcut / fc_0 accumulator starts here"""
         ah, al, bh, bl = kg or (XAH, XAL, XBH, XBL)
-        P.block(W0[:, col0:col0 + 64], bh, bl, 0, first)
+        P.block(W0[:, col0:col0 + 64], bh, bl, 0, first if fc0_first is None else fc0_first)
         P.block(Ws[:, col0:col0 + 64], ah, al, 256, first)
 
     # ---- R1: x = [xy | yt | xt] of scale 0.  The activation buffer H is idle until R1's hidden layer is published, so pieces
@@ -645,20 +645,24 @@ def _pack_video_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     # ---- R2, R3: x = [h (256) | xy | yt | xt]
     for i in (2, 3):
         Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
-        for q in range(4):                             # shortcut over RAW h
+        for q in range(4):                             # shortcut over RAW h (piece 0 was stored before h: same barriers)
             P.wait(q)
             P.block(Ws[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 256, q == 0)
-        P.commit(0)
-        P.wait(4)                                      # relu(h) quarter 0 (+ piece 0, gathered meanwhile)
-        P.block(W0[:, 0:64], HH, HL, 0, True)
-        piece(Ws, W0, 256, False)
+        P.commit(0)                                    # raw h consumed: the epilogue threads rewrite H with relu(h) ...
+        piece(Ws, W0, 256, False, fc0_first=True)       # ... while piece 0 (fc_0 starts its accumulator here) keeps the pipe busy
         P.commit(1)
-        for q in range(1, 4):
-            P.wait(4 + q)
-            P.block(W0[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 0, False)
+        # relu(h) quarters with the two remaining pieces in between: each piece's store (after the previous D1) hides
+        # behind a quarter's MMAs
+        P.wait(4)
+        P.block(W0[:, 0:64], HH, HL, 0, False)
+        P.wait(5)
+        P.block(W0[:, 64:128], HH + 8, HL + 8, 0, False)
         P.wait(0)
         piece(Ws, W0, 320, False)
         P.commit(1)
+        for q in (2, 3):
+            P.wait(4 + q)
+            P.block(W0[:, 64 * q:64 * q + 64], HH + 8 * q, HL + 8 * q, 0, False)
         P.wait(1)
         piece(Ws, W0, 384, False)
         P.commit(0)
