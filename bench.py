@@ -461,13 +461,21 @@ class OtherWorkload:
             for blk in (self.m.net_res1, self.m.net_res2, self.m.net_res3, self.m.net_res4):
                 torch.nn.init.kaiming_uniform_(blk.fc_1.weight, a=5 ** 0.5)
             self.host = [[pin(torch.randn(B, 64, s, s, generator=g)) for s in (16, 32, 64)] for _ in range(3)]
-            self.pts = torch.cat([1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3),
-                                  (torch.rand(100000, 3, generator=g) - 0.5) * 1.1]).to(dev)
-            self.n_per_item = self.pts.shape[0]
+            # the dense grid is queried as a lattice (MLP3D.decode_logits_lattice = the mesh generator's query,
+            # 1.1 * make_3d_grid((-.5,)*3, (.5,)*3, (128,)*3), logits bit-identical to the point list), the random points as a point list
+            self.axis = (1.1 * torch.linspace(-0.5, 0.5, 128)).to(dev)
+            self.pts = ((torch.rand(100000, 3, generator=g) - 0.5) * 1.1).to(dev)
+            self.n_per_item = 128 ** 3 + self.pts.shape[0]
             self.out_item = ((self.n_per_item,), torch.float32)
-            self.decode = lambda planes: self.m(self.pts[None].expand(planes[0][0].shape[0], -1, -1), planes).logits
-            self.desc = (f"ShapeNet-shape occupancy decode (BASELINE configs[3]): triplanes 16^2/32^2/64^2 x64ch, 128^3 grid + "
-                         f"100k random points, batch {B}")
+
+            def decode(planes):
+                b = planes[0][0].shape[0]
+                grid = self.m.decode_logits_lattice((self.axis,) * 3, planes).reshape(b, -1)
+                return torch.cat([grid, self.m.decode_logits(self.pts[None].expand(b, -1, -1), planes)], dim=1)
+            self.decode = decode
+            self.launches = 4              # lattice tables, lattice decode, point-list decode, the concatenation
+            self.desc = (f"ShapeNet-shape occupancy decode (BASELINE configs[3]): triplanes 16^2/32^2/64^2 x64ch, 128^3 grid "
+                         f"(lattice query) + 100k random points (point list), batch {B}")
         elif kind == 'video':
             self.flop_kind, self.kernel = 'video', 'video_umma_kernel'
             B = self.B = args.batch if args.batch != 64 else 16
@@ -483,6 +491,7 @@ class OtherWorkload:
             self.n_per_item = 256 * 256 * 16
             self.out_item = ((3, 16, 256, 256), torch.float32)
             self.decode = lambda planes: self.m(self.coords, planes)
+            self.launches = 2              # feature tables + decode
             self.desc = f"SkyTimelapse-shape video decode (BASELINE configs[2]): xy/yt/xt planes, 256x256x16 volume, batch {B}"
         else:
             self.flop_kind, self.kernel = 'nerf', 'nerf_umma_kernel'
@@ -637,7 +646,7 @@ def run_other(args):
             "e2e": {"value": coords * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W.h2d_bytes(),
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "steps": e2e_steps,
                     "pipeline": f"items walked in chunks of {CH}; uploads / read-backs on side streams"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * getattr(W, 'launches', 1),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                          "traffic": None, "peak_source": which + " (bf16 sustained)", "kernel": W.kernel,

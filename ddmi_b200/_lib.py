@@ -25,6 +25,7 @@ EXPORTS = (
     "ddmi_abi_version", "ddmi_last_error", "ddmi_status_string", "ddmi_device_info",
     "ddmi_decode_image", "ddmi_decode_image_store", "ddmi_decode_image_noise", "ddmi_planes_to_channels_last", "ddmi_decode_occupancy",
     "ddmi_decode_video", "ddmi_decode_video_store", "ddmi_decode_video_ws", "ddmi_video_workspace_bytes",
+    "ddmi_decode_occupancy_lattice", "ddmi_occupancy_lattice_workspace_bytes",
     "ddmi_nerf_mlp", "ddmi_nerf_render", "ddmi_nerf_render_z", "ddmi_sample_pdf", "ddmi_plane_head", "ddmi_plane_tail", "ddmi_mcubes_workspace_bytes", "ddmi_mcubes_count", "ddmi_mcubes_emit", "ddmi_selftest_tma", "ddmi_selftest_umma", "ddmi_selftest_umma2", "ddmi_selftest_f16f8", "ddmi_debug_profile",
     "ddmi_debug_trace", "ddmi_debug_set", "ddmi_debug_gatherbench", "ddmi_debug_ringbench", "ddmi_debug_microbench",
 )
@@ -88,6 +89,10 @@ def lib():
         L.ddmi_decode_video_ws.argtypes = [ctypes.POINTER(Plane), i32, i32, vp, vp, vp, i32, i32, i32,
                                            ctypes.POINTER(Weights), i32, vp, vp, ctypes.c_uint64, vp]
         L.ddmi_video_workspace_bytes.argtypes = [i32, i32, i32, i32, i32]
+        L.ddmi_occupancy_lattice_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        L.ddmi_occupancy_lattice_workspace_bytes.restype = ctypes.c_int64
+        L.ddmi_decode_occupancy_lattice.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i32, i32, i32, f32,
+                                                    ctypes.POINTER(Weights), vp, vp, ctypes.c_uint64, vp]
         L.ddmi_video_workspace_bytes.restype = ctypes.c_int64
         L.ddmi_nerf_mlp.argtypes = [vp, i64, i32, i32, f32, ctypes.POINTER(Weights), vp, vp]
         L.ddmi_nerf_render.argtypes = [ctypes.POINTER(Plane), i32, i32, i32, vp, i64, i32, vp, i32, f32, f32,

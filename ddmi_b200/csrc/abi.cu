@@ -33,6 +33,8 @@ int launch_occupancy_umma_entry(const PlaneSet&, int, int, const float*, long lo
 int launch_planes_to_nhwc(const float*, float*, int, int, int, cudaStream_t);
 int launch_video_umma_entry(const PlaneSet&, int, int, const float*, const float*, const float*, int, int, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, void*, int, int, int, void*, size_t, cudaStream_t);
 size_t video_workspace_bytes(int, int, int, int);
+size_t occupancy_lattice_workspace_bytes(int, int, int, int);
+int launch_occupancy_lattice_umma_entry(const PlaneSet&, int, int, const float*, int, int, int, float, float, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, int, int, int, void*, size_t, cudaStream_t);
 int launch_nerf_composite(const float*, const float*, int, const float*, int, int, long long, int, int, float*, cudaStream_t);
 int launch_nerf_umma_entry(const PlaneSet&, int, int, const float*, long long, int, const float*, int, int, float, float, int, const void*, size_t, const uint32_t*, size_t, const uint32_t*, const float*, size_t, float*, float*, int, int, cudaStream_t);
 int debug_profile(unsigned long long*, int);
@@ -218,6 +220,46 @@ DDMI_API int ddmi_decode_occupancy(const ddmi_plane_t planes[9], int32_t batch, 
   if (rc) return rc;
   return launch_occupancy_fp32(ps, batch, channels, points, n_points, point_batch_stride, divisor, upper,
                                (const float*)weights->gemm, weights->vec, logits, (cudaStream_t)stream);
+}
+
+DDMI_API int64_t ddmi_occupancy_lattice_workspace_bytes(int32_t batch, int32_t nx, int32_t ny, int32_t nz) {
+  if (batch < 1 || nx < 1 || ny < 1 || nz < 1 || (int64_t)nx * ny * nz > 2147483647LL) return 0;
+  return (int64_t)occupancy_lattice_workspace_bytes(batch, nx, ny, nz);
+}
+
+DDMI_API int ddmi_decode_occupancy_lattice(const ddmi_plane_t planes[9], int32_t batch, int32_t channels, int32_t plane_layout,
+                                           const float* axes, int32_t nx, int32_t ny, int32_t nz, float padding,
+                                           const ddmi_weights_t* weights, float* logits, void* workspace,
+                                           uint64_t workspace_bytes, void* stream) {
+  PlaneSet ps = {};
+  int rc = check_planes(planes, 9, &ps);
+  if (rc) return rc;
+  DDMI_REQUIRE(batch >= 1, "batch must be >= 1 (got %d)", batch);
+  DDMI_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && (int64_t)nx * ny * nz <= 2147483647LL, "lattice %d x %d x %d", nx, ny, nz);
+  DDMI_REQUIRE(axes && logits && workspace, "axes / logits / workspace is NULL");
+  DDMI_REQUIRE(plane_layout == DDMI_LAYOUT_NCHW || plane_layout == DDMI_LAYOUT_NHWC, "unknown plane_layout %d", plane_layout);
+  if (channels != 64) {
+    set_error("occupancy decode is built for latent_dim = 64 planes (got %d channels)", channels);
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(weights != nullptr, "weights is NULL");
+  if (weights->precision != DDMI_PREC_BF16X3 && weights->precision != DDMI_PREC_F16F8) {
+    set_error("lattice queries exist for the tcgen05 precisions only (expand the lattice and call ddmi_decode_occupancy)");
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  if (!(weights->reserved & 1)) {
+    set_error("lattice queries need weights packed for CTA pairs");
+    return DDMI_ERR_UNSUPPORTED;
+  }
+  DDMI_REQUIRE(weights->gemm && weights->vec, "weights->gemm / weights->vec is NULL");
+  DDMI_REQUIRE(((uintptr_t)weights->gemm & 127) == 0, "weights->gemm must be 128-byte aligned");
+  const float divisor = (float)(1.0 + (double)padding + 10e-6);
+  const float upper = (float)(1.0 - 10e-6);
+  return launch_occupancy_lattice_umma_entry(ps, batch, channels, axes, nx, ny, nz, divisor, upper, weights->gemm,
+                                             weights->gemm_bytes, weights->program_host, weights->program_words,
+                                             weights->program, weights->vec, weights->vec_floats, logits, 1, plane_layout,
+                                             weights->precision == DDMI_PREC_F16F8, workspace, (size_t)workspace_bytes,
+                                             (cudaStream_t)stream);
 }
 
 DDMI_API int ddmi_decode_video(const ddmi_plane_t planes[9], int32_t batch, int32_t channels,

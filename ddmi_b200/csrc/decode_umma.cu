@@ -902,6 +902,18 @@ int launch_video_umma_entry(const PlaneSet& ps, int batch, int C, const float* c
 }
 size_t video_workspace_bytes(int batch, int T, int H, int W) { return video_table_bytes(batch, T, H, W); }
 
+size_t occupancy_lattice_workspace_bytes(int batch, int nx, int ny, int nz) { return occupancy_lattice_bytes(batch, nx, ny, nz); }
+int launch_occupancy_lattice_umma_entry(const PlaneSet& ps, int batch, int C, const float* axes, int nx, int ny, int nz,
+                                        float divisor, float upper, const void* gemm, size_t gemm_bytes,
+                                        const uint32_t* program_host, size_t program_words, const uint32_t* program_dev,
+                                        const float* vec, size_t vec_floats, float* logits, int pair, int nhwc, int f16f8,
+                                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  ummak::OccLattice lat = {nullptr, axes, nx, ny, nz};
+  return launch_occupancy_umma(ps, batch, C, nullptr, (long long)nx * ny * nz, 0, divisor, upper, gemm, gemm_bytes, program_host,
+                               program_words, program_dev, vec, vec_floats, logits, pair, nhwc, f16f8, st, &lat, workspace,
+                               workspace_bytes);
+}
+
 int debug_trace(unsigned long long* out, int cap, int* n, int reset) {
   // the whole buffer (unwritten slots are 0: the caller drops them)
   int cnt = ummak::kTraceCap < cap ? ummak::kTraceCap : cap;

@@ -77,10 +77,6 @@ video_table_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __re
     *reinterpret_cast<uint2*>(rec + 192 + kg * 8) = a8;
   }
 }
-// relu of an operand word = the word with its negative channels cleared (fp16 pairs / e5m2 quads; the sign of every format
-// is the value's own: cvt keeps it even when the magnitude rounds to zero)
-__device__ __forceinline__ uint32_t relu_h2(uint32_t h) { return h & ~(((h >> 15) & 0x00010001u) * 0xFFFFu); }
-__device__ __forceinline__ uint32_t neg_mask8(uint32_t a8) { return ((a8 >> 7) & 0x01010101u) * 0xFFu; }
 struct VidRec { uint4 a[4], r[2], e[2]; };   // this thread's 32 channels of one record
 struct VidDst { uint32_t a_hi, a_lo, b_hi, b_lo; };   // where a piece goes: raw (a) and relu (b) copies, hi / lo K groups
 

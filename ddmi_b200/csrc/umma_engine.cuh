@@ -427,6 +427,36 @@ __device__ __forceinline__ void store8(uint32_t h_hi, uint32_t h_lo, int row, in
   }
 }
 
+// relu of an f16f8 operand word = the word with its negative channels cleared (fp16 pairs / e5m2 quads; the sign of every
+// format is the value's own: cvt keeps it even when the magnitude rounds to zero), i.e. split(relu(v)) bit for bit
+__device__ __forceinline__ uint32_t relu_h2(uint32_t h) { return h & ~(((h >> 15) & 0x00010001u) * 0xFFFFu); }
+__device__ __forceinline__ uint32_t neg_mask8(uint32_t a8) { return ((a8 >> 7) & 0x01010101u) * 0xFFu; }
+// K group kg of a row, raw -> (a_hi, a_lo) and relu'd -> (b_hi, b_lo): f16f8 converts once and masks
+template <int SCHEME>
+__device__ __forceinline__ void store8_raw_relu(uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, int row, int kg,
+                                                const float (&y)[8]) {
+  if (SCHEME) {
+    uint4 a16;
+    uint2 r8, a8;
+    split8_f16f8(y, a16, r8, a8);
+    const uint32_t o16 = (uint32_t)(kg * KG_BYTES + row * 16);
+    const uint32_t o8 = (uint32_t)(((kg >> 2) * 4 + ((kg >> 1) & 1)) * KG_BYTES + row * 16 + (kg & 1) * 8);
+    st_shared_v4(a_hi + o16, a16);
+    st_shared_v2(a_lo + o8, r8);
+    st_shared_v2(a_lo + o8 + 2 * KG_BYTES, a8);
+    const uint2 m = make_uint2(~neg_mask8(a8.x), ~neg_mask8(a8.y));
+    st_shared_v4(b_hi + o16, make_uint4(relu_h2(a16.x), relu_h2(a16.y), relu_h2(a16.z), relu_h2(a16.w)));
+    st_shared_v2(b_lo + o8, make_uint2(r8.x & m.x, r8.y & m.y));
+    st_shared_v2(b_lo + o8 + 2 * KG_BYTES, make_uint2(a8.x & m.x, a8.y & m.y));
+  } else {
+    float yr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yr[i] = fmaxf(y[i], 0.f);
+    store8<SCHEME>(a_hi, a_lo, row, kg, y);
+    store8<SCHEME>(b_hi, b_lo, row, kg, yr);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // kernel prologue / epilogue shared by every decoder
 // ---------------------------------------------------------------------------

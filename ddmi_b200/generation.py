@@ -91,14 +91,27 @@ def _query_grid(nx, box_size, dev):
     return (box_size * make_3d_grid((-0.5,) * 3, (0.5,) * 3, (nx,) * 3)).to(dev)
 
 
+@functools.lru_cache(maxsize=4)
+def _query_axis(nx, box_size, dev):
+    """The lattice's axis: row k of box_size * make_3d_grid(...) has z = box_size * linspace(-0.5, 0.5, nx)[k] (common.py:145-164
+    builds the grid from these linspace values; the elementwise product gives every point of a lattice line the same fp32)."""
+    return (box_size * torch.linspace(-0.5, 0.5, nx)).to(dev)
+
+
 def generate_mesh(c, mlp, resolution0=128, threshold=0.2, padding=0.1, points_batch_size=100000):
     """Dense-grid path of Generator3D.generate_mesh_fromdiffusion (generation.py:84-98, upsampling_steps == 0) for one
     decoded latent c: query box_size * make_3d_grid((-0.5,)*3, (0.5,)*3, (nx,)*3), reshape to (nx, nx, nx), extract the mesh.
+    The query goes down as a LATTICE (MLP3D.decode_logits_lattice: same logits bit for bit, a quarter of the gather bytes);
+    decoders without that entry point get the point list through eval_points.
     -> (vertices, triangles, value_grid), all on the planes' device."""
     dev = c[0][0].device
     nx = resolution0
     box_size = 1 + padding
-    pointsf = _query_grid(nx, box_size, str(dev))
-    value_grid = eval_points(pointsf, c, mlp, points_batch_size).reshape(nx, nx, nx)
+    if hasattr(mlp, 'decode_logits_lattice'):
+        ax = _query_axis(nx, box_size, str(dev))
+        value_grid = mlp.decode_logits_lattice((ax, ax, ax), c)[0]
+    else:
+        pointsf = _query_grid(nx, box_size, str(dev))
+        value_grid = eval_points(pointsf, c, mlp, points_batch_size).reshape(nx, nx, nx)
     vertices, triangles = extract_mesh(value_grid, threshold, padding)
     return vertices, triangles, value_grid

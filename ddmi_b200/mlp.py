@@ -314,6 +314,41 @@ class MLP3D(_FusedDecoder):
             del keep
         return logits
 
+    def decode_logits_lattice(self, axes, hdbf):
+        """Logits on the query lattice axes = (xs, ys, zs) (1-D tensors): (B, nx, ny, nz), bit-identical to
+        decode_logits(torch.cartesian_prod(xs, ys, zs)[None], hdbf).reshape(B, nx, ny, nz) -- the reference's dense-grid query
+        `box_size * make_3d_grid(...)` (convocc/src/conv_onet/generation.py:90-97) without the point list: on a lattice each
+        plane's sample depends on two of the three indices only, so the library samples nx ny + ny nz + nx nz feature vectors
+        per scale once and every point reads three of them (include/ddmi_b200.h, ddmi_decode_occupancy_lattice)."""
+        assert len(hdbf) == 3 and all(len(axis) == 3 for axis in hdbf) and len(axes) == 3
+        self._guard_grad(*axes, *[t for axis in hdbf for t in axis])
+        sources = [hdbf[a][s] for a in range(3) for s in range(3)]
+        names = [f'hdbf[{a}][{s}]' for a in range(3) for s in range(3)]
+        planes = [_as_plane(t, nm, keep_channels_last=True) for t, nm in zip(sources, names)]
+        self._check_device(planes[0])
+        _check_plane_set(planes, self.latent_dim, names)
+        dev = planes[0].device
+        b = planes[0].shape[0]
+        ax = [a.detach().to(device=dev, dtype=torch.float32).reshape(-1) for a in axes]
+        nx, ny, nz = (int(a.numel()) for a in ax)
+        prec = _resolve_precision(self.precision, self._supported, self._default_precision)
+        if prec != _lib.PREC_FP32:
+            prec, packed = self._packed_auto(prec, lambda pr: ('occ', pr, True), lambda pr: packing.pack_occupancy(self, pr, True))
+        ws_bytes = int(_lib.lib().ddmi_occupancy_lattice_workspace_bytes(b, nx, ny, nz)) if min(nx, ny, nz) > 0 else 0
+        if prec == _lib.PREC_FP32 or ws_bytes == 0 or ws_bytes > int(os.environ.get('DDMI_B200_LATTICE_TABLE_MAX', 8 << 30)):
+            pts = torch.cartesian_prod(*ax).reshape(1, nx * ny * nz, 3)          # exact-arithmetic path / oversized lattices
+            return self.decode_logits(pts, hdbf).reshape(b, nx, ny, nz)
+        logits = torch.empty((b, nx, ny, nz), device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            st = _stream_ptr(dev)
+            keep, arr = self._nhwc_cache.get(planes, sources, st)
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            _lib.check(_lib.lib().ddmi_decode_occupancy_lattice(
+                arr, b, planes[0].shape[1], 1, torch.cat(ax).data_ptr(), nx, ny, nz, 0.1, _lib.weights_struct(packed),
+                logits.data_ptr(), ws.data_ptr(), ws_bytes, st))
+            del keep, ws
+        return logits
+
     def forward(self, coords, hdbf):
         """coords (B,N,3); hdbf = (xy, yz, xz), each a 3-list of (B,64,R,R);
         returns Bernoulli(logits (B,N)).  mlp.py:82-111."""

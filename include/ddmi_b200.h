@@ -195,6 +195,21 @@ DDMI_API int ddmi_decode_video_store(const ddmi_plane_t planes[9], int32_t batch
                             void* out, void* stream);
 
 /*
+ * Occupancy logits on a query LATTICE {xs[i]} x {ys[j]} x {zs[k]} (ABI 10): the dense grid of the reference's mesh generator,
+ * box_size * make_3d_grid(...) (convocc/src/conv_onet/generation.py:90-97, convocc/src/common.py:145-164).  axes = device array
+ * [xs (nx) | ys (ny) | zs (nz)]; logits: (batch, nx * ny * nz), point index (i * ny + j) * nz + k -- bit-identical to
+ * ddmi_decode_occupancy on the expanded point list.  On a lattice the 'xy' sample depends on (i, j) only, 'yz' on (j, k), 'xz'
+ * on (i, k): the nx ny + ny nz + nx nz distinct vectors per scale are sampled once into `workspace`
+ * (ddmi_occupancy_lattice_workspace_bytes() bytes, 16-byte aligned, scratch for this call) and every point reads three
+ * records instead of twelve texels.  tcgen05 precisions, pair-packed weights.
+ */
+DDMI_API int64_t ddmi_occupancy_lattice_workspace_bytes(int32_t batch, int32_t nx, int32_t ny, int32_t nz);
+DDMI_API int ddmi_decode_occupancy_lattice(const ddmi_plane_t planes[9], int32_t batch, int32_t channels, int32_t plane_layout,
+                                  const float* axes, int32_t nx, int32_t ny, int32_t nz, float padding,
+                                  const ddmi_weights_t* weights, float* logits, void* workspace,
+                                  uint64_t workspace_bytes, void* stream);
+
+/*
  * ddmi_decode_video_store with a caller-provided device workspace (ABI 10).  The three query grids of a video are separable
  * by construction (xy by (h,w), yt by (t,h), xt by (t,w): utils/general_utils.py:38-52), so only H W + T H + T W distinct
  * feature vectors exist per scale; with a workspace of ddmi_video_workspace_bytes() bytes (16-byte aligned; 0 = this

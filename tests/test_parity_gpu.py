@@ -805,6 +805,28 @@ def test_video_ragged_volume():
     assert float((out - ref).abs().max()) < TOL
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
+@pytest.mark.parametrize("shape", [(5, 7, 50), (33, 17, 129), (16, 16, 256)])
+def test_occupancy_lattice_matches_the_point_list(shape, precision):
+    """decode_logits_lattice (feature tables per (i,j) / (j,k) / (i,k), ddmi_decode_occupancy_lattice) == the expanded point list,
+    bit for bit: lattice lines that straddle tiles, unequal axes, axis values beyond the padded box (clamped), batch 2."""
+    m = cases.build_module('occupancy').to(DEV)
+    m.precision = precision
+    g = torch.Generator().manual_seed(61)
+    hdbf = _cuda(tuple([torch.randn(2, 64, s, s, generator=g) for s in (16, 32, 64)] for _ in range(3)))
+    nx, ny, nz = shape
+    axes = [torch.linspace(-0.62, 0.58, nx), torch.linspace(-0.5, 0.5, ny) * 1.1, (torch.rand(nz, generator=g) - 0.5) * 1.3]
+    lat = m.decode_logits_lattice([a.to(DEV) for a in axes], hdbf)
+    assert lat.shape == (2, nx, ny, nz)
+    pts = torch.cartesian_prod(*axes)[None].to(DEV)
+    ref = m.decode_logits(pts, hdbf).reshape(2, nx, ny, nz)
+    assert torch.equal(lat, ref)
+    assert float(lat.std()) > 0
+    m.precision = 'fp32'                                   # the exact-arithmetic path expands the lattice itself
+    exact = m.decode_logits_lattice([a.to(DEV) for a in axes], hdbf)
+    assert float((lat - exact).abs().max()) < TOL
+
+
 @pytest.mark.parametrize("shape", [(3, 7, 19), (4, 16, 128), (2, 24, 320)])
 def test_video_feature_tables_match_the_direct_gather(shape, monkeypatch):
     """f16f8: the operand-format feature tables (one record per distinct (h,w) / (t,h) / (t,w) grid entry, ddmi_decode_video_ws)

@@ -11,11 +11,15 @@ torch.manual_seed(1)
 m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
 g = torch.Generator().manual_seed(1)
 hdbf = tuple([torch.randn(B, 64, s, s, generator=g).to(dev) for s in (16, 32, 64)] for _ in range(3))
-if mode == 'grid':
+if mode in ('grid', 'lattice'):
     pts = (1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3)).to(dev)
 else:
     pts = ((torch.rand(2097152, 3, generator=g) - 0.5) * 1.1).to(dev)
-f = lambda: m(pts[None].expand(B, -1, -1), hdbf).logits
+if mode == 'lattice':
+    ax = (1.1 * torch.linspace(-0.5, 0.5, 128)).to(dev)
+    f = lambda: m.decode_logits_lattice((ax, ax, ax), hdbf)
+else:
+    f = lambda: m(pts[None].expand(B, -1, -1), hdbf).logits
 for _ in range(2): f()
 torch.cuda.synchronize()
 buf = (ctypes.c_uint64 * 8)()
