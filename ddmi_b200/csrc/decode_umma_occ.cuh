@@ -7,7 +7,9 @@
 // phases: the epilogue keeps h (fp32) in registers, publishes RAW h (shortcut GEMM -> acc2),
 // and after that GEMM committed rewrites the same buffer with relu(h) (fc_0 GEMM -> acc1);
 // fc_1 then accumulates ONTO the shortcut in acc2, so x_s + dx never leaves TMEM.
-// The 64-wide plane features are kept in both forms (Xa raw, Xb relu).
+// The 64-wide plane features are kept in both forms (Xa raw, Xb relu); in R2 / R3 they are published on their own barrier
+// (A4) and their MMAs (shortcut part + the start of fc_0's accumulator) run right behind the shortcut's commit, i.e. while the
+// epilogue threads rewrite H -- the tensor core is not idle across that hand-over.
 //
 // What bounds this kernel (round 2, profiles/r02_occupancy_timeline_grid.txt, r02_gatherbench_scattered_texels.txt): the
 // GATHERS.  A point needs 9 planes x 4 taps x 256 B of channels-last texels (9 KB); a B200 SM sustains ~32 B/clk on scattered
@@ -210,21 +212,26 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
     const int ghalf = tid >> 7;
     const uint32_t a_bar = PAIR ? mapa_rank(bar + BAR_A0, 0) : bar + BAR_A0;
     uint32_t ph_mma = 0;
+    bool tr = false;        // profiling build: E thread 0 of CTA 0 traces tile iteration kTraceIter
+    uint32_t trn = 0;
 
     auto signal = [&](int q) {
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
+      trace(tr, 0x10 + q, trn, 0);
     };
     auto signal_all = [&]() {
 #pragma unroll
       for (int q = 0; q < 4; ++q) signal(q);
     };
     auto wait_mma = [&]() {
+      trace(tr, 0x01, trn, 0);
       mbar_wait(bar + BAR_MMADONE, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
+      trace(tr, 0x02, trn, 0);
     };
     // this thread's query point of a tile (rows past the end replay the last point)
     auto point_of = [&](long long tile, float (&p)[3]) {
@@ -248,6 +255,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
     //   (two float4 per tap), so one warp instruction touches 4 points x 2 cache lines; 4 passes of 32 points.
     // NCHW: one thread per (point, 32-channel half), scalar loads (layout the VAE decoder emits).
     auto gather = [&](long long tile, int s) {
+      trace(tr, 0x20, trn, 0);
       if (tile > total_tiles - 1) tile = total_tiles - 1;
       const int b = (int)(tile / tiles_per_item);
       const long long r0 = (tile % tiles_per_item) * TILE;
@@ -338,6 +346,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
           store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g, yr);
         }
       }
+      trace(tr, 0x21, trn, 0);
     };
     // wait for the fc_0 GEMM, then relu(acc1 + b) -> H, quarter by quarter
     auto stage_net = [&](const float* __restrict__ b0) {
@@ -351,6 +360,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
     }
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
+      tr = DDMI_PROFILE && blockIdx.x == 0 && tid == 0 && it == kTraceIter;
       // ---- R1.fc_0 (N = 64): net = relu(acc1[:, 0:64] + b0) -> H[:, 0:64]
       {
         float2 v[16], b[16];
@@ -369,9 +379,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
         signal_all();
       }
-      // R1's fc_0 AND shortcut ran in that group, so both feature buffers are free: gather the next scale now,
-      // overlapping R1.fc_1 (every gather sits right after the group that last reads Xa / Xb)
-      gather(tile, 1);
+      // R1's fc_0 AND shortcut ran in that group, so both feature buffers are free; R1.fc_1 is a single K = 64 run, too short
+      // to hide a gather: scale 1 is gathered behind R1's output stage instead, under R2's shortcut GEMM over h
       // ---- R1 output h1 = acc2 + b1' + net_p(p); R2, R3: two operand phases (raw, then relu)
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
@@ -393,13 +402,15 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
                                       }
                                     },
                                     signal, 0);
+        // the PE operands have their own barrier (A4): the program runs them between the two h phases
+        if (blk == 1) { gather(tile, 1); signal(4); }
         // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
         wait_mma();
 #pragma unroll
         for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
         // fc_0 epilogue; Xa / Xb are free again: gather what comes next while fc_1 runs
         stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
-        if (blk == 1) gather(tile, 2);
+        if (blk == 1) { gather(tile, 2); signal(4); }
         else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
       }
       // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
@@ -417,6 +428,9 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         load_vec<16>(vec + OV_WOUT + sub * 32, w);
         wait_mma();
         drain128(tmem_lane, 256, sub, v);
+        // acc2 is in registers and the next tile's PE operands are in place: the tensor core starts the next tile's R1 while
+        // the head is evaluated
+        if (it + 1 < ntiles) signal_all();
         float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -441,7 +455,6 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // part[] may be rewritten by the next tile
       }
-      if (it + 1 < ntiles) signal_all();
     }
   } else {
     engine_service_warps<PAIR, OccL::RING_BYTES, SCHEME, 0>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);

@@ -556,7 +556,8 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     """Program + stream + vec of csrc/decode_umma_occ.cuh.  A-region K groups: H hi 0..31, H lo 32..63,
     Xa (raw PE) hi 64..71 / lo 80..87, Xb (relu PE) hi 72..79 / lo 88..95; acc1 = TMEM cols 0.., acc2 = 256..
     Each ResnetBlockFC with a shortcut is three GEMM groups: shortcut on RAW h -> acc2, fc_0 on relu(h) -> acc1,
-    fc_1 on relu(net) accumulated ONTO acc2.  K runs over h follow the epilogue's quarter-by-quarter publication."""
+    fc_1 on relu(net) accumulated ONTO acc2.  K runs over h follow the epilogue's quarter-by-quarter publication (operand
+    barriers A0..A3); the PE operands of R2 / R3 have their own barrier (A4) and run between the two h phases."""
     HH, HL, XAH, XBH, XAL, XBL = 0, 32, 64, 72, 80, 88    # f16f8: "hi" = fp16 K groups, "lo" = FP8 K groups (same numbers)
     P = UmmaProgram(pair=pair, scheme='f16f8' if precision == PREC_F16F8 else 'bf16x3')
 
@@ -580,10 +581,11 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     for i in (2, 3):                                                            # x = [h(256) | PE(64)]
         Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
         over_h(Ws, 256, True)
-        P.block(Ws[:, 256:320], XAH, XAL, 256, False)
-        P.commit()
-        over_h(W0, 0, True)
-        P.block(W0[:, 256:320], XBH, XBL, 0, False)
+        P.commit()                                # raw h consumed: the epilogue threads rewrite H with relu(h) ...
+        P.wait(4)                                 # ... while the PE parts (gathered behind the raw-h publication, barrier A4)
+        P.block(Ws[:, 256:320], XAH, XAL, 256, False)                           # keep the tensor core busy;
+        P.block(W0[:, 256:320], XBH, XBL, 0, True)                              # fc_0's accumulator starts here
+        over_h(W0, 0, False)
         P.commit()
         over_h(W1, 256, False)                                                  # x_s + dx accumulate in TMEM
         P.commit()

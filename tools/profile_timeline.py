@@ -33,11 +33,15 @@ else:
     import ddmi_b200
     m = ddmi_b200.MLP3D(in_ch=3, latent_dim=64, out_ch=1, ch=256).to(dev)
     hdbf = tuple([torch.randn(4, 64, s, s, generator=g).to(dev) for s in (16, 32, 64)] for _ in range(3))
-    if os.environ.get('PTS', 'grid') == 'grid':
-        pts = (1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3)).to(dev)
+    if os.environ.get('PTS', 'grid') == 'lattice':
+        ax = (1.1 * torch.linspace(-0.5, 0.5, 128)).to(dev)
+        run = lambda: m.decode_logits_lattice((ax, ax, ax), hdbf)
     else:
-        pts = ((torch.rand(2000000, 3, generator=g) - 0.5) * 1.1).to(dev)
-    run = lambda: m(pts[None].expand(4, -1, -1), hdbf).logits
+        if os.environ.get('PTS', 'grid') == 'grid':
+            pts = (1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3)).to(dev)
+        else:
+            pts = ((torch.rand(2000000, 3, generator=g) - 0.5) * 1.1).to(dev)
+        run = lambda: m(pts[None].expand(4, -1, -1), hdbf).logits
 m.precision = os.environ.get('PREC', 'f16f8')
 L = _lib.lib()
 run()
