@@ -25,7 +25,8 @@
 // three 256-byte table reads + the same two additions instead of twelve scattered texels: a quarter of the bytes, contiguous
 // along z, and 1/43 of the tap arithmetic at 128^3.  Bit-identical to querying the expanded point list.
 //
-// vec layout (floats): b0_1[64] b1_1'[256] Wp[3][256] b0_2[256] b1_2[256] b0_3[256] b1_3[256]
+// net_p (the Linear(3, 256) on the query point) rides on R1.fc_1's accumulator: the point is published as columns 64..95 of H.
+// vec layout (floats): b0_1[64] b1_1'[256] Wp[3][256] (unused by this kernel) b0_2[256] b1_2[256] b0_3[256] b1_3[256]
 //                      b0_4[256] (b1_3+b1_4)[256] w_out[256] b_out[1]          (b1_1' = b1_1 + net_p.bias)
 #pragma once
 #include "umma_engine.cuh"
@@ -233,6 +234,14 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
       tc_fence_after();
       trace(tr, 0x02, trn, 0);
     };
+    uint32_t ph_d1 = 0;
+    auto wait_d1 = [&]() {   // completion barrier D1: the PE operands of R2 / R3 are consumed (Xa / Xb free)
+      trace(tr, 0x01, trn, 0);
+      mbar_wait(bar + BAR_MMADONE + 8, ph_d1);
+      ph_d1 ^= 1;
+      tc_fence_after();
+      trace(tr, 0x04, trn, 0);
+    };
     // this thread's query point of a tile (rows past the end replay the last point)
     auto point_of = [&](long long tile, float (&p)[3]) {
       if (tile > total_tiles - 1) tile = total_tiles - 1;
@@ -254,7 +263,9 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
     // NHWC: 8 threads cooperate on one point -- thread (tid & 7) owns K group kg = 8 consecutive channels
     //   (two float4 per tap), so one warp instruction touches 4 points x 2 cache lines; 4 passes of 32 points.
     // NCHW: one thread per (point, 32-channel half), scalar loads (layout the VAE decoder emits).
-    auto gather = [&](long long tile, int s) {
+    // part: -1 = the whole tile, 0 / 1 = its first / second half (rows in the vectorised forms, channels in the NCHW one)
+    auto gather = [&](long long tile, int s, int part = -1) {
+      const int p0 = part == 1 ? 2 : 0, p1 = part == 0 ? 2 : 4;
       trace(tr, 0x20, trn, 0);
       if (tile > total_tiles - 1) tile = total_tiles - 1;
       const int b = (int)(tile / tiles_per_item);
@@ -270,6 +281,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         float4 u[4][6];
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {
+          if (pass < p0 || pass >= p1) continue;
           long long gi = r0 + pass * 32 + (tid >> 3);
           if (gi > n - 1) gi = n - 1;
           const unsigned g = (unsigned)gi, k = g % (unsigned)lat.nz, ij = g / (unsigned)lat.nz;
@@ -283,6 +295,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         }
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {
+          if (pass < p0 || pass >= p1) continue;
           const float a[8] = {u[pass][0].x, u[pass][0].y, u[pass][0].z, u[pass][0].w, u[pass][1].x, u[pass][1].y, u[pass][1].z, u[pass][1].w};
           const float c[8] = {u[pass][2].x, u[pass][2].y, u[pass][2].z, u[pass][2].w, u[pass][3].x, u[pass][3].y, u[pass][3].z, u[pass][3].w};
           const float d[8] = {u[pass][4].x, u[pass][4].y, u[pass][4].z, u[pass][4].w, u[pass][5].x, u[pass][5].y, u[pass][5].z, u[pass][5].w};
@@ -297,7 +310,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         const float* b1 = ps.data[3 + s] + (size_t)b * hw1 * C;
         const float* b2 = ps.data[6 + s] + (size_t)b * hw2 * C;
 #pragma unroll 1
-        for (int pass = 0; pass < 4; ++pass) {
+        for (int pass = p0; pass < p1; ++pass) {
           const int prow = pass * 32 + (tid >> 3);
           long long gi = r0 + prow;
           if (gi > n - 1) gi = n - 1;
@@ -331,7 +344,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         const float* b1 = ps.data[3 + s] + ((size_t)b * C + ghalf * 32) * hw1;
         const float* b2 = ps.data[6 + s] + ((size_t)b * C + ghalf * 32) * hw2;
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
+        for (int g = p0; g < p1; ++g) {
           float y[8], yr[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -377,41 +390,40 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
           for (int i = 0; i < 8; ++i) y[i] = v[c * 8 + i];
           store16<SCHEME>(h_hi, h_lo, row, sub * 32 + c * 16, y);
         }
+        {   // the query point as columns 64..95 of H: net_p runs on the tensor core behind R1.fc_1
+          float p[3];
+          point_of(tile, p);
+          float2 y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = make_float2(0.f, 0.f);
+          if (sub == 0) { y[0] = make_float2(p[0], p[1]); y[1] = make_float2(p[2], 0.f); }
+          store16<SCHEME>(h_hi, h_lo, row, 64 + sub * 16, y);
+        }
         signal_all();
       }
       // R1's fc_0 AND shortcut ran in that group, so both feature buffers are free; R1.fc_1 is a single K = 64 run, too short
-      // to hide a gather: scale 1 is gathered behind R1's output stage instead, under R2's shortcut GEMM over h
+      // to hide a gather: half of scale 1 is gathered here (these threads would park on fc_1's commit for as long), the other
+      // half behind R1's output stage, under R2's shortcut GEMM over h
+      gather(tile, 1, 0);
       // ---- R1 output h1 = acc2 + b1' + net_p(p); R2, R3: two operand phases (raw, then relu)
 #pragma unroll 1
       for (int blk = 1; blk < 3; ++blk) {
         float2 v[4][16];
         const float* b1 = vec + (blk == 1 ? OV_B11 : OV_B12);
-        float p[3] = {0.f, 0.f, 0.f};
-        if (blk == 1) point_of(tile, p);
-        // phase 1: raw h (shortcut operand); R1's output also takes + net_p(p): 3 FMAs per output, fp32 (mlp.py:103)
-        output_stage<SCHEME, false>(tmem_lane, 256, sub, row, h_hi, h_lo, b1, v, wait_mma,
-                                    [&](int q, float2 (&vq)[16]) {
-                                      if (blk != 1) return;
-#pragma unroll
-                                      for (int k = 0; k < 3; ++k) {
-                                        const float2 pk = make_float2(p[k], p[k]);
-                                        float2 w[16];
-                                        load_vec<16>(vec + OV_WP + k * 256 + q * 64 + sub * 32, w);
-#pragma unroll
-                                        for (int i = 0; i < 16; ++i) vq[i] = __ffma2_rn(pk, w[i], vq[i]);
-                                      }
-                                    },
-                                    signal, 0);
+        // phase 1: raw h (shortcut operand)
+        output_stage<SCHEME, false>(tmem_lane, 256, sub, row, h_hi, h_lo, b1, v, wait_mma, [](int, float2 (&)[16]) {}, signal, 0);
         // the PE operands have their own barrier (A4): the program runs them between the two h phases
-        if (blk == 1) { gather(tile, 1); signal(4); }
+        if (blk == 1) { gather(tile, 1, 1); signal(4); }
         // phase 2: relu(h) (fc_0 operand) once the shortcut GEMM has consumed the raw copy
         wait_mma();
 #pragma unroll
         for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
-        // fc_0 epilogue; Xa / Xb are free again: gather what comes next while fc_1 runs
-        stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
+        // the PE operands ran right behind the shortcut's commit (D1): Xa / Xb are free, what comes next is gathered under
+        // fc_0's MMAs over h
+        wait_d1();
         if (blk == 1) { gather(tile, 2); signal(4); }
         else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
+        stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
       }
       // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
       {

@@ -577,6 +577,11 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
     P.commit()
     wait_all()
     P.block(p['net_res1.fc_1.weight'], HH, HL, 256, False)                      # K = 64 hidden, onto the shortcut
+    # net_p (Linear(3, 256) on the query point, mlp.py:103) rides on the same accumulator: the epilogue threads publish
+    # [p | 0] as columns 64..95 of H next to R1's hidden layer (three FMAs per output in the epilogue cost ~4 K cycles of the
+    # stage every other layer waits for)
+    Wp = p['net_p.weight']
+    P.block(torch.cat([Wp, Wp.new_zeros(Wp.shape[0], 32 - Wp.shape[1])], dim=1), HH + 8, HL + 8, 256, False)
     P.commit()
     for i in (2, 3):                                                            # x = [h(256) | PE(64)]
         Ws, W0, W1 = (p[f'net_res{i}.shortcut.weight'], p[f'net_res{i}.fc_0.weight'], p[f'net_res{i}.fc_1.weight'])
@@ -585,6 +590,7 @@ def _pack_occupancy_umma(p, pair, precision=PREC_BF16X3, dev='cpu'):
         P.wait(4)                                 # ... while the PE parts (gathered behind the raw-h publication, barrier A4)
         P.block(Ws[:, 256:320], XAH, XAL, 256, False)                           # keep the tensor core busy;
         P.block(W0[:, 256:320], XBH, XBL, 0, True)                              # fc_0's accumulator starts here
+        P.commit(1)                               # PE buffers free: the next gather runs under fc_0's MMAs over h
         over_h(W0, 0, False)
         P.commit()
         over_h(W1, 256, False)                                                  # x_s + dx accumulate in TMEM
