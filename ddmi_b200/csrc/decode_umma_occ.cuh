@@ -320,17 +320,13 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
           const Tap txy = make_tap<true>(g0, g1, ps.h[s], ps.w[s]);
           const Tap tyz = make_tap<true>(g1, g2, ps.h[3 + s], ps.w[3 + s]);
           const Tap txz = make_tap<true>(g0, g2, ps.h[6 + s], ps.w[6 + s]);
-          float y[8], u[8], w[8], yr[8];
+          float y[8], u[8], w[8];
           tap_sample8_nhwc(b0, txy, C, kg * 8, y);
           tap_sample8_nhwc(b1, tyz, C, kg * 8, u);
           tap_sample8_nhwc(b2, txz, C, kg * 8, w);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            y[i] = __fadd_rn(__fadd_rn(y[i], u[i]), w[i]);
-            yr[i] = fmaxf(y[i], 0.f);
-          }
-          store8<SCHEME>(xa_hi, xa_lo, prow, kg, y);
-          store8<SCHEME>(xb_hi, xb_lo, prow, kg, yr);
+          for (int i = 0; i < 8; ++i) y[i] = __fadd_rn(__fadd_rn(y[i], u[i]), w[i]);
+          store8_raw_relu<SCHEME>(xa_hi, xa_lo, xb_hi, xb_lo, prow, kg, y);
         }
       } else {
         float p[3];
@@ -345,7 +341,7 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         const float* b2 = ps.data[6 + s] + ((size_t)b * C + ghalf * 32) * hw2;
 #pragma unroll 1
         for (int g = p0; g < p1; ++g) {
-          float y[8], yr[8];
+          float y[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int c = g * 8 + i;
@@ -353,10 +349,8 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
             v = __fadd_rn(v, tap_sample(b1 + c * hw1, tyz));
             v = __fadd_rn(v, tap_sample(b2 + c * hw2, txz));
             y[i] = v;
-            yr[i] = fmaxf(v, 0.f);
           }
-          store8<SCHEME>(xa_hi, xa_lo, row, ghalf * 4 + g, y);
-          store8<SCHEME>(xb_hi, xb_lo, row, ghalf * 4 + g, yr);
+          store8_raw_relu<SCHEME>(xa_hi, xa_lo, xb_hi, xb_lo, row, ghalf * 4 + g, y);
         }
       }
       trace(tr, 0x21, trn, 0);

@@ -151,14 +151,10 @@ video_umma_kernel(PlaneSet ps, const float* __restrict__ cxy, const float* __res
         tap_sample_n<16>(base + (size_t)(g2 * 16) * hw, hw, tp, y16);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          float y[8], yr[8];
+          float y[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            y[i] = y16[g * 8 + i];
-            yr[i] = fmaxf(y[i], 0.f);
-          }
-          store8<SCHEME>(d.a_hi, d.a_lo, row, ghalf * 4 + g2 * 2 + g, y);
-          store8<SCHEME>(d.b_hi, d.b_lo, row, ghalf * 4 + g2 * 2 + g, yr);
+          for (int i = 0; i < 8; ++i) y[i] = y16[g * 8 + i];
+          store8_raw_relu<SCHEME>(d.a_hi, d.a_lo, d.b_hi, d.b_lo, row, ghalf * 4 + g2 * 2 + g, y);
         }
       }
       trace(tr, 0x21, trn, 0);
