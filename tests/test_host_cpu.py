@@ -35,6 +35,16 @@ def test_abi_rejects_bad_arguments_without_gpu():
     assert rc == 1 and b'planes[0].data is NULL' in L.ddmi_last_error()
     rc = L.ddmi_selftest_umma(None, None, None, 256, 256, None)
     assert rc == 1
+    # ABI 10: workspace sizes are pure host arithmetic; the workspace entry points validate before any launch
+    assert L.ddmi_video_workspace_bytes(2, 16, 256, 256, _lib.PREC_F16F8) == 2 * 3 * (256 * 256 + 2 * 16 * 256) * 256
+    assert L.ddmi_video_workspace_bytes(2, 16, 256, 256, _lib.PREC_BF16X3) == 0      # the table path is f16f8's
+    assert L.ddmi_occupancy_lattice_workspace_bytes(3, 128, 128, 128) == 3 * 3 * (3 * 128 * 128) * 256
+    assert L.ddmi_occupancy_lattice_workspace_bytes(1, 2048, 2048, 2048) == 0           # more than 2^31 - 1 points
+    p9 = (_lib.Plane * 9)()
+    rc = L.ddmi_decode_video_ws(p9, 1, 64, None, None, None, 1, 1, 1, ctypes.byref(w), 0, None, None, 0, None)
+    assert rc == 1 and b'planes[0].data is NULL' in L.ddmi_last_error()
+    rc = L.ddmi_decode_occupancy_lattice(p9, 1, 64, 1, None, 4, 4, 4, 0.1, ctypes.byref(w), None, None, 0, None)
+    assert rc == 1 and b'planes[0].data is NULL' in L.ddmi_last_error()
 
 
 EXPECTED_KEYS = {
