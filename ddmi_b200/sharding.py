@@ -169,6 +169,22 @@ def decode_occupancy_sharded(mlp, points, hdbf, group=None, gather=False):
     return _finish(results, plan, (b, n), 1, group, gather)
 
 
+def decode_occupancy_lattice_sharded(mlp, axes, hdbf, group=None, gather=False):
+    """Occupancy logits on the query lattice axes = (xs, ys, zs) (MLP3D.decode_logits_lattice: the mesh generator's dense grid)
+    with items, then x-slabs of the lattice, sharded: a rank decodes the sub-lattice (xs[i0:i1], ys, zs) of its items.
+    Returns [((item, i0, i1), logits (i1-i0, ny, nz))] or the assembled (B, nx, ny, nz)."""
+    world, rank = _world_rank(group)
+    b = hdbf[0][0].shape[0]
+    xs, ys, zs = axes
+    nx, ny, nz = int(xs.numel()), int(ys.numel()), int(zs.numel())
+    plan = plan_units(b, nx, world)
+    results = []
+    for item, i0, i1 in plan[rank]:
+        c = tuple([p[item:item + 1] for p in axis] for axis in hdbf)
+        results.append(((item, i0, i1), mlp.decode_logits_lattice((xs[i0:i1], ys, zs), c)[0]))
+    return _finish(results, plan, (b, nx, ny, nz), 1, group, gather)
+
+
 def render_rays_sharded(module, rays, fea, N_samples, white_bkgd, group=None, gather=False, **kw):
     """NeRF render with objects, then ray ranges (whole rays: compositing is per ray), sharded.
     Returns [((object, ray0, ray1), rgb (ray1-ray0, 3))] or the assembled (B, N_rays, 3)."""

@@ -75,8 +75,18 @@ def _worker(rank, world, port, q):
         def decode_logits(self, p, c):
             return orc.occupancy_logits(sdo, p, c)
 
+        def decode_logits_lattice(self, axes, c):
+            nx, ny, nz = (a.numel() for a in axes)
+            return orc.occupancy_logits(sdo, torch.cartesian_prod(*axes)[None], c).reshape(-1, nx, ny, nz)
+
     lo = sharding.decode_occupancy_sharded(OccStub(), pts, hdbf, gather=True)
     err = max(err, float((lo - orc.occupancy_logits(sdo, pts, hdbf)).abs().max()))
+    # lattice queries: items then x-slabs of the lattice
+    axes = (torch.linspace(-.5, .5, 5), torch.linspace(-.4, .5, 3), torch.linspace(-.5, .3, 4))
+    la = sharding.decode_occupancy_lattice_sharded(OccStub(), axes, hdbf, gather=True)
+    ref_l = orc.occupancy_logits(sdo, torch.cartesian_prod(*axes)[None].expand(3, -1, -1), hdbf).reshape(3, 5, 3, 4)
+    assert la.shape == ref_l.shape
+    err = max(err, float((la - ref_l).abs().max()))
 
     # video: batch items
     sdv = cases.state_dict32(cases.build_module('video'))
