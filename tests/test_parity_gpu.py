@@ -805,6 +805,29 @@ def test_video_ragged_volume():
     assert float((out - ref).abs().max()) < TOL
 
 
+def test_full_size_table_paths_are_bit_identical_to_the_direct_paths(monkeypatch):
+    """BASELINE configs[2] / [3] at full size, two items each: the video feature tables against per-voxel gathers and the 128^3
+    lattice query against the expanded point list -- equal bit for bit (size-independent property; the oracle comparisons at
+    these shapes are test_video_config_shape_vs_oracle / test_occupancy_config_shape_vs_oracle)."""
+    g = torch.Generator().manual_seed(71)
+    mv = cases.build_module('video').to(DEV)
+    hd = _cuda(([torch.randn(2, 64, s, s, generator=g) for s in (64, 128, 256)],
+                [torch.randn(2, 64, 16, s, generator=g) for s in (64, 128, 256)],
+                [torch.randn(2, 64, 16, s, generator=g) for s in (64, 128, 256)]))
+    cv = _cuda(ddmi_b200.convert_to_coord_format_3d(1, 256, 256, 16, hstart=-255 / 256, hend=255 / 256, wstart=-255 / 256,
+                                                    wend=255 / 256, tstart=-15 / 16, tend=15 / 16))
+    tab = mv(cv, hd)
+    monkeypatch.setenv('DDMI_B200_VIDEO_TABLE_MAX', '0')
+    assert torch.equal(tab, mv(cv, hd))
+    mo = cases.build_module('occupancy').to(DEV)
+    ho = _cuda(tuple([torch.randn(2, 64, s, s, generator=g) for s in (16, 32, 64)] for _ in range(3)))
+    ax = (1.1 * torch.linspace(-0.5, 0.5, 128)).to(DEV)
+    lat = mo.decode_logits_lattice((ax, ax, ax), ho)
+    pts = (1.1 * ddmi_b200.make_3d_grid((-.5,) * 3, (.5,) * 3, (128,) * 3)).to(DEV)
+    assert torch.equal(lat.reshape(2, -1), mo.decode_logits(pts[None], ho))
+    assert float(lat.std()) > 0 and float(tab.std()) > 0
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "f16f8"])
 @pytest.mark.parametrize("shape", [(5, 7, 50), (33, 17, 129), (16, 16, 256)])
 def test_occupancy_lattice_matches_the_point_list(shape, precision):
