@@ -110,21 +110,26 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     const int ghalf = tid >> 7;
     const uint32_t a_bar = mapa_rank(bar + BAR_A0, 0);
     uint32_t ph_mma = 0;
+    bool tr = false;        // profiling build: E thread 0 of CTA 0 traces tile iteration kTraceIter
+    uint32_t trn = 0;
 
     auto signal = [&](int q) {
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(a_bar + 8 * q);
+      trace(tr, 0x10 + q, trn, 0);
     };
     auto signal_all = [&]() {
 #pragma unroll
       for (int q = 0; q < 4; ++q) signal(q);
     };
     auto wait_mma = [&]() {
+      trace(tr, 0x01, trn, 0);
       mbar_wait(bar + BAR_MMADONE, ph_mma);
       ph_mma ^= 1;
       tc_fence_after();
+      trace(tr, 0x02, trn, 0);
     };
     // row -> (object, ray, sample); rows past the end replay the last one
     struct RowInfo { int b; long long ray; int smp; long long gi; };
@@ -142,9 +147,35 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       return nerf_z(t_vals, z_stride, ray, smp, __ldg(rr + 6), __ldg(rr + 7));
     };
     // X = [latent xy|yz|xz (3 x 32) | gamma(pts) 63 | 0] = 12 gathered + 8 embedding K groups per row, split evenly over the
-    // row's two threads: gathers [6 ghalf, +6), embedding groups [12 + 4 ghalf, +4).  The gathers are L2-latency bound (there
-    // is no L1 beside ~200 KB of shared memory), so the 24 float4 loads of three K groups are issued before any is consumed.
-    auto build_x = [&](long long tile) {
+    // row's two threads.  The gathers are L2-latency bound (there is no L1 beside ~200 KB of shared memory), so the 16 float4
+    // loads of two K groups are issued before any is consumed.
+    // The NEXT tile's X is built in two parts: X is dead once the second skip layer has committed and only its first 4 K
+    // groups are reused (for the view-direction embedding of the last GEMM), so
+    //   parts bit 0 | bit 1: gamma(pts) (K groups 12..19) and the 'yz' | 'xz' latents (K groups 4..11) are written after the
+    //                        final layer's epilogue, while these threads would park on the last two GEMMs,
+    //   parts bit 2:         the 'xy' latent (K groups 0..3) once the last GEMM has committed -- its taps are loaded with the
+    //                        first part and only blended + stored then; the tile is handed over right after
+    // (the whole build between tiles kept the tensor core idle for ~10 K cycles per tile: profiles/r02b_nerf_timeline_before.txt)
+    struct XTaps { float4 q[2][8]; float w[4]; };   // the 16 tap loads of two K groups of one plane + the bilinear weights
+    auto x_finish = [&](int j0, const XTaps& t) {   // blend -> X K groups j0, j0 + 1 (caller waits for the tensor-memory stores)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float y[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {   // same FMA order as common.cuh::tap_sample8_nhwc
+          const float4 a0 = t.q[u][h], b0 = t.q[u][2 + h], c0 = t.q[u][4 + h], d0 = t.q[u][6 + h];
+          y[4 * h + 0] = fmaf(d0.x, t.w[3], fmaf(c0.x, t.w[2], fmaf(b0.x, t.w[1], a0.x * t.w[0])));
+          y[4 * h + 1] = fmaf(d0.y, t.w[3], fmaf(c0.y, t.w[2], fmaf(b0.y, t.w[1], a0.y * t.w[0])));
+          y[4 * h + 2] = fmaf(d0.z, t.w[3], fmaf(c0.z, t.w[2], fmaf(b0.z, t.w[1], a0.z * t.w[0])));
+          y[4 * h + 3] = fmaf(d0.w, t.w[3], fmaf(c0.w, t.w[2], fmaf(b0.w, t.w[1], a0.w * t.w[0])));
+        }
+        x_store8<SCHEME>(tmem_lane, j0 + u, y);
+      }
+    };
+    // xy_later != nullptr: the 'xy' taps are only LOADED (the caller finishes them with x_finish(2 * ghalf, ..) once X's first
+    // 4 K groups are free)
+    auto build_x = [&](long long tile, int parts, XTaps* xy_later = nullptr) {
+      trace(tr, 0x20, trn, 0);
       const RowInfo ri = row_of(tile);
       const float* rr = rays + (size_t)ri.ray * ray_stride;
       const float z = zval(rr, ri.ray, ri.smp);
@@ -154,40 +185,36 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         p[i] = __fadd_rn(__ldg(rr + i), __fmul_rn(__ldg(rr + 3 + i), z));
         g[i] = __fdiv_rn(p[i], plane_extent);
       }
-#pragma unroll 1
-      for (int bb = 0; bb < 2; ++bb) {
-        float4 q[3][8];
-        Tap tp[3];
+      // K groups j0, j0 + 1 of one plane a = j0 / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate -> column
+      auto planes2_load = [&](int j0, XTaps& t) {
+        const int a = j0 >> 2;
+        const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
+        const Tap tp = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
+        const float* img = ps.data[a] + (size_t)ri.b * ps.h[a] * ps.w[a] * C + (j0 & 3) * 8;
+        const int o[4] = {tp.o00, tp.o01, tp.o10, tp.o11};
+        t.w[0] = tp.w00; t.w[1] = tp.w01; t.w[2] = tp.w10; t.w[3] = tp.w11;
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {   // plane a = j / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate -> column
-          const int j = ghalf * 6 + bb * 3 + u, a = j >> 2;
-          const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
-          tp[u] = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
-          const float* img = ps.data[a] + (size_t)ri.b * ps.h[a] * ps.w[a] * C + (j & 3) * 8;
-          const int o[4] = {tp[u].o00, tp[u].o01, tp[u].o10, tp[u].o11};
+        for (int u = 0; u < 2; ++u) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float4* pp = reinterpret_cast<const float4*>(img + (size_t)o[t] * C);
-            q[u][2 * t] = __ldg(pp);
-            q[u][2 * t + 1] = __ldg(pp + 1);
+          for (int k = 0; k < 4; ++k) {
+            const float4* pp = reinterpret_cast<const float4*>(img + (size_t)o[k] * C + u * 8);
+            t.q[u][2 * k] = __ldg(pp);
+            t.q[u][2 * k + 1] = __ldg(pp + 1);
           }
         }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const float w[4] = {tp[u].w00, tp[u].w01, tp[u].w10, tp[u].w11};
-          float y[8];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {   // same FMA order as common.cuh::tap_sample8_nhwc
-            const float4 a0 = q[u][h], b0 = q[u][2 + h], c0 = q[u][4 + h], d0 = q[u][6 + h];
-            y[4 * h + 0] = fmaf(d0.x, w[3], fmaf(c0.x, w[2], fmaf(b0.x, w[1], a0.x * w[0])));
-            y[4 * h + 1] = fmaf(d0.y, w[3], fmaf(c0.y, w[2], fmaf(b0.y, w[1], a0.y * w[0])));
-            y[4 * h + 2] = fmaf(d0.z, w[3], fmaf(c0.z, w[2], fmaf(b0.z, w[1], a0.z * w[0])));
-            y[4 * h + 3] = fmaf(d0.w, w[3], fmaf(c0.w, w[2], fmaf(b0.w, w[1], a0.w * w[0])));
-          }
-          x_store8<SCHEME>(tmem_lane, ghalf * 6 + bb * 3 + u, y);
-        }
+      };
+      auto planes2 = [&](int j0) {
+        XTaps t;
+        planes2_load(j0, t);
+        x_finish(j0, t);
+      };
+      if (xy_later) planes2_load(2 * ghalf, *xy_later);
+      else if (parts & 4) planes2(2 * ghalf);
+      if (parts & 2) {
+        planes2(4 + 4 * ghalf);
+        planes2(6 + 4 * ghalf);
       }
-      {
+      if (parts & 1) {
         float e[32];
         if (ghalf == 0) embed_half<0, 10, 32>(p, e); else embed_half<1, 10, 32>(p, e);
 #pragma unroll
@@ -199,6 +226,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         }
       }
       tmem_st_wait();
+      trace(tr, 0x21, trn, 0);
     };
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
     auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {   // waits for the GEMM first
@@ -212,11 +240,12 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     };
 
     if (ntiles > 0) {
-      build_x(tile_of(0));
+      build_x(tile_of(0), 7);
       signal_all();
     }
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
+      tr = DDMI_PROFILE && blockIdx.x == 0 && tid == 0 && it == kTraceIter;
       const RowInfo ri = row_of(tile);
       const float* rr = rays + (size_t)ri.ray * ray_stride;
       float sigma = 0.f;
@@ -260,6 +289,9 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         float2 v[4][16];
         stage_act(vec + NV_BF, false, v);
       }
+      const bool more = it + 1 < ntiles;
+      XTaps xy;
+      if (more) build_x(tile_of(it + 1), 3, &xy);
       // ---- dir_encoding (N = 128) + rgb head
       float rgb[3];
       {
@@ -270,10 +302,12 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         tmem_ld32(tmem_lane + sub * 32, v[0]);
         tmem_ld32(tmem_lane + 64 + sub * 32, v[1]);
         tmem_ld_wait();
-        // Every MMA of this tile has committed and its last accumulator is in registers: build the next tile's X and hand
-        // over NOW, so that the rgb head and the compositing below run under the next tile's first GEMM.
-        if (it + 1 < ntiles) {
-          build_x(tile_of(it + 1));
+        // Every MMA of this tile has committed and its last accumulator is in registers: finish the next tile's X (the 'xy'
+        // latent, where the direction embedding sat) and hand over NOW, so that the rgb head and the compositing below run
+        // under the next tile's first GEMM.
+        if (more) {
+          x_finish(2 * ghalf, xy);
+          tmem_st_wait();
           signal_all();
         }
         float2 acc3[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
@@ -351,6 +385,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
           asm volatile("bar.sync 2, 128;" ::: "memory");
         }
       }
+      trace(tr, 0x05, trn, 0);   // tile done on the epilogue side
     }
   } else {
     engine_service_warps<PAIR, NrfL::RING_BYTES, SCHEME>(prog.op, wstream, sbase, ring, bar, tmem, ntiles, rank);

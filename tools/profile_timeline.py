@@ -19,6 +19,19 @@ if kind == 'image':
     e = (R - 1) / R
     c = convert_to_coord_format_2d(1, R, R, hstart=-e, hend=e, wstart=-e, wend=e).to(dev)
     run = lambda: m(c, hdbf=planes, si=get_scale_injection(R))
+elif kind == 'nerf':
+    import numpy as np
+    import ddmi_b200
+    from ddmi_b200 import nerf_helpers as nh
+    m = ddmi_b200.MLPNeRF(D=6, W=256, in_channels_xyz=159, skips=[2, 4], in_channels_dir=27).to(dev)
+    fea = {k: torch.randn(4, 32, 64, 64, generator=g).to(dev) for k in ('xy', 'yz', 'xz')}
+    H = W = 128
+    focal = .5 * W / np.tan(.5 * 0.6911112070083618)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]])
+    ro, rd = nh.get_rays(H, W, K, nh.pose_spherical(40.0, -20, 5)[:3, :4], dev)
+    vd = (rd / torch.norm(rd, dim=-1, keepdim=True)).reshape(-1, 3)
+    rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), 2. * torch.ones(H * W, 1, device=dev), 6. * torch.ones(H * W, 1, device=dev), vd], -1)
+    run = lambda: nh.render_rays_fused(rays, fea, m, 128, True)
 elif kind == 'video':
     import ddmi_b200
     m = ddmi_b200.MLPVideo(in_ch=2, latent_dim=64, out_ch=3, ch=256).to(dev)
@@ -59,7 +72,7 @@ if not ev:
     print("no trace records: load the profiling build (DDMI_B200_LIB=ddmi_b200/libddmi_b200_prof.so)")
     sys.exit(1)
 t0 = ev[0][0]
-names = {0x01: 'E park', 0x02: 'E woke (COMMIT 0)', 0x03: 'E drained', 0x04: 'E COMMIT 1 seen', 0x14: 'E acc cols 128.. drained', 0x15: 'E acc cols 0..127 drained',
+names = {0x05: 'E tile done', 0x01: 'E park', 0x02: 'E woke (COMMIT 0)', 0x03: 'E drained', 0x04: 'E COMMIT 1 seen', 0x14: 'E acc cols 128.. drained', 0x15: 'E acc cols 0..127 drained',
          0x20: 'E gather begin', 0x21: 'E gather end'}
 prev = t0
 for t, i in ev:
