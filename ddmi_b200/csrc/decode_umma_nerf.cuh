@@ -25,7 +25,8 @@ namespace ummak {
 using NrfL = Layout<0, 65536>;    // shared memory: H + 8 x 8 KB ring slots (CTA pairs only); X is in tensor memory
 constexpr int NRF_KG_XH = 64, NRF_KG_XL = 84;   // X K groups (4 TMEM columns each): hi 64..83 -> columns 256..335, lo 84..103 -> 336..415
 constexpr int NRF_OFF_SCRATCH = NrfL::OFF_BAR + BAR_BYTES;
-constexpr int NRF_SMEM = NRF_OFF_SCRATCH + 5120;
+constexpr int NRF_OFF_WRGB = NRF_OFF_SCRATCH + 5120;   // [w_rgb 3 x 128 | b_rgb 3 | pad] staged once per CTA: the rgb head runs
+constexpr int NRF_SMEM = NRF_OFF_WRGB + 1552;          // between tiles, where six dependent L2 round trips were exposed
 constexpr int NV_B = 0, NV_BF = 1536, NV_BD = 1792, NV_WS = 1920, NV_BS = 2176, NV_WRGB = 2180, NV_BRGB = 2564, NV_TOTAL = 2567;
 
 __device__ __forceinline__ float2 lrelu_pair(float2 t, float slope) {
@@ -96,6 +97,9 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t tmem = engine_begin<PAIR, SCHEME>(smem, NrfL::OFF_BAR);
+  float* wrgb = reinterpret_cast<float*>(smem + NRF_OFF_WRGB);
+  for (int i = threadIdx.x; i < 387; i += NTHREADS) wrgb[i] = __ldg(vec + NV_WRGB + i);   // NV_BRGB = NV_WRGB + 384
+  __syncthreads();
 
   const long long nwork = (total_tiles + 1) / 2;
   const long long wfirst = blockIdx.x / 2, wstride = gridDim.x / 2;
@@ -320,8 +324,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
           }
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            float2 w[16];
-            load_vec<16>(vec + NV_WRGB + c * 128 + q * 64 + sub * 32, w);
+            const float2* w = reinterpret_cast<const float2*>(wrgb + c * 128 + q * 64 + sub * 32);   // warp-uniform: broadcast
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc3[c] = __ffma2_rn(v[q][i], w[i], acc3[c]);
           }
@@ -331,7 +334,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float s = scratch[(c * 2) * 128 + row] + scratch[(c * 2 + 1) * 128 + row] + __ldg(vec + NV_BRGB + c);
+          const float s = scratch[(c * 2) * 128 + row] + scratch[(c * 2 + 1) * 128 + row] + wrgb[384 + c];
           rgb[c] = 1.f / (1.f + expf(-s));
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
