@@ -155,8 +155,9 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     // loads of two K groups are issued before any is consumed.
     // The NEXT tile's X is built in two parts: X is dead once the second skip layer has committed and only its first 4 K
     // groups are reused (for the view-direction embedding of the last GEMM), so
-    //   parts bit 0 | bit 1: gamma(pts) (K groups 12..19) and the 'yz' | 'xz' latents (K groups 4..11) are written after the
-    //                        final layer's epilogue, while these threads would park on the last two GEMMs,
+    //   parts bit 0:         gamma(pts) (K groups 12..19) after layer 5's epilogue, under layer 6's GEMM,
+    //   parts bit 1:         the 'yz' | 'xz' latents (K groups 4..11) after the final layer's epilogue, while these threads
+    //                        would park on the last two GEMMs,
     //   parts bit 2:         the 'xy' latent (K groups 0..3) once the last GEMM has committed -- its taps are loaded with the
     //                        first part and only blended + stored then; the tile is handed over right after
     // (the whole build between tiles kept the tensor core idle for ~10 K cycles per tile: profiles/r02b_nerf_timeline_before.txt)
@@ -258,6 +259,9 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       for (int l = 0; l < 6; ++l) {
         float2 v[4][16];
         stage_act(vec + NV_B + l * 256, true, v);
+        // X is dead from here on (the second skip layer, xyz_encoding_5, has committed): the next tile's gamma(pts) -- 16
+        // sincosf per thread, ~5 K cycles -- goes under layer 6's GEMM
+        if (l == 4 && it + 1 < ntiles) build_x(tile_of(it + 1), 1);
         if (l == 5) {
           // X is dead (the last skip layer committed): view-direction embedding -> X's first 4 K groups,
           // sigma = w_sigma . h6 + b_sigma (this thread's 128 columns, summed across the two sub-warps below)
@@ -295,7 +299,7 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       }
       const bool more = it + 1 < ntiles;
       XTaps xy;
-      if (more) build_x(tile_of(it + 1), 3, &xy);
+      if (more) build_x(tile_of(it + 1), 2, &xy);
       // ---- dir_encoding (N = 128) + rgb head
       float rgb[3];
       {
