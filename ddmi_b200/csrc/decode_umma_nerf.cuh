@@ -81,6 +81,12 @@ __device__ __forceinline__ void embed_half(const float (&p)[3], float (&y)[N]) {
   }
 }
 
+template <int NK>
+struct XTaps {   // the tap loads of NK K groups of one plane + the bilinear weights
+  float4 q[NK][8];
+  float w[4];
+};
+
 template <int SCHEME>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_stride, const float* __restrict__ t_vals,
@@ -151,20 +157,62 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
       return nerf_z(t_vals, z_stride, ray, smp, __ldg(rr + 6), __ldg(rr + 7));
     };
     // X = [latent xy|yz|xz (3 x 32) | gamma(pts) 63 | 0] = 12 gathered + 8 embedding K groups per row, split evenly over the
-    // row's two threads.  The gathers are L2-latency bound (there is no L1 beside ~200 KB of shared memory), so the 16 float4
-    // loads of two K groups are issued before any is consumed.
-    // The NEXT tile's X is built in two parts: X is dead once the second skip layer has committed and only its first 4 K
-    // groups are reused (for the view-direction embedding of the last GEMM), so
-    //   parts bit 0:         gamma(pts) (K groups 12..19) after layer 5's epilogue, under layer 6's GEMM,
-    //   parts bit 1:         the 'yz' | 'xz' latents (K groups 4..11) after the final layer's epilogue, while these threads
-    //                        would park on the last two GEMMs,
-    //   parts bit 2:         the 'xy' latent (K groups 0..3) once the last GEMM has committed -- its taps are loaded with the
-    //                        first part and only blended + stored then; the tile is handed over right after
+    // row's two threads: thread 0 gathers 'xy' K groups 0, 1 and 'yz' 4..7, thread 1 'xy' 2, 3 and 'xz' 8..11 (one plane = one
+    // tap set per batch); embedding groups [12 + 4 ghalf, +4).  The gathers are L2-latency bound (there is no L1 beside ~200 KB
+    // of shared memory), so all tap loads of a batch are issued before any is consumed.
+    // The NEXT tile's X is built in three windows where these threads would otherwise park: X is dead once the second skip
+    // layer has committed and only its first 4 K groups are reused (view-direction embedding of the last GEMM), so
+    //   x_point + x_embed: the sample point and gamma(pts) (16 sincosf per thread, ~5 K cycles) under layer 6's GEMM,
+    //   x_planes<4>:       the 'yz' | 'xz' latents after the final layer's epilogue, under the last two GEMMs, together with
+    //   x_taps<2>:         the LOADS of the 'xy' taps, which are blended + stored (x_finish<2>) once the last GEMM has
+    //                      committed; the tile is handed over right after
     // (the whole build between tiles kept the tensor core idle for ~10 K cycles per tile: profiles/r02b_nerf_timeline_before.txt)
-    struct XTaps { float4 q[2][8]; float w[4]; };   // the 16 tap loads of two K groups of one plane + the bilinear weights
-    auto x_finish = [&](int j0, const XTaps& t) {   // blend -> X K groups j0, j0 + 1 (caller waits for the tensor-memory stores)
+    auto x_point = [&](long long tile, float (&p)[3]) {   // -> object index
+      const RowInfo ri = row_of(tile);
+      const float* rr = rays + (size_t)ri.ray * ray_stride;
+      const float z = zval(rr, ri.ray, ri.smp);
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int i = 0; i < 3; ++i) p[i] = __fadd_rn(__ldg(rr + i), __fmul_rn(__ldg(rr + 3 + i), z));
+      return ri.b;
+    };
+    auto x_embed = [&](const float (&p)[3]) {
+      float e[32];
+      if (ghalf == 0) embed_half<0, 10, 32>(p, e); else embed_half<1, 10, 32>(p, e);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = e[jj * 8 + i];
+        x_store8<SCHEME>(tmem_lane, 12 + ghalf * 4 + jj, y);
+      }
+    };
+    // tap loads of K groups j0 .. j0 + NK - 1 (all of plane a = j0 / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate
+    // -> column) of object b at point p
+    auto x_taps = [&](int b, const float (&p)[3], int j0, auto& t) {
+      constexpr int NK = sizeof(t.q) / sizeof(t.q[0]);
+      float g[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) g[i] = __fdiv_rn(p[i], plane_extent);
+      const int a = j0 >> 2;
+      const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
+      const Tap tp = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
+      const float* img = ps.data[a] + (size_t)b * ps.h[a] * ps.w[a] * C + (j0 & 3) * 8;
+      const int o[4] = {tp.o00, tp.o01, tp.o10, tp.o11};
+      t.w[0] = tp.w00; t.w[1] = tp.w01; t.w[2] = tp.w10; t.w[3] = tp.w11;
+#pragma unroll
+      for (int u = 0; u < NK; ++u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4* pp = reinterpret_cast<const float4*>(img + (size_t)o[k] * C + u * 8);
+          t.q[u][2 * k] = __ldg(pp);
+          t.q[u][2 * k + 1] = __ldg(pp + 1);
+        }
+      }
+    };
+    auto x_finish = [&](int j0, const auto& t) {   // blend -> X K groups j0.. (the caller waits for the tensor-memory stores)
+      constexpr int NK = sizeof(t.q) / sizeof(t.q[0]);
+#pragma unroll
+      for (int u = 0; u < NK; ++u) {
         float y[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {   // same FMA order as common.cuh::tap_sample8_nhwc
@@ -177,61 +225,10 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         x_store8<SCHEME>(tmem_lane, j0 + u, y);
       }
     };
-    // xy_later != nullptr: the 'xy' taps are only LOADED (the caller finishes them with x_finish(2 * ghalf, ..) once X's first
-    // 4 K groups are free)
-    auto build_x = [&](long long tile, int parts, XTaps* xy_later = nullptr) {
-      trace(tr, 0x20, trn, 0);
-      const RowInfo ri = row_of(tile);
-      const float* rr = rays + (size_t)ri.ray * ray_stride;
-      const float z = zval(rr, ri.ray, ri.smp);
-      float p[3], g[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        p[i] = __fadd_rn(__ldg(rr + i), __fmul_rn(__ldg(rr + 3 + i), z));
-        g[i] = __fdiv_rn(p[i], plane_extent);
-      }
-      // K groups j0, j0 + 1 of one plane a = j0 / 4: xy = (x, y), yz = (y, z), xz = (x, z); first coordinate -> column
-      auto planes2_load = [&](int j0, XTaps& t) {
-        const int a = j0 >> 2;
-        const float ga = a == 1 ? g[1] : g[0], gb = a == 0 ? g[1] : g[2];
-        const Tap tp = make_tap<true>(ga, gb, ps.h[a], ps.w[a]);
-        const float* img = ps.data[a] + (size_t)ri.b * ps.h[a] * ps.w[a] * C + (j0 & 3) * 8;
-        const int o[4] = {tp.o00, tp.o01, tp.o10, tp.o11};
-        t.w[0] = tp.w00; t.w[1] = tp.w01; t.w[2] = tp.w10; t.w[3] = tp.w11;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float4* pp = reinterpret_cast<const float4*>(img + (size_t)o[k] * C + u * 8);
-            t.q[u][2 * k] = __ldg(pp);
-            t.q[u][2 * k + 1] = __ldg(pp + 1);
-          }
-        }
-      };
-      auto planes2 = [&](int j0) {
-        XTaps t;
-        planes2_load(j0, t);
-        x_finish(j0, t);
-      };
-      if (xy_later) planes2_load(2 * ghalf, *xy_later);
-      else if (parts & 4) planes2(2 * ghalf);
-      if (parts & 2) {
-        planes2(4 + 4 * ghalf);
-        planes2(6 + 4 * ghalf);
-      }
-      if (parts & 1) {
-        float e[32];
-        if (ghalf == 0) embed_half<0, 10, 32>(p, e); else embed_half<1, 10, 32>(p, e);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = e[jj * 8 + i];
-          x_store8<SCHEME>(tmem_lane, 12 + ghalf * 4 + jj, y);
-        }
-      }
-      tmem_st_wait();
-      trace(tr, 0x21, trn, 0);
+    auto x_planes4 = [&](int b, const float (&p)[3]) {   // 'yz' (thread 0) / 'xz' (thread 1): 32 float4 loads in flight
+      XTaps<4> t;
+      x_taps(b, p, 4 + 4 * ghalf, t);
+      x_finish(4 + 4 * ghalf, t);
     };
     // h = lrelu(acc1 + b, slope) -> H, quarter by quarter
     auto stage_act = [&](const float* __restrict__ b, bool act, float2 (&v)[4][16]) {   // waits for the GEMM first
@@ -245,9 +242,18 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
     };
 
     if (ntiles > 0) {
-      build_x(tile_of(0), 7);
+      float p0[3];
+      const int b0 = x_point(tile_of(0), p0);
+      XTaps<2> t0;
+      x_taps(b0, p0, 2 * ghalf, t0);
+      x_finish(2 * ghalf, t0);
+      x_planes4(b0, p0);
+      x_embed(p0);
+      tmem_st_wait();
       signal_all();
     }
+    float pn[3] = {0.f, 0.f, 0.f};   // the next tile's sample point / object (set under layer 6's GEMM)
+    int bn = 0;
     for (long long it = 0; it < ntiles; ++it) {
       const long long tile = tile_of(it);
       tr = DDMI_PROFILE && blockIdx.x == 0 && tid == 0 && it == kTraceIter;
@@ -261,7 +267,13 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         stage_act(vec + NV_B + l * 256, true, v);
         // X is dead from here on (the second skip layer, xyz_encoding_5, has committed): the next tile's gamma(pts) -- 16
         // sincosf per thread, ~5 K cycles -- goes under layer 6's GEMM
-        if (l == 4 && it + 1 < ntiles) build_x(tile_of(it + 1), 1);
+        if (l == 4 && it + 1 < ntiles) {
+          trace(tr, 0x20, trn, 0);
+          bn = x_point(tile_of(it + 1), pn);
+          x_embed(pn);
+          tmem_st_wait();
+          trace(tr, 0x21, trn, 0);
+        }
         if (l == 5) {
           // X is dead (the last skip layer committed): view-direction embedding -> X's first 4 K groups,
           // sigma = w_sigma . h6 + b_sigma (this thread's 128 columns, summed across the two sub-warps below)
@@ -298,8 +310,14 @@ nerf_umma_kernel(PlaneSet ps, int C, const float* __restrict__ rays, int ray_str
         stage_act(vec + NV_BF, false, v);
       }
       const bool more = it + 1 < ntiles;
-      XTaps xy;
-      if (more) build_x(tile_of(it + 1), 2, &xy);
+      XTaps<2> xy;
+      if (more) {
+        trace(tr, 0x20, trn, 0);
+        x_planes4(bn, pn);
+        x_taps(bn, pn, 2 * ghalf, xy);
+        tmem_st_wait();
+        trace(tr, 0x21, trn, 0);
+      }
       // ---- dir_encoding (N = 128) + rgb head
       float rgb[3];
       {
