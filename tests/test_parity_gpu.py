@@ -805,6 +805,23 @@ def test_video_ragged_volume():
     assert float((out - ref).abs().max()) < TOL
 
 
+def test_single_cta_kernels_of_the_resnet_decoders(monkeypatch):
+    """DDMI_B200_CTA_PAIR=0 (bf16x3 only): the single-CTA instantiations of the occupancy / video kernels run the same programs
+    (PE operands on their own barrier, R1's video pieces parked in H, net_p on the tensor core) -- against the oracle."""
+    monkeypatch.setenv('DDMI_B200_CTA_PAIR', '0')
+    m = cases.build_module('occupancy').to(DEV)
+    m.precision = 'bf16x3'
+    pts, hdbf = cases.occupancy_inputs(batch=2, n=777)
+    out = m(pts.to(DEV), _cuda(hdbf)).logits.cpu()
+    ref = orc.occupancy_logits(cases.state_dict32(m), pts, hdbf)
+    assert float((out - ref).abs().max()) < TOL
+    mv = cases.build_module('video').to(DEV)
+    mv.precision = 'bf16x3'
+    coords, hv = cases.video_inputs()
+    outv = mv(_cuda(coords), _cuda(hv)).cpu()
+    assert float((outv - orc.video_decode(cases.state_dict32(mv), coords, hv)).abs().max()) < TOL
+
+
 def test_full_size_table_paths_are_bit_identical_to_the_direct_paths(monkeypatch):
     """BASELINE configs[2] / [3] at full size, two items each: the video feature tables against per-voxel gathers and the 128^3
     lattice query against the expanded point list -- equal bit for bit (size-independent property; the oracle comparisons at
