@@ -17,7 +17,10 @@
 // ~12-13 K cycles, three times per tile, against 39 K cycles of MMA work -- and the epilogue threads that gather are the
 // ones the next stage waits for.  Tried and measured slower: one X buffer + a 64 KB weight ring (the ring is not the limit
 // here), dedicated gather warps staging texels with cp.async (scattered LDGSTS tops out near 13 B/clk/SM; two warps cannot
-// hold enough LDG results in registers either).
+// hold enough LDG results in registers either).  Second half of round 2: the PE operands' MMAs commit on their own completion
+// barrier (D1) right behind the shortcut, so the next gather runs under fc_0's MMAs over h instead of in front of the next
+// stage; lattice queries (below) move a quarter of the bytes.  With that the kernel sits at ~70 % of its shared-memory-operand
+// tensor bound (profiles/r02b_occupancy_timeline_lattice.txt).
 //
 // LATTICE QUERIES (LAT = 1; round 2).  On a query lattice {xs[i]} x {ys[j]} x {zs[k]} (the mesh generator's and BASELINE
 // configs[3]'s dense grid) the 'xy' sample depends on (i, j) only, 'yz' on (j, k), 'xz' on (i, k): `occ_table_kernel` samples
