@@ -574,28 +574,43 @@ def quick_other(kind, args, dev):
 
 
 def run_other(args):
-    """configs[0], [2], [3], [4]: the same line as the headline (value, e2e, clocks, roofline, cpu / eager-GPU baselines), 1 GPU."""
+    """configs[0], [2], [3], [4]: the same line as the headline (value, e2e, clocks, roofline, cpu / eager-GPU baselines).
+    Under torchrun (N ranks, one per GPU): weak scaling like the headline -- every rank decodes the config's batch of its own
+    items (the path shards by item with no exchange), barrier + synchronize around the timed region, time = max over ranks,
+    value = N x the per-rank coordinates / that time; rank 0 prints."""
+    import torch.distributed as dist
     torch.set_grad_enabled(False)
-    dev = torch.device('cuda', 0)
-    torch.cuda.set_device(0)
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     W = OtherWorkload(args.workload, args, dev)
     B = W.B
     coords = B * W.n_per_item
     planes = W.slice(W.host, 0, B, dev)
     torch.cuda.synchronize()
     fn = lambda: W.decode(planes)
-    sampler = ClockSampler(0)                      # before the warm-up: nvidia-smi's start-up stalls the device briefly
+    sampler = ClockSampler(local) if rank == 0 else None   # before the warm-up: nvidia-smi's start-up stalls the device briefly
     for _ in range(args.warmup):
         fn()
-    torch.cuda.synchronize()
+    barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
         fn()
     t1.record()
-    torch.cuda.synchronize()
+    barrier()
     ms = t0.elapsed_time(t1)
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host planes -> HBM, decode through the public call, result -> pinned host; items walked in chunks
     CH = max(1, min(args.e2e_chunk, B))
@@ -625,26 +640,36 @@ def run_other(args):
 
     for _ in range(2):              # two untimed passes: the caching allocator's per-stream pools settle on the second
         e2e_step()
-    torch.cuda.synchronize()
+    barrier()
     e2e_steps = max(1, min(args.steps, 3))
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
     for _ in range(e2e_steps):
         e2e_step()
     a1.record()
-    torch.cuda.synchronize()
+    barrier()
     e2e_ms = a0.elapsed_time(a1)
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
 
     tf_peak, _, which = peaks()
-    value = coords * args.steps / (ms * 1e-3)
-    achieved = value * FLOP_PER_COORD[W.flop_kind] / 1e12
+    per_gpu = coords * args.steps / (ms * 1e-3)
+    value = world * per_gpu
+    achieved = per_gpu * FLOP_PER_COORD[W.flop_kind] / 1e12          # roofline: per GPU (the kernel's own rate)
     pi = PREC_INFO[args.precision]
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": pi['dtype'], "data": "synthetic",
             "config": {"workload": W.desc, "coords_per_step_per_gpu": coords, "precision": args.precision,
+                       "parallelism": f"{world} GPU(s), one batch of items per GPU, no exchange on the path",
                        "l2": "planes %.2f GB per step; every step re-reads them (larger than L2 for batch >= 8)" % (W.h2d_bytes() / 1e9)},
-            "e2e": {"value": coords * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W.h2d_bytes(),
+            "e2e": {"value": world * coords * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W.h2d_bytes(),
                     "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "steps": e2e_steps,
                     "pipeline": f"items walked in chunks of {CH}; uploads / read-backs on side streams"},
             "gpu_launches": args.steps * getattr(W, 'launches', 1),
@@ -672,7 +697,7 @@ def run_other(args):
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf
         line["gpu_eager_baseline"] = {"value": n / dtg, "unit": UNIT, "kind": "oracle restatement of the reference decoder, eager "
                                       "PyTorch fp32 (TF32 off) on this GPU", "sample": what + ", best of 3",
-                                      "speedup_of_value": value / (n / dtg)}
+                                      "speedup_of_value": per_gpu / (n / dtg)}
     print(json.dumps(line))
 
 
@@ -918,7 +943,7 @@ if __name__ == '__main__':
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-strong', action='store_true', help='N > 1: skip the strong-scaling (sharded batch 64 + all-gather) leg')
     ap.add_argument('--workload', default='image', choices=['image', 'c1', 'occupancy', 'video', 'nerf', 'mesh', 'planes'],
-                    help='image = the headline (BASELINE configs[1]); c1 / video / occupancy / nerf = configs[0], [2], [3], [4], 1 GPU')
+                    help='image = the headline (BASELINE configs[1]); c1 / video / occupancy / nerf = configs[0], [2], [3], [4] (1 GPU, or N under torchrun: weak scaling)')
     ap.add_argument('--cpu-coords', type=int, default=131072, help='coordinates in the CPU-baseline sample of the non-headline workloads')
     ARGS = ap.parse_args()
     if ARGS.impl == 'reference':
