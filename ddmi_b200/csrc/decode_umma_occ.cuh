@@ -417,10 +417,14 @@ occupancy_umma_kernel(PlaneSet ps, const float* __restrict__ pts, long long n, l
         for (int q = 0; q < 4; ++q) { put_quarter<true, SCHEME>(h_hi, h_lo, row, q, sub, v[q]); signal(q); }
         // the PE operands ran right behind the shortcut's commit (D1): Xa / Xb are free, what comes next is gathered under
         // fc_0's MMAs over h
+        // -- in two halves, one under fc_0's MMAs over h and one under fc_1's: a scattered gather (12 K cycles at the SM's L2
+        // read rate) does not fit one of those windows
         wait_d1();
-        if (blk == 1) { gather(tile, 2); signal(4); }
-        else if (it + 1 < ntiles) gather(tile_of(it + 1), 0);
+        if (blk == 1) gather(tile, 2, 0);
+        else if (it + 1 < ntiles) gather(tile_of(it + 1), 0, 0);
         stage_net(vec + (blk == 1 ? OV_B02 : OV_B03));
+        if (blk == 1) { gather(tile, 2, 1); signal(4); }
+        else if (it + 1 < ntiles) gather(tile_of(it + 1), 0, 1);
       }
       // ---- R3 output h3 = acc2 + b1_3; R4 has an identity shortcut: only relu(h3) is needed, acc2 keeps accumulating
       {
